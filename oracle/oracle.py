@@ -1,0 +1,362 @@
+"""CPU oracle for the geometry hot path -- TEST INFRASTRUCTURE ONLY.
+
+Restates, function by function, what the reference
+(BarnitaSharma/Part-based-3D-Reconstruction, pure NumPy/SciPy) computes on the
+north-star path.  Scalar numerics (projection, trilinear resample, connected
+components, IoU counts) are in ``p3d_oracle.c`` with a fixed FP operation
+order; the array bookkeeping around them is NumPy here.  Each function cites
+the reference ``file:line`` it follows.
+
+Who may import this module: ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py`` (``cpu_baseline`` / ``--impl reference`` legs).  The product
+package never does; it raises if its CUDA library is missing.
+
+Pinned by: ``tests/test_oracle_golden.py`` against fixtures generated from the
+live reference by ``tests/golden/make_golden.py`` (run in the build container,
+where ``/root/reference`` is importable).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libp3d_oracle.so")
+
+# utils/config.py:29-40 (data, not code)
+PART_COLORS = {
+    "full_building": (253, 248, 96),
+    "chhatris": (1, 220, 5),
+    "plinth": (63, 138, 173),
+    "dome": (190, 0, 255),
+    "front_minarets": (0, 0, 255),
+    "back_minarets": (5, 223, 223),
+    "small_minarets": (255, 180, 80),
+    "main_door": (180, 140, 255),
+    "windows": (255, 120, 230),
+    "background": (216, 224, 251),
+}
+PART_COLORS_NP = {k: np.array(v) for k, v in PART_COLORS.items()}
+INTERIOR_PARTS = ["main_door", "windows"]
+
+
+def build(force: bool = False) -> str:
+    """Compile p3d_oracle.c with gcc (idempotent)."""
+    src = os.path.join(_HERE, "p3d_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        f64, f32 = ctypes.c_double, ctypes.c_float
+        L.orc_look_at_f64.argtypes = [vp, vp, vp]
+        L.orc_look_at_f32.argtypes = [vp, vp, vp]
+        L.orc_project_f64.argtypes = [vp, vp, i64, vp, vp, f64, f64, f64, i32, i32, vp, vp]
+        L.orc_project_f32.argtypes = [vp, vp, i64, vp, vp, f32, f32, f32, i32, i32, vp, vp]
+        L.orc_partwise_counts.argtypes = [vp, vp, i64, vp, i32, vp, vp]
+        L.orc_affine_order1_u8.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+        L.orc_label6.argtypes = [vp, i32, i32, i32, vp]
+        L.orc_label6.restype = i32
+        for fn in (L.orc_look_at_f64, L.orc_look_at_f32, L.orc_project_f64, L.orc_project_f32,
+                   L.orc_partwise_counts, L.orc_affine_order1_u8):
+            fn.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# --------------------------------------------------------------------------- #
+# stage 2: camera scoring
+# --------------------------------------------------------------------------- #
+def _working_dtype(*arrs) -> np.dtype:
+    """numpy promotion of `pts3d - cam_pos` etc. (projection_utils.py:7)."""
+    t = np.result_type(*[np.asarray(a).dtype for a in arrs])
+    return np.dtype(np.float32) if t == np.float32 else np.dtype(np.float64)
+
+
+def look_at_rotation(eye, target):
+    """camera_geometry.py:3-14 (default up = [0,1,0])."""
+    dt = _working_dtype(eye, target)
+    e = np.ascontiguousarray(eye, dtype=dt)
+    t = np.ascontiguousarray(target, dtype=dt)
+    R = np.empty((3, 3), dt)
+    (lib().orc_look_at_f32 if dt == np.float32 else lib().orc_look_at_f64)(_p(e), _p(t), _p(R))
+    return R
+
+
+def project_points(pts3d, colors, cam_pos, target, f, cx, cy, H, W, want_image=True):
+    """projection_utils.py:5-23.  Returns (image (H,W,3) u8 | None, winner (H,W) u32)
+    where winner = 1 + index of the point that owns the pixel (0 = untouched)."""
+    pts = np.ascontiguousarray(pts3d, dtype=np.float32).reshape(-1, 3)
+    n = pts.shape[0]
+    col = np.ascontiguousarray(colors, dtype=np.uint8).reshape(-1, 3) if colors is not None \
+        else np.zeros((n, 3), np.uint8)
+    dt = _working_dtype(pts, cam_pos, target)
+    cp = np.ascontiguousarray(cam_pos, dtype=dt)
+    tg = np.ascontiguousarray(target, dtype=dt)
+    img = np.empty((H, W, 3), np.uint8) if want_image else None
+    pix = np.empty((H, W), np.uint32)
+    fn = lib().orc_project_f32 if dt == np.float32 else lib().orc_project_f64
+    fn(_p(pts), _p(col), n, _p(cp), _p(tg), float(f), float(cx), float(cy), int(H), int(W),
+       _p(img) if want_image else None, _p(pix))
+    return img, pix
+
+
+def project_colored_voxels(pts3d, colors, cam_pos, target, f, cx, cy, H, W):
+    """projection_utils.py:5-23."""
+    return project_points(pts3d, colors, cam_pos, target, f, cx, cy, H, W)[0]
+
+
+def partwise_counts(proj_mask, gt_mask, part_colors: dict):
+    """Integer (inter, union) pixel counts per part (camera_estimation.py:777-783)."""
+    a = np.ascontiguousarray(proj_mask, dtype=np.uint8).reshape(-1, 3)
+    b = np.ascontiguousarray(gt_mask, dtype=np.uint8).reshape(-1, 3)
+    rgb = np.ascontiguousarray([part_colors[k] for k in part_colors], dtype=np.uint8).reshape(-1, 3)
+    P = rgb.shape[0]
+    inter = np.zeros(P, np.int64)
+    uni = np.zeros(P, np.int64)
+    lib().orc_partwise_counts(_p(a), _p(b), a.shape[0], _p(rgb), P, _p(inter), _p(uni))
+    return inter, uni
+
+
+def iou_from_counts(inter, uni):
+    """camera_estimation.py:783-787: iou = inter/union or 0.0; score = mean over all parts."""
+    ious = [float(i) / float(u) if u > 0 else 0.0 for i, u in zip(inter, uni)]
+    return ious, float(np.mean(ious))
+
+
+def compute_partwise_iou(proj_mask, gt_mask, part_colors: dict):
+    """camera_estimation.py:770-787."""
+    inter, uni = partwise_counts(proj_mask, gt_mask, part_colors)
+    ious, mean = iou_from_counts(inter, uni)
+    return dict(zip(part_colors.keys(), ious)), mean
+
+
+def get_voxel_points_by_parts(grid, part_colors, part_names):
+    """voxel_utils.py:7-21: points of the selected colours in ascending flat index,
+    as float32 [x=a2, y=a1, z=a0]."""
+    g = np.asarray(grid)
+    sel = np.zeros(g.shape[:3], bool)
+    for name in part_names:
+        c = np.asarray(part_colors[name])
+        sel |= (g[..., 0] == c[0]) & (g[..., 1] == c[1]) & (g[..., 2] == c[2])
+    flat = np.flatnonzero(sel)
+    a0, a1, a2 = np.unravel_index(flat, sel.shape)
+    pts = np.stack([a2, a1, a0], axis=1).astype(np.float32)
+    return pts, g.reshape(-1, 3)[flat]
+
+
+def mask_parts_from_image(image, part_colors, selected_parts):
+    """mask_utils.py:89-97."""
+    img = np.asarray(image)
+    out = np.zeros_like(img)
+    for part in selected_parts:
+        c = np.asarray(part_colors[part], dtype=img.dtype)
+        hit = (img[..., 0] == c[0]) & (img[..., 1] == c[1]) & (img[..., 2] == c[2])
+        out[hit] = c
+    return out
+
+
+def score_candidate(pts, cols, seg_img, selected_labels, p, H, W):
+    """The `evaluate` closure, camera_estimation.py:597-603 (returns +IoU and counts)."""
+    proj = project_colored_voxels(pts, cols, p["cam_pos"], p["target"], p["f"], p["cx"], p["cy"], H, W)
+    inter, uni = partwise_counts(proj, seg_img, selected_labels)
+    return iou_from_counts(inter, uni)[1], inter, uni
+
+
+# --------------------------------------------------------------------------- #
+# stage 1: carving
+# --------------------------------------------------------------------------- #
+def rotation_matrix_inv(angle):
+    """voxel_carving_utils.py:65-69 (host NumPy/LAPACK, as in the reference)."""
+    a = np.deg2rad(angle)
+    c, s = np.cos(a), np.sin(a)
+    return np.linalg.inv(np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]))
+
+
+def affine_order1(vol_u8, M, off):
+    """scipy.ndimage.affine_transform(order=1, mode='constant', cval=0) on a u8 volume."""
+    v = np.ascontiguousarray(vol_u8, dtype=np.uint8)
+    out = np.empty_like(v)
+    Mc = np.ascontiguousarray(M, dtype=np.float64)
+    oc = np.ascontiguousarray(off, dtype=np.float64)
+    lib().orc_affine_order1_u8(_p(v), v.shape[0], v.shape[1], v.shape[2], _p(Mc), _p(oc), _p(out))
+    return out
+
+
+def mask_to_wh(mask, W, H):
+    """voxel_carving_utils.py:19-28: the (H,W) test comes first, so square masks are
+    always transposed."""
+    if mask.shape[:2] == (H, W):
+        return mask.T
+    if mask.shape[:2] == (W, H):
+        return mask
+    raise ValueError(f"Mask shape {mask.shape} incompatible with (W,H)=({W},{H})")
+
+
+def carve_with_mask(vol, mask):
+    """voxel_carving_utils.py:76-87 (2-D mask branch) on a (W,H,D) occupancy volume."""
+    W, H, _ = vol.shape
+    m = mask_to_wh(np.asarray(mask), W, H)
+    return np.where(m[:, :, None], vol, 0).astype(vol.dtype)
+
+
+def process_voxel_grid(vol, mask, angle_interval=90):
+    """voxel_carving_utils.py:104-126: cumulative rotate (about shape/2) + mask carve."""
+    ctr = np.array(vol.shape) / 2
+    out = vol
+    for angle in range(0, 91, angle_interval):
+        M = rotation_matrix_inv(angle)
+        out = affine_order1(out, M, ctr - M @ ctr)
+        out = carve_with_mask(out, mask)
+    return out
+
+
+def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90):
+    """voxel_carving_utils.py:269-298 (+ :128-136 colouring)."""
+    h, w = binary_mask.shape
+    carved = process_voxel_grid(np.ones((w, h, w), np.uint8), binary_mask, angle_interval)
+    colour_wh = np.asarray(semantic_mask_exterior).transpose(1, 0, 2)          # (W,H,3)
+    return np.where((carved == 1)[..., None], colour_wh[:, :, None, :], 0).astype(np.uint8)
+
+
+def _colour_eq(arr, colour):
+    c = np.asarray(colour)
+    return (arr[..., 0] == c[0]) & (arr[..., 1] == c[1]) & (arr[..., 2] == c[2])
+
+
+def part_carve(colored_grid, semantic_mask, group_jobs):
+    """voxel_carving_utils.py:139-160."""
+    final = np.zeros_like(colored_grid)
+    for names, angle in group_jobs:
+        in_group = np.zeros(semantic_mask.shape[:2], bool)
+        for n in names:
+            in_group |= _colour_eq(semantic_mask, PART_COLORS[n])
+        if not in_group.any():
+            continue
+        m = in_group.T.astype(np.uint8)                                         # (W,H)
+        sub = colored_grid * m[:, :, None, None]
+        occ = (sub > 0).any(-1).astype(np.uint8)
+        carved = process_voxel_grid(occ, m, angle)
+        part = sub * carved[..., None]
+        keep = (part > 0).any(-1)
+        final[keep] = part[keep]
+    return final
+
+
+def label6(mask):
+    """scipy.ndimage.label default structure; ids in raster order of first voxel."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty(m.shape, np.int32)
+    n = lib().orc_label6(_p(m), m.shape[0], m.shape[1], m.shape[2], _p(out))
+    return out, int(n)
+
+
+def left_right_guided_carve(colored_grid, semantic_mask, target_color, angle=60, log=None):
+    """voxel_carving_utils.py:163-210.  `log` (list) collects the lines the reference prints."""
+    out = colored_grid.copy()
+    in_part = _colour_eq(semantic_mask, target_color)                            # (H,W)
+    if not in_part.any():
+        if log is not None:
+            log.append(f"[SKIP] No mask for color {target_color}")
+        return out
+    lab, n = label6(_colour_eq(colored_grid, target_color))
+    if log is not None:
+        log.append(f"[{target_color}] 3D components: {n}")
+    for i in range(1, n + 1):
+        member = lab == i
+        idx = np.argwhere(member)
+        if idx.size == 0:
+            continue
+        x0, y0, z0 = idx.min(0)
+        x1, y1, z1 = idx.max(0) + 1
+        if log is not None:
+            log.append(f"  - Component {i}: bbox ({x0},{y0},{z0}) → ({x1},{y1},{z1})")
+        crop2d = in_part[y0:y1, x0:x1]
+        sub = colored_grid[x0:x1, y0:y1, z0:z1].copy()
+        occ = (sub > 0).any(-1).astype(np.uint8)
+        kept = process_voxel_grid(occ, crop2d, angle)
+        if log is not None:
+            log.append(f"    carved voxels: {np.count_nonzero(kept)}")
+        kept_rgb = sub * kept[..., None]
+        view = out[x0:x1, y0:y1, z0:z1]
+        view[member[x0:x1, y0:y1, z0:z1]] = 0
+        nz = (kept_rgb > 0).any(-1)
+        view[nz] = kept_rgb[nz]
+    return out
+
+
+def extrude_from_surface(grid, mask_2d, axis, direction="+", depth=5, fill_color=None):
+    """voxel_carving_utils.py:213-248 (argmax of an empty column is 0)."""
+    occ = (grid > 0).any(-1)
+    W, H, D = occ.shape
+    fill = np.zeros((W, H, D), bool)
+    sign = 1 if direction == "+" else -1
+    if axis == 2:
+        first = np.argmax(occ, axis=2) if sign > 0 else D - 1 - np.argmax(occ[:, :, ::-1], axis=2)
+        ok2d = np.asarray(mask_2d).T.astype(bool)                                # (W,H)
+        xs, ys = np.nonzero(ok2d)
+        for d in range(depth):
+            z = first[xs, ys] + sign * d
+            k = (z >= 0) & (z < D)
+            fill[xs[k], ys[k], z[k]] = True
+    elif axis == 0:
+        first = np.argmax(occ, axis=0) if sign > 0 else W - 1 - np.argmax(occ[::-1], axis=0)
+        ok2d = np.asarray(mask_2d).astype(bool)                                  # (H, W) used as [y, z]
+        if ok2d.shape != first.shape:
+            raise ValueError("operands could not be broadcast together")
+        ys, zs = np.nonzero(ok2d)
+        for d in range(depth):
+            x = first[ys, zs] + sign * d
+            k = (x >= 0) & (x < W)
+            fill[x[k], ys[k], zs[k]] = True
+    out = grid.copy()
+    out[fill] = 0 if fill_color is None else fill_color
+    return out
+
+
+def recolor_backward_components(voxel_grid, color, new_color, k=4, sort_axis=2):
+    """voxel_carving_utils.py:252-266."""
+    lab, n = label6(_colour_eq(voxel_grid, color))
+    means = []
+    for i in range(1, n + 1):
+        idx = np.argwhere(lab == i)
+        means.append((i, idx[:, sort_axis].mean()))
+    keep = {i for i, _ in sorted(means, key=lambda t: t[1])[:k]}
+    out = np.ascontiguousarray(voxel_grid).copy()
+    for i in range(1, n + 1):
+        if i not in keep:
+            out[lab == i] = new_color
+    return out
+
+
+def partwise_carve(colored_voxel_grid, semantic_mask_exterior, semantic_mask_full, part_colors_np,
+                   group_jobs, part_symmetry, extrusion_depths, recolor_back_minarets=True, log=None):
+    """voxel_carving_utils.py:302-400."""
+    grid = part_carve(colored_voxel_grid, semantic_mask_exterior, group_jobs)
+    for part, angle in part_symmetry.items():
+        grid = left_right_guided_carve(grid, semantic_mask_exterior, part_colors_np[part], angle, log)
+    for part, depth in extrusion_depths.items():
+        m = _colour_eq(np.asarray(semantic_mask_full), part_colors_np[part])
+        for axis, direction in ((2, "+"), (2, "-"), (0, "+"), (0, "-")):
+            grid = extrude_from_surface(grid, m, axis, direction, depth, part_colors_np[part])
+    if recolor_back_minarets:
+        oriented = np.flip(grid.transpose(2, 1, 0, 3), axis=1)
+        grid = recolor_backward_components(oriented, part_colors_np["front_minarets"],
+                                           part_colors_np["back_minarets"], k=2, sort_axis=0)
+    return grid
