@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the camera-candidate sweep (BASELINE.json metric: camera candidates scored/s at a
+512^3 grid) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): the deterministic synthetic 512^3 semantic monument
+(part-based-3d-reconstruction_b200/synthetic.py), all 9 parts scored (21.9 M points), one
+1024x1024 ground-truth label image rendered through a hidden camera, 65 536 candidate cameras
+(base + U(-1,1)*reference step sizes, seed 20240607).  One "step" = every rank scores its block of
+`--cands-per-step` candidates and the ranks agree on the best (score, index) with one 16-byte
+all-gather.  Candidates are sharded across ranks, so per-GPU work is fixed (weak scaling).
+
+value   : candidates/s with grid points, ground truth and candidates resident in HBM.
+e2e     : the same through the public API with HOST candidate arrays in and host scores/counts out.
+roofline: the splat kernel, algorithmic bytes = cameras/launch * (G*1 B + 9 B*H*W)  (SURVEY 8d),
+          duration from CUDA events recorded around every splat launch inside the timed region.
+cpu_baseline: the NumPy port of the reference path (oracle/np_port.py) on this box's host cores.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "part-based-3d-reconstruction_b200"
+METRIC = "camera candidates scored/s at 512^3 grid"
+UNIT = "candidates/s"
+TOTAL_CANDIDATES = 65536
+HIDDEN_DELTA = np.array([3.0, -2.0, 5.0, 1.0, 2.0, -3.0, 4.0, 1.5, -2.5])
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--mask", type=int, default=1024)
+    ap.add_argument("--cands-per-step", type=int, default=2048, help="candidates per rank per step")
+    ap.add_argument("--parts", default="all", choices=["all", "minarets"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or not (t0 - 0.2 <= t <= t1 + 0.2):
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    syn = importlib.import_module(PKG + ".synthetic")
+    ce = importlib.import_module(PKG + ".utils.camera_estimation")
+    cfg = importlib.import_module(PKG + ".utils.config")
+    nv = importlib.import_module(PKG + ".utils._native")
+    sweep_mod = importlib.import_module(PKG + ".utils.sweep")
+
+    N, H, W, B = args.grid, args.mask, args.mask, args.cands_per_step
+    parts = syn.PART_NAMES if args.parts == "all" else ["front_minarets", "back_minarets"]
+    t_setup = time.perf_counter()
+    lut = torch.from_numpy(syn.label_lut()).to(dev)
+    rgb = lut[syn.monument_labels(N, dev).long()]
+    base = syn.base_camera(N, H, W, "front")
+    hidden = base + HIDDEN_DELTA
+    full = ce.CandidateScorer(rgb, torch.zeros((H, W, 3), dtype=torch.uint8, device=dev), cfg.PART_COLORS, syn.PART_NAMES)
+    gt = torch.from_numpy(full.render(ce.row_to_params(hidden))).to(dev)
+    del full
+    scorer = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, parts)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    n_points = scorer.n_points
+    P = scorer.P
+
+    cand_all = syn.candidates(base, TOTAL_CANDIDATES)                       # (65536, 9) float64, host
+    steps_total = args.warmup + args.steps
+
+    def step_block(s):
+        """Global candidate indices of step s for this rank (contiguous shard of the step's chunk)."""
+        g0 = (s * B * world) % TOTAL_CANDIDATES
+        idx = (g0 + rank * B + np.arange(B)) % TOTAL_CANDIDATES
+        return idx
+
+    host_blocks = [torch.from_numpy(np.ascontiguousarray(cand_all[step_block(s)])).pin_memory() for s in range(steps_total)]
+    offsets = [int(step_block(s)[0]) for s in range(steps_total)]
+    dev_blocks = [b.to(dev) for b in host_blocks]
+    reducer = sweep_mod.BestReducer(dev, world)
+
+    def device_step(s):
+        counts, scores, best = scorer.score_device(dev_blocks[s])
+        return reducer.reduce(scores, best, offsets[s]), counts
+
+    # ---- value: device-resident inputs ------------------------------------------------------------
+    for s in range(args.warmup):
+        device_step(s)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = nv.launch_count
+    nv.lib.p3d_sweep_timing_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for s in range(args.warmup, steps_total):
+        result, _ = device_step(s)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    splat_ms, splat_launches = ctypes.c_double(), ctypes.c_int()
+    nv.lib.p3d_sweep_timing_read(ctypes.byref(splat_ms), ctypes.byref(splat_launches))
+    nv.lib.p3d_sweep_timing_enable(0)
+    launches = nv.launch_count - launches0 + args.steps * reducer.launches_per_reduce
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host candidates in, host scores/counts out, through the public API ------------------
+    for s in range(min(2, args.warmup)):
+        scorer.score(host_blocks[s].numpy())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for s in range(args.warmup, steps_total):
+        sc, cn, bi = scorer.score(host_blocks[s].numpy())
+    e3.record()
+    torch.cuda.synchronize()
+    t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / (float(t2.item()) * 1e-3)
+    h2d = B * 9 * 8
+    d2h = B * 8 + B * cn.shape[1] * 2 * 8 + 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (splat) --------------------------------------------------
+    peak, peak_src = peaks()
+    G = N ** 3
+    batch = max(1, min(B, 64, (64 << 20) // (H * W * 4)))
+    alg_per_launch = batch * (G * 1 + 9 * H * W)
+    avg_launch_s = (splat_ms.value / max(1, splat_launches.value)) * 1e-3
+    achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "splat_kernel<double,joint>",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch,
+                "cameras_per_launch": batch, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
+                "splat_share_of_step": round(splat_ms.value / ms, 4),
+                "point_candidates_per_s": round(n_points * batch / avg_launch_s, 1) if avg_launch_s > 0 else None,
+                "note": "streaming model of SURVEY 8(d): dense u8 grid once per camera + 9 B/pixel; the kernel is "
+                        "FP64-issue bound, see DESIGN.md"}
+
+    # ---- CPU baseline: NumPy port of the reference path on this box's host cores -----------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline(scorer, gt, parts, cfg, cand_all, H, W, n_points, args.cpu_sample, processes=1)
+
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {N}^3 semantic monument, {len(parts)} parts ({n_points} points), "
+                               f"{H}x{W} label mask, {TOTAL_CANDIDATES} candidate cameras sharded over {world} GPU(s), "
+                               f"{B} candidates/GPU/step",
+                   "grid": N, "mask": [H, W], "parts": len(parts), "points": n_points,
+                   "candidates_total": TOTAL_CANDIDATES, "candidates_per_gpu_per_step": B,
+                   "l2": "inputs larger than L2 (point list %.0f MB streamed by every launch); fresh candidates each step"
+                         % (n_points * 13 / 1e6),
+                   "setup_s_once_per_sweep": round(t_setup, 3)},
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "best": {"index": int(result[1]), "score": float(result[0])},
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(scorer, gt, parts, cfg, cand_all, H, W, n_points, sample, processes):
+    import torch
+    from oracle import np_port
+    pts = scorer.pts.cpu().numpy()
+    lut = np.zeros((256, 3), np.uint8)
+    lut[1:1 + len(scorer.colours)] = np.array(scorer.colours, np.uint8)
+    cols = lut[scorer.pt_label.cpu().numpy()]
+    gt_np = gt.cpu().numpy() if isinstance(gt, torch.Tensor) else gt
+    sel = {p: cfg.PART_COLORS[p] for p in parts}
+    seg = np.zeros_like(gt_np)
+    for c in sel.values():
+        seg[np.all(gt_np == c, axis=-1)] = c
+    if sample <= 0:
+        sample = max(processes, int(round(processes * 2.2e7 * 6 / max(n_points, 1))))   # ~10-30 s of host work
+        sample = max(1, min(sample, 4096))
+    dt, scores = np_port.timed_sweep(pts, cols, seg, sel, cand_all[:sample], H, W, processes=processes)
+    return {"value": round(sample / dt, 4), "unit": UNIT, "cores": processes, "kind": "port",
+            "sample": f"first {sample} of the {TOTAL_CANDIDATES} candidates on the same grid/mask, NumPy port of the "
+                      f"reference path (oracle/np_port.py), {processes} process(es), {dt:.1f} s",
+            "score0": float(scores[0])}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU path (NumPy port; the reference is pure Python and cannot
+# travel to the GPU box), all host cores, bounded sample per step
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import np_port, oracle as orc
+    syn = importlib.import_module(PKG + ".synthetic")
+    N, H, W = args.grid, args.mask, args.mask
+    parts = syn.PART_NAMES if args.parts == "all" else ["front_minarets", "back_minarets"]
+    labels = syn.monument_labels(N, "cpu").numpy()
+    lut = syn.label_lut()
+    base = syn.base_camera(N, H, W, "front")
+    hidden = base + HIDDEN_DELTA
+
+    def points_of(names):
+        keep = np.isin(labels, [syn.LABEL[n] for n in names])
+        flat = np.flatnonzero(keep)
+        a0, a1, a2 = np.unravel_index(flat, labels.shape)
+        return np.stack([a2, a1, a0], axis=1).astype(np.float32), lut[labels.reshape(-1)[flat]]
+
+    pts_all, cols_all = points_of(syn.PART_NAMES)
+    gt = orc.project_colored_voxels(pts_all, cols_all, hidden[0:3], hidden[3:6], hidden[6], hidden[7], hidden[8], H, W)
+    pts, cols = (pts_all, cols_all) if args.parts == "all" else points_of(parts)
+    del labels
+    sel = {p: orc.PART_COLORS[p] for p in parts}
+    seg = orc.mask_parts_from_image(gt, orc.PART_COLORS, parts)
+    cand_all = syn.candidates(base, TOTAL_CANDIDATES)
+    procs = np_port.host_threads()
+    per_step = args.cpu_sample if args.cpu_sample > 0 else max(procs, int(round(procs * 2.2e7 * 1.5 / max(len(pts), 1))))
+    for s in range(args.warmup):
+        np_port.timed_sweep(pts, cols, seg, sel, cand_all[:procs], H, W, processes=procs)
+    total = 0.0
+    score0 = None
+    for s in range(args.steps):
+        blk = cand_all[(s * per_step) % TOTAL_CANDIDATES:][:per_step]
+        dt, scores = np_port.timed_sweep(pts, cols, seg, sel, blk, H, W, processes=procs)
+        total += dt
+        score0 = scores[0] if score0 is None else score0
+    value = per_step * args.steps / total
+    sample = (f"{per_step} candidates per step (bounded sample of the {TOTAL_CANDIDATES}-candidate sweep) on the same "
+              f"{N}^3 grid / {H}x{W} mask, candidate-parallel over {procs} host processes")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {N}^3 semantic monument, {len(parts)} parts ({len(pts)} points), {H}x{W} label "
+                               f"mask, NumPy port of the reference CPU path", "grid": N, "mask": [H, W],
+                   "parts": len(parts), "points": int(len(pts))},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "score0": float(score0),
+    }))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,156 @@
+/*
+ * p3d_b200.h -- C ABI of libp3d_b200.so: the B200 (sm_100a) geometry hot path of
+ * part-based 3-D reconstruction (orthographic semantic voxel carving + perspective
+ * camera-candidate scoring).
+ *
+ * The reference (BarnitaSharma/Part-based-3D-Reconstruction) has no FFI; its
+ * boundary is the set of Python functions the notebooks import.  Each entry point
+ * below names the reference function (file:line under the reference root) whose
+ * inner loop it replaces.  The Python layer in
+ * part-based-3d-reconstruction_b200/utils/ keeps the reference signatures and calls
+ * these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the parameter is
+ *     documented as "host"; the library never allocates persistent memory --
+ *     scratch comes from caller-provided workspaces sized by *_workspace_bytes();
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream); the caller synchronises;
+ *   - return value 0 = success, <0 = error (P3D_E_*); p3d_last_error() returns a
+ *     thread-local message for the last failing call on this thread;
+ *   - no global mutable state; re-entrant per stream;
+ *   - arrays are C-order; grids are (A0,A1,A2) with flat index (a0*A1 + a1)*A2 + a2;
+ *     RGB arrays carry a trailing channel axis of 3 uint8.
+ */
+#ifndef P3D_B200_H
+#define P3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3D_OK 0
+#define P3D_E_INVALID (-1)   /* bad argument */
+#define P3D_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define P3D_E_WORKSPACE (-3) /* workspace too small */
+
+typedef void* p3d_stream_t; /* cudaStream_t */
+
+/* p3d_sweep mode */
+#define P3D_MODE_JOINT 0    /* one label image per camera, last point in index order wins a pixel
+                               (launch_smart_aligner: camera_estimation.py:552-572, 597-603) */
+#define P3D_MODE_PER_PART 1 /* every part rendered on its own: pixel has part p iff any point of p lands
+                               on it (visualize_voxel_projection_iou: camera_estimation.py:381-403) */
+
+int p3d_version(void);
+const char* p3d_last_error(void);
+/* sm_count / cc_major / cc_minor / l2_bytes of the current device (host out-pointers, any may be NULL). */
+int p3d_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* --------------------------------------------------------------------------------------------- *
+ * Colour <-> label conversion (the reference compares RGB triples everywhere; the kernels work on
+ * one-byte palette indices).
+ * --------------------------------------------------------------------------------------------- */
+/* labels[i] = 1 + (index of the first palette colour equal to rgb[i]), 0 if none.  n_colors <= 255.
+ * Replaces the `np.all(x == colour, axis=-1)` scans at voxel_utils.py:12-15, mask_utils.py:92-95,
+ * camera_estimation.py:777-779.  palette_rgb: device, n_colors*3 bytes. */
+int p3d_rgb_to_labels(const uint8_t* rgb, int64_t n, const uint8_t* palette_rgb, int n_colors,
+                      uint8_t* labels, p3d_stream_t stream);
+/* rgb[i] = lut_rgb[labels[i]] ; lut_rgb: device, 256*3 bytes. */
+int p3d_labels_to_rgb(const uint8_t* labels, int64_t n, const uint8_t* lut_rgb, uint8_t* rgb,
+                      p3d_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------- *
+ * get_voxel_points_by_parts            utils/voxel_utils.py:7-21
+ * Stream compaction of the non-zero labels of a dense grid, in ascending flat index (the order of
+ * np.where), as float32 points [x = a2, y = a1, z = a0].
+ *   p3d_points_count : fills the workspace with per-tile offsets and writes the total to n_out[0]
+ *   p3d_points_fill  : writes pts (n,3) f32 and pt_label (n) u8 using that workspace
+ * --------------------------------------------------------------------------------------------- */
+size_t p3d_points_workspace_bytes(int64_t n_voxels);
+int p3d_points_count(const uint8_t* labels, int64_t n_voxels, int64_t* n_out, void* workspace,
+                     size_t workspace_bytes, p3d_stream_t stream);
+int p3d_points_fill(const uint8_t* labels, int A0, int A1, int A2, const void* workspace,
+                    float* pts, uint8_t* pt_label, int64_t capacity, p3d_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------- *
+ * look_at_rotation                     utils/camera_geometry.py:3-14
+ * cand: (K,9) = cam_pos[3], target[3], f, cx, cy.  cams: (K,16) = cam_pos[3], R[9] row-major,
+ * f, cx, cy, 0.  Same operation order as NumPy/OpenBLAS on the reference host.
+ * --------------------------------------------------------------------------------------------- */
+int p3d_setup_cameras_f64(const double* cand, int K, double* cams, p3d_stream_t stream);
+int p3d_setup_cameras_f32(const float* cand, int K, float* cams, p3d_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------- *
+ * project_colored_voxels (scatter)     utils/projection_utils.py:5-21
+ * For each of K cameras and each point i: project, round half-even, bounds-test, then
+ *   joint    : zbuf[k][v*W+u] = max(zbuf, i+1)        (last write wins == largest index wins)
+ *   per-part : zbuf[k][v*W+u] |= 1 << (pt_label[i]-1) (pt_label required, values 1..32)
+ * zbuf (K,H,W) uint32 must be zero on entry.  n < 2^32-1.
+ * --------------------------------------------------------------------------------------------- */
+int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K,
+                  int H, int W, int mode, uint32_t* zbuf, p3d_stream_t stream);
+int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K,
+                  int H, int W, int mode, uint32_t* zbuf, p3d_stream_t stream);
+
+/* project_colored_voxels (image)       utils/projection_utils.py:20-23
+ * img[p] = pt_rgb[zbuf[p]-1] or (0,0,0) where zbuf[p]==0.  One camera (joint-mode zbuf). */
+int p3d_resolve_rgb(const uint32_t* zbuf, const uint8_t* pt_rgb, int64_t n_pixels, uint8_t* img,
+                    p3d_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------- *
+ * compute_partwise_iou                 utils/camera_estimation.py:770-787
+ * --------------------------------------------------------------------------------------------- */
+/* Two RGB images -> counts (P,2) int64 = (inter, union) per part colour.  part_rgb: device P*3. */
+int p3d_partwise_counts_rgb(const uint8_t* proj_rgb, const uint8_t* gt_rgb, int64_t n_pixels,
+                            const uint8_t* part_rgb, int P, int64_t* counts, p3d_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------- *
+ * The candidate sweep: `evaluate` for K cameras in one call
+ *                                      utils/camera_estimation.py:597-603 (+ :646 selection)
+ *   pts (n,3) f32, pt_label (n) u8 in 1..P : the points of the selected parts, in index order
+ *   cand (K,9)                            : candidate cameras (f64 or f32 arithmetic per entry point)
+ *   gt_label (H,W) u8 in 0..P             : ground-truth part label per pixel (0 = none of the parts)
+ *   counts (K,P,2) int64                  : (inter, union) per camera and part
+ *   scores (K) f64                        : mean over the P parts of inter/union (0.0 if union == 0),
+ *                                           summed in NumPy's pairwise order
+ *   best (2) int64                        : [index of the first camera with the greatest score, 0]
+ *                                           (may be NULL)
+ * In P3D_MODE_PER_PART one extra row is appended per camera: counts is (K,P+1,2) and row P holds the
+ * combined binary IoU counts against gt_any (H,W) u8 (camera_estimation.py:433-447); scores is the mean
+ * over the P parts only.  gt_any may be NULL in joint mode.
+ * Workspace: p3d_sweep_workspace_bytes(); cameras are processed in batches sized so that the
+ * batch's z-buffers stay L2-resident.
+ * --------------------------------------------------------------------------------------------- */
+size_t p3d_sweep_workspace_bytes(int K, int H, int W, int P, int elem_bytes);
+int p3d_sweep_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cand, int K,
+                  const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
+                  int64_t* counts, double* scores, int64_t* best, void* workspace,
+                  size_t workspace_bytes, p3d_stream_t stream);
+int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cand, int K,
+                  const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
+                  int64_t* counts, double* scores, int64_t* best, void* workspace,
+                  size_t workspace_bytes, p3d_stream_t stream);
+/* Number of kernel launches the last p3d_sweep_* call on this thread issued (for bench accounting). */
+int p3d_sweep_last_launches(void);
+/* Best-candidate reduction across GPUs (camera_estimation.py:646: the first candidate with the greatest
+ * score wins).  p3d_best_pack writes pair = [bits of scores[best[0]], best[0] + offset] (index -1 if the
+ * block was empty); the caller all-gathers the 16-byte pairs (NCCL); p3d_best_select picks the greatest
+ * score with the lowest global index among n pairs into out (2) int64 = [score bits, index]. */
+int p3d_best_pack(const double* scores, const int64_t* best, int64_t offset, int64_t* pair,
+                  p3d_stream_t stream);
+int p3d_best_select(const int64_t* pairs, int n, int64_t* out, p3d_stream_t stream);
+
+/* Measurement hook: while enabled on the calling thread, p3d_sweep_* records a CUDA-event pair on the launch
+ * stream around every splat launch; p3d_sweep_timing_read() waits for them, returns the summed splat
+ * duration (ms) and the number of launches (host out-pointers), and resets the counters. */
+int p3d_sweep_timing_enable(int on);
+int p3d_sweep_timing_read(double* splat_ms, int* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3D_B200_H */

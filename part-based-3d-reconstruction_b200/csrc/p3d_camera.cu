@@ -1,0 +1,689 @@
+// libp3d_b200: perspective camera-candidate scoring (stage 2 of the reference).
+//
+// Reference call sites replaced here (paths under the reference root):
+//   look_at_rotation            utils/camera_geometry.py:3-14
+//   project_colored_voxels      utils/projection_utils.py:5-23
+//   compute_partwise_iou        utils/camera_estimation.py:770-787
+//   evaluate / run_random loop  utils/camera_estimation.py:597-603, 606-650
+//
+// Exactness contract (DESIGN.md "Projection arithmetic"): every FP operation is an explicit
+// round-to-nearest intrinsic in the order NumPy/OpenBLAS use on the reference host --
+//   d = p - c ; (X,Y,Z)[j] = fma(d2,R[j][2], fma(d1,R[j][1], d0*R[j][0])) ; Z<1e-8 -> 1e-8 ;
+//   u = (X/Z)*f + cx ; v = (-(Y/Z))*f + cy ; rint half-even ; bounds test in floating point.
+// Visibility is "largest point index wins" (NumPy fancy-assignment order), resolved with a
+// 32-bit atomicMax on index+1; a plain load in front of the atomic skips pixels that already hold
+// a larger index (valid because the buffer only grows), and tiles are walked from the high-index
+// end so that this filter hits for most points.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "p3d_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// FP helpers: explicit rounding, no contraction.
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Fp;
+template <> struct Fp<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  // round half to even for |x| < 2^51; larger magnitudes stay far outside any image
+  static __device__ __forceinline__ double rint(double x) {
+    const double m = 6755399441055744.0;  // 1.5 * 2^52
+    return __dsub_rn(__dadd_rn(x, m), m);
+  }
+  // OpenBLAS ddot tail loop, contracted by the compiler: FMA chain
+  static __device__ __forceinline__ double dot3(const double* a, const double* b) {
+    return __fma_rn(a[2], b[2], __fma_rn(a[1], b[1], __dmul_rn(a[0], b[0])));
+  }
+  static __device__ __forceinline__ double eps() { return 1e-8; }
+};
+template <> struct Fp<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ float rint(float x) { return rintf(x); }
+  // OpenBLAS sdot tail loop: float products, double accumulator, one final rounding
+  static __device__ __forceinline__ float dot3(const float* a, const float* b) {
+    float p0 = __fmul_rn(a[0], b[0]), p1 = __fmul_rn(a[1], b[1]), p2 = __fmul_rn(a[2], b[2]);
+    double s = __dadd_rn((double)p0, (double)p1);
+    s = __dadd_rn(s, (double)p2);
+    return (float)s;
+  }
+  static __device__ __forceinline__ float eps() { return (float)1e-8; }
+};
+
+// ------------------------------------------------------------------------------------------
+// look_at_rotation for K candidates (one thread each).  cams[k] = cam_pos[3], R[9], f, cx, cy, 0.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) setup_cameras_kernel(const T* __restrict__ cand, int K, T* __restrict__ cams) {
+  using F = Fp<T>;
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const T* c = cand + (size_t)k * 9;
+  T eye[3] = {c[0], c[1], c[2]};
+  T z[3], x[3], y[3], up[3] = {(T)0, (T)1, (T)0};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) z[i] = F::sub(c[3 + i], eye[i]);
+  T n = F::sqrt(F::dot3(z, z));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) z[i] = F::div(z[i], n);
+  T dzu = F::dot3(z, up);
+  double a = fabs((double)dzu);
+  if (fabs(__dsub_rn(a, 1.0)) <= 1e-8 + 1e-5 * 1.0) { up[0] = (T)0; up[1] = (T)0; up[2] = (T)1; }
+  x[0] = F::sub(F::mul(up[1], z[2]), F::mul(up[2], z[1]));
+  x[1] = F::sub(F::mul(up[2], z[0]), F::mul(up[0], z[2]));
+  x[2] = F::sub(F::mul(up[0], z[1]), F::mul(up[1], z[0]));
+  T nx = F::sqrt(F::dot3(x, x));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x[i] = F::div(x[i], nx);
+  y[0] = F::sub(F::mul(z[1], x[2]), F::mul(z[2], x[1]));
+  y[1] = F::sub(F::mul(z[2], x[0]), F::mul(z[0], x[2]));
+  y[2] = F::sub(F::mul(z[0], x[1]), F::mul(z[1], x[0]));
+  T* o = cams + (size_t)k * 16;
+  o[0] = eye[0]; o[1] = eye[1]; o[2] = eye[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { o[3 + i] = x[i]; o[6 + i] = y[i]; o[9 + i] = z[i]; }
+  o[12] = c[6]; o[13] = c[7]; o[14] = c[8]; o[15] = (T)0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Splat.  CTA = 256 threads x kPpt points; blockIdx.y selects a group of `cams_per_block` cameras.
+// ------------------------------------------------------------------------------------------
+constexpr int kSplatThreads = 256;
+constexpr int kPpt = 2;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kSplatThreads)
+splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label, int64_t n,
+             const T* __restrict__ cams, int K, int cams_per_block, int H, int W,
+             uint32_t* __restrict__ zbuf) {
+  using F = Fp<T>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s_cam = reinterpret_cast<T*>(smem_raw);
+  const int c0 = blockIdx.y * cams_per_block;
+  const int nc = min(cams_per_block, K - c0);
+  for (int i = threadIdx.x; i < nc * 16; i += kSplatThreads) s_cam[i] = cams[(size_t)c0 * 16 + i];
+  __syncthreads();
+
+  // walk the point list from its high-index end: later points own the pixels
+  const int64_t tile = (int64_t)gridDim.x - 1 - blockIdx.x;
+  const int64_t base = tile * (kSplatThreads * kPpt) + threadIdx.x;
+  T px[kPpt], py[kPpt], pz[kPpt];
+  uint32_t key[kPpt];
+#pragma unroll
+  for (int j = 0; j < kPpt; ++j) {
+    const int64_t i = base + (int64_t)j * kSplatThreads;
+    key[j] = 0;
+    px[j] = py[j] = pz[j] = (T)0;
+    if (i < n) {
+      px[j] = (T)__ldg(pts + 3 * i + 0);
+      py[j] = (T)__ldg(pts + 3 * i + 1);
+      pz[j] = (T)__ldg(pts + 3 * i + 2);
+      if (MODE == P3D_MODE_JOINT) key[j] = (uint32_t)(i + 1);
+      else key[j] = 1u << ((uint32_t)__ldg(pt_label + i) - 1u);
+    }
+  }
+  const T fW = (T)W, fH = (T)H;
+  const size_t HW = (size_t)H * W;
+  for (int c = 0; c < nc; ++c) {
+    const T* cam = s_cam + c * 16;
+    const T e0 = cam[0], e1 = cam[1], e2 = cam[2];
+    const T r00 = cam[3], r01 = cam[4], r02 = cam[5];
+    const T r10 = cam[6], r11 = cam[7], r12 = cam[8];
+    const T r20 = cam[9], r21 = cam[10], r22 = cam[11];
+    const T f = cam[12], cx = cam[13], cy = cam[14];
+    uint32_t* zb = zbuf + (size_t)(c0 + c) * HW;
+#pragma unroll
+    for (int j = 0; j < kPpt; ++j) {
+      const T d0 = F::sub(px[j], e0), d1 = F::sub(py[j], e1), d2 = F::sub(pz[j], e2);
+      const T X = F::fma(d2, r02, F::fma(d1, r01, F::mul(d0, r00)));
+      const T Y = F::fma(d2, r12, F::fma(d1, r11, F::mul(d0, r10)));
+      T Z = F::fma(d2, r22, F::fma(d1, r21, F::mul(d0, r20)));
+      if (Z < F::eps()) Z = F::eps();
+      const T u = F::add(F::mul(F::div(X, Z), f), cx);
+      const T v = F::add(F::mul(-F::div(Y, Z), f), cy);
+      const T ur = F::rint(u), vr = F::rint(v);
+      const bool ok = key[j] != 0 && ur >= (T)0 && ur < fW && vr >= (T)0 && vr < fH;
+      if (ok) {
+        uint32_t* p = zb + ((size_t)(int)vr * W + (size_t)(int)ur);
+        const uint32_t cur = __ldcg(p);
+        if (MODE == P3D_MODE_JOINT) {
+          if (cur < key[j]) atomicMax(p, key[j]);
+        } else {
+          if ((cur & key[j]) == 0) atomicOr(p, key[j]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Score: z-buffer (+ point labels) vs ground-truth labels -> per-part (area, inter) counts.
+// Warp ballots over the distinct labels present in the warp, popc, per-warp shared counters, one
+// global atomic per (block, part).  The z-buffer is cleared on the way (only touched pixels).
+// raw layout: [camera][P+1][2] = (area, inter); row P = combined binary (per-part mode).
+// ------------------------------------------------------------------------------------------
+constexpr int kScoreThreads = 256;
+constexpr int kMaxParts = 32;
+
+template <int MODE>
+__global__ void __launch_bounds__(kScoreThreads)
+score_kernel(uint32_t* __restrict__ zbuf, const uint8_t* __restrict__ pt_label,
+             const uint8_t* __restrict__ gt_label, const uint8_t* __restrict__ gt_any, int HW, int P,
+             unsigned long long* __restrict__ raw) {
+  __shared__ unsigned int s_acc[kScoreThreads / 32][(kMaxParts + 1) * 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = (P + 1) * 2;
+  for (int i = lane; i < rows; i += 32) s_acc[warp][i] = 0;
+  __syncwarp();
+  uint32_t* zb = zbuf + (size_t)blockIdx.y * HW;
+  const int stride = gridDim.x * kScoreThreads;
+  const int iters = (HW + stride - 1) / stride;
+  for (int it = 0; it < iters; ++it) {
+    const int pix = it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
+    const bool in = pix < HW;
+    const uint32_t key = in ? __ldcg(zb + pix) : 0u;
+    if (!__any_sync(0xffffffffu, key != 0)) continue;
+    if (key) zb[pix] = 0u;
+    const uint32_t g = in ? (uint32_t)__ldg(gt_label + pix) : 0u;
+    if (MODE == P3D_MODE_JOINT) {
+      const uint32_t lab = key ? (uint32_t)__ldg(pt_label + (key - 1)) : 0u;
+      uint32_t rem = __ballot_sync(0xffffffffu, lab != 0);
+      while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const uint32_t l = __shfl_sync(0xffffffffu, lab, leader);
+        const uint32_t m = __ballot_sync(0xffffffffu, lab == l);
+        const uint32_t mi = __ballot_sync(0xffffffffu, lab == l && g == l);
+        if (lane == 0 && l <= (uint32_t)P) {
+          s_acc[warp][(l - 1) * 2] += __popc(m);
+          s_acc[warp][(l - 1) * 2 + 1] += __popc(mi);
+        }
+        rem &= ~m;
+      }
+    } else {
+      uint32_t present = __reduce_or_sync(0xffffffffu, key);
+      while (present) {
+        const int b = __ffs(present) - 1;
+        present &= present - 1;
+        const bool has = (key >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, has);
+        const uint32_t mi = __ballot_sync(0xffffffffu, has && g == (uint32_t)(b + 1));
+        if (lane == 0 && b < P) {
+          s_acc[warp][b * 2] += __popc(m);
+          s_acc[warp][b * 2 + 1] += __popc(mi);
+        }
+      }
+      const bool ga = in && gt_any != nullptr && __ldg(gt_any + pix) != 0;
+      const uint32_t m = __ballot_sync(0xffffffffu, key != 0);
+      const uint32_t mi = __ballot_sync(0xffffffffu, key != 0 && ga);
+      if (lane == 0) {
+        s_acc[warp][P * 2] += __popc(m);
+        s_acc[warp][P * 2 + 1] += __popc(mi);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long* out = raw + (size_t)blockIdx.y * rows;
+  for (int i = threadIdx.x; i < rows; i += kScoreThreads) {
+    unsigned int s = 0;
+#pragma unroll
+    for (int w = 0; w < kScoreThreads / 32; ++w) s += s_acc[w][i];
+    if (s) atomicAdd(out + i, (unsigned long long)s);
+  }
+}
+
+// Histogram of the ground-truth labels: gt_area[p-1] = |gt == p| for p = 1..P, gt_area[P] = |gt_any != 0|.
+__global__ void __launch_bounds__(256) gt_area_kernel(const uint8_t* __restrict__ gt_label,
+                                                      const uint8_t* __restrict__ gt_any, int HW, int P,
+                                                      unsigned long long* __restrict__ gt_area) {
+  __shared__ unsigned int s_hist[kMaxParts + 2];
+  for (int i = threadIdx.x; i < kMaxParts + 2; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    const uint32_t g = gt_label[pix];
+    if (g >= 1 && g <= (uint32_t)P) atomicAdd(&s_hist[g - 1], 1u);
+    if (gt_any && gt_any[pix]) atomicAdd(&s_hist[P], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= P; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(gt_area + i, (unsigned long long)s_hist[i]);
+}
+
+// np.mean of P doubles exactly as NumPy reduces a contiguous 1-D float64 array (add.reduce starts from
+// the identity 0.0 and hands all P values to DOUBLE_pairwise_sum): pairwise(n<8) = sequential from -0.0;
+// pairwise(8<=n<=128) = 8 interleaved accumulators combined as ((0+1)+(2+3))+((4+5)+(6+7)), then the
+// tail; finally / P.  (P <= 32 here, so the recursive n > 128 branch never runs.)
+__device__ double numpy_mean(const double* a, int P) {
+  if (P <= 0) return __longlong_as_double(0x7ff8000000000000ll);
+  const int n = P;
+  double s;
+  if (n < 8) {
+    s = -0.0;
+    for (int i = 0; i < n; ++i) s = __dadd_rn(s, a[i]);
+  } else {
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                  __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) s = __dadd_rn(s, a[i]);
+  }
+  s = __dadd_rn(0.0, s);
+  return __ddiv_rn(s, (double)P);
+}
+
+__global__ void __launch_bounds__(128) finalize_kernel(const unsigned long long* __restrict__ raw,
+                                                       const unsigned long long* __restrict__ gt_area, int K,
+                                                       int P, int rows_out, int64_t* __restrict__ counts,
+                                                       double* __restrict__ scores) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double iou[kMaxParts];
+  const unsigned long long* r = raw + (size_t)k * (P + 1) * 2;
+  int64_t* c = counts + (size_t)k * rows_out * 2;
+  for (int p = 0; p < rows_out; ++p) {
+    const long long area = (long long)r[2 * p], inter = (long long)r[2 * p + 1];
+    const long long uni = area + (long long)gt_area[p] - inter;
+    c[2 * p] = inter;
+    c[2 * p + 1] = uni;
+    if (p < P) iou[p] = uni > 0 ? __ddiv_rn((double)inter, (double)uni) : 0.0;
+  }
+  scores[k] = numpy_mean(iou, P);
+}
+
+// First index with the greatest score (strict '>' in the reference loop keeps the earliest).
+__global__ void __launch_bounds__(1024) argmax_kernel(const double* __restrict__ scores, int K,
+                                                      int64_t* __restrict__ best) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  double bv = -1.0;
+  int bi = K;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const double v = scores[i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  auto better = [](double v, int i, double w, int j) { return v > w || (v == w && i < j); };
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, bv, d);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, d);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    bv = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, d);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, d);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { best[0] = bi < K ? bi : -1; best[1] = 0; }
+  }
+}
+
+// (score bits, global index) of the local best; index -1 when the block is empty.
+__global__ void best_pack_kernel(const double* __restrict__ scores, const int64_t* __restrict__ best, int64_t offset,
+                                 int64_t* __restrict__ pair) {
+  const int64_t b = best[0];
+  pair[0] = b >= 0 ? __double_as_longlong(scores[b]) : __double_as_longlong(-1.0);
+  pair[1] = b >= 0 ? b + offset : -1;
+}
+
+// Greatest score, ties -> lowest global index, over n gathered pairs (one warp).
+__global__ void best_select_kernel(const int64_t* __restrict__ pairs, int n, int64_t* __restrict__ out) {
+  double bv = -1.0;
+  long long bi = -1;
+  for (int i = threadIdx.x; i < n; i += 32) {
+    const double v = __longlong_as_double(pairs[2 * i]);
+    const long long idx = pairs[2 * i + 1];
+    if (idx >= 0 && (bi < 0 || v > bv || (v == bv && idx < bi))) { bv = v; bi = idx; }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, bv, d);
+    const long long oi = __shfl_down_sync(0xffffffffu, bi, d);
+    if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+  }
+  if (threadIdx.x == 0) { out[0] = __double_as_longlong(bv); out[1] = bi; }
+}
+
+__global__ void __launch_bounds__(256) resolve_rgb_kernel(const uint32_t* __restrict__ zbuf,
+                                                          const uint8_t* __restrict__ pt_rgb, int64_t n_pixels,
+                                                          uint8_t* __restrict__ img) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t key = zbuf[p];
+    uint8_t r = 0, g = 0, b = 0;
+    if (key) {
+      const uint8_t* c = pt_rgb + 3 * (size_t)(key - 1);
+      r = c[0]; g = c[1]; b = c[2];
+    }
+    img[3 * p] = r; img[3 * p + 1] = g; img[3 * p + 2] = b;
+  }
+}
+
+// compute_partwise_iou on two RGB images (camera_estimation.py:770-787); counts[p] = (inter, union).
+__global__ void __launch_bounds__(256) partwise_counts_rgb_kernel(const uint8_t* __restrict__ proj,
+                                                                  const uint8_t* __restrict__ gt, int64_t n_pixels,
+                                                                  const uint8_t* __restrict__ part_rgb, int P,
+                                                                  unsigned long long* __restrict__ counts) {
+  __shared__ uint32_t s_col[kMaxParts];
+  __shared__ unsigned int s_acc[kMaxParts * 2];
+  for (int i = threadIdx.x; i < P; i += blockDim.x)
+    s_col[i] = part_rgb[3 * i] | (part_rgb[3 * i + 1] << 8) | (part_rgb[3 * i + 2] << 16);
+  for (int i = threadIdx.x; i < 2 * P; i += blockDim.x) s_acc[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t iters = (n_pixels + stride - 1) / stride;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t p = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a = 0xffffffffu, b = 0xffffffffu;  // sentinel: matches no 24-bit colour
+    if (p < n_pixels) {
+      a = proj[3 * p] | (proj[3 * p + 1] << 8) | (proj[3 * p + 2] << 16);
+      b = gt[3 * p] | (gt[3 * p + 1] << 8) | (gt[3 * p + 2] << 16);
+    }
+    for (int q = 0; q < P; ++q) {
+      const uint32_t c = s_col[q];
+      const uint32_t ma = __ballot_sync(0xffffffffu, a == c);
+      const uint32_t mb = __ballot_sync(0xffffffffu, b == c);
+      if (lane == 0 && (ma | mb)) {
+        atomicAdd(&s_acc[2 * q], __popc(ma & mb));
+        atomicAdd(&s_acc[2 * q + 1], __popc(ma | mb));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * P; i += blockDim.x)
+    if (s_acc[i]) atomicAdd(counts + i, (unsigned long long)s_acc[i]);
+}
+
+inline int grid_for(int64_t items, int threads, int waves) {
+  int64_t blocks = (items + threads - 1) / threads;
+  int64_t cap = (int64_t)p3d::sm_count() * waves;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+thread_local int g_last_launches = 0;
+
+// Optional per-launch timing of the splat kernel (bench.py's roofline leg): CUDA events recorded on the
+// launch stream around every splat launch of p3d_sweep_* while enabled on this thread.
+struct SplatTiming {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;     // start/stop pairs
+  size_t used = 0;
+};
+thread_local SplatTiming g_timing;
+
+inline cudaEvent_t timing_event() {
+  if (g_timing.used == g_timing.pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    g_timing.pool.push_back(e);
+  }
+  return g_timing.pool[g_timing.used++];
+}
+
+template <typename T>
+int setup_cameras(const T* cand, int K, T* cams, p3d_stream_t stream) {
+  P3D_REQUIRE(K >= 0, "setup_cameras: K=%d", K);
+  if (K == 0) return P3D_OK;
+  P3D_REQUIRE(cand && cams, "setup_cameras: null pointer");
+  setup_cameras_kernel<T><<<(K + 127) / 128, 128, 0, p3d::as_stream(stream)>>>(cand, K, cams);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// cameras handled by one CTA: enough CTAs for ~8 waves when the point list is short
+inline int pick_cams_per_block(int64_t tiles, int K) {
+  const int64_t want = (int64_t)p3d::sm_count() * 24;
+  int groups = (int)((want + tiles - 1) / (tiles > 0 ? tiles : 1));
+  if (groups < 1) groups = 1;
+  if (groups > K) groups = K;
+  int cpb = (K + groups - 1) / groups;
+  if (cpb < 4) cpb = K < 4 ? K : 4;
+  return cpb;
+}
+
+template <typename T>
+int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, int K, int H, int W, int mode,
+          uint32_t* zbuf, p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && K >= 0 && H > 0 && W > 0, "splat: n=%lld K=%d H=%d W=%d", (long long)n, K, H, W);
+  P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
+  P3D_REQUIRE(n < 0xffffffffll, "splat: n=%lld does not fit 32-bit keys", (long long)n);
+  P3D_REQUIRE((int64_t)H * W < (1ll << 31), "splat: image too large");
+  if (n == 0 || K == 0) return P3D_OK;
+  P3D_REQUIRE(pts && cams && zbuf, "splat: null pointer");
+  P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: per-part mode needs pt_label");
+  const int64_t tiles = (n + kSplatThreads * kPpt - 1) / (kSplatThreads * kPpt);
+  P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
+  const int cpb = pick_cams_per_block(tiles, K);
+  dim3 grid((unsigned)tiles, (unsigned)((K + cpb - 1) / cpb));
+  const size_t smem = (size_t)cpb * 16 * sizeof(T);
+  cudaStream_t st = p3d::as_stream(stream);
+  if (mode == P3D_MODE_JOINT)
+    splat_kernel<T, P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
+  else
+    splat_kernel<T, P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// cameras per batch: keep the batch's z-buffers within an L2-sized budget
+inline int batch_cameras(int K, int H, int W, size_t zbuf_budget) {
+  const size_t per = (size_t)H * W * sizeof(uint32_t);
+  int64_t c = (int64_t)(zbuf_budget / per);
+  if (c > 64) c = 64;
+  if (c > K) c = K;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+inline size_t default_zbuf_budget() {
+  const char* e = getenv("P3D_ZBUF_BUDGET_MB");
+  long mb = e ? atol(e) : 64;
+  if (mb < 1) mb = 64;
+  return (size_t)mb << 20;
+}
+
+struct SweepLayout {
+  size_t cams, raw, gt_area, zbuf, total;
+  int batch;
+};
+
+inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
+  SweepLayout L;
+  L.batch = batch_cameras(K, H, W, default_zbuf_budget());
+  size_t off = 0;
+  L.cams = off; off = p3d_align_up(off + (size_t)K * 16 * elem_bytes, 256);
+  L.raw = off; off = p3d_align_up(off + (size_t)K * (P + 1) * 2 * sizeof(unsigned long long), 256);
+  L.gt_area = off; off = p3d_align_up(off + (size_t)(P + 1) * sizeof(unsigned long long), 256);
+  L.zbuf = off; off = p3d_align_up(off + (size_t)L.batch * H * W * sizeof(uint32_t), 256);
+  L.total = off;
+  return L;
+}
+
+template <typename T>
+int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, int K, const uint8_t* gt_label,
+          const uint8_t* gt_any, int H, int W, int P, int mode, int64_t* counts, double* scores, int64_t* best,
+          void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  g_last_launches = 0;
+  P3D_REQUIRE(K > 0 && H > 0 && W > 0 && n >= 0, "sweep: K=%d H=%d W=%d n=%lld", K, H, W, (long long)n);
+  P3D_REQUIRE(P >= 1 && P <= kMaxParts, "sweep: P=%d (1..%d)", P, kMaxParts);
+  P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "sweep: mode=%d", mode);
+  P3D_REQUIRE((int64_t)H * W < (1ll << 31), "sweep: image too large");
+  P3D_REQUIRE(cand && gt_label && counts && scores && workspace, "sweep: null pointer");
+  P3D_REQUIRE(n == 0 || (pts && pt_label), "sweep: null points");
+  P3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sweep: workspace must be 256-byte aligned");
+  const SweepLayout L = sweep_layout(K, H, W, P, (int)sizeof(T));
+  if (workspace_bytes < L.total) {
+    p3d::set_error("sweep: workspace %zu < %zu", workspace_bytes, L.total);
+    return P3D_E_WORKSPACE;
+  }
+  cudaStream_t st = p3d::as_stream(stream);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  T* cams = reinterpret_cast<T*>(ws + L.cams);
+  unsigned long long* raw = reinterpret_cast<unsigned long long*>(ws + L.raw);
+  unsigned long long* gt_area = reinterpret_cast<unsigned long long*>(ws + L.gt_area);
+  uint32_t* zbuf = reinterpret_cast<uint32_t*>(ws + L.zbuf);
+  const int HW = H * W;
+  const int rows = mode == P3D_MODE_PER_PART ? P + 1 : P;
+
+  P3D_CUDA(cudaMemsetAsync(ws + L.raw, 0, L.zbuf - L.raw, st));   // raw + gt_area
+  P3D_CUDA(cudaMemsetAsync(zbuf, 0, (size_t)L.batch * HW * sizeof(uint32_t), st));
+  int rc = setup_cameras<T>(cand, K, cams, stream);
+  if (rc) return rc;
+  gt_area_kernel<<<grid_for(HW, 256, 4), 256, 0, st>>>(gt_label, mode == P3D_MODE_PER_PART ? gt_any : nullptr, HW, P,
+                                                      gt_area);
+  P3D_LAUNCH_CHECK();
+  g_last_launches += 2;
+  for (int k0 = 0; k0 < K; k0 += L.batch) {
+    const int kb = K - k0 < L.batch ? K - k0 : L.batch;
+    if (n > 0) {
+      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+      if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
+      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, mode, zbuf, stream);
+      if (rc) return rc;
+      if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
+      dim3 grid((unsigned)grid_for(HW, kScoreThreads, 2), (unsigned)kb);
+      // spread one camera's pixels over at most ~2 waves / kb CTAs
+      int per_cam = (p3d::sm_count() * 8 + kb - 1) / kb;
+      if ((int)grid.x > per_cam) grid.x = per_cam < 1 ? 1 : per_cam;
+      if (mode == P3D_MODE_JOINT)
+        score_kernel<P3D_MODE_JOINT><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, nullptr, HW, P,
+                                                                     raw + (size_t)k0 * (P + 1) * 2);
+      else
+        score_kernel<P3D_MODE_PER_PART><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, gt_any, HW, P,
+                                                                        raw + (size_t)k0 * (P + 1) * 2);
+      P3D_LAUNCH_CHECK();
+      g_last_launches += 2;
+    }
+  }
+  finalize_kernel<<<(K + 127) / 128, 128, 0, st>>>(raw, gt_area, K, P, rows, counts, scores);
+  P3D_LAUNCH_CHECK();
+  ++g_last_launches;
+  if (best) {
+    argmax_kernel<<<1, 1024, 0, st>>>(scores, K, best);
+    P3D_LAUNCH_CHECK();
+    ++g_last_launches;
+  }
+  return P3D_OK;
+}
+
+}  // namespace
+
+P3D_API int p3d_setup_cameras_f64(const double* cand, int K, double* cams, p3d_stream_t stream) {
+  return setup_cameras<double>(cand, K, cams, stream);
+}
+P3D_API int p3d_setup_cameras_f32(const float* cand, int K, float* cams, p3d_stream_t stream) {
+  return setup_cameras<float>(cand, K, cams, stream);
+}
+
+P3D_API int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K, int H,
+                          int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
+  return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, stream);
+}
+P3D_API int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K, int H,
+                          int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
+  return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, stream);
+}
+
+P3D_API int p3d_resolve_rgb(const uint32_t* zbuf, const uint8_t* pt_rgb, int64_t n_pixels, uint8_t* img,
+                            p3d_stream_t stream) {
+  P3D_REQUIRE(n_pixels >= 0, "resolve_rgb: n_pixels=%lld", (long long)n_pixels);
+  if (n_pixels == 0) return P3D_OK;
+  P3D_REQUIRE(zbuf && img, "resolve_rgb: null pointer");
+  resolve_rgb_kernel<<<grid_for(n_pixels, 256, 8), 256, 0, p3d::as_stream(stream)>>>(zbuf, pt_rgb, n_pixels, img);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_partwise_counts_rgb(const uint8_t* proj_rgb, const uint8_t* gt_rgb, int64_t n_pixels,
+                                    const uint8_t* part_rgb, int P, int64_t* counts, p3d_stream_t stream) {
+  P3D_REQUIRE(n_pixels >= 0 && P >= 0 && P <= kMaxParts, "partwise_counts_rgb: n=%lld P=%d", (long long)n_pixels, P);
+  if (P == 0) return P3D_OK;
+  P3D_REQUIRE(counts && part_rgb, "partwise_counts_rgb: null pointer");
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(counts, 0, (size_t)P * 2 * sizeof(int64_t), st));
+  if (n_pixels == 0) return P3D_OK;
+  P3D_REQUIRE(proj_rgb && gt_rgb, "partwise_counts_rgb: null image");
+  partwise_counts_rgb_kernel<<<grid_for(n_pixels, 256, 4), 256, 0, st>>>(
+      proj_rgb, gt_rgb, n_pixels, part_rgb, P, reinterpret_cast<unsigned long long*>(counts));
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API size_t p3d_sweep_workspace_bytes(int K, int H, int W, int P, int elem_bytes) {
+  if (K <= 0 || H <= 0 || W <= 0 || P <= 0 || (elem_bytes != 4 && elem_bytes != 8)) return 0;
+  return sweep_layout(K, H, W, P, elem_bytes).total;
+}
+
+P3D_API int p3d_sweep_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cand, int K,
+                          const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
+                          int64_t* counts, double* scores, int64_t* best, void* workspace, size_t workspace_bytes,
+                          p3d_stream_t stream) {
+  return sweep<double>(pts, pt_label, n, cand, K, gt_label, gt_any, H, W, P, mode, counts, scores, best, workspace,
+                       workspace_bytes, stream);
+}
+P3D_API int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cand, int K,
+                          const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
+                          int64_t* counts, double* scores, int64_t* best, void* workspace, size_t workspace_bytes,
+                          p3d_stream_t stream) {
+  return sweep<float>(pts, pt_label, n, cand, K, gt_label, gt_any, H, W, P, mode, counts, scores, best, workspace,
+                      workspace_bytes, stream);
+}
+
+P3D_API int p3d_sweep_last_launches(void) { return g_last_launches; }
+
+P3D_API int p3d_best_pack(const double* scores, const int64_t* best, int64_t offset, int64_t* pair,
+                          p3d_stream_t stream) {
+  P3D_REQUIRE(scores && best && pair, "best_pack: null pointer");
+  best_pack_kernel<<<1, 1, 0, p3d::as_stream(stream)>>>(scores, best, offset, pair);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_best_select(const int64_t* pairs, int n, int64_t* out, p3d_stream_t stream) {
+  P3D_REQUIRE(pairs && out && n >= 1, "best_select: bad arguments");
+  best_select_kernel<<<1, 32, 0, p3d::as_stream(stream)>>>(pairs, n, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_sweep_timing_enable(int on) {
+  g_timing.enabled = on != 0;
+  g_timing.used = 0;
+  return P3D_OK;
+}
+
+P3D_API int p3d_sweep_timing_read(double* splat_ms, int* n_launches) {
+  double total = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < g_timing.used; i += 2) {
+    P3D_CUDA(cudaEventSynchronize(g_timing.pool[i + 1]));
+    float ms = 0.f;
+    P3D_CUDA(cudaEventElapsedTime(&ms, g_timing.pool[i], g_timing.pool[i + 1]));
+    total += ms;
+    ++n;
+  }
+  g_timing.used = 0;
+  if (splat_ms) *splat_ms = total;
+  if (n_launches) *n_launches = n;
+  return P3D_OK;
+}

@@ -1,0 +1,338 @@
+// libp3d_b200: error plumbing, colour<->label conversion, ordered point compaction.
+//
+// Reference call sites replaced here (paths under the reference root):
+//   np.all(x == colour, axis=-1) scans   utils/voxel_utils.py:12-15, utils/mask_utils.py:92-95
+//   get_voxel_points_by_parts            utils/voxel_utils.py:7-21
+#include <stdarg.h>
+#include <string.h>
+
+#include "p3d_common.cuh"
+
+namespace p3d {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static thread_local int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+}  // namespace p3d
+
+P3D_API int p3d_version(void) { return 100; }
+P3D_API const char* p3d_last_error(void) { return p3d::g_err; }
+
+P3D_API int p3d_device_info(int* sm, int* major, int* minor, int64_t* l2_bytes) {
+  int dev = 0, v = 0;
+  P3D_CUDA(cudaGetDevice(&dev));
+  if (sm) { P3D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm = v; }
+  if (major) { P3D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *major = v; }
+  if (minor) { P3D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *minor = v; }
+  if (l2_bytes) { P3D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev)); *l2_bytes = v; }
+  return P3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RGB -> label.  One thread converts 4 pixels: three aligned 32-bit loads, one 32-bit store.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kMaxPalette = 255;
+
+__device__ __forceinline__ uint32_t match_palette(uint32_t c, const uint32_t* pal, int n) {
+  for (int k = 0; k < n; ++k)
+    if (pal[k] == c) return (uint32_t)(k + 1);
+  return 0u;
+}
+
+__global__ void __launch_bounds__(256) rgb_to_labels_kernel(const uint8_t* __restrict__ rgb, int64_t n,
+                                                            const uint8_t* __restrict__ palette, int n_colors,
+                                                            uint8_t* __restrict__ labels, int vec_ok) {
+  __shared__ uint32_t pal[kMaxPalette + 1];
+  __shared__ int has_black;
+  if (threadIdx.x == 0) has_black = 0;
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_colors; k += blockDim.x) {
+    uint32_t c = palette[3 * k] | (palette[3 * k + 1] << 8) | (palette[3 * k + 2] << 16);
+    pal[k] = c;
+    if (c == 0) has_black = 1;
+  }
+  __syncthreads();
+  const bool black = has_black != 0;
+  const int64_t ngroups = (n + 3) >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = g << 2;
+    if (vec_ok && i0 + 4 <= n) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(rgb + 3 * i0);
+      uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+      uint32_t out = 0;
+      if ((w0 | w1 | w2) != 0 || black) {
+        uint32_t c0 = w0 & 0xffffffu;
+        uint32_t c1 = (w0 >> 24) | ((w1 & 0xffffu) << 8);
+        uint32_t c2 = (w1 >> 16) | ((w2 & 0xffu) << 16);
+        uint32_t c3 = w2 >> 8;
+        out = ((c0 | black) ? match_palette(c0, pal, n_colors) : 0u) |
+              (((c1 | black) ? match_palette(c1, pal, n_colors) : 0u) << 8) |
+              (((c2 | black) ? match_palette(c2, pal, n_colors) : 0u) << 16) |
+              (((c3 | black) ? match_palette(c3, pal, n_colors) : 0u) << 24);
+      }
+      *reinterpret_cast<uint32_t*>(labels + i0) = out;
+    } else {
+      for (int64_t i = i0; i < n && i < i0 + 4; ++i) {
+        uint32_t c = rgb[3 * i] | (rgb[3 * i + 1] << 8) | (rgb[3 * i + 2] << 16);
+        labels[i] = (uint8_t)match_palette(c, pal, n_colors);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) labels_to_rgb_kernel(const uint8_t* __restrict__ labels, int64_t n,
+                                                            const uint8_t* __restrict__ lut,
+                                                            uint8_t* __restrict__ rgb, int vec_ok) {
+  __shared__ uint32_t s_lut[256];
+  for (int k = threadIdx.x; k < 256; k += blockDim.x)
+    s_lut[k] = lut[3 * k] | (lut[3 * k + 1] << 8) | (lut[3 * k + 2] << 16);
+  __syncthreads();
+  const int64_t ngroups = (n + 3) >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = g << 2;
+    if (vec_ok && i0 + 4 <= n) {
+      uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(labels + i0));
+      uint32_t c0 = s_lut[l & 0xff], c1 = s_lut[(l >> 8) & 0xff], c2 = s_lut[(l >> 16) & 0xff],
+               c3 = s_lut[l >> 24];
+      uint32_t* o = reinterpret_cast<uint32_t*>(rgb + 3 * i0);
+      o[0] = c0 | (c1 << 24);
+      o[1] = (c1 >> 8) | (c2 << 16);
+      o[2] = (c2 >> 16) | (c3 << 8);
+    } else {
+      for (int64_t i = i0; i < n && i < i0 + 4; ++i) {
+        uint32_t c = s_lut[labels[i]];
+        rgb[3 * i] = c & 0xff; rgb[3 * i + 1] = (c >> 8) & 0xff; rgb[3 * i + 2] = (c >> 16) & 0xff;
+      }
+    }
+  }
+}
+
+inline int stream_grid(int64_t work_items, int threads, int waves = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)p3d::sm_count() * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+P3D_API int p3d_rgb_to_labels(const uint8_t* rgb, int64_t n, const uint8_t* palette_rgb, int n_colors,
+                              uint8_t* labels, p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && n_colors >= 0 && n_colors <= kMaxPalette, "rgb_to_labels: n=%lld n_colors=%d",
+              (long long)n, n_colors);
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(rgb && labels && (palette_rgb || n_colors == 0), "rgb_to_labels: null pointer");
+  int vec_ok = ((reinterpret_cast<uintptr_t>(rgb) | reinterpret_cast<uintptr_t>(labels)) & 3) == 0;
+  rgb_to_labels_kernel<<<stream_grid((n + 3) / 4, 256), 256, 0, p3d::as_stream(stream)>>>(
+      rgb, n, palette_rgb, n_colors, labels, vec_ok);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_labels_to_rgb(const uint8_t* labels, int64_t n, const uint8_t* lut_rgb, uint8_t* rgb,
+                              p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0, "labels_to_rgb: n=%lld", (long long)n);
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(labels && lut_rgb && rgb, "labels_to_rgb: null pointer");
+  int vec_ok = ((reinterpret_cast<uintptr_t>(rgb) | reinterpret_cast<uintptr_t>(labels)) & 3) == 0;
+  labels_to_rgb_kernel<<<stream_grid((n + 3) / 4, 256), 256, 0, p3d::as_stream(stream)>>>(
+      labels, n, lut_rgb, rgb, vec_ok);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered compaction of non-zero labels.  Tile = 256 threads x 16 labels.  Pass 1 counts per tile,
+// pass 2 scans the tile counts (one CTA), pass 3 rewrites each tile in index order.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kTileThreads = 256;
+constexpr int kPerThread = 16;
+constexpr int kTile = kTileThreads * kPerThread;
+
+__device__ __forceinline__ uint4 load16(const uint8_t* __restrict__ labels, int64_t i0, int64_t n, bool vec_ok) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (i0 >= n) return v;
+  if (vec_ok && i0 + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(labels + i0));
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (int j = 0; j < 16 && i0 + j < n; ++j) w[j >> 2] |= (uint32_t)labels[i0 + j] << (8 * (j & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// number of non-zero bytes in a 32-bit word
+__device__ __forceinline__ int nz_bytes(uint32_t w) {
+  uint32_t m = (w | (w >> 1) | (w >> 2) | (w >> 3) | (w >> 4) | (w >> 5) | (w >> 6) | (w >> 7)) & 0x01010101u;
+  return __popc(m);
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[kTileThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int base = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kTileThreads / 32; ++w) {
+    int s = warp_sums[w];
+    if (w < warp) base += s;
+    all += s;
+  }
+  *total = all;
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kTileThreads) points_count_kernel(const uint8_t* __restrict__ labels, int64_t n,
+                                                                    int64_t* __restrict__ tile_counts, int vec_ok) {
+  const int64_t i0 = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kPerThread;
+  uint4 v = load16(labels, i0, n, vec_ok);
+  int c = nz_bytes(v.x) + nz_bytes(v.y) + nz_bytes(v.z) + nz_bytes(v.w);
+  int total;
+  block_exclusive_scan(c, &total);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+// In-place exclusive scan of tile_counts[0..m) with the grand total written to tile_counts[m] and n_out.
+__global__ void __launch_bounds__(1024) points_scan_kernel(int64_t* __restrict__ tile_counts, int64_t m,
+                                                           int64_t* __restrict__ n_out) {
+  __shared__ int64_t warp_sums[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < m; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    int64_t v = i < m ? tile_counts[i] : 0;
+    int64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int64_t wbase = 0, all = 0;
+    for (int w = 0; w < 32; ++w) {
+      int64_t s = warp_sums[w];
+      if (w < warp) wbase += s;
+      all += s;
+    }
+    const int64_t c = carry;
+    if (i < m) tile_counts[i] = c + wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tile_counts[m] = carry;
+    n_out[0] = carry;
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads) points_fill_kernel(const uint8_t* __restrict__ labels, int64_t n,
+                                                                   int A1, int A2,
+                                                                   const int64_t* __restrict__ tile_offsets,
+                                                                   float* __restrict__ pts,
+                                                                   uint8_t* __restrict__ pt_label,
+                                                                   int64_t capacity, int vec_ok) {
+  const int64_t i0 = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kPerThread;
+  uint4 v = load16(labels, i0, n, vec_ok);
+  int c = nz_bytes(v.x) + nz_bytes(v.y) + nz_bytes(v.z) + nz_bytes(v.w);
+  int total;
+  int excl = block_exclusive_scan(c, &total);
+  if (c == 0) return;
+  int64_t out = tile_offsets[blockIdx.x] + excl;
+  // first voxel of this thread in (a0, a1, a2); then walk a2 with carries
+  const int64_t plane = (int64_t)A1 * A2;
+  int a0 = (int)(i0 / plane);
+  int64_t rem = i0 - (int64_t)a0 * plane;
+  int a1 = (int)(rem / A2);
+  int a2 = (int)(rem - (int64_t)a1 * A2);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < kPerThread; ++j) {
+    uint32_t lab = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+    if (lab && out < capacity) {
+      pts[3 * out + 0] = (float)a2;
+      pts[3 * out + 1] = (float)a1;
+      pts[3 * out + 2] = (float)a0;
+      pt_label[out] = (uint8_t)lab;
+      ++out;
+    }
+    if (++a2 == A2) { a2 = 0; if (++a1 == A1) { a1 = 0; ++a0; } }
+  }
+}
+
+}  // namespace
+
+P3D_API size_t p3d_points_workspace_bytes(int64_t n_voxels) {
+  if (n_voxels < 0) return 0;
+  int64_t tiles = (n_voxels + kTile - 1) / kTile;
+  return (size_t)(tiles + 1) * sizeof(int64_t);
+}
+
+P3D_API int p3d_points_count(const uint8_t* labels, int64_t n_voxels, int64_t* n_out, void* workspace,
+                             size_t workspace_bytes, p3d_stream_t stream) {
+  P3D_REQUIRE(n_voxels >= 0 && n_out && workspace, "points_count: bad arguments");
+  P3D_REQUIRE(labels || n_voxels == 0, "points_count: null labels");
+  if (workspace_bytes < p3d_points_workspace_bytes(n_voxels)) {
+    p3d::set_error("points_count: workspace %zu < %zu", workspace_bytes, p3d_points_workspace_bytes(n_voxels));
+    return P3D_E_WORKSPACE;
+  }
+  int64_t tiles = (n_voxels + kTile - 1) / kTile;
+  P3D_REQUIRE(tiles < (1ll << 31), "points_count: grid too large");
+  int64_t* tc = static_cast<int64_t*>(workspace);
+  int vec_ok = (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
+  cudaStream_t st = p3d::as_stream(stream);
+  if (tiles > 0) {
+    points_count_kernel<<<(unsigned)tiles, kTileThreads, 0, st>>>(labels, n_voxels, tc, vec_ok);
+    P3D_LAUNCH_CHECK();
+  }
+  points_scan_kernel<<<1, 1024, 0, st>>>(tc, tiles, n_out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_points_fill(const uint8_t* labels, int A0, int A1, int A2, const void* workspace, float* pts,
+                            uint8_t* pt_label, int64_t capacity, p3d_stream_t stream) {
+  P3D_REQUIRE(A0 >= 0 && A1 >= 0 && A2 >= 0 && capacity >= 0 && workspace, "points_fill: bad arguments");
+  int64_t n = (int64_t)A0 * A1 * A2;
+  if (n == 0 || capacity == 0) return P3D_OK;
+  P3D_REQUIRE(labels && pts && pt_label, "points_fill: null pointer");
+  int64_t tiles = (n + kTile - 1) / kTile;
+  int vec_ok = (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
+  points_fill_kernel<<<(unsigned)tiles, kTileThreads, 0, p3d::as_stream(stream)>>>(
+      labels, n, A1, A2, static_cast<const int64_t*>(workspace), pts, pt_label, capacity, vec_ok);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}

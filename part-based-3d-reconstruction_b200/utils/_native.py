@@ -1,0 +1,125 @@
+"""ctypes binding of libp3d_b200.so (the C ABI declared in include/p3d_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or calling
+into it without a CUDA device, raises.  PyTorch is used only for device memory and
+streams; all signatures at the C boundary are plain pointers and sizes.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libp3d_b200.so"))
+
+MODE_JOINT = 0
+MODE_PER_PART = 1
+MAX_PARTS = 32
+
+
+class P3DError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with "
+        "`python part-based-3d-reconstruction_b200/build_native.py` (needs nvcc); "
+        "there is no CPU fallback for this package")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+
+_SIGNATURES = {
+    "p3d_version": ([], _i32),
+    "p3d_last_error": ([], ctypes.c_char_p),
+    "p3d_device_info": ([_vp, _vp, _vp, _vp], _i32),
+    "p3d_rgb_to_labels": ([_vp, _i64, _vp, _i32, _vp, _vp], _i32),
+    "p3d_labels_to_rgb": ([_vp, _i64, _vp, _vp, _vp], _i32),
+    "p3d_points_workspace_bytes": ([_i64], _sz),
+    "p3d_points_count": ([_vp, _i64, _vp, _vp, _sz, _vp], _i32),
+    "p3d_points_fill": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp], _i32),
+    "p3d_setup_cameras_f64": ([_vp, _i32, _vp, _vp], _i32),
+    "p3d_setup_cameras_f32": ([_vp, _i32, _vp, _vp], _i32),
+    "p3d_splat_f64": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_splat_f32": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_resolve_rgb": ([_vp, _vp, _i64, _vp, _vp], _i32),
+    "p3d_partwise_counts_rgb": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp], _i32),
+    "p3d_sweep_workspace_bytes": ([_i32, _i32, _i32, _i32, _i32], _sz),
+    "p3d_sweep_f64": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp], _i32),
+    "p3d_sweep_f32": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp], _i32),
+    "p3d_sweep_last_launches": ([], _i32),
+    "p3d_best_pack": ([_vp, _vp, _i64, _vp, _vp], _i32),
+    "p3d_best_select": ([_vp, _i32, _vp, _vp], _i32),
+    "p3d_sweep_timing_enable": ([_i32], _i32),
+    "p3d_sweep_timing_read": ([_vp, _vp], _i32),
+}
+
+
+def _bind(signatures):
+    for name, (argtypes, restype) in signatures.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+
+
+_bind(_SIGNATURES)
+
+# kernel launches issued through this binding (bench.py's `gpu_launches` claim)
+launch_count = 0
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.p3d_last_error().decode("utf-8", "replace")
+        raise P3DError(f"{what or 'libp3d_b200'} failed (code {rc}): {msg}")
+
+
+def require_cuda(device=None) -> torch.device:
+    """Return the CUDA device to run on; raise (never fall back to the CPU)."""
+    if not torch.cuda.is_available():
+        raise P3DError("no CUDA device: this package runs its hot path only on a B200 "
+                       "(sm_100a) GPU and has no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise P3DError(f"device must be a CUDA device, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def ptr(t) -> ctypes.c_void_p:
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_device(a, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    """numpy array / torch tensor -> contiguous device tensor of `dtype` (no copy if already there)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        arr = np.ascontiguousarray(a)
+        t = torch.from_numpy(arr)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def palette_tensor(colors, device) -> torch.Tensor:
+    pal = np.ascontiguousarray(np.asarray(colors, dtype=np.int64).reshape(-1, 3))
+    if pal.size and (pal.min() < 0 or pal.max() > 255):
+        raise ValueError("palette colours must be in 0..255")
+    return torch.from_numpy(pal.astype(np.uint8)).to(device)

@@ -1,0 +1,112 @@
+"""Multi-GPU candidate sweep: candidates are sharded over ranks (one process per GPU), every rank
+scores its contiguous block with no data-path collective, and ONE 16-byte-per-rank all-gather of
+(score, global index) picks the winner.  Selection rule = the reference's strict `>` loop
+(utils/camera_estimation.py:646): the FIRST candidate with the greatest score wins.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as nv
+from ._native import check, lib, ptr, stream_ptr
+
+
+def shard_range(K: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of rank `rank` when K candidates are split over `world` ranks."""
+    base, rem = divmod(K, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def select_best(pairs):
+    """pairs: iterable of (score, global_index); index < 0 marks an empty shard.  Greatest score, ties ->
+    lowest index."""
+    best_s, best_i = -np.inf, -1
+    for s, i in pairs:
+        i = int(i)
+        if i < 0:
+            continue
+        if s > best_s or (s == best_s and i < best_i):
+            best_s, best_i = float(s), i
+    return best_s, best_i
+
+
+class BestReducer:
+    """Device-side, sync-free reduction of the per-rank best candidate (NCCL all-gather of 16 B per rank
+    followed by a one-warp select kernel)."""
+
+    launches_per_reduce = 2
+
+    def __init__(self, device, world: int, group=None):
+        self.device, self.world, self.group = device, world, group
+        self.pair = torch.zeros(2, dtype=torch.int64, device=device)
+        self.gathered = torch.zeros((world, 2), dtype=torch.int64, device=device)
+        self.out = torch.zeros(2, dtype=torch.int64, device=device)
+
+    def reduce(self, scores: torch.Tensor, best: torch.Tensor, offset: int):
+        """scores (K) f64 + best (2) i64 of the local block whose first candidate has global index `offset`.
+        Returns a LazyBest; reading it synchronises."""
+        check(lib.p3d_best_pack(ptr(scores), ptr(best), int(offset), ptr(self.pair), stream_ptr()), "p3d_best_pack")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.pair, group=self.group)
+            src, n = self.gathered, self.world
+        else:
+            src, n = self.pair, 1
+        check(lib.p3d_best_select(ptr(src), n, ptr(self.out), stream_ptr()), "p3d_best_select")
+        nv.launch_count += 2
+        return LazyBest(self.out)
+
+
+class LazyBest:
+    def __init__(self, t):
+        self.t = t
+
+    def __getitem__(self, i):
+        v = self.t.cpu().numpy()
+        return (float(v[:1].view(np.float64)[0]), int(v[1]))[i]
+
+
+def all_gather_best(score: float, index: int, group=None, device=None):
+    """Backend-agnostic version (NCCL on GPUs, gloo on CPUs): returns the global (score, index)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(score), int(index)
+    world = dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    pair = torch.tensor([np.float64(score).view(np.int64), index], dtype=torch.int64, device=device)
+    out = torch.empty((world, 2), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out.view(-1), pair, group=group)
+    host = out.cpu().numpy()
+    return select_best(zip(host[:, 0].copy().view(np.float64), host[:, 1]))
+
+
+def score_candidates_sharded(scorer, candidates, group=None, gather_scores=False):
+    """Score this rank's shard of `candidates` (K,9) with `scorer.score` and agree on the best.
+
+    Returns (best_score, best_global_index, local_scores, (lo, hi)) -- or, with gather_scores=True, the full
+    (K,) score vector in place of local_scores (one extra all-gather of 8*K bytes)."""
+    cand = np.asarray(candidates).reshape(-1, 9)
+    K = cand.shape[0]
+    inited = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if inited else 1
+    rank = dist.get_rank(group) if inited else 0
+    lo, hi = shard_range(K, world, rank)
+    if hi > lo:
+        scores, _, best = scorer.score(cand[lo:hi])
+        local = (float(scores[best]), lo + int(best))
+    else:
+        scores, local = np.zeros(0), (-np.inf, -1)
+    best_score, best_index = all_gather_best(local[0], local[1], group)
+    if gather_scores and world > 1:
+        backend_dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        sizes = [shard_range(K, world, r) for r in range(world)]
+        width = max(h - l for l, h in sizes)
+        buf = torch.zeros(width, dtype=torch.float64, device=backend_dev)
+        buf[:hi - lo] = torch.from_numpy(np.asarray(scores, dtype=np.float64)).to(backend_dev)
+        out = torch.empty((world, width), dtype=torch.float64, device=backend_dev)
+        dist.all_gather_into_tensor(out.view(-1), buf, group=group)
+        out = out.cpu().numpy()
+        scores = np.concatenate([out[r, :h - l] for r, (l, h) in enumerate(sizes)])
+    return best_score, best_index, scores, (lo, hi)

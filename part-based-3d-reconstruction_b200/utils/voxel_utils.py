@@ -1,0 +1,53 @@
+"""Drop-in for the hot-path part of the reference's utils/voxel_utils.py."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _engine as eng
+from . import _native as nv
+
+
+def selected_palette(part_colors, part_names):
+    """Distinct colours of the selected parts (first occurrence order) and, per part name, the 1-based
+    label its colour maps to."""
+    colours, label_of = [], {}
+    for name in part_names:
+        c = tuple(int(v) for v in np.asarray(part_colors[name]).reshape(3))
+        if c not in colours:
+            colours.append(c)
+        label_of[name] = colours.index(c) + 1
+    return colours, label_of
+
+
+def grid_to_device(grid, device) -> torch.Tensor:
+    """(A0,A1,A2,3) uint8 grid as a contiguous device tensor."""
+    t = grid if isinstance(grid, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(grid))
+    if t.dim() != 4 or t.shape[-1] != 3:
+        raise ValueError(f"expected a (A0,A1,A2,3) grid, got {tuple(t.shape)}")
+    if t.dtype != torch.uint8:
+        raise TypeError("voxel grid must be uint8")
+    return t.to(device).contiguous()
+
+
+def device_points_by_parts(grid, part_colors, part_names, device=None):
+    """Device-resident form of get_voxel_points_by_parts: (pts (N,3) f32, pt_label (N) u8,
+    colours list, label_of dict).  `grid` may be a NumPy array or a CUDA tensor."""
+    dev = nv.require_cuda(device)
+    g = grid_to_device(grid, dev)
+    colours, label_of = selected_palette(part_colors, part_names)
+    pal = nv.palette_tensor(colours, dev) if colours else torch.zeros((0, 3), dtype=torch.uint8, device=dev)
+    labels = eng.rgb_to_labels(g, pal)
+    pts, pt_label = eng.compact_points(labels)
+    return pts, pt_label, colours, label_of
+
+
+def get_voxel_points_by_parts(grid, part_colors, part_names, device=None):
+    """voxel_utils.py:7-21.  Returns (pts float32 (N,3) as [x=a2, y=a1, z=a0], colors uint8 (N,3)) of
+    the voxels whose colour equals one of the selected part colours, in ascending flat index."""
+    pts, pt_label, colours, _ = device_points_by_parts(grid, part_colors, part_names, device)
+    if pts.shape[0] == 0:
+        return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint8)
+    pal = nv.palette_tensor(colours, pts.device)
+    cols = eng.labels_to_rgb(pt_label, eng.make_lut(pal))
+    return pts.cpu().numpy(), cols.cpu().numpy()

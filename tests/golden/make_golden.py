@@ -1,0 +1,284 @@
+"""Generate the committed golden fixtures from the LIVE reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified reference (tests/golden/_live_reference.py stubs the plotting
+modules), runs the hot-path functions on real and synthetic inputs, and writes
+  tests/golden/data/...            input assets copied from the reference's data/ and results/
+                                   (mask PNGs, the stored Taj voxel grid, Taj camera JSONs)
+  tests/golden/camera_golden.npz   look_at / projection / IoU outputs
+  tests/golden/carve_golden.npz    affine / label / global_carve / partwise_carve outputs
+Nothing under tests/ reads /root/reference at test time.
+"""
+import contextlib
+import hashlib
+import io
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+import scipy.ndimage
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import _live_reference  # noqa: E402
+
+ref = _live_reference.load()
+C = ref.cfg
+DATA = os.path.join(HERE, "data")
+SEED = 20240607
+
+GROUP_JOBS = [(["full_building"], 90), (["chhatris"], 90), (["plinth"], 90), (["front_minarets"], 90),
+              (["small_minarets"], 90), (["dome"], 90)]                                   # nb1 cell 7
+PART_SYMMETRY = {"dome": 5, "chhatris": 45, "front_minarets": 5, "small_minarets": 5}
+EXTRUSION_DEPTHS = {"main_door": 20, "windows": 10}
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def copy_assets():
+    for name, views in (("Bibi", ["front"]), ("Taj", ["front", "drone"]), ("Akbar", ["front"])):
+        d = os.path.join(DATA, name, "masks")
+        os.makedirs(d, exist_ok=True)
+        for v in views:
+            fn = f"{name}_{v}_mask.png"
+            shutil.copyfile(os.path.join(ref.root, "data", name, "masks", fn), os.path.join(d, fn))
+    r1 = os.path.join(DATA, "results", "1.Orthographic_Voxel_Carving")
+    r2 = os.path.join(DATA, "results", "2.Perspective_Camera_Estimation")
+    os.makedirs(r1, exist_ok=True)
+    os.makedirs(r2, exist_ok=True)
+    shutil.copyfile(os.path.join(ref.root, "results/1.Orthographic_Voxel_Carving/Taj_voxel_grid.npz"),
+                    os.path.join(r1, "Taj_voxel_grid.npz"))
+    for tag in ("init", "kp", "final"):
+        fn = f"Taj_camera_params_{tag}.json"
+        shutil.copyfile(os.path.join(ref.root, "results/2.Perspective_Camera_Estimation", fn), os.path.join(r2, fn))
+    for root, _, files in os.walk(DATA):
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
+
+
+def perturb(base, K, rng):
+    """Index 0 = base, then base + U(-1,1)*steps in the reference's draw order (camera_estimation.py:619-625)."""
+    steps = np.array([50, 50, 100, 50, 50, 100, 50, 20, 20], float)
+    out = np.empty((K, 9))
+    out[0] = base
+    out[1:] = base + rng.uniform(-1, 1, (K - 1, 9)) * steps
+    return out
+
+
+def ref_score(pts, cols, seg, sel, row, H, W, dtype=np.float64):
+    cp, tg = row[0:3].astype(dtype), row[3:6].astype(dtype)
+    f, cx, cy = (dtype(row[6]), dtype(row[7]), dtype(row[8])) if dtype is np.float32 else (row[6], row[7], row[8])
+    proj = ref.pu.project_colored_voxels(pts, cols, cp, tg, f, cx, cy, H, W)
+    per, mean = ref.ce.compute_partwise_iou(proj, seg, sel)
+    counts = []
+    for c in sel.values():
+        a = np.all(proj.reshape(-1, 3) == c, axis=1)
+        b = np.all(seg.reshape(-1, 3) == c, axis=1)
+        counts.append(((a & b).sum(), (a | b).sum()))
+    return proj, np.array(counts, np.int64), float(mean)
+
+
+def camera_golden():
+    out = {}
+    rng = np.random.default_rng(SEED)
+    # --- look_at vectors -----------------------------------------------------------------------
+    eyes = rng.uniform(-800, 800, (256, 3))
+    tgts = rng.uniform(-300, 600, (256, 3))
+    tgts[::16, 0] = eyes[::16, 0]
+    tgts[::16, 2] = eyes[::16, 2]                      # straight up/down: the allclose branch
+    out["lookat_eye"], out["lookat_target"] = eyes, tgts
+    out["lookat_R64"] = np.stack([ref.cg.look_at_rotation(e.copy(), t.copy()) for e, t in zip(eyes, tgts)])
+    out["lookat_R32"] = np.stack([ref.cg.look_at_rotation(e.astype(np.float32), t.astype(np.float32))
+                                  for e, t in zip(eyes, tgts)])
+    assert out["lookat_R32"].dtype == np.float32
+
+    # --- Taj (config 2): stored grid, front + drone masks, stored cameras ---------------------------
+    grid = np.load(os.path.join(ref.root, "results/1.Orthographic_Voxel_Carving/Taj_voxel_grid.npz"))["voxel_grid"]
+    cams = json.load(open(os.path.join(ref.root, "results/2.Perspective_Camera_Estimation/Taj_camera_params_final.json")))
+    masks = {"front": ref.mu.load_mask(os.path.join(ref.root, "data"), "Taj", "front", int(np.max(grid.shape))),
+             "drone": ref.mu.load_mask(os.path.join(ref.root, "data"), "Taj", "drone")}
+    minarets = ["front_minarets", "back_minarets"]
+    allparts = [p for p in C.PART_COLORS if p != "background"]
+    for view in ("front", "drone"):
+        img = masks[view]
+        H, W = img.shape[:2]
+        base = np.array([*cams[view]["cam_pos"], *cams[view]["target"], cams[view]["f"], cams[view]["cx"], cams[view]["cy"]])
+        for tag, parts, K in (("min", minarets, 24), ("all", allparts, 4)):
+            cand = perturb(base, K, rng)
+            seg = ref.mu.mask_parts_from_image(img, C.PART_COLORS, parts)
+            sel = {p: C.PART_COLORS[p] for p in parts}
+            pts, cols = ref.vu.get_voxel_points_by_parts(grid, C.PART_COLORS, parts)
+            counts, scores, hashes = [], [], []
+            for k in range(K):
+                proj, c, s = ref_score(pts, cols, seg, sel, cand[k], H, W)
+                counts.append(c); scores.append(s); hashes.append(sha(proj))
+                if k == 0:
+                    out[f"taj_{view}_{tag}_image0"] = proj
+            key = f"taj_{view}_{tag}"
+            out[key + "_cand"] = cand
+            out[key + "_counts"] = np.array(counts)
+            out[key + "_scores"] = np.array(scores)
+            out[key + "_sha"] = np.array(hashes)
+            out[key + "_npts"] = np.array(pts.shape[0])
+            print(key, "pts", pts.shape[0], "base score", scores[0])
+        # float32 path (notebooks 3/4 pass float32 camera arrays)
+        parts = minarets
+        cand = perturb(base, 6, rng)
+        seg = ref.mu.mask_parts_from_image(img, C.PART_COLORS, parts)
+        sel = {p: C.PART_COLORS[p] for p in parts}
+        pts, cols = ref.vu.get_voxel_points_by_parts(grid, C.PART_COLORS, parts)
+        counts, hashes = [], []
+        for k in range(6):
+            proj, c, s = ref_score(pts, cols, seg, sel, cand[k], H, W, dtype=np.float32)
+            counts.append(c); hashes.append(sha(proj))
+        out[f"taj_{view}_f32_cand"] = cand.astype(np.float32)
+        out[f"taj_{view}_f32_counts"] = np.array(counts)
+        out[f"taj_{view}_f32_sha"] = np.array(hashes)
+
+    # --- per-part scoring core of visualize_voxel_projection_iou (camera_estimation.py:381-403, 433-447)
+    img = masks["front"]
+    H, W = img.shape[:2]
+    p = cams["front"]
+    bg = np.array(C.PART_COLORS["background"], np.uint8)
+    comb_prj = np.zeros((H, W), bool)
+    rows = []
+    for part, color in C.PART_COLORS.items():
+        pts, col = ref.vu.get_voxel_points_by_parts(grid, C.PART_COLORS, [part])
+        if pts.shape[0] == 0:
+            rows.append((0, int(np.all(img == color, axis=-1).sum())))
+            continue
+        proj = ref.pu.project_colored_voxels(pts, col, np.array(p["cam_pos"]), np.array(p["target"]), p["f"], p["cx"], p["cy"], H, W)
+        mg, mp = np.all(img == color, axis=-1), np.all(proj == color, axis=-1)
+        comb_prj |= mp
+        rows.append(((mg & mp).sum(), (mg | mp).sum()))
+    comb_gt = np.any(img != bg, axis=-1)
+    rows.append(((comb_gt & comb_prj).sum(), (comb_gt | comb_prj).sum()))
+    out["taj_front_perpart_counts"] = np.array(rows, np.int64)
+    out["taj_front_perpart_parts"] = np.array(list(C.PART_COLORS.keys()))
+
+    # --- adversarial synthetic: camera inside the cloud (points behind the camera), tiny image, empty part
+    g = np.zeros((12, 10, 14, 3), np.uint8)
+    r2 = np.random.default_rng(7)
+    lab = r2.integers(0, 4, g.shape[:3])
+    g[lab == 1] = C.PART_COLORS["dome"]
+    g[lab == 2] = C.PART_COLORS["plinth"]
+    parts = ["dome", "plinth", "windows"]                 # windows: absent from grid and image
+    img = np.zeros((20, 24, 3), np.uint8)
+    img[4:15, 5:20] = C.PART_COLORS["dome"]
+    img[12:18, 2:22] = C.PART_COLORS["plinth"]
+    seg = ref.mu.mask_parts_from_image(img, C.PART_COLORS, parts)
+    sel = {q: C.PART_COLORS[q] for q in parts}
+    pts, cols = ref.vu.get_voxel_points_by_parts(g, C.PART_COLORS, parts)
+    cand = np.array([[7.0, 5.0, 6.0, 7.0, 5.0, 30.0, 20.0, 12.0, 10.0],      # inside the cloud
+                     [7.0, 5.0, -20.0, 7.0, 5.0, 6.0, 25.0, 12.0, 10.0],     # in front
+                     [7.0, 40.0, 6.0, 7.0, 5.0, 6.0, 25.0, 12.0, 10.0],      # straight down (allclose branch)
+                     [7.0, 5.0, 6.0, 7.0, 5.0, 6.0, 25.0, 12.0, 10.0],       # eye == target -> NaN
+                     [6.5, 4.5, -15.0, 6.5, 4.5, 6.0, 12.0, 11.5, 9.5]])     # exact .5 pixel ties
+    counts, hashes, scores = [], [], []
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(len(cand)):
+            proj, c, s = ref_score(pts, cols, seg, sel, cand[k], 20, 24)
+            counts.append(c); hashes.append(sha(proj)); scores.append(s)
+    out["adv_grid"], out["adv_image"], out["adv_cand"] = g, img, cand
+    out["adv_counts"], out["adv_sha"], out["adv_scores"] = np.array(counts), np.array(hashes), np.array(scores)
+    np.savez_compressed(os.path.join(HERE, "camera_golden.npz"), **out)
+
+
+def blocky_semantic(rng, H, W, last_col=False):
+    """Random blocky semantic mask in the PART_COLORS palette (background elsewhere)."""
+    names = ["full_building", "chhatris", "plinth", "dome", "front_minarets", "small_minarets", "main_door", "windows"]
+    sem = np.empty((H, W, 3), np.uint8)
+    sem[:] = C.PART_COLORS["background"]
+    for _ in range(14):
+        n = names[rng.integers(len(names))]
+        y0, x0 = rng.integers(0, H - 4), rng.integers(0, W - 4)
+        y1, x1 = y0 + rng.integers(3, max(4, H // 2)), x0 + rng.integers(3, max(4, W // 2))
+        sem[y0:y1, x0:x1] = C.PART_COLORS[n]
+    if last_col:
+        sem[H // 4: H // 2, W - 3:] = C.PART_COLORS["plinth"]
+    return sem
+
+
+def carve_golden():
+    out = {}
+    rng = np.random.default_rng(SEED)
+    # --- scipy affine_transform / label unit vectors ------------------------------------------------
+    k = 0
+    for shape in [(43, 47, 44), (30, 58, 30), (16, 5, 16), (15, 4, 15), (31, 3, 31), (20, 6, 33)]:
+        for ang in (0, 5, 45, 60, 90):
+            vol = (rng.random(shape) < 0.55).astype(np.uint8)
+            M = ref.vc._rotation_matrix_inv(ang)
+            ctr = np.array(shape) / 2
+            res = scipy.ndimage.affine_transform(vol, M, offset=ctr - M @ ctr, order=1, mode="constant", cval=0)
+            out[f"aff{k}_vol"], out[f"aff{k}_angle"], out[f"aff{k}_out"] = np.packbits(vol), np.array(ang), np.packbits(res)
+            out[f"aff{k}_shape"] = np.array(shape)
+            assert res.max() <= 1
+            k += 1
+    out["aff_n"] = np.array(k)
+    for i, (shape, p) in enumerate([((20, 30, 25), 0.3), ((24, 24, 24), 0.55), ((9, 40, 17), 0.7)]):
+        m = rng.random(shape) < p
+        lab, n = scipy.ndimage.label(m)
+        out[f"lab{i}_mask"], out[f"lab{i}_shape"] = np.packbits(m), np.array(shape)
+        out[f"lab{i}_out"], out[f"lab{i}_n"] = lab.astype(np.int32), np.array(n)
+    out["lab_n"] = np.array(3)
+
+    # --- real masks ---------------------------------------------------------------------------------
+    cases = [("Bibi", 64), ("Taj", 96), ("Akbar", 128), ("Bibi", 256)]
+    for name, md in cases:
+        sem, ext, binm = ref.mu.load_and_prepare_masks(os.path.join(ref.root, "data"), name, "front", md,
+                                                       C.PART_COLORS_NP, C.INTERIOR_PARTS)
+        g = ref.vc.global_carve(binm, ext, 90)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            p = ref.vc.partwise_carve(g, ext, sem, C.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS)
+        key = f"real_{name}_{md}"
+        out[key + "_sem"], out[key + "_ext"], out[key + "_bin"] = sem, ext, binm
+        out[key + "_global_sha"], out[key + "_partwise_sha"] = np.array(sha(g)), np.array(sha(p))
+        out[key + "_global_occ"] = np.array(np.count_nonzero(g.any(-1)))
+        out[key + "_partwise_occ"] = np.array(np.count_nonzero(p.any(-1)))
+        out[key + "_log"] = np.array(buf.getvalue())
+        if md <= 128:
+            out[key + "_global"], out[key + "_partwise"] = g, p
+        print(key, sem.shape, out[key + "_partwise_sha"], out[key + "_partwise_occ"])
+    out["real_cases"] = np.array([f"{n}_{m}" for n, m in cases])
+
+    # --- synthetic quirk cases: square image (_mask_to_wh), last-column foreground, W in the odd-offset set --
+    syn = [("sq64", 64, 64, False), ("rect40x64", 40, 64, False), ("sq63", 63, 63, True), ("rect50x31", 50, 31, True),
+           ("rect33x48", 33, 48, True)]
+    for tag, H, W, last in syn:
+        sem = blocky_semantic(rng, H, W, last)
+        ext = sem.copy()
+        for q in C.INTERIOR_PARTS:
+            ext[np.all(sem == C.PART_COLORS_NP[q], axis=-1)] = C.PART_COLORS_NP["full_building"]
+        binm = (~np.all(ext == C.PART_COLORS_NP["background"], axis=-1)).astype(np.uint8)
+        g = ref.vc.global_carve(binm, ext, 90)
+        pc = ref.vc.part_carve(g, ext, GROUP_JOBS)
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = ref.vc.partwise_carve(g, ext, sem, C.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS)
+            p2 = ref.vc.partwise_carve(g, ext, sem, C.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS,
+                                       recolor_back_minarets=False)
+        key = "syn_" + tag
+        out[key + "_sem"], out[key + "_ext"], out[key + "_bin"] = sem, ext, binm
+        out[key + "_global"], out[key + "_partcarve"], out[key + "_partwise"] = g, pc, p
+        out[key + "_partwise_norecolor_sha"] = np.array(sha(p2))
+        print(key, g.shape, np.count_nonzero(g.any(-1)), np.count_nonzero(p.any(-1)))
+    out["syn_cases"] = np.array([s[0] for s in syn])
+    np.savez_compressed(os.path.join(HERE, "carve_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    copy_assets()
+    camera_golden()
+    carve_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

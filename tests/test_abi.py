@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, the Python binding covers them, and the product refuses to run without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import PKG, ROOT, pkg
+
+HEADER = os.path.join(ROOT, "include", "p3d_b200.h")
+LIB = os.path.join(ROOT, PKG, "csrc", "libp3d_b200.so")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(p3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "build the library first: python __graft_entry__.py"
+    lib = ctypes.CDLL(LIB)
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in p3d_b200.h but not exported"
+
+
+def test_binding_covers_header():
+    nv = pkg("utils._native")
+    missing = [n for n in declared_symbols() if n not in nv._SIGNATURES]
+    assert not missing, missing
+    assert nv.lib.p3d_version() >= 100
+
+
+def test_pure_host_entry_points_work_without_gpu():
+    nv = pkg("utils._native")
+    assert nv.lib.p3d_points_workspace_bytes(4096 * 10) == 11 * 8
+    assert nv.lib.p3d_sweep_workspace_bytes(8, 64, 64, 2, 8) > 8 * 64 * 64 * 4
+    assert nv.lib.p3d_sweep_workspace_bytes(0, 64, 64, 2, 8) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_fails_loudly_without_cuda():
+    import numpy as np
+    nv = pkg("utils._native")
+    ce = pkg("utils.camera_estimation")
+    pu = pkg("utils.projection_utils")
+    with pytest.raises(nv.P3DError):
+        ce.compute_partwise_iou(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4, 3), np.uint8), {"a": (1, 2, 3)})
+    with pytest.raises(nv.P3DError):
+        pu.project_colored_voxels(np.zeros((1, 3), np.float32), np.zeros((1, 3), np.uint8), np.zeros(3), np.ones(3),
+                                  1.0, 0.0, 0.0, 4, 4)
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for root, _, files in os.walk(os.path.join(ROOT, PKG)):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "p3d_oracle" in src:
+                    bad.append(os.path.join(root, f))
+    assert not bad, bad

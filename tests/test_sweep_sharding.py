@@ -1,0 +1,95 @@
+"""Host logic of the multi-GPU sweep on CPU: shard ranges, best-candidate selection (first index with the
+greatest score) and the all-gather, with world_size 2 and 3 over gloo.  The scorer is a stub backed by the
+oracle, so no GPU is needed."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import pkg
+
+
+def test_shard_range_partitions_everything():
+    sw = pkg("utils.sweep")
+    for K in (0, 1, 7, 64, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [sw.shard_range(K, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == K
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [h - l for l, h in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_select_best_prefers_first_index_on_ties():
+    sw = pkg("utils.sweep")
+    assert sw.select_best([(0.5, 10), (0.7, 30), (0.7, 20), (0.1, 0)]) == (0.7, 20)
+    assert sw.select_best([(-np.inf, -1), (0.0, 5)]) == (0.0, 5)
+    assert sw.select_best([(-np.inf, -1)]) == (-np.inf, -1)
+
+
+class OracleScorer:
+    """Same interface as CandidateScorer.score, computed by the oracle."""
+
+    def __init__(self):
+        from oracle import oracle as orc
+        self.orc = orc
+        rng = np.random.default_rng(2)
+        g = np.zeros((10, 9, 11, 3), np.uint8)
+        lab = rng.integers(0, 3, g.shape[:3])
+        g[lab == 1] = orc.PART_COLORS["dome"]
+        g[lab == 2] = orc.PART_COLORS["plinth"]
+        self.parts = ["dome", "plinth"]
+        self.pts, self.cols = orc.get_voxel_points_by_parts(g, orc.PART_COLORS, self.parts)
+        img = np.zeros((24, 24, 3), np.uint8)
+        img[5:15, 4:20] = orc.PART_COLORS["dome"]
+        img[13:20, 2:22] = orc.PART_COLORS["plinth"]
+        self.seg = orc.mask_parts_from_image(img, orc.PART_COLORS, self.parts)
+        self.sel = {p: orc.PART_COLORS[p] for p in self.parts}
+
+    def score(self, cand):
+        scores, counts = [], []
+        for row in np.asarray(cand).reshape(-1, 9):
+            s, inter, uni = self.orc.score_candidate(self.pts, self.cols, self.seg, self.sel,
+                                                     {"cam_pos": row[0:3], "target": row[3:6], "f": row[6], "cx": row[7],
+                                                      "cy": row[8]}, 24, 24)
+            scores.append(s)
+            counts.append(np.stack([inter, uni], 1))
+        scores = np.array(scores)
+        return scores, np.array(counts), int(np.argmax(scores)) if len(scores) else -1
+
+
+def make_candidates(K):
+    rng = np.random.default_rng(9)
+    base = np.array([5.0, 4.0, -25.0, 5.0, 4.0, 5.0, 30.0, 12.0, 12.0])
+    cand = base + rng.uniform(-1, 1, (K, 9)) * np.array([2, 2, 4, 2, 2, 4, 3, 2, 2.0])
+    if K > 4:
+        cand[K - 2] = cand[3]                  # duplicate scores in different shards
+    return cand
+
+
+def _worker(rank, world, port, K, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sw = pkg("utils.sweep")
+    scorer = OracleScorer()
+    cand = make_candidates(K)
+    best_s, best_i, scores, (lo, hi) = sw.score_candidates_sharded(scorer, cand, gather_scores=True)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), best_s=best_s, best_i=best_i, scores=scores, lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,K", [(2, 13), (3, 10), (2, 1)])
+def test_sharded_sweep_gloo(tmp_path, world, K):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, K, str(tmp_path)), nprocs=world, join=True)
+    full, _, _ = OracleScorer().score(make_candidates(K))
+    want_i = int(np.argmax(full))               # first index of the maximum
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert int(z["best_i"]) == want_i and float(z["best_s"]) == full[want_i]
+        assert np.array_equal(z["scores"], full)
