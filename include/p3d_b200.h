@@ -150,6 +150,78 @@ int p3d_best_select(const int64_t* pairs, int n, int64_t* out, p3d_stream_t stre
 int p3d_sweep_timing_enable(int on);
 int p3d_sweep_timing_read(double* splat_ms, int* n_launches);
 
+/* ============================================================================================= *
+ * Stage 1: orthographic semantic voxel carving            utils/voxel_carving_utils.py
+ * Grids are (W,H,D) uint8 occupancy or (W,H,D,3) uint8 RGB.  2-D masks are passed already oriented:
+ * mask_wh = (W,H) row-major (the result of the reference's _mask_to_wh :19-28), mask_hw = (H,W).
+ * M (9 doubles, row-major) and off (3 doubles) are HOST pointers: the inverse rotation and offset that
+ * the reference computes with NumPy (:65-69, :108, :119) and hands to scipy.ndimage.affine_transform.
+ * ============================================================================================= */
+
+/* One pass of process_voxel_grid :116-124 for any angle: scipy.ndimage.affine_transform(order=1,
+ * mode="constant", cval=0) of a uint8 volume followed by the mask carve (mask_wh may be NULL). */
+int p3d_resample_carve(const uint8_t* vol_in, int n0, int n1, int n2, const double* M, const double* off,
+                       const uint8_t* mask_wh, uint8_t* vol_out, p3d_stream_t stream);
+
+/* For a transform that leaves axis 1 alone: table (n0,n2) int32 = (src0 << 16 | src2) of the nearest source
+ * voxel, -1 where scipy's bounds rule rejects the point; flag[0] != 0 when some in-range coordinate is not
+ * within 1e-9 of an integer, i.e. the pass is NOT a pure index fold and needs p3d_resample_carve. */
+int p3d_fold_table(int n0, int n2, const double* M, const double* off, int32_t* table, int* flag,
+                   p3d_stream_t stream);
+/* The same pass as p3d_resample_carve for a foldable transform: out = mask ? in[src0, y, src2] : 0. */
+int p3d_fold_gather(const uint8_t* vol_in, int n0, int n1, int n2, const int32_t* table,
+                    const uint8_t* mask_wh, uint8_t* vol_out, p3d_stream_t stream);
+
+/* global_carve :269-298 at angle_interval = 90, fused with apply_colored_mask_to_voxel_grid :128-136:
+ *   out[x,y,z] = colour[y,x] if mask[y,x] && table[x,z] >= 0 && mask[y, src0(x,z)] else 0
+ * rgb != 0: colour_hw is (H,W,3) and out (W,H,D,3); rgb == 0: colour_hw is (H,W) labels and out (W,H,D). */
+int p3d_global_carve_fold(int W, int H, int D, const int32_t* table, const uint8_t* mask_hw,
+                          const uint8_t* colour_hw, int rgb, uint8_t* out, p3d_stream_t stream);
+/* carve_voxel_grid_with_masks :76-97: out = where(mask, grid, 0).  grid (W,H,D[,3]) with channels = 1 or 3;
+ * mask_wh (W,H) with mask_channels = 1, or (W,H,3) with mask_channels = 3 (per-channel RGB branch :90-95). */
+int p3d_mask_carve(const uint8_t* grid, int W, int H, int D, int channels, const uint8_t* mask_wh,
+                   int mask_channels, uint8_t* out, p3d_stream_t stream);
+/* apply_colored_mask_to_voxel_grid :128-136 (general path): out = colour[y,x,:] where carved == 1. */
+int p3d_colourise(const uint8_t* carved, int W, int H, int D, const uint8_t* colour_hw, uint8_t* out,
+                  p3d_stream_t stream);
+
+/* part_carve :139-160 with every group at 90 degrees, all groups in one pass.  group_mask_hw (H,W) uint32:
+ * bit g set when pixel (y,x) is in group g's mask AND in that mask after _mask_to_wh (square quirk). */
+int p3d_part_carve_fold(const uint8_t* grid, int W, int H, int D, const int32_t* table,
+                        const uint32_t* group_mask_hw, uint8_t* out, p3d_stream_t stream);
+
+/* Building blocks of the general-angle part_carve and of left_right_guided_carve :163-210. */
+int p3d_crop_occupancy(const uint8_t* grid, int W, int H, int D, int x0, int y0, int z0, int w, int h, int d,
+                       const uint8_t* sel_wh /* (w,h) or NULL */, uint8_t* occ, p3d_stream_t stream);
+int p3d_accumulate_part(const uint8_t* grid, const uint8_t* carved, int W, int H, int D, const uint8_t* sel_wh,
+                        uint8_t* final_grid, p3d_stream_t stream);
+int p3d_paste_component(const uint8_t* src, const int32_t* labels, int comp, const uint8_t* kept, int W, int H,
+                        int D, int x0, int y0, int z0, int w, int h, int d, uint8_t* out, p3d_stream_t stream);
+
+/* np.all(grid == colour, axis=-1) :175,253 -> uint8 mask; a colour outside 0..255 matches nothing. */
+int p3d_colour_mask(const uint8_t* grid_rgb, int64_t n, int r, int g, int b, uint8_t* mask, p3d_stream_t stream);
+
+/* scipy.ndimage.label, default structure (6-connectivity) :175,254: labels (n0,n1,n2) int32 with ids
+ * 1..n in raster order of each component's first voxel; n written to n_components[0] (device). */
+size_t p3d_label6_workspace_bytes(int64_t n_voxels);
+int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components,
+               void* workspace, size_t workspace_bytes, p3d_stream_t stream);
+/* Per component: bbox (n,6) int32 = min0,min1,min2,max0,max1,max2 (inclusive) and sums (n,4) int64 =
+ * voxel count and coordinate sums per axis (:184-185, :258-259). */
+int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, int n_components, int32_t* bbox,
+                        int64_t* sums, p3d_stream_t stream);
+/* recolor_backward_components :263-265: voxels of components with recolour[id-1] != 0 get the colour. */
+int p3d_recolour_components(const int32_t* labels, const uint8_t* recolour, int64_t n, int r, int g, int b,
+                            uint8_t* grid_rgb, p3d_stream_t stream);
+
+/* extrude_from_surface :213-248, in place.  axis 2: mask_hw is (H,W) indexed [y][x]; axis 0: mask_hw is
+ * (H,D) indexed [y][z].  sign = +1 / -1 for direction "+" / "-". */
+int p3d_extrude(uint8_t* grid_rgb, int W, int H, int D, const uint8_t* mask_hw, int mask_h, int mask_w, int axis,
+                int sign, int depth, int r, int g, int b, p3d_stream_t stream);
+
+/* partwise_carve :384-385: out (D,H,W,3) = flip(transpose(in (W,H,D,3), (2,1,0,3)), axis=1). */
+int p3d_reorient(const uint8_t* in, int W, int H, int D, uint8_t* out, p3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,857 @@
+// libp3d_b200: orthographic semantic voxel carving (stage 1 of the reference).
+//
+// Reference call sites replaced here (paths under the reference root, utils/voxel_carving_utils.py):
+//   process_voxel_grid :104-126  (scipy.ndimage.affine_transform order=1 + carve_voxel_grid_with_masks :76-87)
+//   apply_colored_mask_to_voxel_grid :128-136,  global_carve :269-298
+//   part_carve :139-160,  left_right_guided_carve :163-210 (crop / paste around scipy.ndimage.label)
+//   extrude_from_surface :213-248,  recolor_backward_components :252-266,  partwise_carve :302-400
+//
+// Grids are (W,H,D[,3]) uint8, C order.  2-D masks arrive already oriented as (W,H) ("mask_wh", the result
+// of the reference's _mask_to_wh) and, where a kernel gathers along x, additionally as (H,W) ("mask_hw").
+//
+// Exactness: the resample follows scipy's NI_GeometricTransform for order=1, mode="constant" --
+//   cc[h] = off[h]; cc[h] += M[h][0]*o0; += M[h][1]*o1; += M[h][2]*o2   (FP64, separately rounded)
+//   outside if cc < 0 or cc > dim-1; fl = floor(cc); t = cc - fl; i1 = min(i0+1, dim-1)
+//   acc = sum over the 8 corners (axis0, axis1, axis2 nesting) of v * w0 * w1 * w2 ; out = (uint8)(acc + 0.5)
+// When every in-range coordinate of a pass is within 1e-9 of an integer (angle 0, and angle 90 on a grid with
+// D == W) the blend collapses to a nearest-index gather; that case is detected at run time from the actual
+// host-computed matrix/offset ("fold table") and served by streaming kernels.
+#include "p3d_common.cuh"
+
+namespace {
+
+struct Affine {
+  double M[9];
+  double off[3];
+};
+
+inline int grid_for(int64_t items, int threads, int waves) {
+  int64_t blocks = (items + threads - 1) / threads;
+  int64_t cap = (int64_t)p3d::sm_count() * waves;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// ------------------------------------------------------------------------------------------
+// General trilinear resample + mask carve (one thread per output voxel).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double coord(const Affine& A, int h, int o0, int o1, int o2) {
+  double c = A.off[h];
+  c = __dadd_rn(c, __dmul_rn(A.M[3 * h + 0], (double)o0));
+  c = __dadd_rn(c, __dmul_rn(A.M[3 * h + 1], (double)o1));
+  c = __dadd_rn(c, __dmul_rn(A.M[3 * h + 2], (double)o2));
+  return c;
+}
+
+__global__ void __launch_bounds__(256)
+resample_carve_kernel(const uint8_t* __restrict__ vin, int n0, int n1, int n2, Affine A,
+                      const uint8_t* __restrict__ mask_wh, uint8_t* __restrict__ vout) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o2 = (int)(i % n2);
+    const int64_t r = i / n2;
+    const int o1 = (int)(r % n1);
+    const int o0 = (int)(r / n1);
+    uint8_t res = 0;
+    if (mask_wh == nullptr || mask_wh[(size_t)o0 * n1 + o1]) {
+      const int dim[3] = {n0, n1, n2};
+      double cc[3];
+      bool inside = true;
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        cc[h] = coord(A, h, o0, o1, o2);
+        if (cc[h] < 0.0 || cc[h] > (double)(dim[h] - 1)) inside = false;
+      }
+      if (inside) {
+        int i0[3], i1[3];
+        double t[3];
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+          const double fl = floor(cc[h]);
+          t[h] = __dsub_rn(cc[h], fl);
+          i0[h] = (int)fl;
+          i1[h] = i0[h] + 1 < dim[h] ? i0[h] + 1 : dim[h] - 1;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int ix = a ? i1[0] : i0[0], iy = b ? i1[1] : i0[1], iz = c ? i1[2] : i0[2];
+              double w = (double)vin[((size_t)ix * n1 + iy) * n2 + iz];
+              w = __dmul_rn(w, a ? t[0] : __dsub_rn(1.0, t[0]));
+              w = __dmul_rn(w, b ? t[1] : __dsub_rn(1.0, t[1]));
+              w = __dmul_rn(w, c ? t[2] : __dsub_rn(1.0, t[2]));
+              acc = __dadd_rn(acc, w);
+            }
+        if (acc > 0.0) {
+          const double rr = __dadd_rn(acc, 0.5);
+          res = rr >= 255.0 ? 255 : (uint8_t)rr;
+        }
+      }
+    }
+    vout[i] = res;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fold table: for a pass whose y axis is decoupled (M row/col 1 = identity, off[1] = 0), the source index of
+// output (o0, o2) as (src0 << 16 | src2), or -1 when scipy treats the point as outside.  flag[0] is set
+// when some in-range coordinate is NOT within 1e-9 of an integer (then the pass needs the general kernel).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fold_table_kernel(int n0, int n2, Affine A, int32_t* __restrict__ table, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0 * n2) return;
+  const int o0 = i / n2, o2 = i - o0 * n2;
+  const double c0 = coord(A, 0, o0, 0, o2), c2 = coord(A, 2, o0, 0, o2);
+  int32_t e = -1;
+  if (!(c0 < 0.0 || c0 > (double)(n0 - 1) || c2 < 0.0 || c2 > (double)(n2 - 1))) {
+    const double f0 = floor(c0), f2 = floor(c2);
+    const double t0 = __dsub_rn(c0, f0), t2 = __dsub_rn(c2, f2);
+    const bool near0 = t0 < 1e-9 || t0 > 1.0 - 1e-9, near2 = t2 < 1e-9 || t2 > 1.0 - 1e-9;
+    if (!(near0 && near2)) atomicOr(flag, 1);
+    int s0 = (int)f0, s2 = (int)f2;
+    if (t0 > 0.5) s0 = s0 + 1 < n0 ? s0 + 1 : n0 - 1;
+    if (t2 > 0.5) s2 = s2 + 1 < n2 ? s2 + 1 : n2 - 1;
+    e = (s0 << 16) | s2;
+  }
+  table[i] = e;
+}
+
+// Gather pass for a collapsible transform: out[x,y,z] = mask[x,y] ? in[src0(x,z), y, src2(x,z)] : 0.
+__global__ void __launch_bounds__(256)
+fold_gather_kernel(const uint8_t* __restrict__ vin, int n0, int n1, int n2, const int32_t* __restrict__ table,
+                   const uint8_t* __restrict__ mask_wh, uint8_t* __restrict__ vout) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o2 = (int)(i % n2);
+    const int64_t r = i / n2;
+    const int o1 = (int)(r % n1);
+    const int o0 = (int)(r / n1);
+    uint8_t res = 0;
+    if (mask_wh == nullptr || mask_wh[(size_t)o0 * n1 + o1]) {
+      const int32_t e = table[o0 * n2 + o2];
+      if (e >= 0) res = vin[((size_t)(e >> 16) * n1 + o1) * n2 + (e & 0xffff)];
+    }
+    vout[i] = res;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// global_carve, 90-degree closed form, fused with the colouring:
+//   out[x,y,z,:] = colour[y,x,:]  if  m[x,y] && table[x,z] >= 0 && m[src0(x,z), y]   else 0
+// (the angle-0 pass is the identity; carved = rot90(ones & m) & m).
+// Vector path (D % 16 == 0): a thread owns 16 voxels of one z-row = 48 output bytes, staged through shared
+// memory so that every store instruction writes 512 contiguous bytes per warp.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void expand4(uint32_t bits, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t* o) {
+  const uint32_t b0 = bits & 1u ? 0xffffffffu : 0u, b1 = bits & 2u ? 0xffffffffu : 0u;
+  const uint32_t b2 = bits & 4u ? 0xffffffffu : 0u, b3 = bits & 8u ? 0xffffffffu : 0u;
+  o[0] = w0 & ((b0 & 0x00ffffffu) | (b1 & 0xff000000u));
+  o[1] = w1 & ((b1 & 0x0000ffffu) | (b2 & 0xffff0000u));
+  o[2] = w2 & ((b2 & 0x000000ffu) | (b3 & 0xffffff00u));
+}
+
+template <bool RGB>
+__global__ void __launch_bounds__(256)
+global_fold_kernel(int W, int H, int D, const int32_t* __restrict__ table, const uint8_t* __restrict__ mask_hw,
+                   const uint8_t* __restrict__ colour_hw /* (H,W,3) if RGB else (H,W) labels */,
+                   uint8_t* __restrict__ out) {
+  __shared__ uint4 stage[8][96];                       // 8 warps x 1536 bytes
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t groups = (int64_t)W * H * D / 16;
+  const int64_t warp_groups = (groups + 31) / 32;
+  for (int64_t wg = (int64_t)blockIdx.x * 8 + warp; wg < warp_groups; wg += (int64_t)gridDim.x * 8) {
+    const int64_t g = wg * 32 + lane;
+    uint32_t bits = 0;
+    uint32_t col = 0;
+    if (g < groups) {
+      const int64_t v0 = g * 16;
+      const int z0 = (int)(v0 % D);
+      const int64_t r = v0 / D;
+      const int y = (int)(r % H), x = (int)(r / H);
+      if (mask_hw[(size_t)y * W + x]) {
+        const int32_t* trow = table + (size_t)x * D + z0;
+        const uint8_t* mrow = mask_hw + (size_t)y * W;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int32_t e = __ldg(trow + j);
+          if (e >= 0 && __ldg(mrow + (e >> 16))) bits |= 1u << j;
+        }
+        if (RGB) {
+          const uint8_t* c = colour_hw + ((size_t)y * W + x) * 3;
+          col = c[0] | (c[1] << 8) | (c[2] << 16);
+        } else {
+          col = colour_hw[(size_t)y * W + x];
+        }
+      }
+    }
+    if (RGB) {
+      const uint32_t r8 = col & 0xff, g8 = (col >> 8) & 0xff, b8 = (col >> 16) & 0xff;
+      const uint32_t w0 = r8 | (g8 << 8) | (b8 << 16) | (r8 << 24);
+      const uint32_t w1 = g8 | (b8 << 8) | (r8 << 16) | (g8 << 24);
+      const uint32_t w2 = b8 | (r8 << 8) | (g8 << 16) | (b8 << 24);
+      uint32_t o[12];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) expand4((bits >> (4 * q)) & 0xfu, w0, w1, w2, o + 3 * q);
+      uint4* mine = &stage[warp][lane * 3];
+      mine[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      mine[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      mine[2] = make_uint4(o[8], o[9], o[10], o[11]);
+      __syncwarp();
+      uint4* dst = reinterpret_cast<uint4*>(out) + wg * 96;
+      const int64_t limit = groups * 3;                // uint4 count of the whole output
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        if (wg * 96 + p * 32 + lane < limit) dst[p * 32 + lane] = stage[warp][p * 32 + lane];
+      __syncwarp();
+    } else if (g < groups) {
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t b = (bits >> (4 * q)) & 0xfu;
+        o[q] = (col * 0x01010101u) & ((b & 1u ? 0xffu : 0u) | (b & 2u ? 0xff00u : 0u) | (b & 4u ? 0xff0000u : 0u) |
+                                     (b & 8u ? 0xff000000u : 0u));
+      }
+      reinterpret_cast<uint4*>(out)[g] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// Scalar path for any D.
+template <bool RGB>
+__global__ void __launch_bounds__(256)
+global_fold_scalar_kernel(int W, int H, int D, const int32_t* __restrict__ table,
+                          const uint8_t* __restrict__ mask_hw, const uint8_t* __restrict__ colour_hw,
+                          uint8_t* __restrict__ out) {
+  const int64_t n = (int64_t)W * H * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % D);
+    const int64_t r = i / D;
+    const int y = (int)(r % H), x = (int)(r / H);
+    bool keep = false;
+    if (mask_hw[(size_t)y * W + x]) {
+      const int32_t e = table[(size_t)x * D + z];
+      keep = e >= 0 && mask_hw[(size_t)y * W + (e >> 16)];
+    }
+    if (RGB) {
+      const uint8_t* c = colour_hw + ((size_t)y * W + x) * 3;
+      out[3 * i + 0] = keep ? c[0] : 0;
+      out[3 * i + 1] = keep ? c[1] : 0;
+      out[3 * i + 2] = keep ? c[2] : 0;
+    } else {
+      out[i] = keep ? colour_hw[(size_t)y * W + x] : 0;
+    }
+  }
+}
+
+// apply_colored_mask_to_voxel_grid: out[x,y,z,:] = colour[y,x,:] if carved[x,y,z] == 1 else 0
+__global__ void __launch_bounds__(256)
+colourise_kernel(const uint8_t* __restrict__ carved, int W, int H, int D, const uint8_t* __restrict__ colour_hw,
+                 uint8_t* __restrict__ out) {
+  const int64_t n = (int64_t)W * H * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    const int y = (int)(r % H), x = (int)(r / H);
+    const bool keep = carved[i] == 1;
+    const uint8_t* c = colour_hw + ((size_t)y * W + x) * 3;
+    out[3 * i + 0] = keep ? c[0] : 0;
+    out[3 * i + 1] = keep ? c[1] : 0;
+    out[3 * i + 2] = keep ? c[2] : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// part_carve, all groups at 90 degrees, fused:
+//   keep(x,y,z) = grid[x,y,z] != 0 && table[x,z] >= 0 && grid[s0,y,s2] != 0 &&
+//                 (G[x,y] & MM[x,y] & G[s0,y] & MM[s0,y]) != 0
+// G  = bit g set when pixel (x,y) belongs to group g's 2-D mask; MM = the same masks after the reference's
+// _mask_to_wh (transposed when W == H).  Both are (H,W) uint32 images.  Output = grid where keep else 0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool rgb_nonzero(const uint8_t* p) { return (p[0] | p[1] | p[2]) != 0; }
+
+__global__ void __launch_bounds__(256)
+part_fold_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const int32_t* __restrict__ table,
+                 const uint32_t* __restrict__ gm_hw, uint8_t* __restrict__ out) {
+  const int64_t n = (int64_t)W * H * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* p = grid + 3 * i;
+    uint8_t r = p[0], g = p[1], b = p[2];
+    bool keep = false;
+    if (r | g | b) {
+      const int z = (int)(i % D);
+      const int64_t q = i / D;
+      const int y = (int)(q % H), x = (int)(q / H);
+      const uint32_t self = gm_hw[(size_t)y * W + x];
+      const int32_t e = table[(size_t)x * D + z];
+      if (self && e >= 0) {
+        const int s0 = e >> 16, s2 = e & 0xffff;
+        const uint32_t src = gm_hw[(size_t)y * W + s0];
+        if ((self & src) && rgb_nonzero(grid + 3 * (((size_t)s0 * H + y) * D + s2))) keep = true;
+      }
+    }
+    out[3 * i + 0] = keep ? r : 0;
+    out[3 * i + 1] = keep ? g : 0;
+    out[3 * i + 2] = keep ? b : 0;
+  }
+}
+
+// Building blocks of the general (any angle) part_carve / left_right_guided_carve path -------------------
+// occ[x,y,z] = any(grid[x0+x, y0+y, z0+z, :] > 0) && (sel == null || sel[x,y])  over a crop
+__global__ void __launch_bounds__(256)
+crop_occupancy_kernel(const uint8_t* __restrict__ grid, int H, int D, int x0, int y0, int z0, int w, int h, int d,
+                      const uint8_t* __restrict__ sel_wh, uint8_t* __restrict__ occ) {
+  const int64_t n = (int64_t)w * h * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % d);
+    const int64_t q = i / d;
+    const int y = (int)(q % h), x = (int)(q / h);
+    const uint8_t* p = grid + 3 * ((((size_t)(x0 + x)) * H + (y0 + y)) * D + (z0 + z));
+    occ[i] = (rgb_nonzero(p) && (sel_wh == nullptr || sel_wh[(size_t)x * h + y])) ? 1 : 0;
+  }
+}
+
+// part_carve accumulate: final[v] = grid[v] where sel[x,y] && grid[v] != 0 && carved[v] != 0
+__global__ void __launch_bounds__(256)
+accumulate_part_kernel(const uint8_t* __restrict__ grid, const uint8_t* __restrict__ carved, int W, int H, int D,
+                       const uint8_t* __restrict__ sel_wh, uint8_t* __restrict__ final_grid) {
+  const int64_t n = (int64_t)W * H * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!carved[i]) continue;
+    const int64_t q = i / D;
+    const int y = (int)(q % H), x = (int)(q / H);
+    const uint8_t* p = grid + 3 * i;
+    if (sel_wh[(size_t)x * H + y] && rgb_nonzero(p)) {
+      final_grid[3 * i] = p[0]; final_grid[3 * i + 1] = p[1]; final_grid[3 * i + 2] = p[2];
+    }
+  }
+}
+
+// left_right_guided_carve paste (:199-201) over the bbox of component `comp`:
+//   if labels == comp: out = 0 ; if kept && src != 0: out = src      (src = the call's INPUT grid)
+__global__ void __launch_bounds__(256)
+paste_component_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ labels, int comp,
+                       const uint8_t* __restrict__ kept, int H, int D, int x0, int y0, int z0, int w, int h, int d,
+                       uint8_t* __restrict__ out) {
+  const int64_t n = (int64_t)w * h * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % d);
+    const int64_t q = i / d;
+    const int y = (int)(q % h), x = (int)(q / h);
+    const size_t v = (((size_t)(x0 + x)) * H + (y0 + y)) * D + (z0 + z);
+    const uint8_t* p = src + 3 * v;
+    if (kept[i] && rgb_nonzero(p)) {
+      out[3 * v] = p[0]; out[3 * v + 1] = p[1]; out[3 * v + 2] = p[2];
+    } else if (labels[v] == comp) {
+      out[3 * v] = 0; out[3 * v + 1] = 0; out[3 * v + 2] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Connected components, 6-connectivity, ids in raster order of each component's first voxel
+// (scipy.ndimage.label default).  Union-find on flat indices with the smaller index as root.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colour_mask_kernel(const uint8_t* __restrict__ grid, int64_t n, uint32_t colour, uint8_t* __restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* p = grid + 3 * i;
+    mask[i] = (p[0] | (p[1] << 8) | (p[2] << 16)) == colour;
+  }
+}
+
+__device__ __forceinline__ int32_t uf_find(volatile int32_t* parent, int32_t i) {
+  int32_t p = parent[i];
+  while (p != i) { i = p; p = parent[i]; }
+  return i;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* parent, int32_t a, int32_t b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) { int32_t t = a; a = b; b = t; }
+    const int32_t old = atomicMin(parent + b, a);       // hook the larger root under the smaller
+    if (old == b) return;
+    b = old;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_init_kernel(const uint8_t* __restrict__ mask, int64_t n, int32_t* __restrict__ parent) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    parent[i] = mask[i] ? (int32_t)i : -1;
+}
+
+__global__ void __launch_bounds__(256)
+ccl_merge_kernel(const uint8_t* __restrict__ mask, int n0, int n1, int n2, int32_t* __restrict__ parent) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!mask[i]) continue;
+    const int c = (int)(i % n2);
+    const int64_t r = i / n2;
+    const int b = (int)(r % n1);
+    const int a = (int)(r / n1);
+    if (c > 0 && mask[i - 1]) uf_union(parent, (int32_t)i, (int32_t)(i - 1));
+    if (b > 0 && mask[i - n2]) uf_union(parent, (int32_t)i, (int32_t)(i - n2));
+    if (a > 0 && mask[i - (int64_t)n1 * n2]) uf_union(parent, (int32_t)i, (int32_t)(i - (int64_t)n1 * n2));
+  }
+}
+
+// parent[i] <- root(i); is_root[i] = (root == i)
+__global__ void __launch_bounds__(256)
+ccl_flatten_kernel(int64_t n, int32_t* __restrict__ parent, uint8_t* __restrict__ is_root) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = parent[i];
+    uint8_t root = 0;
+    if (p >= 0) {
+      const int32_t r = uf_find(parent, (int32_t)i);
+      root = r == (int32_t)i;
+      if (!root) parent[i] = r;                         // roots keep parent == self
+    }
+    is_root[i] = root;
+  }
+}
+
+// rank[root] = 1-based position of the root among all roots in raster order (ordered compaction offsets)
+constexpr int kRankThreads = 256, kRankPer = 16, kRankTile = kRankThreads * kRankPer;
+
+__device__ __forceinline__ int block_excl_scan(int v, int* total) {
+  __shared__ int warp_sums[kRankThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int base = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kRankThreads / 32; ++w) {
+    int s = warp_sums[w];
+    if (w < warp) base += s;
+    all += s;
+  }
+  *total = all;
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kRankThreads)
+root_count_kernel(const uint8_t* __restrict__ is_root, int64_t n, int32_t* __restrict__ tile_counts) {
+  const int64_t i0 = (int64_t)blockIdx.x * kRankTile + (int64_t)threadIdx.x * kRankPer;
+  int c = 0;
+  for (int j = 0; j < kRankPer; ++j)
+    if (i0 + j < n) c += is_root[i0 + j];
+  int total;
+  block_excl_scan(c, &total);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+root_scan_kernel(int32_t* __restrict__ tile_counts, int m, int32_t* __restrict__ n_components) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < m; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < m ? tile_counts[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int wbase = 0, all = 0;
+    for (int w = 0; w < 32; ++w) {
+      int s = warp_sums[w];
+      if (w < warp) wbase += s;
+      all += s;
+    }
+    const int c = carry;
+    if (i < m) tile_counts[i] = c + wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_components[0] = carry;
+}
+
+// labels[root] = rank (1-based), written in place of parent[root]; non-roots resolved in the next kernel
+__global__ void __launch_bounds__(kRankThreads)
+root_rank_kernel(const uint8_t* __restrict__ is_root, int64_t n, const int32_t* __restrict__ tile_offsets,
+                 int32_t* __restrict__ rank_of) {
+  const int64_t i0 = (int64_t)blockIdx.x * kRankTile + (int64_t)threadIdx.x * kRankPer;
+  int c = 0;
+  for (int j = 0; j < kRankPer; ++j)
+    if (i0 + j < n) c += is_root[i0 + j];
+  int total;
+  int excl = block_excl_scan(c, &total);
+  int next = tile_offsets[blockIdx.x] + excl + 1;
+  for (int j = 0; j < kRankPer; ++j)
+    if (i0 + j < n && is_root[i0 + j]) rank_of[i0 + j] = next++;
+}
+
+// labels[i] = rank_of[root(i)] (0 for background).  parent holds root indices after ccl_flatten.
+__global__ void __launch_bounds__(256)
+ccl_relabel_kernel(const int32_t* parent, const int32_t* __restrict__ rank_of, int64_t n, int32_t* labels) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = parent[i];
+    labels[i] = p < 0 ? 0 : rank_of[p];
+  }
+}
+
+// per component: bbox (min0,min1,min2,max0,max1,max2), voxel count and coordinate sums along each axis
+__global__ void __launch_bounds__(256)
+component_stats_kernel(const int32_t* __restrict__ labels, int n0, int n1, int n2, int32_t* __restrict__ bbox,
+                       unsigned long long* __restrict__ sums /* [comp][4] = count, sum0, sum1, sum2 */) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t l = labels[i];
+    if (l <= 0) continue;
+    const int c = (int)(i % n2);
+    const int64_t r = i / n2;
+    const int b = (int)(r % n1);
+    const int a = (int)(r / n1);
+    int32_t* bb = bbox + (size_t)(l - 1) * 6;
+    atomicMin(bb + 0, a); atomicMin(bb + 1, b); atomicMin(bb + 2, c);
+    atomicMax(bb + 3, a); atomicMax(bb + 4, b); atomicMax(bb + 5, c);
+    unsigned long long* s = sums + (size_t)(l - 1) * 4;
+    atomicAdd(s + 0, 1ull); atomicAdd(s + 1, (unsigned long long)a);
+    atomicAdd(s + 2, (unsigned long long)b); atomicAdd(s + 3, (unsigned long long)c);
+  }
+}
+
+__global__ void __launch_bounds__(256) bbox_init_kernel(int32_t* __restrict__ bbox, int ncomp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncomp * 6) bbox[i] = (i % 6) < 3 ? 0x7fffffff : -1;
+}
+
+// recolor_backward_components: voxels of components flagged in `recolour[comp-1]` get `colour`
+__global__ void __launch_bounds__(256)
+recolour_kernel(const int32_t* __restrict__ labels, const uint8_t* __restrict__ recolour, int64_t n, uint32_t colour,
+                uint8_t* __restrict__ grid) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t l = labels[i];
+    if (l > 0 && recolour[l - 1]) {
+      grid[3 * i] = colour & 0xff; grid[3 * i + 1] = (colour >> 8) & 0xff; grid[3 * i + 2] = (colour >> 16) & 0xff;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// extrude_from_surface (:213-248), in place.  One thread per column that the 2-D mask selects: find the first
+// occupied voxel from the chosen end (index 0 / last when the column is empty -- np.argmax of all-False), then
+// paint `depth` voxels from there in the chosen direction.
+//   axis 2: columns (x,y) along z, valid = mask[y][x];   axis 0: columns (y,z) along x, valid = mask[y][z]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+extrude_kernel(uint8_t* __restrict__ grid, int W, int H, int D, const uint8_t* __restrict__ mask_hw, int mask_w,
+               int axis, int sign, int depth, uint32_t colour) {
+  const int ncol = axis == 2 ? W * H : H * D;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncol) return;
+  int x = 0, y, z = 0, len;
+  size_t stride;
+  if (axis == 2) { x = t / H; y = t - x * H; if (!mask_hw[(size_t)y * mask_w + x]) return; len = D; stride = 1; }
+  else { y = t / D; z = t - y * D; if (!mask_hw[(size_t)y * mask_w + z]) return; len = W; stride = (size_t)H * D; }
+  uint8_t* col = grid + 3 * (axis == 2 ? ((size_t)x * H + y) * D : (size_t)y * D + z);
+  int start = sign > 0 ? 0 : len - 1;
+  for (int k = 0; k < len; ++k) {
+    const int idx = sign > 0 ? k : len - 1 - k;
+    if (rgb_nonzero(col + 3 * stride * idx)) { start = idx; break; }
+  }
+  const uint8_t r = colour & 0xff, g = (colour >> 8) & 0xff, b = (colour >> 16) & 0xff;
+  for (int dd = 0; dd < depth; ++dd) {
+    const int idx = start + sign * dd;
+    if (idx < 0 || idx >= len) continue;
+    uint8_t* p = col + 3 * stride * idx;
+    p[0] = r; p[1] = g; p[2] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// partwise_carve's re-orientation (:384-385): out[z][H-1-y][x][:] = in[x][y][z][:]  ((W,H,D,3) -> (D,H,W,3)),
+// 32x32 (x,z) tiles through shared memory so that reads run along z and writes along x.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+reorient_kernel(const uint8_t* __restrict__ in, int W, int H, int D, uint8_t* __restrict__ out) {
+  __shared__ uint8_t tile[32][32 * 3 + 4];
+  const int y = blockIdx.y;
+  const int tiles_z = (D + 31) / 32;
+  const int x0 = (blockIdx.x / tiles_z) * 32, z0 = (blockIdx.x % tiles_z) * 32;
+  for (int k = threadIdx.x; k < 32 * 96; k += 256) {
+    const int xr = k / 96, bz = k - xr * 96;              // byte bz of row xr (z-major, 3 bytes per voxel)
+    const int x = x0 + xr, z = z0 + bz / 3;
+    tile[xr][bz] = (x < W && z < D) ? in[(((size_t)x * H + y) * D + z0) * 3 + bz] : 0;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 32 * 96; k += 256) {
+    const int zr = k / 96, bx = k - zr * 96;
+    const int z = z0 + zr, x = x0 + bx / 3;
+    if (z < D && x < W) out[(((size_t)z * H + (H - 1 - y)) * W + x0) * 3 + bx] = tile[bx / 3][zr * 3 + bx % 3];
+  }
+}
+
+// carve_voxel_grid_with_masks :76-97: out[x,y,z,c] = mask[x,y,(c)] ? grid[x,y,z,c] : 0
+__global__ void __launch_bounds__(256)
+mask_carve_kernel(const uint8_t* __restrict__ grid, int64_t n_vox, int D, int C, const uint8_t* __restrict__ mask_wh,
+                  int MC, uint8_t* __restrict__ out) {
+  const int64_t n = n_vox * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t xy = (i / C) / D;
+    out[i] = mask_wh[xy * MC + (MC == 1 ? 0 : c)] ? grid[i] : 0;
+  }
+}
+
+int check_affine(const double* M, const double* off, Affine* A) {
+  P3D_REQUIRE(M && off, "affine: null matrix/offset (host pointers)");
+  for (int i = 0; i < 9; ++i) A->M[i] = M[i];
+  for (int i = 0; i < 3; ++i) A->off[i] = off[i];
+  return P3D_OK;
+}
+
+}  // namespace
+
+// ==============================================================================================
+// C ABI
+// ==============================================================================================
+P3D_API int p3d_resample_carve(const uint8_t* vol_in, int n0, int n1, int n2, const double* M, const double* off,
+                               const uint8_t* mask_wh, uint8_t* vol_out, p3d_stream_t stream) {
+  P3D_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0, "resample_carve: bad shape");
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(vol_in && vol_out && vol_in != vol_out, "resample_carve: null or aliased volumes");
+  Affine A;
+  int rc = check_affine(M, off, &A);
+  if (rc) return rc;
+  resample_carve_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(vol_in, n0, n1, n2, A, mask_wh, vol_out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_fold_table(int n0, int n2, const double* M, const double* off, int32_t* table, int* flag,
+                           p3d_stream_t stream) {
+  P3D_REQUIRE(n0 > 0 && n2 > 0 && n0 < 32768 && n2 < 65536 && (int64_t)n0 * n2 < (1ll << 31), "fold_table: bad shape");
+  P3D_REQUIRE(table && flag, "fold_table: null pointer");
+  Affine A;
+  int rc = check_affine(M, off, &A);
+  if (rc) return rc;
+  // the y axis must be decoupled for a per-(x,z) table to describe the pass
+  P3D_REQUIRE(A.M[1] == 0.0 && A.M[3] == 0.0 && A.M[4] == 1.0 && A.M[5] == 0.0 && A.M[7] == 0.0 && A.off[1] == 0.0,
+              "fold_table: transform couples the y axis");
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  fold_table_kernel<<<(n0 * n2 + 255) / 256, 256, 0, st>>>(n0, n2, A, table, flag);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_fold_gather(const uint8_t* vol_in, int n0, int n1, int n2, const int32_t* table,
+                            const uint8_t* mask_wh, uint8_t* vol_out, p3d_stream_t stream) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  P3D_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0, "fold_gather: bad shape");
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(vol_in && vol_out && table && vol_in != vol_out, "fold_gather: null or aliased pointers");
+  fold_gather_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(vol_in, n0, n1, n2, table, mask_wh, vol_out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_global_carve_fold(int W, int H, int D, const int32_t* table, const uint8_t* mask_hw,
+                                  const uint8_t* colour_hw, int rgb, uint8_t* out, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0, "global_carve_fold: bad shape");
+  P3D_REQUIRE(table && mask_hw && colour_hw && out, "global_carve_fold: null pointer");
+  const int64_t n = (int64_t)W * H * D;
+  cudaStream_t st = p3d::as_stream(stream);
+  const bool vec = (D % 16 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec) {
+    const int64_t warp_groups = (n / 16 + 31) / 32;
+    const int blocks = grid_for(warp_groups, 8, 32);
+    if (rgb) global_fold_kernel<true><<<blocks, 256, 0, st>>>(W, H, D, table, mask_hw, colour_hw, out);
+    else global_fold_kernel<false><<<blocks, 256, 0, st>>>(W, H, D, table, mask_hw, colour_hw, out);
+  } else {
+    const int blocks = grid_for(n, 256, 16);
+    if (rgb) global_fold_scalar_kernel<true><<<blocks, 256, 0, st>>>(W, H, D, table, mask_hw, colour_hw, out);
+    else global_fold_scalar_kernel<false><<<blocks, 256, 0, st>>>(W, H, D, table, mask_hw, colour_hw, out);
+  }
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_mask_carve(const uint8_t* grid, int W, int H, int D, int channels, const uint8_t* mask_wh,
+                           int mask_channels, uint8_t* out, p3d_stream_t stream) {
+  P3D_REQUIRE(W >= 0 && H >= 0 && D >= 0 && (channels == 1 || channels == 3) &&
+              (mask_channels == 1 || (mask_channels == 3 && channels == 3)), "mask_carve: bad arguments");
+  const int64_t n = (int64_t)W * H * D;
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(grid && mask_wh && out, "mask_carve: null pointer");
+  mask_carve_kernel<<<grid_for(n * channels, 256, 16), 256, 0, p3d::as_stream(stream)>>>(grid, n, D, channels, mask_wh,
+                                                                                      mask_channels, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_colourise(const uint8_t* carved, int W, int H, int D, const uint8_t* colour_hw, uint8_t* out,
+                          p3d_stream_t stream) {
+  const int64_t n = (int64_t)W * H * D;
+  P3D_REQUIRE(W >= 0 && H >= 0 && D >= 0, "colourise: bad shape");
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(carved && colour_hw && out, "colourise: null pointer");
+  colourise_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(carved, W, H, D, colour_hw, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_part_carve_fold(const uint8_t* grid, int W, int H, int D, const int32_t* table,
+                                const uint32_t* group_mask_hw, uint8_t* out, p3d_stream_t stream) {
+  const int64_t n = (int64_t)W * H * D;
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0, "part_carve_fold: bad shape");
+  P3D_REQUIRE(grid && table && group_mask_hw && out && grid != out, "part_carve_fold: null or aliased pointers");
+  part_fold_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(grid, W, H, D, table, group_mask_hw, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_crop_occupancy(const uint8_t* grid, int W, int H, int D, int x0, int y0, int z0, int w, int h, int d,
+                               const uint8_t* sel_wh, uint8_t* occ, p3d_stream_t stream) {
+  P3D_REQUIRE(x0 >= 0 && y0 >= 0 && z0 >= 0 && w >= 0 && h >= 0 && d >= 0 && x0 + w <= W && y0 + h <= H && z0 + d <= D,
+              "crop_occupancy: crop outside the grid");
+  const int64_t n = (int64_t)w * h * d;
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(grid && occ, "crop_occupancy: null pointer");
+  crop_occupancy_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(grid, H, D, x0, y0, z0, w, h, d, sel_wh, occ);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_accumulate_part(const uint8_t* grid, const uint8_t* carved, int W, int H, int D, const uint8_t* sel_wh,
+                                uint8_t* final_grid, p3d_stream_t stream) {
+  const int64_t n = (int64_t)W * H * D;
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(grid && carved && sel_wh && final_grid, "accumulate_part: null pointer");
+  accumulate_part_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(grid, carved, W, H, D, sel_wh, final_grid);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_paste_component(const uint8_t* src, const int32_t* labels, int comp, const uint8_t* kept, int W, int H,
+                                int D, int x0, int y0, int z0, int w, int h, int d, uint8_t* out, p3d_stream_t stream) {
+  P3D_REQUIRE(x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + w <= W && y0 + h <= H && z0 + d <= D, "paste_component: bad crop");
+  const int64_t n = (int64_t)w * h * d;
+  if (n <= 0) return P3D_OK;
+  P3D_REQUIRE(src && labels && kept && out, "paste_component: null pointer");
+  paste_component_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(src, labels, comp, kept, H, D, x0, y0,
+                                                                                 z0, w, h, d, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_colour_mask(const uint8_t* grid_rgb, int64_t n, int r, int g, int b, uint8_t* mask, p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0, "colour_mask: n < 0");
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(grid_rgb && mask, "colour_mask: null pointer");
+  const bool representable = r >= 0 && r < 256 && g >= 0 && g < 256 && b >= 0 && b < 256;
+  const uint32_t colour = representable ? (uint32_t)(r | (g << 8) | (b << 16)) : 0xffffffffu;
+  colour_mask_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(grid_rgb, n, colour, mask);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API size_t p3d_label6_workspace_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  const int64_t tiles = (n + kRankTile - 1) / kRankTile;
+  return p3d_align_up((size_t)n * 4, 256) + p3d_align_up((size_t)n, 256) + p3d_align_up((size_t)(tiles + 1) * 4, 256);
+}
+
+P3D_API int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components,
+                       void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  P3D_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0 && n_components, "label6: bad arguments");
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  cudaStream_t st = p3d::as_stream(stream);
+  if (n == 0) { P3D_CUDA(cudaMemsetAsync(n_components, 0, 4, st)); return P3D_OK; }
+  P3D_REQUIRE(n < (1ll << 31), "label6: volume too large for 32-bit labels");
+  P3D_REQUIRE(mask && labels && workspace, "label6: null pointer");
+  if (workspace_bytes < p3d_label6_workspace_bytes(n)) {
+    p3d::set_error("label6: workspace %zu < %zu", workspace_bytes, p3d_label6_workspace_bytes(n));
+    return P3D_E_WORKSPACE;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  int32_t* rank_of = reinterpret_cast<int32_t*>(ws);
+  uint8_t* is_root = ws + p3d_align_up((size_t)n * 4, 256);
+  int32_t* tiles_buf = reinterpret_cast<int32_t*>(is_root + p3d_align_up((size_t)n, 256));
+  const int tiles = (int)((n + kRankTile - 1) / kRankTile);
+  const int blocks = grid_for(n, 256, 16);
+  int32_t* parent = labels;                              // labels doubles as the union-find forest
+  ccl_init_kernel<<<blocks, 256, 0, st>>>(mask, n, parent);
+  ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, n0, n1, n2, parent);
+  ccl_flatten_kernel<<<blocks, 256, 0, st>>>(n, parent, is_root);
+  root_count_kernel<<<tiles, kRankThreads, 0, st>>>(is_root, n, tiles_buf);
+  root_scan_kernel<<<1, 1024, 0, st>>>(tiles_buf, tiles, n_components);
+  root_rank_kernel<<<tiles, kRankThreads, 0, st>>>(is_root, n, tiles_buf, rank_of);
+  // labels are rewritten from the forest: out of place via rank_of, then in place
+  ccl_relabel_kernel<<<blocks, 256, 0, st>>>(parent, rank_of, n, labels);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, int n_components, int32_t* bbox,
+                                int64_t* sums, p3d_stream_t stream) {
+  P3D_REQUIRE(n_components >= 0, "component_stats: n_components < 0");
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  if (n_components == 0 || n == 0) return P3D_OK;
+  P3D_REQUIRE(labels && bbox && sums, "component_stats: null pointer");
+  cudaStream_t st = p3d::as_stream(stream);
+  bbox_init_kernel<<<(n_components * 6 + 255) / 256, 256, 0, st>>>(bbox, n_components);
+  P3D_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_components * 4 * sizeof(int64_t), st));
+  component_stats_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(labels, n0, n1, n2, bbox,
+                                                             reinterpret_cast<unsigned long long*>(sums));
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_recolour_components(const int32_t* labels, const uint8_t* recolour, int64_t n, int r, int g, int b,
+                                    uint8_t* grid_rgb, p3d_stream_t stream) {
+  if (n <= 0) return P3D_OK;
+  P3D_REQUIRE(labels && recolour && grid_rgb, "recolour_components: null pointer");
+  const uint32_t colour = (uint32_t)((r & 0xff) | ((g & 0xff) << 8) | ((b & 0xff) << 16));
+  recolour_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(labels, recolour, n, colour, grid_rgb);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_extrude(uint8_t* grid_rgb, int W, int H, int D, const uint8_t* mask_hw, int mask_h, int mask_w, int axis,
+                        int sign, int depth, int r, int g, int b, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && (axis == 0 || axis == 2) && (sign == 1 || sign == -1) && depth >= 0,
+              "extrude: bad arguments");
+  P3D_REQUIRE(grid_rgb && mask_hw, "extrude: null pointer");
+  if (axis == 2) P3D_REQUIRE(mask_h == H && mask_w == W, "extrude: mask (%d,%d) does not match (H,W)=(%d,%d)", mask_h, mask_w, H, W);
+  else P3D_REQUIRE(mask_h == H && mask_w == D, "extrude: mask (%d,%d) does not match (H,D)=(%d,%d)", mask_h, mask_w, H, D);
+  const int ncol = axis == 2 ? W * H : H * D;
+  const uint32_t colour = (uint32_t)((r & 0xff) | ((g & 0xff) << 8) | ((b & 0xff) << 16));
+  extrude_kernel<<<(ncol + 127) / 128, 128, 0, p3d::as_stream(stream)>>>(grid_rgb, W, H, D, mask_hw, mask_w, axis, sign,
+                                                                      depth, colour);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_reorient(const uint8_t* in, int W, int H, int D, uint8_t* out, p3d_stream_t stream) {
+  P3D_REQUIRE(W >= 0 && H >= 0 && D >= 0, "reorient: bad shape");
+  if ((int64_t)W * H * D == 0) return P3D_OK;
+  P3D_REQUIRE(in && out && in != out, "reorient: null or aliased pointers");
+  P3D_REQUIRE(H <= 65535, "reorient: H too large");
+  dim3 grid((unsigned)(((W + 31) / 32) * ((D + 31) / 32)), (unsigned)H);
+  reorient_kernel<<<grid, 256, 0, p3d::as_stream(stream)>>>(in, W, H, D, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}

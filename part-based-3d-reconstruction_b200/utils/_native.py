@@ -57,6 +57,23 @@ _SIGNATURES = {
     "p3d_best_select": ([_vp, _i32, _vp, _vp], _i32),
     "p3d_sweep_timing_enable": ([_i32], _i32),
     "p3d_sweep_timing_read": ([_vp, _vp], _i32),
+    "p3d_resample_carve": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "p3d_fold_table": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "p3d_fold_gather": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),
+    "p3d_global_carve_fold": ([_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp], _i32),
+    "p3d_mask_carve": ([_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
+    "p3d_colourise": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "p3d_part_carve_fold": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),
+    "p3d_crop_occupancy": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "p3d_accumulate_part": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "p3d_paste_component": ([_vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_colour_mask": ([_vp, _i64, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_label6_workspace_bytes": ([_i64], _sz),
+    "p3d_label6": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp], _i32),
+    "p3d_component_stats": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "p3d_recolour_components": ([_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_extrude": ([_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp], _i32),
+    "p3d_reorient": ([_vp, _i32, _i32, _i32, _vp, _vp], _i32),
 }
 
 

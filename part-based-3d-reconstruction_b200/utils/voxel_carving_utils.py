@@ -1,0 +1,416 @@
+"""Drop-in for the reference's utils/voxel_carving_utils.py (stage 1: orthographic semantic voxel carving).
+
+Same function names, argument order, defaults and return conventions as the reference.  NumPy arrays in ->
+NumPy arrays out (fresh arrays, inputs never mutated); CUDA tensors in -> CUDA tensors out, so that the stages
+can be chained on the device.  All voxel work runs in the CUDA kernels of csrc/p3d_carve.cu; what stays on the
+host is what the reference also does with tiny data: the 3x3 inverse rotation (NumPy/LAPACK, :65-69), the
+2-D mask preparation (O(H*W)), and the per-component bookkeeping (bounding boxes, the stable sort of component
+means).
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+
+from . import _native as nv
+from ._native import check, lib, ptr, stream_ptr
+from .config import PART_COLORS, PART_COLORS_NP  # noqa: F401  (re-exported like the reference module)
+
+try:                                              # progress bar as in the reference (:111-115); optional
+    from tqdm import tqdm
+except Exception:                                 # pragma: no cover
+    def tqdm(it, **kwargs):
+        return it
+
+
+# =========================================================
+# helpers
+# =========================================================
+def _launched(n=1):
+    nv.launch_count += n
+
+
+def _is_tensor(a):
+    return isinstance(a, torch.Tensor)
+
+
+def _to_dev_u8(a, dev, what="array"):
+    if _is_tensor(a):
+        t = a
+    else:
+        arr = np.asarray(a)
+        if arr.dtype == np.bool_:
+            arr = arr.astype(np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.dtype == torch.bool:
+        t = t.to(torch.uint8)
+    if t.dtype != torch.uint8:
+        raise TypeError(f"{what} must be uint8 (got {t.dtype})")
+    return t.to(dev).contiguous()
+
+
+def _ret(t, as_tensor):
+    return t if as_tensor else t.cpu().numpy()
+
+
+def _mask_to_wh(mask, W, H):
+    """voxel_carving_utils.py:19-28.  The (H,W) test comes first, so a square mask is always transposed."""
+    if tuple(mask.shape[:2]) == (H, W):
+        return mask.T
+    if tuple(mask.shape[:2]) == (W, H):
+        return mask
+    raise ValueError(f"Mask shape {tuple(mask.shape)} incompatible with (W,H)=({W},{H})")
+
+
+def _rotation_matrix_inv(angle):
+    """voxel_carving_utils.py:65-69 (host NumPy, as in the reference)."""
+    a = np.deg2rad(angle)
+    c, s = np.cos(a), np.sin(a)
+    R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+    return np.linalg.inv(R)
+
+
+def _pass_transform(shape, angle):
+    """Matrix and offset handed to scipy.ndimage.affine_transform at :116-123."""
+    M = np.ascontiguousarray(_rotation_matrix_inv(angle), dtype=np.float64)
+    ctr = np.array(shape) / 2
+    off = np.ascontiguousarray(ctr - M @ ctr, dtype=np.float64)
+    return M, off
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _y_decoupled(M, off):
+    return M[0, 1] == 0 and M[1, 0] == 0 and M[1, 1] == 1 and M[1, 2] == 0 and M[2, 1] == 0 and off[1] == 0
+
+
+def _fold_table(n0, n2, M, off, dev):
+    """(table (n0,n2) int32, foldable) for a y-decoupled pass, else (None, False)."""
+    if not _y_decoupled(M, off) or n0 >= 32768 or n2 >= 65536:
+        return None, False
+    table = torch.empty((n0, n2), dtype=torch.int32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.p3d_fold_table(n0, n2, _dptr(M), _dptr(off), ptr(table), ptr(flag), stream_ptr()), "p3d_fold_table")
+    _launched()
+    return table, int(flag.item()) == 0
+
+
+def _process_device(vol, mask_wh, angle_interval):
+    """process_voxel_grid on device tensors: vol (n0,n1,n2) u8, mask_wh (n0,n1) u8 -> carved (n0,n1,n2) u8."""
+    n0, n1, n2 = vol.shape
+    dev = vol.device
+    cur = vol
+    for angle in tqdm(range(0, 91, angle_interval), desc="90 Carving", leave=True, disable=None):
+        M, off = _pass_transform((n0, n1, n2), angle)
+        out = torch.empty_like(cur)
+        table, foldable = _fold_table(n0, n2, M, off, dev)
+        if foldable:
+            check(lib.p3d_fold_gather(ptr(cur), n0, n1, n2, ptr(table), ptr(mask_wh), ptr(out), stream_ptr()),
+                  "p3d_fold_gather")
+        else:
+            check(lib.p3d_resample_carve(ptr(cur), n0, n1, n2, _dptr(M), _dptr(off), ptr(mask_wh), ptr(out),
+                                         stream_ptr()), "p3d_resample_carve")
+        _launched()
+        cur = out
+    return cur
+
+
+def _mask2d_bool(semantic_mask, colours):
+    """any over colours of all(semantic_mask == colour, axis=-1) on the host (2-D, O(H*W))."""
+    sem = semantic_mask.cpu().numpy() if _is_tensor(semantic_mask) else np.asarray(semantic_mask)
+    out = np.zeros(sem.shape[:2], bool)
+    for c in colours:
+        out |= np.all(sem == np.asarray(c), axis=-1)
+    return out
+
+
+def _colour_args(colour):
+    c = [int(v) for v in np.asarray(colour).reshape(3)]
+    return c
+
+
+# =========================================================
+# Public API (reference names and signatures)
+# =========================================================
+def carve_voxel_grid_with_masks(voxel_grid, combined_mask):
+    """voxel_carving_utils.py:76-97: np.where(mask, voxel_grid, 0) with the mask broadcast along depth."""
+    as_tensor = _is_tensor(voxel_grid)
+    dev = nv.require_cuda(voxel_grid.device if as_tensor and voxel_grid.is_cuda else None)
+    is_color = voxel_grid.ndim == 4
+    W, H, D = voxel_grid.shape[:3]
+    mask = _mask_to_wh(combined_mask, W, H)
+    if not ((mask.ndim == 2) or (mask.ndim == 3 and mask.shape[2] == 3)):
+        raise ValueError("Unsupported mask shape")
+    if mask.ndim == 3 and not is_color:
+        raise ValueError("Unsupported mask shape")
+    grid = _to_dev_u8(voxel_grid, dev, "voxel_grid")
+    m = mask if _is_tensor(mask) else np.asarray(mask)
+    m = _to_dev_u8((m != 0), dev, "mask")
+    out = torch.empty_like(grid)
+    check(lib.p3d_mask_carve(ptr(grid), W, H, D, 3 if is_color else 1, ptr(m), 3 if mask.ndim == 3 else 1, ptr(out),
+                             stream_ptr()), "p3d_mask_carve")
+    _launched()
+    return _ret(out, as_tensor)
+
+
+def process_voxel_grid(voxel_grid, combined_mask, angle_interval=90):
+    """voxel_carving_utils.py:104-126: for angle in range(0, 91, angle_interval): rotate the (already rotated)
+    grid by `angle` about shape/2 with trilinear interpolation, then carve with the mask."""
+    as_tensor = _is_tensor(voxel_grid)
+    dev = nv.require_cuda(voxel_grid.device if as_tensor and voxel_grid.is_cuda else None)
+    if voxel_grid.ndim != 3:
+        raise ValueError("process_voxel_grid expects a (W,H,D) occupancy grid")
+    W, H, D = voxel_grid.shape
+    mask = _mask_to_wh(combined_mask, W, H)
+    if mask.ndim != 2:
+        raise ValueError("Unsupported mask shape")
+    vol = _to_dev_u8(voxel_grid, dev, "voxel_grid")
+    m = mask if _is_tensor(mask) else np.asarray(mask)
+    m = _to_dev_u8((m != 0), dev, "mask")
+    return _ret(_process_device(vol, m, angle_interval), as_tensor)
+
+
+def apply_colored_mask_to_voxel_grid(carved_voxel_grid, colored_mask):
+    """voxel_carving_utils.py:128-136: out[x,y,z,:] = colored_mask[y,x,:] where carved == 1, else 0."""
+    as_tensor = _is_tensor(carved_voxel_grid)
+    dev = nv.require_cuda(carved_voxel_grid.device if as_tensor and carved_voxel_grid.is_cuda else None)
+    W, H, D = carved_voxel_grid.shape
+    carved = _to_dev_u8(carved_voxel_grid, dev, "carved_voxel_grid")
+    col = _to_dev_u8(colored_mask, dev, "colored_mask")
+    if tuple(col.shape) != (H, W, 3):
+        raise ValueError(f"colored_mask {tuple(col.shape)} does not match (H,W,3)=({H},{W},3)")
+    out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
+    check(lib.p3d_colourise(ptr(carved), W, H, D, ptr(col), ptr(out), stream_ptr()), "p3d_colourise")
+    _launched()
+    return _ret(out, as_tensor)
+
+
+def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
+    """voxel_carving_utils.py:139-160: per part group, carve the group's voxels with the group's own mask under
+    the group's symmetry angle and merge the survivors."""
+    as_tensor = _is_tensor(colored_grid)
+    dev = nv.require_cuda(colored_grid.device if as_tensor and colored_grid.is_cuda else None)
+    grid = _to_dev_u8(colored_grid, dev, "colored_grid")
+    W, H, D, _ = grid.shape
+    jobs = []
+    for names, angle in group_jobs:
+        m2d = _mask2d_bool(semantic_mask, [PART_COLORS[n] for n in names])          # (H,W)
+        if not m2d.any():
+            continue
+        jobs.append((np.ascontiguousarray(m2d.T), angle))                           # m: (W,H) bool
+    out = None
+    if jobs and all(a == 90 for _, a in jobs) and len(jobs) <= 32 and D == W:
+        M, off = _pass_transform((W, H, D), 90)
+        table, foldable = _fold_table(W, D, M, off, dev)
+        M0, off0 = _pass_transform((W, H, D), 0)
+        identity0 = np.array_equal(M0, np.eye(3)) and not off0.any()
+        if foldable and identity0:
+            gm = np.zeros((W, H), np.uint32)
+            for g, (m, _) in enumerate(jobs):
+                mm = _mask_to_wh(m, W, H)                                            # square quirk: m.T
+                gm |= (m & mm).astype(np.uint32) << np.uint32(g)
+            gm_hw = torch.from_numpy(np.ascontiguousarray(gm.T).view(np.int32)).to(dev)
+            out = torch.empty_like(grid)
+            check(lib.p3d_part_carve_fold(ptr(grid), W, H, D, ptr(table), ptr(gm_hw), ptr(out), stream_ptr()),
+                  "p3d_part_carve_fold")
+            _launched()
+    if out is None:
+        out = torch.zeros_like(grid)
+        for m, angle in jobs:
+            sel = torch.from_numpy(m.astype(np.uint8)).to(dev)                       # (W,H)
+            occ = torch.empty((W, H, D), dtype=torch.uint8, device=dev)
+            check(lib.p3d_crop_occupancy(ptr(grid), W, H, D, 0, 0, 0, W, H, D, ptr(sel), ptr(occ), stream_ptr()),
+                  "p3d_crop_occupancy")
+            mm = _to_dev_u8(np.ascontiguousarray(_mask_to_wh(m, W, H)), dev)
+            carved = _process_device(occ, mm, angle)
+            check(lib.p3d_accumulate_part(ptr(grid), ptr(carved), W, H, D, ptr(sel), ptr(out), stream_ptr()),
+                  "p3d_accumulate_part")
+            _launched(2)
+    return _ret(out, as_tensor)
+
+
+def _label_components(mask_u8):
+    """scipy.ndimage.label (6-connectivity) on device: (labels int32, n, bbox (n,6) ndarray, sums (n,4) ndarray)."""
+    n0, n1, n2 = mask_u8.shape
+    dev = mask_u8.device
+    nvox = mask_u8.numel()
+    labels = torch.empty((n0, n1, n2), dtype=torch.int32, device=dev)
+    ncomp = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.p3d_label6_workspace_bytes(nvox))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    check(lib.p3d_label6(ptr(mask_u8), n0, n1, n2, ptr(labels), ptr(ncomp), ptr(ws), ws_bytes, stream_ptr()), "p3d_label6")
+    _launched(7)
+    n = int(ncomp.item())
+    bbox = torch.empty((max(n, 1), 6), dtype=torch.int32, device=dev)
+    sums = torch.empty((max(n, 1), 4), dtype=torch.int64, device=dev)
+    check(lib.p3d_component_stats(ptr(labels), n0, n1, n2, n, ptr(bbox), ptr(sums), stream_ptr()), "p3d_component_stats")
+    _launched(2 if n else 0)
+    return labels, n, bbox.cpu().numpy()[:n], sums.cpu().numpy()[:n]
+
+
+def _colour_mask(grid, colour):
+    n = grid.numel() // 3
+    mask = torch.empty(grid.shape[:3], dtype=torch.uint8, device=grid.device)
+    r, g, b = _colour_args(colour)
+    check(lib.p3d_colour_mask(ptr(grid), n, r, g, b, ptr(mask), stream_ptr()), "p3d_colour_mask")
+    _launched()
+    return mask
+
+
+def left_right_guided_carve(colored_grid, semantic_mask, target_color, angle=60, visualize=False, stride=2):
+    """voxel_carving_utils.py:163-210: for every 6-connected 3-D component of `target_color`, carve the
+    component's bounding-box crop with the matching crop of the part's 2-D mask under `angle` symmetry."""
+    as_tensor = _is_tensor(colored_grid)
+    dev = nv.require_cuda(colored_grid.device if as_tensor and colored_grid.is_cuda else None)
+    grid = _to_dev_u8(colored_grid, dev, "colored_grid")
+    W, H, D, _ = grid.shape
+    carved = grid.clone()
+    mask2d = _mask2d_bool(semantic_mask, [target_color])
+    if not np.any(mask2d):
+        print(f"[SKIP] No mask for color {target_color}")
+        return _ret(carved, as_tensor)
+    labels, n, bbox, _ = _label_components(_colour_mask(grid, target_color))
+    print(f"[{target_color}] 3D components: {n}")
+    for i in range(1, n + 1):
+        x0, y0, z0 = (int(v) for v in bbox[i - 1, 0:3])
+        x1, y1, z1 = (int(v) + 1 for v in bbox[i - 1, 3:6])
+        print(f"  - Component {i}: bbox ({x0},{y0},{z0}) → ({x1},{y1},{z1})")
+        w, h, d = x1 - x0, y1 - y0, z1 - z0
+        crop2d = mask2d[y0:y1, x0:x1]
+        m_wh = _to_dev_u8(np.ascontiguousarray(_mask_to_wh(crop2d, w, h)), dev)
+        occ = torch.empty((w, h, d), dtype=torch.uint8, device=dev)
+        check(lib.p3d_crop_occupancy(ptr(grid), W, H, D, x0, y0, z0, w, h, d, None, ptr(occ), stream_ptr()),
+              "p3d_crop_occupancy")
+        kept = _process_device(occ, m_wh, angle)
+        print(f"    carved voxels: {int(torch.count_nonzero(kept).item())}")
+        check(lib.p3d_paste_component(ptr(grid), ptr(labels), i, ptr(kept), W, H, D, x0, y0, z0, w, h, d, ptr(carved),
+                                      stream_ptr()), "p3d_paste_component")
+        _launched(2)
+        if visualize:
+            warnings.warn("visualize=True is ignored: plotting is outside this package's scope")
+    return _ret(carved, as_tensor)
+
+
+def _extrude_inplace(out, mask_2d, axis, direction, depth, fill_color):
+    W, H, D, _ = out.shape
+    if axis not in (0, 2):
+        return
+    m = mask_2d.cpu().numpy() if _is_tensor(mask_2d) else np.asarray(mask_2d)
+    m = np.ascontiguousarray(m != 0).astype(np.uint8)
+    want = (H, W) if axis == 2 else (H, D)
+    if m.shape != want:
+        raise ValueError(f"operands could not be broadcast together: mask {m.shape} vs {want}")
+    colour = (0, 0, 0) if fill_color is None else _colour_args(fill_color)
+    sign = 1 if direction == "+" else -1
+    md = torch.from_numpy(m).to(out.device)
+    check(lib.p3d_extrude(ptr(out), W, H, D, ptr(md), m.shape[0], m.shape[1], axis, sign, int(depth), colour[0],
+                          colour[1], colour[2], stream_ptr()), "p3d_extrude")
+    _launched()
+
+
+def extrude_from_surface(grid, mask_2d, axis, direction="+", depth=5, fill_color=None):
+    """voxel_carving_utils.py:213-248: from the first occupied voxel of each masked column (index 0 / last when
+    the column is empty), paint `depth` voxels along `axis` in `direction`."""
+    as_tensor = _is_tensor(grid)
+    dev = nv.require_cuda(grid.device if as_tensor and grid.is_cuda else None)
+    out = _to_dev_u8(grid, dev, "grid").clone()
+    _extrude_inplace(out, mask_2d, axis, direction, depth, fill_color)
+    return _ret(out, as_tensor)
+
+
+def recolor_backward_components(voxel_grid, color, new_color, k=4, sort_axis=2):
+    """voxel_carving_utils.py:252-266: keep the k components of `color` with the smallest mean coordinate on
+    `sort_axis` (stable: ties keep the lower scipy id), recolour the others to `new_color`."""
+    as_tensor = _is_tensor(voxel_grid)
+    dev = nv.require_cuda(voxel_grid.device if as_tensor and voxel_grid.is_cuda else None)
+    if as_tensor:
+        grid = voxel_grid.to(dev).contiguous().clone()
+    else:
+        grid = torch.from_numpy(np.ascontiguousarray(voxel_grid)).to(dev)
+    if grid.dtype != torch.uint8:
+        raise TypeError("voxel_grid must be uint8")
+    labels, n, _, sums = _label_components(_colour_mask(grid, color))
+    if n:
+        means = [(i, np.float64(sums[i - 1, 1 + sort_axis]) / np.float64(sums[i - 1, 0])) for i in range(1, n + 1)]
+        keep = {i for i, _ in sorted(means, key=lambda t: t[1])[:k]}
+        flags = np.array([0 if i in keep else 1 for i in range(1, n + 1)], np.uint8)
+        if flags.any():
+            r, g, b = _colour_args(new_color)
+            fl = torch.from_numpy(flags).to(dev)
+            check(lib.p3d_recolour_components(ptr(labels), ptr(fl), labels.numel(), r, g, b, ptr(grid), stream_ptr()),
+                  "p3d_recolour_components")
+            _launched()
+    return _ret(grid, as_tensor)
+
+
+def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=4, visualize=False,
+                 device=None, return_tensor=False):
+    """voxel_carving_utils.py:269-298: start from a full (w,h,w) grid, carve it with the binary front mask under
+    4-way symmetry (rotate-and-carve every `angle_interval` degrees), then colour every surviving voxel with
+    the semantic colour of its (x,y) pixel.  Returns the (W,H,D=W,3) uint8 grid."""
+    as_tensor = return_tensor or _is_tensor(binary_mask)
+    dev = nv.require_cuda(device if device is not None else (binary_mask.device if _is_tensor(binary_mask) and binary_mask.is_cuda else None))
+    bm = binary_mask.cpu().numpy() if _is_tensor(binary_mask) else np.asarray(binary_mask)
+    if bm.ndim != 2:
+        raise ValueError("binary_mask must be 2-D (H,W)")
+    h, w = bm.shape
+    W, H, D = w, h, w
+    col = _to_dev_u8(semantic_mask_exterior, dev, "semantic_mask_exterior")
+    if tuple(col.shape) != (H, W, 3):
+        raise ValueError(f"semantic_mask_exterior {tuple(col.shape)} does not match (H,W,3)=({H},{W},3)")
+    m_wh = np.ascontiguousarray(_mask_to_wh(bm != 0, W, H))                          # (W,H) bool
+    out = None
+    if angle_interval == 90:
+        M0, off0 = _pass_transform((W, H, D), 0)
+        M, off = _pass_transform((W, H, D), 90)
+        if np.array_equal(M0, np.eye(3)) and not off0.any():
+            table, foldable = _fold_table(W, D, M, off, dev)
+            if foldable:
+                m_hw = torch.from_numpy(np.ascontiguousarray(m_wh.T).astype(np.uint8)).to(dev)
+                out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
+                check(lib.p3d_global_carve_fold(W, H, D, ptr(table), ptr(m_hw), ptr(col), 1, ptr(out), stream_ptr()),
+                      "p3d_global_carve_fold")
+                _launched()
+    if out is None:
+        vol = torch.ones((W, H, D), dtype=torch.uint8, device=dev)
+        carved = _process_device(vol, torch.from_numpy(m_wh.astype(np.uint8)).to(dev), angle_interval)
+        out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
+        check(lib.p3d_colourise(ptr(carved), W, H, D, ptr(col), ptr(out), stream_ptr()), "p3d_colourise")
+        _launched()
+    if visualize:
+        warnings.warn("visualize=True is ignored: plotting is outside this package's scope")
+    return _ret(out, as_tensor)
+
+
+def partwise_carve(colored_voxel_grid, semantic_mask_exterior, semantic_mask_full, part_colors_np, group_jobs,
+                   part_symmetry, extrusion_depths, recolor_back_minarets=True, visualize=False, stride=4):
+    """voxel_carving_utils.py:302-400: part_carve -> left_right_guided_carve per symmetric part -> interior
+    extrusion (4 directions per part) -> re-orientation to (D, H-flipped, W) and back-minaret recolouring.
+    The whole chain stays on the device; only the result is copied back for NumPy callers."""
+    as_tensor = _is_tensor(colored_voxel_grid)
+    dev = nv.require_cuda(colored_voxel_grid.device if as_tensor and colored_voxel_grid.is_cuda else None)
+    grid = _to_dev_u8(colored_voxel_grid, dev, "colored_voxel_grid")
+
+    grid = part_carve(grid, semantic_mask_exterior, group_jobs, visualize=False)     # fresh tensor from here on
+    for part, angle in part_symmetry.items():
+        grid = left_right_guided_carve(colored_grid=grid, semantic_mask=semantic_mask_exterior,
+                                       target_color=part_colors_np[part], angle=angle, visualize=False, stride=stride)
+    for part, depth in extrusion_depths.items():
+        mask = _mask2d_bool(semantic_mask_full, [part_colors_np[part]])
+        for axis, direction in ((2, "+"), (2, "-"), (0, "+"), (0, "-")):     # extrude_4dirs :356-361
+            _extrude_inplace(grid, mask, axis, direction, depth, part_colors_np[part])
+    if recolor_back_minarets:
+        W, H, D, _ = grid.shape
+        oriented = torch.empty((D, H, W, 3), dtype=torch.uint8, device=dev)
+        check(lib.p3d_reorient(ptr(grid), W, H, D, ptr(oriented), stream_ptr()), "p3d_reorient")
+        _launched()
+        grid = recolor_backward_components(oriented, part_colors_np["front_minarets"],
+                                           new_color=part_colors_np["back_minarets"], k=2, sort_axis=0)
+    if visualize:
+        warnings.warn("visualize=True is ignored: plotting is outside this package's scope")
+    return _ret(grid, as_tensor)

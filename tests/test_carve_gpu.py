@@ -1,0 +1,187 @@
+"""GPU parity tests of the carving path (stage 1): CUDA kernels through the reference-signature Python layer
+against the oracle and the golden vectors produced by the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import pkg
+from helpers import EXTRUSION_DEPTHS, GROUP_JOBS, PART_SYMMETRY, sha, unpack
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vc():
+    assert torch.cuda.is_available()
+    return pkg("utils.voxel_carving_utils")
+
+
+def test_affine_golden_vectors(vc, carve_golden):
+    """process_voxel_grid's resample against scipy outputs recorded from the live reference environment."""
+    g = carve_golden
+    for k in range(int(g["aff_n"])):
+        shape = tuple(int(v) for v in g[f"aff{k}_shape"])
+        vol = unpack(g[f"aff{k}_vol"], shape)
+        ang = int(g[f"aff{k}_angle"])
+        M, off = vc._pass_transform(shape, ang)
+        dev = torch.device("cuda")
+        vin = torch.from_numpy(vol).to(dev)
+        out = torch.empty_like(vin)
+        import ctypes
+        nv = pkg("utils._native")
+        nv.check(nv.lib.p3d_resample_carve(nv.ptr(vin), *shape, M.ctypes.data_as(ctypes.c_void_p),
+                                           off.ctypes.data_as(ctypes.c_void_p), None, nv.ptr(out), nv.stream_ptr()))
+        assert np.array_equal(out.cpu().numpy(), unpack(g[f"aff{k}_out"], shape)), (k, shape, ang)
+
+
+@pytest.mark.parametrize("shape", [(15, 4, 15), (16, 5, 16), (31, 3, 31), (63, 2, 63), (64, 3, 64), (43, 47, 44),
+                                   (30, 9, 58), (100, 2, 100), (127, 2, 127), (128, 2, 128)])
+@pytest.mark.parametrize("interval", [90, 45, 60, 5])
+def test_process_voxel_grid_vs_oracle(vc, oracle, shape, interval):
+    rng = np.random.default_rng(shape[0] * 1000 + interval)
+    vol = (rng.random(shape) < 0.6).astype(np.uint8)
+    mask = rng.random((shape[1], shape[0])) < 0.8              # (H,W)
+    got = vc.process_voxel_grid(vol, mask, interval)
+    want = oracle.process_voxel_grid(vol, mask, interval)
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+
+
+def test_fold_fast_path_is_taken_for_cubic_90(vc):
+    dev = torch.device("cuda")
+    for W in (15, 16, 64, 255, 256):
+        M, off = vc._pass_transform((W, 3, W), 90)
+        _, foldable = vc._fold_table(W, W, M, off, dev)
+        assert foldable, W
+    M, off = vc._pass_transform((43, 3, 44), 90)
+    assert not vc._fold_table(43, 44, M, off, dev)[1]          # half-integer offsets: genuine blend
+    M, off = vc._pass_transform((32, 3, 32), 5)
+    assert not vc._fold_table(32, 32, M, off, dev)[1]
+
+
+def test_label6_vs_scipy(vc, oracle, carve_golden):
+    import scipy.ndimage
+    g = carve_golden
+    dev = torch.device("cuda")
+    cases = [unpack(g[f"lab{i}_mask"], tuple(int(v) for v in g[f"lab{i}_shape"])) for i in range(int(g["lab_n"]))]
+    rng = np.random.default_rng(4)
+    cases += [(rng.random((33, 17, 70)) < p).astype(np.uint8) for p in (0.05, 0.35, 0.5, 0.9)]
+    cases += [np.zeros((4, 5, 6), np.uint8), np.ones((7, 3, 9), np.uint8)]
+    for m in cases:
+        labels, n, bbox, sums = vc._label_components(torch.from_numpy(np.ascontiguousarray(m, dtype=np.uint8)).to(dev))
+        want, wn = scipy.ndimage.label(m)
+        assert n == wn and np.array_equal(labels.cpu().numpy(), want)
+        for i in range(1, n + 1):
+            idx = np.argwhere(want == i)
+            assert np.array_equal(bbox[i - 1], np.concatenate([idx.min(0), idx.max(0)]))
+            assert sums[i - 1, 0] == len(idx) and np.array_equal(sums[i - 1, 1:], idx.sum(0))
+
+
+@pytest.mark.parametrize("case", ["Bibi_64", "Taj_96", "Akbar_128", "Bibi_256"])
+def test_real_mask_carving_matches_reference(vc, carve_golden, case, capsys):
+    g = carve_golden
+    key = "real_" + case
+    sem, ext, binm = g[key + "_sem"], g[key + "_ext"], g[key + "_bin"]
+    cfg = pkg("utils.config")
+    grid = vc.global_carve(binm, ext, 90)
+    assert grid.dtype == np.uint8 and grid.shape == (binm.shape[1], binm.shape[0], binm.shape[1], 3)
+    assert sha(grid) == str(g[key + "_global_sha"])
+    capsys.readouterr()
+    out = vc.partwise_carve(grid, ext, sem, cfg.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS)
+    log = capsys.readouterr().out
+    assert sha(out) == str(g[key + "_partwise_sha"])
+    assert np.count_nonzero(out.any(-1)) == int(g[key + "_partwise_occ"])
+    assert log.strip("\n") == str(g[key + "_log"]).strip("\n")
+    if key + "_partwise" in g.files:
+        assert np.array_equal(out, g[key + "_partwise"])
+
+
+def test_synthetic_quirk_cases_match_reference(vc, carve_golden):
+    """Square image (_mask_to_wh transposes), foreground in the last column, widths with the odd FP offsets."""
+    g = carve_golden
+    cfg = pkg("utils.config")
+    for tag in g["syn_cases"]:
+        key = f"syn_{tag}"
+        sem, ext, binm = g[key + "_sem"], g[key + "_ext"], g[key + "_bin"]
+        grid = vc.global_carve(binm, ext, 90)
+        assert np.array_equal(grid, g[key + "_global"]), tag
+        assert np.array_equal(vc.part_carve(grid, ext, GROUP_JOBS), g[key + "_partcarve"]), tag
+        out = vc.partwise_carve(grid, ext, sem, cfg.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS)
+        assert np.array_equal(out, g[key + "_partwise"]), tag
+        out2 = vc.partwise_carve(grid, ext, sem, cfg.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS,
+                                 recolor_back_minarets=False)
+        assert sha(out2) == str(g[key + "_partwise_norecolor_sha"]), tag
+
+
+def test_general_angle_paths_vs_oracle(vc, oracle, carve_golden):
+    """global_carve / part_carve away from the 90-degree fast path (angle_interval 45 and mixed group angles)."""
+    g = carve_golden
+    key = "syn_rect40x64"
+    sem, ext, binm = g[key + "_sem"], g[key + "_ext"], g[key + "_bin"]
+    assert np.array_equal(vc.global_carve(binm, ext, 45), oracle.global_carve(binm, ext, 45))
+    grid = g[key + "_global"]
+    jobs = [(["full_building"], 45), (["chhatris", "dome"], 90), (["plinth"], 30)]
+    assert np.array_equal(vc.part_carve(grid, ext, jobs), oracle.part_carve(grid, ext, jobs))
+
+
+def test_building_blocks_vs_oracle(vc, oracle, carve_golden):
+    g = carve_golden
+    cfg = pkg("utils.config")
+    key = "syn_sq64"
+    sem, ext = g[key + "_sem"], g[key + "_ext"]
+    grid = g[key + "_partcarve"]
+    # inputs are not mutated, outputs are fresh arrays
+    before = grid.copy()
+    for part, depth in EXTRUSION_DEPTHS.items():
+        m = np.all(sem == cfg.PART_COLORS_NP[part], axis=-1)
+        for axis, direction in ((2, "+"), (2, "-"), (0, "+"), (0, "-")):
+            got = vc.extrude_from_surface(grid, m, axis, direction, depth, cfg.PART_COLORS_NP[part])
+            assert np.array_equal(got, oracle.extrude_from_surface(grid, m, axis, direction, depth, cfg.PART_COLORS_NP[part]))
+        assert np.array_equal(vc.extrude_from_surface(grid, m, 2, "+", 3, None),
+                              oracle.extrude_from_surface(grid, m, 2, "+", 3, None))
+    assert np.array_equal(grid, before)
+    for colour in ("front_minarets", "plinth", "full_building"):
+        for k, axis in ((2, 0), (1, 2), (4, 1)):
+            got = vc.recolor_backward_components(grid, cfg.PART_COLORS_NP[colour], cfg.PART_COLORS_NP["back_minarets"], k, axis)
+            want = oracle.recolor_backward_components(grid, cfg.PART_COLORS_NP[colour], cfg.PART_COLORS_NP["back_minarets"], k, axis)
+            assert np.array_equal(got, want), (colour, k, axis)
+    for part, angle in PART_SYMMETRY.items():
+        got = vc.left_right_guided_carve(grid, ext, cfg.PART_COLORS_NP[part], angle)
+        assert np.array_equal(got, oracle.left_right_guided_carve(grid, ext, cfg.PART_COLORS_NP[part], angle)), part
+    occ = (grid.any(-1)).astype(np.uint8)
+    m2 = np.all(ext != cfg.PART_COLORS_NP["background"], axis=-1) if False else (~np.all(ext == cfg.PART_COLORS_NP["background"], axis=-1))
+    assert np.array_equal(vc.carve_voxel_grid_with_masks(occ, m2), oracle.carve_with_mask(occ, m2))
+    got = vc.carve_voxel_grid_with_masks(grid, m2)
+    assert np.array_equal(got, np.where(oracle.mask_to_wh(m2, 64, 64)[:, :, None, None], grid, 0))
+    assert np.array_equal(vc.apply_colored_mask_to_voxel_grid(occ, ext),
+                          np.where((occ == 1)[..., None], ext.transpose(1, 0, 2)[:, :, None, :], 0))
+    with pytest.raises(ValueError):
+        vc.carve_voxel_grid_with_masks(occ, np.ones((5, 7), np.uint8))
+
+
+def test_device_tensor_chain(vc, carve_golden):
+    """CUDA tensors in -> CUDA tensors out, same bytes as the NumPy path."""
+    g = carve_golden
+    cfg = pkg("utils.config")
+    key = "real_Bibi_64"
+    sem, ext, binm = g[key + "_sem"], g[key + "_ext"], g[key + "_bin"]
+    grid = vc.global_carve(binm, ext, 90, return_tensor=True)
+    assert isinstance(grid, torch.Tensor) and grid.is_cuda
+    out = vc.partwise_carve(grid, ext, sem, cfg.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS)
+    assert isinstance(out, torch.Tensor) and np.array_equal(out.cpu().numpy(), g[key + "_partwise"])
+
+
+def test_global_carve_512_synthetic_vs_oracle(vc, oracle):
+    """Config-4-sized carve (512^3, vector store path) against the oracle's scipy restatement."""
+    syn = pkg("synthetic")
+    cfg = pkg("utils.config")
+    N = 512
+    lab = syn.monument_labels(N).numpy()
+    front = lab.max(axis=0)[::-1]                              # (y down, x): silhouette labels seen from the front
+    lut = syn.label_lut()
+    lut0 = lut.copy()
+    lut0[0] = cfg.PART_COLORS["background"]
+    ext = lut0[front]
+    binm = (front > 0).astype(np.uint8)
+    got = vc.global_carve(binm, ext, 90)
+    want = oracle.global_carve(binm, ext, 90)
+    assert np.array_equal(got, want)
