@@ -103,12 +103,38 @@ __global__ void __launch_bounds__(128) setup_cameras_kernel(const T* __restrict_
 constexpr int kSplatThreads = 256;
 constexpr int kPpt = 2;
 
+template <int MODE>
+__device__ __forceinline__ void zbuf_update(uint32_t* p, uint32_t key) {
+  const uint32_t cur = __ldcg(p);
+  if (MODE == P3D_MODE_JOINT) {
+    if (cur < key) atomicMax(p, key);
+  } else {
+    if ((cur & key) == 0) atomicOr(p, key);
+  }
+}
+
+// The reference's projection of one point through one camera, operation by operation (see file header).
+template <typename T, int MODE>
+__device__ __forceinline__ void exact_splat(T px, T py, T pz, uint32_t key, const T* __restrict__ cam,
+                                            uint32_t* __restrict__ zb, int W, T fW, T fH) {
+  using F = Fp<T>;
+  const T d0 = F::sub(px, cam[0]), d1 = F::sub(py, cam[1]), d2 = F::sub(pz, cam[2]);
+  const T X = F::fma(d2, cam[5], F::fma(d1, cam[4], F::mul(d0, cam[3])));
+  const T Y = F::fma(d2, cam[8], F::fma(d1, cam[7], F::mul(d0, cam[6])));
+  T Z = F::fma(d2, cam[11], F::fma(d1, cam[10], F::mul(d0, cam[9])));
+  if (Z < F::eps()) Z = F::eps();
+  const T u = F::add(F::mul(F::div(X, Z), cam[12]), cam[13]);
+  const T v = F::add(F::mul(-F::div(Y, Z), cam[12]), cam[14]);
+  const T ur = F::rint(u), vr = F::rint(v);
+  if (key != 0 && ur >= (T)0 && ur < fW && vr >= (T)0 && vr < fH)
+    zbuf_update<MODE>(zb + ((size_t)(int)vr * W + (size_t)(int)ur), key);
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kSplatThreads)
 splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label, int64_t n,
              const T* __restrict__ cams, int K, int cams_per_block, int H, int W,
              uint32_t* __restrict__ zbuf) {
-  using F = Fp<T>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* s_cam = reinterpret_cast<T*>(smem_raw);
   const int c0 = blockIdx.y * cams_per_block;
@@ -137,35 +163,227 @@ splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label
   const T fW = (T)W, fH = (T)H;
   const size_t HW = (size_t)H * W;
   for (int c = 0; c < nc; ++c) {
-    const T* cam = s_cam + c * 16;
-    const T e0 = cam[0], e1 = cam[1], e2 = cam[2];
-    const T r00 = cam[3], r01 = cam[4], r02 = cam[5];
-    const T r10 = cam[6], r11 = cam[7], r12 = cam[8];
-    const T r20 = cam[9], r21 = cam[10], r22 = cam[11];
-    const T f = cam[12], cx = cam[13], cy = cam[14];
     uint32_t* zb = zbuf + (size_t)(c0 + c) * HW;
 #pragma unroll
-    for (int j = 0; j < kPpt; ++j) {
-      const T d0 = F::sub(px[j], e0), d1 = F::sub(py[j], e1), d2 = F::sub(pz[j], e2);
-      const T X = F::fma(d2, r02, F::fma(d1, r01, F::mul(d0, r00)));
-      const T Y = F::fma(d2, r12, F::fma(d1, r11, F::mul(d0, r10)));
-      T Z = F::fma(d2, r22, F::fma(d1, r21, F::mul(d0, r20)));
-      if (Z < F::eps()) Z = F::eps();
-      const T u = F::add(F::mul(F::div(X, Z), f), cx);
-      const T v = F::add(F::mul(-F::div(Y, Z), f), cy);
-      const T ur = F::rint(u), vr = F::rint(v);
-      const bool ok = key[j] != 0 && ur >= (T)0 && ur < fW && vr >= (T)0 && vr < fH;
-      if (ok) {
-        uint32_t* p = zb + ((size_t)(int)vr * W + (size_t)(int)ur);
-        const uint32_t cur = __ldcg(p);
-        if (MODE == P3D_MODE_JOINT) {
-          if (cur < key[j]) atomicMax(p, key[j]);
-        } else {
-          if ((cur & key[j]) == 0) atomicOr(p, key[j]);
-        }
-      }
+    for (int j = 0; j < kPpt; ++j)
+      exact_splat<T, MODE>(px[j], py[j], pz[j], key[j], s_cam + c * 16, zb, W, fW, fH);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Filtered FP64 splat.  The pixel a point lands on is decided in FP32 together with a rigorous bound on
+// |u32 - u_ref| (u_ref = the reference's FP64 value); only when rounding could go either way within that bound is
+// the point re-projected with the exact FP64 sequence.  Undecided (point, camera) pairs are parked in a per-warp
+// shared-memory queue and drained 32 at a time, so the FP64 pass runs with full warps instead of diverging.
+// The result is bit-identical to splat_kernel<double> (tests/test_camera_gpu.py).
+//
+// Error model (eps = 2^-24; p exact in float; e32/R32/f32/c32 = camera rounded to float; |R| <= 1):
+//   d32_k = fl(p_k - e32_k)                      |d32_k - d_k| <= eps (|d32_k| + 2|e_k|)
+//   X32 = fma chain (same for Y, Z)              |X32 - X| <= 1.01 eps D,   D = 5 sum_k|d_k| + 2 sum_k|e_k|
+//   q32 = X32 * rcp.approx(Z32)                  |q32 - X/Z| <= 1.03 eps (D/Z)(1 + |q32|) + 3 eps |q32|   (Z >= 64 eps D)
+//   u32 = fma(q32, f32, c32)                     |u32 - u_ref| <= eps [1.05 t (f + |u32| + |c|) + 5 (|u32| + |c|)],  t = D/Z
+// D and Z are bounded per camera over the bounding box of the point list (D <= Dmax, Z >= Zmin, both evaluated in
+// FP64 from the box corners), so t <= tmax = Dmax/Zmin and the bound becomes  B(u) = b0 + b1 |u32|  with
+//   b1 = 2 (1.05 eps tmax + 5 eps),  b0 = 2 * 1.05 eps tmax f + |c| b1 + 1e-7       (twice the derived bound + slack).
+// A coordinate is decided when |u32 - rint(u32)| + B(u32) < 0.5.  Cameras whose box comes within max(1e-3, 2^-17 Dmax)
+// of the camera plane, or with non-finite / non-positive-f parameters, get b0 = inf: every point takes the exact path.
+// ------------------------------------------------------------------------------------------
+constexpr int kPptF = 4;
+constexpr int kQueueCap = 160;       // per warp: up to 4 x 32 new entries on top of < 32 pending
+
+struct FastCam {                     // 20 floats per camera
+  float e[3], R[9], f, cx, cy, b1, b0u, b0v, pad0, pad1;
+};
+
+__device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, const float* __restrict__ bbox,
+                                              FastCam* out) {
+  FastCam fc;
+  bool ok = true;
+  double se = 0.0, sd = 0.0, zmin = 0.0, zabs = 0.0;
+  for (int k = 0; k < 15; ++k) ok = ok && (fabs(cam[k]) < 1e30);                 // false for NaN / Inf
+  for (int k = 3; k < 12; ++k) ok = ok && (fabs(cam[k]) <= 1.0001);
+  for (int k = 0; k < 3; ++k) {
+    fc.e[k] = (float)cam[k];
+    const double lo = (double)bbox[k] - cam[k], hi = (double)bbox[3 + k] - cam[k];
+    ok = ok && (fabs(lo) < 1e30) && (fabs(hi) < 1e30) && lo <= hi;
+    se += fabs(cam[k]);
+    sd += fmax(fabs(lo), fabs(hi));
+    const double a = lo * cam[9 + k], b = hi * cam[9 + k];
+    zmin += fmin(a, b);
+    zabs += fmax(fabs(a), fabs(b));
+  }
+  for (int k = 0; k < 9; ++k) fc.R[k] = (float)cam[3 + k];
+  fc.f = (float)cam[12]; fc.cx = (float)cam[13]; fc.cy = (float)cam[14];
+  const double eps = 5.9604644775390625e-08;                                    // 2^-24
+  const double dmax = (5.0 * sd + 2.0 * se) * (1.0 + 1e-6);
+  zmin -= 1e-9 * zabs;
+  ok = ok && cam[12] > 1e-3 && zmin > fmax(1e-3, dmax * 7.62939453125e-06);      // 2^-17
+  const double tmax = ok ? dmax / zmin * (1.0 + 1e-6) : 0.0;
+  const double b1 = 2.0 * (1.05 * eps * tmax + 5.0 * eps);
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  fc.b1 = ok ? __double2float_ru(b1) : 0.f;
+  fc.b0u = ok ? __double2float_ru(2.0 * 1.05 * eps * tmax * cam[12] + fabs(cam[13]) * b1 + 1e-7) : (float)inf;
+  fc.b0v = ok ? __double2float_ru(2.0 * 1.05 * eps * tmax * cam[12] + fabs(cam[14]) * b1 + 1e-7) : (float)inf;
+  fc.pad0 = fc.pad1 = 0.f;
+  *out = fc;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kSplatThreads)
+splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label, int64_t n,
+                      const double* __restrict__ cams, int K, int cams_per_block, int H, int W,
+                      uint32_t* __restrict__ zbuf, const float* __restrict__ bbox) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_cam = reinterpret_cast<double*>(smem_raw);                                   // nc x 16 doubles
+  FastCam* s_fast = reinterpret_cast<FastCam*>(s_cam + (size_t)cams_per_block * 16);      // nc x FastCam
+  float4* s_queue = reinterpret_cast<float4*>(s_fast + cams_per_block);                   // 8 warps x kQueueCap
+  uint32_t* s_qcam = reinterpret_cast<uint32_t*>(s_queue + (kSplatThreads / 32) * kQueueCap);
+
+  const int c0 = blockIdx.y * cams_per_block;
+  const int nc = min(cams_per_block, K - c0);
+  for (int i = threadIdx.x; i < nc * 16; i += kSplatThreads) s_cam[i] = cams[(size_t)c0 * 16 + i];
+  __syncthreads();
+  if (threadIdx.x < nc) make_fast_cam(s_cam + threadIdx.x * 16, bbox, s_fast + threadIdx.x);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* q = s_queue + warp * kQueueCap;
+  uint32_t* qc = s_qcam + warp * kQueueCap;
+  int qn = 0;                                              // warp-uniform queue length
+
+  const int64_t tile = (int64_t)gridDim.x - 1 - blockIdx.x;
+  const int64_t base = tile * (kSplatThreads * kPptF) + threadIdx.x;
+  float px[kPptF], py[kPptF], pz[kPptF];
+  uint32_t key[kPptF];
+#pragma unroll
+  for (int j = 0; j < kPptF; ++j) {
+    const int64_t i = base + (int64_t)j * kSplatThreads;
+    key[j] = 0;
+    px[j] = py[j] = pz[j] = 0.f;
+    if (i < n) {
+      px[j] = __ldg(pts + 3 * i + 0);
+      py[j] = __ldg(pts + 3 * i + 1);
+      pz[j] = __ldg(pts + 3 * i + 2);
+      if (MODE == P3D_MODE_JOINT) key[j] = (uint32_t)(i + 1);
+      else key[j] = 1u << ((uint32_t)__ldg(pt_label + i) - 1u);
     }
   }
+  const double dW = (double)W, dH = (double)H;
+  const size_t HW = (size_t)H * W;
+  const float kMagic = 12582912.f;                         // 1.5 * 2^23: (x + m) - m == rint(x) for |x| < 2^22
+
+  auto drain = [&](int keep_below) {
+    while (qn > keep_below) {
+      const int take = qn < 32 ? qn : 32;
+      const int idx = qn - take + lane;
+      if (lane < take) {
+        const float4 e = q[idx];
+        const uint32_t c = qc[idx];
+        exact_splat<double, MODE>((double)e.x, (double)e.y, (double)e.z, __float_as_uint(e.w), s_cam + c * 16,
+                                  zbuf + (size_t)(c0 + c) * HW, W, dW, dH);
+      }
+      qn -= take;
+      __syncwarp();
+    }
+  };
+
+  for (int c = 0; c < nc; ++c) {
+    const float4* fcv = reinterpret_cast<const float4*>(s_fast + c);
+    const float4 v0 = fcv[0], v1 = fcv[1], v2 = fcv[2], v3 = fcv[3], v4 = fcv[4];
+    const float e0 = v0.x, e1 = v0.y, e2 = v0.z;
+    const float r00 = v0.w, r01 = v1.x, r02 = v1.y, r10 = v1.z, r11 = v1.w, r12 = v2.x, r20 = v2.y, r21 = v2.z, r22 = v2.w;
+    const float f = v3.x, cx = v3.y, cy = v3.z, b1 = v3.w, b0u = v4.x, b0v = v4.y;
+    uint32_t* zb = zbuf + (size_t)(c0 + c) * HW;
+    int pix[kPptF];
+    uint32_t parked = 0;
+#pragma unroll
+    for (int j = 0; j < kPptF; ++j) {
+      const float d0 = px[j] - e0, d1 = py[j] - e1, d2 = pz[j] - e2;
+      const float X = fmaf(d2, r02, fmaf(d1, r01, d0 * r00));
+      const float Y = fmaf(d2, r12, fmaf(d1, r11, d0 * r10));
+      const float Z = fmaf(d2, r22, fmaf(d1, r21, d0 * r20));
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(Z));
+      const float u = fmaf(X * r, f, cx);
+      const float v = fmaf(-(Y * r), f, cy);
+      const float su = u + kMagic, sv = v + kMagic;
+      const float eu = fabsf(u - (su - kMagic)) + fmaf(b1, fabsf(u), b0u);
+      const float ev = fabsf(v - (sv - kMagic)) + fmaf(b1, fabsf(v), b0v);
+      const bool decided = eu < 0.5f && ev < 0.5f;            // false for NaN
+      const int iu = __float_as_int(su) - 0x4B400000, iv = __float_as_int(sv) - 0x4B400000;
+      const bool inside = (unsigned)iu < (unsigned)W && (unsigned)iv < (unsigned)H;
+      const bool live = key[j] != 0;
+      pix[j] = (live && decided && inside) ? iv * W + iu : -1;
+      if (live && !decided) parked |= 1u << j;
+    }
+    uint32_t cur[kPptF];
+#pragma unroll
+    for (int j = 0; j < kPptF; ++j) cur[j] = pix[j] >= 0 ? __ldcg(zb + pix[j]) : 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < kPptF; ++j) {
+      if (MODE == P3D_MODE_JOINT) {
+        if (cur[j] < key[j]) atomicMax(zb + pix[j], key[j]);
+      } else {
+        if (pix[j] >= 0 && (cur[j] & key[j]) == 0) atomicOr(zb + pix[j], key[j]);
+      }
+    }
+    if (__any_sync(0xffffffffu, parked != 0)) {
+#pragma unroll
+      for (int j = 0; j < kPptF; ++j) {
+        const bool park = (parked >> j) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, park);
+        if (park) {
+          const int pos = qn + __popc(m & ((1u << lane) - 1u));
+          q[pos] = make_float4(px[j], py[j], pz[j], __uint_as_float(key[j]));
+          qc[pos] = (uint32_t)c;
+        }
+        qn += __popc(m);
+      }
+      __syncwarp();
+      if (qn >= 32) drain(31);
+    }
+  }
+  drain(0);
+}
+
+// Bounding box of a point list: bbox = (min x, min y, min z, max x, max y, max z); NaNs are ignored.
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  int old = __float_as_int(*addr);
+  while (v < __int_as_float(old)) {
+    const int seen = atomicCAS(reinterpret_cast<int*>(addr), old, __float_as_int(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  int old = __float_as_int(*addr);
+  while (v > __int_as_float(old)) {
+    const int seen = atomicCAS(reinterpret_cast<int*>(addr), old, __float_as_int(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+
+__global__ void bbox_init_kernel(float* __restrict__ bbox) {
+  if (threadIdx.x < 6) bbox[threadIdx.x] = threadIdx.x < 3 ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ pts, int64_t n, float* __restrict__ bbox) {
+  float lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) { lo[k] = __int_as_float(0x7f800000); hi[k] = __int_as_float(0xff800000); }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int k = 0; k < 3; ++k) {
+      const float v = __ldg(pts + 3 * i + k);
+      lo[k] = fminf(lo[k], v);
+      hi[k] = fmaxf(hi[k], v);
+    }
+  for (int k = 0; k < 3; ++k)
+    for (int d = 16; d > 0; d >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], d));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], d));
+    }
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 3; ++k) { atomic_min_float(bbox + k, lo[k]); atomic_max_float(bbox + 3 + k, hi[k]); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -422,6 +640,12 @@ inline int grid_for(int64_t items, int threads, int waves) {
 
 thread_local int g_last_launches = 0;
 
+// P3D_SPLAT_EXACT=1 forces the unfiltered FP64 kernel (A/B testing of the FP32 filter).
+inline bool splat_exact_only() {
+  const char* e = getenv("P3D_SPLAT_EXACT");
+  return e && e[0] == '1';
+}
+
 // Optional per-launch timing of the splat kernel (bench.py's roofline leg): CUDA events recorded on the
 // launch stream around every splat launch of p3d_sweep_* while enabled on this thread.
 struct SplatTiming {
@@ -461,9 +685,21 @@ inline int pick_cams_per_block(int64_t tiles, int K) {
   return cpb;
 }
 
+int points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && bbox, "points_bbox: bad arguments");
+  cudaStream_t st = p3d::as_stream(stream);
+  bbox_init_kernel<<<1, 32, 0, st>>>(bbox);
+  if (n > 0) {
+    P3D_REQUIRE(pts, "points_bbox: null points");
+    bbox_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(pts, n, bbox);
+  }
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
 template <typename T>
 int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, int K, int H, int W, int mode,
-          uint32_t* zbuf, p3d_stream_t stream) {
+          uint32_t* zbuf, const float* bbox, p3d_stream_t stream) {
   P3D_REQUIRE(n >= 0 && K >= 0 && H > 0 && W > 0, "splat: n=%lld K=%d H=%d W=%d", (long long)n, K, H, W);
   P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
   P3D_REQUIRE(n < 0xffffffffll, "splat: n=%lld does not fit 32-bit keys", (long long)n);
@@ -471,16 +707,28 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   if (n == 0 || K == 0) return P3D_OK;
   P3D_REQUIRE(pts && cams && zbuf, "splat: null pointer");
   P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: per-part mode needs pt_label");
-  const int64_t tiles = (n + kSplatThreads * kPpt - 1) / (kSplatThreads * kPpt);
+  const bool filtered = sizeof(T) == 8 && bbox != nullptr && !splat_exact_only();
+  const int ppt = filtered ? kPptF : kPpt;
+  const int64_t tiles = (n + kSplatThreads * ppt - 1) / (kSplatThreads * ppt);
   P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
   const int cpb = pick_cams_per_block(tiles, K);
   dim3 grid((unsigned)tiles, (unsigned)((K + cpb - 1) / cpb));
-  const size_t smem = (size_t)cpb * 16 * sizeof(T);
   cudaStream_t st = p3d::as_stream(stream);
-  if (mode == P3D_MODE_JOINT)
-    splat_kernel<T, P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
-  else
-    splat_kernel<T, P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
+  if (filtered) {
+    const size_t smem = (size_t)cpb * (16 * sizeof(double) + sizeof(FastCam)) +
+                        (size_t)(kSplatThreads / 32) * kQueueCap * (sizeof(float4) + sizeof(uint32_t));
+    const double* dc = reinterpret_cast<const double*>(cams);
+    if (mode == P3D_MODE_JOINT)
+      splat_filtered_kernel<P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, bbox);
+    else
+      splat_filtered_kernel<P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, bbox);
+  } else {
+    const size_t smem = (size_t)cpb * 16 * sizeof(T);
+    if (mode == P3D_MODE_JOINT)
+      splat_kernel<T, P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
+    else
+      splat_kernel<T, P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
+  }
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -503,7 +751,7 @@ inline size_t default_zbuf_budget() {
 }
 
 struct SweepLayout {
-  size_t cams, raw, gt_area, zbuf, total;
+  size_t cams, raw, gt_area, bbox, zbuf, total;
   int batch;
 };
 
@@ -514,6 +762,7 @@ inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
   L.cams = off; off = p3d_align_up(off + (size_t)K * 16 * elem_bytes, 256);
   L.raw = off; off = p3d_align_up(off + (size_t)K * (P + 1) * 2 * sizeof(unsigned long long), 256);
   L.gt_area = off; off = p3d_align_up(off + (size_t)(P + 1) * sizeof(unsigned long long), 256);
+  L.bbox = off; off = p3d_align_up(off + 8 * sizeof(float), 256);
   L.zbuf = off; off = p3d_align_up(off + (size_t)L.batch * H * W * sizeof(uint32_t), 256);
   L.total = off;
   return L;
@@ -545,7 +794,8 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
   const int HW = H * W;
   const int rows = mode == P3D_MODE_PER_PART ? P + 1 : P;
 
-  P3D_CUDA(cudaMemsetAsync(ws + L.raw, 0, L.zbuf - L.raw, st));   // raw + gt_area
+  float* bbox = reinterpret_cast<float*>(ws + L.bbox);
+  P3D_CUDA(cudaMemsetAsync(ws + L.raw, 0, L.bbox - L.raw, st));   // raw + gt_area
   P3D_CUDA(cudaMemsetAsync(zbuf, 0, (size_t)L.batch * HW * sizeof(uint32_t), st));
   int rc = setup_cameras<T>(cand, K, cams, stream);
   if (rc) return rc;
@@ -553,12 +803,17 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
                                                       gt_area);
   P3D_LAUNCH_CHECK();
   g_last_launches += 2;
+  if (n > 0 && sizeof(T) == 8) {
+    rc = points_bbox(pts, n, bbox, stream);
+    if (rc) return rc;
+    g_last_launches += 2;
+  }
   for (int k0 = 0; k0 < K; k0 += L.batch) {
     const int kb = K - k0 < L.batch ? K - k0 : L.batch;
     if (n > 0) {
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
-      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, mode, zbuf, stream);
+      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, mode, zbuf, sizeof(T) == 8 ? bbox : nullptr, stream);
       if (rc) return rc;
       if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
       dim3 grid((unsigned)grid_for(HW, kScoreThreads, 2), (unsigned)kb);
@@ -595,13 +850,17 @@ P3D_API int p3d_setup_cameras_f32(const float* cand, int K, float* cams, p3d_str
   return setup_cameras<float>(cand, K, cams, stream);
 }
 
+P3D_API int p3d_points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream) {
+  return points_bbox(pts, n, bbox, stream);
+}
+
 P3D_API int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K, int H,
-                          int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
-  return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, stream);
+                          int W, int mode, uint32_t* zbuf, const float* bbox, p3d_stream_t stream) {
+  return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, bbox, stream);
 }
 P3D_API int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K, int H,
                           int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
-  return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, stream);
+  return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, nullptr, stream);
 }
 
 P3D_API int p3d_resolve_rgb(const uint32_t* zbuf, const uint8_t* pt_rgb, int64_t n_pixels, uint8_t* img,

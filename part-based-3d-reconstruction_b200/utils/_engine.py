@@ -85,14 +85,30 @@ def setup_cameras(cand: torch.Tensor) -> torch.Tensor:
     return cams
 
 
-def splat(pts: torch.Tensor, pt_label, cams: torch.Tensor, H: int, W: int, mode: int = nv.MODE_JOINT) -> torch.Tensor:
+def points_bbox(pts: torch.Tensor) -> torch.Tensor:
+    """(6,) f32 = min x,y,z, max x,y,z of the point list (feeds the FP32 filter of the f64 splat)."""
+    bbox = torch.empty(8, dtype=torch.float32, device=pts.device)
+    check(lib.p3d_points_bbox(ptr(pts), pts.shape[0], ptr(bbox), stream_ptr()), "p3d_points_bbox")
+    _launched(2 if pts.shape[0] else 1)
+    return bbox
+
+
+def splat(pts: torch.Tensor, pt_label, cams: torch.Tensor, H: int, W: int, mode: int = nv.MODE_JOINT,
+          bbox=None) -> torch.Tensor:
     """Scatter the points through K cameras into a fresh (K,H,W) z-buffer (int32 storage of uint32 keys)."""
     assert pts.is_cuda and pts.dtype == torch.float32 and pts.is_contiguous()
     K = cams.shape[0]
     zbuf = torch.zeros((K, H, W), dtype=torch.int32, device=pts.device)
-    fn = getattr(lib, f"p3d_splat_{_elem(cams.dtype)}")
-    check(fn(ptr(pts), ptr(pt_label), pts.shape[0], ptr(cams), K, H, W, mode, ptr(zbuf), stream_ptr()), "p3d_splat")
-    _launched(1 if (K and pts.shape[0]) else 0)
+    n = pts.shape[0]
+    if _elem(cams.dtype) == "f64":
+        if bbox is None and n:
+            bbox = points_bbox(pts)
+        check(lib.p3d_splat_f64(ptr(pts), ptr(pt_label), n, ptr(cams), K, H, W, mode, ptr(zbuf), ptr(bbox),
+                                stream_ptr()), "p3d_splat_f64")
+    else:
+        check(lib.p3d_splat_f32(ptr(pts), ptr(pt_label), n, ptr(cams), K, H, W, mode, ptr(zbuf), stream_ptr()),
+              "p3d_splat_f32")
+    _launched(1 if (K and n) else 0)
     return zbuf
 
 

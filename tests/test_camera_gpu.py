@@ -205,3 +205,48 @@ def test_numpy_mean_order_on_device(mods):
         scores, counts, _ = mods.ce.score_camera_candidates(grid, img, colors, names, cand)
         ious = [c[0] / c[1] if c[1] > 0 else 0.0 for c in counts[0]]
         assert scores[0] == np.mean(ious), P
+
+
+def test_filtered_splat_is_bit_identical_to_exact_fp64(mods, taj, monkeypatch):
+    """The FP32-filter + FP64-queue kernel against the plain FP64 kernel: identical z-buffers, including
+    cameras inside the cloud, behind it, degenerate (eye == target), tiny / huge focal lengths and far offsets."""
+    rng = np.random.default_rng(77)
+    dev = torch.device("cuda")
+    p = taj["cams"]["front"]
+    base = np.array([*p["cam_pos"], *p["target"], p["f"], p["cx"], p["cy"]])
+    cand = mods.ce.random_candidates(base, 24, rng)
+    wild = np.tile(base, (12, 1))
+    wild[0, 0:3] = [250.0, 100.0, 250.0]                       # inside the model
+    wild[1, 0:3] = wild[1, 3:6]                                # eye == target
+    wild[2, 6] = 1e-2                                          # tiny f
+    wild[3, 6] = 1e5                                           # huge f
+    wild[4, 2] = 2000.0                                        # behind, looking back
+    wild[5, 0:3] = [1e6, -3e5, -2e6]                           # very far
+    wild[6, 6] = -500.0                                        # negative f
+    wild[7, 7:9] = [-5000.0, 9000.0]                           # principal point far off
+    wild[8, 0:3] = [256.3, 139.2, 255.9]                       # inside, off-grid
+    wild[9, 0:3] = wild[9, 3:6] + [0.0, 300.0, 0.0]            # straight down
+    wild[10, 6] = float("nan")
+    wild[11, 0] = float("inf")
+    cand = np.concatenate([cand, wild])
+    parts = all_parts(mods.cfg)
+    pts, pt_label, _, _ = mods.vu.device_points_by_parts(taj["grid"], mods.cfg.PART_COLORS, parts)
+    for (H, W) in ((278, 512), (64, 48)):
+        cams = mods.eng.setup_cameras(torch.from_numpy(cand).to(dev))
+        for mode in (mods.nv.MODE_JOINT, mods.nv.MODE_PER_PART):
+            monkeypatch.setenv("P3D_SPLAT_EXACT", "1")
+            ref = mods.eng.splat(pts, pt_label, cams, H, W, mode).cpu()
+            monkeypatch.setenv("P3D_SPLAT_EXACT", "0")
+            got = mods.eng.splat(pts, pt_label, cams, H, W, mode).cpu()
+            assert torch.equal(ref, got), (H, W, mode, int((ref != got).sum()))
+    # synthetic 256^3, 1024^2 image: the benchmark geometry
+    syn = mods.syn
+    rgb = torch.from_numpy(syn.label_lut()).to(dev)[syn.monument_labels(256, dev).long()]
+    pts, pt_label, _, _ = mods.vu.device_points_by_parts(rgb, mods.cfg.PART_COLORS, syn.PART_NAMES)
+    cand = syn.candidates(syn.base_camera(256, 1024, 1024), 48)
+    cams = mods.eng.setup_cameras(torch.from_numpy(cand).to(dev))
+    monkeypatch.setenv("P3D_SPLAT_EXACT", "1")
+    ref = mods.eng.splat(pts, pt_label, cams, 1024, 1024, mods.nv.MODE_JOINT).cpu()
+    monkeypatch.setenv("P3D_SPLAT_EXACT", "0")
+    got = mods.eng.splat(pts, pt_label, cams, 1024, 1024, mods.nv.MODE_JOINT).cpu()
+    assert torch.equal(ref, got)
