@@ -90,17 +90,22 @@ int p3d_setup_cameras_f32(const float* cand, int K, float* cams, p3d_stream_t st
  *   joint    : zbuf[k][v*W+u] = max(zbuf, i+1)        (last write wins == largest index wins)
  *   per-part : zbuf[k][v*W+u] |= 1 << (pt_label[i]-1) (pt_label required, values 1..32)
  * zbuf (K,H,W) uint32 must be zero on entry.  n < 2^32-1.
- * bbox (f64 entry point only; may be NULL): the 6 floats written by p3d_points_bbox for `pts`.  With it the
- * kernel decides most pixels in FP32 under a proven error bound and re-projects only the undecided points in
- * FP64 -- the z-buffer is bit-identical either way; without it every point takes the FP64 path.
+ * fast (f64 entry point only; may be NULL): the (K,16) float blocks written by p3d_fast_cameras_f64 for these
+ * cameras, this image size and the bounding box of `pts`.  With it the kernel decides most pixels in FP32 under a
+ * proven error bound and re-projects only the undecided points in FP64 -- the z-buffer is bit-identical either
+ * way; without it every point takes the FP64 path.
  * --------------------------------------------------------------------------------------------- */
 int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K,
-                  int H, int W, int mode, uint32_t* zbuf, const float* bbox, p3d_stream_t stream);
+                  int H, int W, int mode, uint32_t* zbuf, const float* fast, p3d_stream_t stream);
 int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K,
                   int H, int W, int mode, uint32_t* zbuf, p3d_stream_t stream);
 
 /* bbox (6 floats, device) = min x,y,z, max x,y,z of pts (n,3); NaN coordinates are ignored. */
 int p3d_points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream);
+/* FP32 companion blocks of K f64 cameras: pre-scaled rows, translation terms and the per-camera rounding
+ * thresholds derived from an FP32 error bound over the box (see csrc/p3d_camera.cu).  fast: (K,16) floats. */
+int p3d_fast_cameras_f64(const double* cams, int K, const float* bbox, int H, int W, float* fast,
+                         p3d_stream_t stream);
 
 /* project_colored_voxels (image)       utils/projection_utils.py:20-23
  * img[p] = pt_rgb[zbuf[p]-1] or (0,0,0) where zbuf[p]==0.  One camera (joint-mode zbuf). */

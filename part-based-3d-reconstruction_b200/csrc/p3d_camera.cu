@@ -177,79 +177,99 @@ splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label
 // shared-memory queue and drained 32 at a time, so the FP64 pass runs with full warps instead of diverging.
 // The result is bit-identical to splat_kernel<double> (tests/test_camera_gpu.py).
 //
-// Error model (eps = 2^-24; p exact in float; e32/R32/f32/c32 = camera rounded to float; |R| <= 1):
-//   d32_k = fl(p_k - e32_k)                      |d32_k - d_k| <= eps (|d32_k| + 2|e_k|)
-//   X32 = fma chain (same for Y, Z)              |X32 - X| <= 1.01 eps D,   D = 5 sum_k|d_k| + 2 sum_k|e_k|
-//   q32 = X32 * rcp.approx(Z32)                  |q32 - X/Z| <= 1.03 eps (D/Z)(1 + |q32|) + 3 eps |q32|   (Z >= 64 eps D)
-//   u32 = fma(q32, f32, c32)                     |u32 - u_ref| <= eps [1.05 t (f + |u32| + |c|) + 5 (|u32| + |c|)],  t = D/Z
-// D and Z are bounded per camera over the bounding box of the point list (D <= Dmax, Z >= Zmin, both evaluated in
-// FP64 from the box corners), so t <= tmax = Dmax/Zmin and the bound becomes  B(u) = b0 + b1 |u32|  with
-//   b1 = 2 (1.05 eps tmax + 5 eps),  b0 = 2 * 1.05 eps tmax f + |c| b1 + 1e-7       (twice the derived bound + slack).
-// A coordinate is decided when |u32 - rint(u32)| + B(u32) < 0.5.  Cameras whose box comes within max(1e-3, 2^-17 Dmax)
-// of the camera plane, or with non-finite / non-positive-f parameters, get b0 = inf: every point takes the exact path.
+// FP32 form (per camera constants computed in FP64 and rounded once):  with A_j = f R_0j, B_j = -f R_1j, C_j = R_2j,
+// T_A = -f e.R_0, T_B = f e.R_1, T_C = -e.R_2:
+//   X' = fma(p2,A2, fma(p1,A1, fma(p0,A0, T_A)))   (= f X),   Y' likewise (= -f Y),   Z = fma chain with C, T_C
+//   r = rcp.approx(Z) ;  u = fma(X', r, cx) ;  v = fma(Y', r, cy)
+// Error model (eps = 2^-24, |R| <= 1, S_p = sum_k max|p_k| over the bounding box of the point list):
+//   |Z32 - Z| <= eps DZ,  DZ = 4.04 (S_p + |T_C|)        |X'32 - f X| <= eps DX,  DX = 4.04 (f S_p + |T_A|)
+//   |u32 - u_ref| <= eps [ DX/Zmin + (|u32| + |cx|) (DZ/Zmin + 6) ]          (Zmin = min of Z over the box, FP64)
+// The kernel uses twice that plus 1e-7, evaluated at |u| = W + 2:  thr_u = 0.5 - Bmax_u.  A coordinate is decided
+// when |u32 - rint(u32)| < thr_u; decided + in range -> pixel; decided + out of range -> dropped; else exact path.
+// (Out-of-range decisions stay valid far from the image because the camera is only "fast" when
+//  b1 * 2 max(W,H) <= 0.25 and Bmax <= 0.25, so |u32 - u_ref| < 1 wherever |u32| <= 2W and < |u32|/2 beyond.)
+// Cameras whose box comes within max(1e-3, 2^-17 DZ) of the camera plane, or with non-finite / non-positive-f
+// parameters, or whose bound exceeds 0.25 px, get thr = -1: every point takes the exact path.
 // ------------------------------------------------------------------------------------------
 constexpr int kPptF = 4;
-constexpr int kQueueCap = 160;       // per warp: up to 4 x 32 new entries on top of < 32 pending
+constexpr int kQueueCap = 64;        // per warp: at most 32 new entries on top of < 32 pending
 
-struct FastCam {                     // 20 floats per camera
-  float e[3], R[9], f, cx, cy, b1, b0u, b0v, pad0, pad1;
+struct FastCam {                     // 16 floats per camera
+  float A[3], TA, B[3], TB, C[3], TC, cx, cy, thr_u, thr_v;
 };
 
-__device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, const float* __restrict__ bbox,
-                                              FastCam* out) {
+__device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, const float* __restrict__ bbox, int H,
+                                              int W, FastCam* out) {
   FastCam fc;
   bool ok = true;
-  double se = 0.0, sd = 0.0, zmin = 0.0, zabs = 0.0;
   for (int k = 0; k < 15; ++k) ok = ok && (fabs(cam[k]) < 1e30);                 // false for NaN / Inf
   for (int k = 3; k < 12; ++k) ok = ok && (fabs(cam[k]) <= 1.0001);
+  const double f = cam[12];
+  double sp = 0.0, zmin = 0.0, zabs = 0.0, ta = 0.0, tb = 0.0, tc = 0.0;
   for (int k = 0; k < 3; ++k) {
-    fc.e[k] = (float)cam[k];
-    const double lo = (double)bbox[k] - cam[k], hi = (double)bbox[3 + k] - cam[k];
+    const double lo = (double)bbox[k], hi = (double)bbox[3 + k];
     ok = ok && (fabs(lo) < 1e30) && (fabs(hi) < 1e30) && lo <= hi;
-    se += fabs(cam[k]);
-    sd += fmax(fabs(lo), fabs(hi));
-    const double a = lo * cam[9 + k], b = hi * cam[9 + k];
+    sp += fmax(fabs(lo), fabs(hi));
+    const double a = (lo - cam[k]) * cam[9 + k], b = (hi - cam[k]) * cam[9 + k];
     zmin += fmin(a, b);
     zabs += fmax(fabs(a), fabs(b));
+    fc.A[k] = (float)(f * cam[3 + k]);
+    fc.B[k] = (float)(-f * cam[6 + k]);
+    fc.C[k] = (float)cam[9 + k];
+    ta -= f * cam[k] * cam[3 + k];
+    tb += f * cam[k] * cam[6 + k];
+    tc -= cam[k] * cam[9 + k];
   }
-  for (int k = 0; k < 9; ++k) fc.R[k] = (float)cam[3 + k];
-  fc.f = (float)cam[12]; fc.cx = (float)cam[13]; fc.cy = (float)cam[14];
+  fc.TA = (float)ta; fc.TB = (float)tb; fc.TC = (float)tc;
+  fc.cx = (float)cam[13]; fc.cy = (float)cam[14];
   const double eps = 5.9604644775390625e-08;                                    // 2^-24
-  const double dmax = (5.0 * sd + 2.0 * se) * (1.0 + 1e-6);
+  const double dz = 4.04 * (sp + fabs(tc)), dxu = 4.04 * (f * sp + fabs(ta)), dxv = 4.04 * (f * sp + fabs(tb));
   zmin -= 1e-9 * zabs;
-  ok = ok && cam[12] > 1e-3 && zmin > fmax(1e-3, dmax * 7.62939453125e-06);      // 2^-17
-  const double tmax = ok ? dmax / zmin * (1.0 + 1e-6) : 0.0;
-  const double b1 = 2.0 * (1.05 * eps * tmax + 5.0 * eps);
-  const double inf = __longlong_as_double(0x7ff0000000000000ll);
-  fc.b1 = ok ? __double2float_ru(b1) : 0.f;
-  fc.b0u = ok ? __double2float_ru(2.0 * 1.05 * eps * tmax * cam[12] + fabs(cam[13]) * b1 + 1e-7) : (float)inf;
-  fc.b0v = ok ? __double2float_ru(2.0 * 1.05 * eps * tmax * cam[12] + fabs(cam[14]) * b1 + 1e-7) : (float)inf;
-  fc.pad0 = fc.pad1 = 0.f;
+  ok = ok && f > 1e-3 && zmin > fmax(1e-3, dz * 7.62939453125e-06);              // 2^-17
+  double bu = 1.0, bv = 1.0, b1 = 1.0;
+  if (ok) {
+    b1 = 2.0 * eps * (dz / zmin + 6.0);
+    bu = 2.0 * eps * dxu / zmin + ((double)W + 2.0 + fabs(cam[13])) * b1 + 1e-7;
+    bv = 2.0 * eps * dxv / zmin + ((double)H + 2.0 + fabs(cam[14])) * b1 + 1e-7;
+  }
+  ok = ok && bu <= 0.25 && bv <= 0.25 && b1 * 2.0 * (double)(W > H ? W : H) <= 0.25;
+  fc.thr_u = ok ? __double2float_rd(0.5 - bu) : -1.f;
+  fc.thr_v = ok ? __double2float_rd(0.5 - bv) : -1.f;
   *out = fc;
 }
 
+__global__ void __launch_bounds__(64) fast_cams_kernel(const double* __restrict__ cams, int K,
+                                                        const float* __restrict__ bbox, int H, int W,
+                                                        float* __restrict__ fast) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) make_fast_cam(cams + (size_t)k * 16, bbox, H, W, reinterpret_cast<FastCam*>(fast) + k);
+}
+
+constexpr int kFlushEvery = 16;      // cameras between queue flushes: 4 bits per camera in a 64-bit mask
+
 template <int MODE>
-__global__ void __launch_bounds__(kSplatThreads)
+__global__ void __launch_bounds__(kSplatThreads, 4)
 splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label, int64_t n,
                       const double* __restrict__ cams, int K, int cams_per_block, int H, int W,
-                      uint32_t* __restrict__ zbuf, const float* __restrict__ bbox) {
+                      uint32_t* __restrict__ zbuf, const float* __restrict__ fast) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_cam = reinterpret_cast<double*>(smem_raw);                                   // nc x 16 doubles
   FastCam* s_fast = reinterpret_cast<FastCam*>(s_cam + (size_t)cams_per_block * 16);      // nc x FastCam
-  float4* s_queue = reinterpret_cast<float4*>(s_fast + cams_per_block);                   // 8 warps x kQueueCap
-  uint32_t* s_qcam = reinterpret_cast<uint32_t*>(s_queue + (kSplatThreads / 32) * kQueueCap);
+  uint2* s_queue = reinterpret_cast<uint2*>(s_fast + cams_per_block);                     // 8 warps x kQueueCap
+  int* s_qn = reinterpret_cast<int*>(s_queue + (kSplatThreads / 32) * kQueueCap);          // 8 counters
 
   const int c0 = blockIdx.y * cams_per_block;
   const int nc = min(cams_per_block, K - c0);
-  for (int i = threadIdx.x; i < nc * 16; i += kSplatThreads) s_cam[i] = cams[(size_t)c0 * 16 + i];
-  __syncthreads();
-  if (threadIdx.x < nc) make_fast_cam(s_cam + threadIdx.x * 16, bbox, s_fast + threadIdx.x);
+  for (int i = threadIdx.x; i < nc * 16; i += kSplatThreads) {
+    s_cam[i] = cams[(size_t)c0 * 16 + i];
+    reinterpret_cast<float*>(s_fast)[i] = fast[(size_t)c0 * 16 + i];
+  }
+  if (threadIdx.x < kSplatThreads / 32) s_qn[threadIdx.x] = 0;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* q = s_queue + warp * kQueueCap;
-  uint32_t* qc = s_qcam + warp * kQueueCap;
-  int qn = 0;                                              // warp-uniform queue length
+  uint2* q = s_queue + warp * kQueueCap;
+  int* qn_ptr = s_qn + warp;
 
   const int64_t tile = (int64_t)gridDim.x - 1 - blockIdx.x;
   const int64_t base = tile * (kSplatThreads * kPptF) + threadIdx.x;
@@ -259,7 +279,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
   for (int j = 0; j < kPptF; ++j) {
     const int64_t i = base + (int64_t)j * kSplatThreads;
     key[j] = 0;
-    px[j] = py[j] = pz[j] = 0.f;
+    px[j] = py[j] = pz[j] = __int_as_float(0x7fc00000);     // NaN: dead lanes never decide and never park (key 0)
     if (i < n) {
       px[j] = __ldg(pts + 3 * i + 0);
       py[j] = __ldg(pts + 3 * i + 1);
@@ -269,81 +289,93 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
     }
   }
   const double dW = (double)W, dH = (double)H;
-  const size_t HW = (size_t)H * W;
+  const uint32_t HW = (uint32_t)H * (uint32_t)W;
   const float kMagic = 12582912.f;                         // 1.5 * 2^23: (x + m) - m == rint(x) for |x| < 2^22
 
-  auto drain = [&](int keep_below) {
-    while (qn > keep_below) {
-      const int take = qn < 32 ? qn : 32;
-      const int idx = qn - take + lane;
-      if (lane < take) {
-        const float4 e = q[idx];
-        const uint32_t c = qc[idx];
-        exact_splat<double, MODE>((double)e.x, (double)e.y, (double)e.z, __float_as_uint(e.w), s_cam + c * 16,
-                                  zbuf + (size_t)(c0 + c) * HW, W, dW, dH);
+  // exact FP64 projection of the newest `take` queue entries (one per lane)
+  auto drain32 = [&](int qn) -> int {
+    const int take = qn < 32 ? qn : 32;
+    if (lane < take) {
+      const uint2 e = q[qn - take + lane];                  // (point index, camera)
+      const float* pp = pts + 3 * (size_t)e.x;
+      const uint32_t k = MODE == P3D_MODE_JOINT ? e.x + 1u : 1u << ((uint32_t)__ldg(pt_label + e.x) - 1u);
+      exact_splat<double, MODE>((double)__ldg(pp), (double)__ldg(pp + 1), (double)__ldg(pp + 2), k, s_cam + e.y * 16,
+                                zbuf + (size_t)(c0 + e.y) * HW, W, dW, dH);
+    }
+    return qn - take;
+  };
+
+  // push the undecided (point, camera) pairs recorded in `mask` (bit 4*cc + j <-> camera cbase + cc, point j);
+  // every round each lane pushes at most one entry, then full groups of 32 are drained: the queue never exceeds 63
+  auto flush = [&](unsigned long long mask, int cbase) {
+    while (__any_sync(0xffffffffu, mask != 0ull)) {
+      if (mask) {
+        const int b = __ffsll((long long)mask) - 1;
+        mask &= mask - 1ull;
+        const int pos = atomicAdd(qn_ptr, 1);
+        q[pos] = make_uint2((uint32_t)(base + (int64_t)(b & 3) * kSplatThreads), (uint32_t)(cbase + (b >> 2)));
       }
-      qn -= take;
+      __syncwarp();
+      int qn = *reinterpret_cast<volatile int*>(qn_ptr);
+      if (qn >= 32) {
+        qn = drain32(qn);
+        __syncwarp();
+        if (lane == 0) *qn_ptr = qn;
+      }
       __syncwarp();
     }
   };
 
+  unsigned long long parked = 0ull;
   for (int c = 0; c < nc; ++c) {
     const float4* fcv = reinterpret_cast<const float4*>(s_fast + c);
-    const float4 v0 = fcv[0], v1 = fcv[1], v2 = fcv[2], v3 = fcv[3], v4 = fcv[4];
-    const float e0 = v0.x, e1 = v0.y, e2 = v0.z;
-    const float r00 = v0.w, r01 = v1.x, r02 = v1.y, r10 = v1.z, r11 = v1.w, r12 = v2.x, r20 = v2.y, r21 = v2.z, r22 = v2.w;
-    const float f = v3.x, cx = v3.y, cy = v3.z, b1 = v3.w, b0u = v4.x, b0v = v4.y;
+    const float4 vA = fcv[0], vB = fcv[1], vC = fcv[2], vD = fcv[3];
     uint32_t* zb = zbuf + (size_t)(c0 + c) * HW;
-    int pix[kPptF];
-    uint32_t parked = 0;
+    asm volatile("" : "+l"(zb));                          // keep the per-camera base in registers
+    uint32_t* addr[kPptF];
+    bool hit[kPptF];
+    uint32_t und = 0;
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
-      const float d0 = px[j] - e0, d1 = py[j] - e1, d2 = pz[j] - e2;
-      const float X = fmaf(d2, r02, fmaf(d1, r01, d0 * r00));
-      const float Y = fmaf(d2, r12, fmaf(d1, r11, d0 * r10));
-      const float Z = fmaf(d2, r22, fmaf(d1, r21, d0 * r20));
+      const float X = fmaf(pz[j], vA.z, fmaf(py[j], vA.y, fmaf(px[j], vA.x, vA.w)));
+      const float Y = fmaf(pz[j], vB.z, fmaf(py[j], vB.y, fmaf(px[j], vB.x, vB.w)));
+      const float Z = fmaf(pz[j], vC.z, fmaf(py[j], vC.y, fmaf(px[j], vC.x, vC.w)));
       float r;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(Z));
-      const float u = fmaf(X * r, f, cx);
-      const float v = fmaf(-(Y * r), f, cy);
+      const float u = fmaf(X, r, vD.x);
+      const float v = fmaf(Y, r, vD.y);
       const float su = u + kMagic, sv = v + kMagic;
-      const float eu = fabsf(u - (su - kMagic)) + fmaf(b1, fabsf(u), b0u);
-      const float ev = fabsf(v - (sv - kMagic)) + fmaf(b1, fabsf(v), b0v);
-      const bool decided = eu < 0.5f && ev < 0.5f;            // false for NaN
-      const int iu = __float_as_int(su) - 0x4B400000, iv = __float_as_int(sv) - 0x4B400000;
-      const bool inside = (unsigned)iu < (unsigned)W && (unsigned)iv < (unsigned)H;
-      const bool live = key[j] != 0;
-      pix[j] = (live && decided && inside) ? iv * W + iu : -1;
-      if (live && !decided) parked |= 1u << j;
+      const bool decided = fabsf(u - (su - kMagic)) < vD.z && fabsf(v - (sv - kMagic)) < vD.w;   // false for NaN
+      const uint32_t iu = (uint32_t)(__float_as_int(su) - 0x4B400000), iv = (uint32_t)(__float_as_int(sv) - 0x4B400000);
+      hit[j] = decided && iu < (uint32_t)W && iv < (uint32_t)H;
+      addr[j] = zb + (iv * (uint32_t)W + iu);            // only dereferenced when hit
+      if (!decided && key[j] != 0) und |= 1u << j;
     }
+    parked |= (unsigned long long)und << (4 * (c & (kFlushEvery - 1)));
+    // all early-out loads first (memory-level parallelism), then the reductions
     uint32_t cur[kPptF];
 #pragma unroll
-    for (int j = 0; j < kPptF; ++j) cur[j] = pix[j] >= 0 ? __ldcg(zb + pix[j]) : 0xffffffffu;
+    for (int j = 0; j < kPptF; ++j) {
+      cur[j] = 0xffffffffu;
+      if (hit[j]) cur[j] = __ldcg(addr[j]);
+    }
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
       if (MODE == P3D_MODE_JOINT) {
-        if (cur[j] < key[j]) atomicMax(zb + pix[j], key[j]);
+        if (cur[j] < key[j]) atomicMax(addr[j], key[j]);
       } else {
-        if (pix[j] >= 0 && (cur[j] & key[j]) == 0) atomicOr(zb + pix[j], key[j]);
+        if ((cur[j] & key[j]) != key[j]) atomicOr(addr[j], key[j]);     // cur == ~0 when no load was issued
       }
     }
-    if (__any_sync(0xffffffffu, parked != 0)) {
-#pragma unroll
-      for (int j = 0; j < kPptF; ++j) {
-        const bool park = (parked >> j) & 1u;
-        const uint32_t m = __ballot_sync(0xffffffffu, park);
-        if (park) {
-          const int pos = qn + __popc(m & ((1u << lane) - 1u));
-          q[pos] = make_float4(px[j], py[j], pz[j], __uint_as_float(key[j]));
-          qc[pos] = (uint32_t)c;
-        }
-        qn += __popc(m);
-      }
-      __syncwarp();
-      if (qn >= 32) drain(31);
+    if ((c & (kFlushEvery - 1)) == kFlushEvery - 1) {
+      flush(parked, c - (kFlushEvery - 1));
+      parked = 0ull;
     }
   }
-  drain(0);
+  flush(parked, (nc - 1) & ~(kFlushEvery - 1));
+  __syncwarp();
+  int qn = *reinterpret_cast<volatile int*>(qn_ptr);
+  while (qn > 0) qn = drain32(qn);
 }
 
 // Bounding box of a point list: bbox = (min x, min y, min z, max x, max y, max z); NaNs are ignored.
@@ -697,9 +729,18 @@ int points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream) {
   return P3D_OK;
 }
 
+int fast_cameras(const double* cams, int K, const float* bbox, int H, int W, float* fast, p3d_stream_t stream) {
+  P3D_REQUIRE(K >= 0 && H > 0 && W > 0, "fast_cameras: bad arguments");
+  if (K == 0) return P3D_OK;
+  P3D_REQUIRE(cams && bbox && fast, "fast_cameras: null pointer");
+  fast_cams_kernel<<<(K + 63) / 64, 64, 0, p3d::as_stream(stream)>>>(cams, K, bbox, H, W, fast);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
 template <typename T>
 int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, int K, int H, int W, int mode,
-          uint32_t* zbuf, const float* bbox, p3d_stream_t stream) {
+          uint32_t* zbuf, const float* fast, p3d_stream_t stream) {
   P3D_REQUIRE(n >= 0 && K >= 0 && H > 0 && W > 0, "splat: n=%lld K=%d H=%d W=%d", (long long)n, K, H, W);
   P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
   P3D_REQUIRE(n < 0xffffffffll, "splat: n=%lld does not fit 32-bit keys", (long long)n);
@@ -707,7 +748,7 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   if (n == 0 || K == 0) return P3D_OK;
   P3D_REQUIRE(pts && cams && zbuf, "splat: null pointer");
   P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: per-part mode needs pt_label");
-  const bool filtered = sizeof(T) == 8 && bbox != nullptr && !splat_exact_only();
+  const bool filtered = sizeof(T) == 8 && fast != nullptr && !splat_exact_only();
   const int ppt = filtered ? kPptF : kPpt;
   const int64_t tiles = (n + kSplatThreads * ppt - 1) / (kSplatThreads * ppt);
   P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
@@ -716,12 +757,12 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   cudaStream_t st = p3d::as_stream(stream);
   if (filtered) {
     const size_t smem = (size_t)cpb * (16 * sizeof(double) + sizeof(FastCam)) +
-                        (size_t)(kSplatThreads / 32) * kQueueCap * (sizeof(float4) + sizeof(uint32_t));
+                        (size_t)(kSplatThreads / 32) * (kQueueCap * sizeof(uint2) + sizeof(int));
     const double* dc = reinterpret_cast<const double*>(cams);
     if (mode == P3D_MODE_JOINT)
-      splat_filtered_kernel<P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, bbox);
+      splat_filtered_kernel<P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast);
     else
-      splat_filtered_kernel<P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, bbox);
+      splat_filtered_kernel<P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast);
   } else {
     const size_t smem = (size_t)cpb * 16 * sizeof(T);
     if (mode == P3D_MODE_JOINT)
@@ -751,7 +792,7 @@ inline size_t default_zbuf_budget() {
 }
 
 struct SweepLayout {
-  size_t cams, raw, gt_area, bbox, zbuf, total;
+  size_t cams, raw, gt_area, bbox, fast, zbuf, total;
   int batch;
 };
 
@@ -763,6 +804,7 @@ inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
   L.raw = off; off = p3d_align_up(off + (size_t)K * (P + 1) * 2 * sizeof(unsigned long long), 256);
   L.gt_area = off; off = p3d_align_up(off + (size_t)(P + 1) * sizeof(unsigned long long), 256);
   L.bbox = off; off = p3d_align_up(off + 8 * sizeof(float), 256);
+  L.fast = off; off = p3d_align_up(off + (size_t)K * sizeof(FastCam), 256);
   L.zbuf = off; off = p3d_align_up(off + (size_t)L.batch * H * W * sizeof(uint32_t), 256);
   L.total = off;
   return L;
@@ -795,6 +837,7 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
   const int rows = mode == P3D_MODE_PER_PART ? P + 1 : P;
 
   float* bbox = reinterpret_cast<float*>(ws + L.bbox);
+  float* fast = reinterpret_cast<float*>(ws + L.fast);
   P3D_CUDA(cudaMemsetAsync(ws + L.raw, 0, L.bbox - L.raw, st));   // raw + gt_area
   P3D_CUDA(cudaMemsetAsync(zbuf, 0, (size_t)L.batch * HW * sizeof(uint32_t), st));
   int rc = setup_cameras<T>(cand, K, cams, stream);
@@ -806,14 +849,17 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
   if (n > 0 && sizeof(T) == 8) {
     rc = points_bbox(pts, n, bbox, stream);
     if (rc) return rc;
-    g_last_launches += 2;
+    rc = fast_cameras(reinterpret_cast<const double*>(cams), K, bbox, H, W, fast, stream);
+    if (rc) return rc;
+    g_last_launches += 3;
   }
   for (int k0 = 0; k0 < K; k0 += L.batch) {
     const int kb = K - k0 < L.batch ? K - k0 : L.batch;
     if (n > 0) {
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
-      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, mode, zbuf, sizeof(T) == 8 ? bbox : nullptr, stream);
+      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, mode, zbuf,
+                    (sizeof(T) == 8 && n > 0) ? fast + (size_t)k0 * 16 : nullptr, stream);
       if (rc) return rc;
       if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
       dim3 grid((unsigned)grid_for(HW, kScoreThreads, 2), (unsigned)kb);
@@ -854,9 +900,14 @@ P3D_API int p3d_points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream
   return points_bbox(pts, n, bbox, stream);
 }
 
+P3D_API int p3d_fast_cameras_f64(const double* cams, int K, const float* bbox, int H, int W, float* fast,
+                                 p3d_stream_t stream) {
+  return fast_cameras(cams, K, bbox, H, W, fast, stream);
+}
+
 P3D_API int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K, int H,
-                          int W, int mode, uint32_t* zbuf, const float* bbox, p3d_stream_t stream) {
-  return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, bbox, stream);
+                          int W, int mode, uint32_t* zbuf, const float* fast, p3d_stream_t stream) {
+  return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, fast, stream);
 }
 P3D_API int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K, int H,
                           int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
