@@ -89,15 +89,27 @@ def _y_decoupled(M, off):
     return M[0, 1] == 0 and M[1, 0] == 0 and M[1, 1] == 1 and M[1, 2] == 0 and M[2, 1] == 0 and off[1] == 0
 
 
+_FOLD_CACHE = {}          # (n0, n2, M bytes, off bytes, device) -> (table, foldable); a table is a few MB at most
+
+
 def _fold_table(n0, n2, M, off, dev):
-    """(table (n0,n2) int32, foldable) for a y-decoupled pass, else (None, False)."""
+    """(table (n0,n2) int32, foldable) for a y-decoupled pass, else (None, False).  Cached per transform: the
+    table depends only on the grid shape and on the host-computed matrix/offset."""
     if not _y_decoupled(M, off) or n0 >= 32768 or n2 >= 65536:
         return None, False
+    cache_key = (n0, n2, M.tobytes(), off.tobytes(), str(dev))
+    hit = _FOLD_CACHE.get(cache_key)
+    if hit is not None:
+        return hit
     table = torch.empty((n0, n2), dtype=torch.int32, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     check(lib.p3d_fold_table(n0, n2, _dptr(M), _dptr(off), ptr(table), ptr(flag), stream_ptr()), "p3d_fold_table")
     _launched()
-    return table, int(flag.item()) == 0
+    res = (table, int(flag.item()) == 0)
+    if len(_FOLD_CACHE) >= 16:
+        _FOLD_CACHE.pop(next(iter(_FOLD_CACHE)))
+    _FOLD_CACHE[cache_key] = res
+    return res
 
 
 def _process_device(vol, mask_wh, angle_interval):
