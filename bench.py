@@ -226,7 +226,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (splat) --------------------------------------------------
     peak, peak_src = peaks()
     G = N ** 3
-    batch = max(1, min(B, 64, (64 << 20) // (H * W * 4)))
+    batch = max(1, min(B, 64, (int(os.environ.get('P3D_ZBUF_BUDGET_MB', '128')) << 20) // (H * W * 4)))
     alg_per_launch = batch * (G * 1 + 9 * H * W)
     avg_launch_s = (splat_ms.value / max(1, splat_launches.value)) * 1e-3
     achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0

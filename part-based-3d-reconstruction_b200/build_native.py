@@ -36,13 +36,16 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile the library.  `defines` / `out` build an experimental variant next to the default one
+    (selected at run time with P3D_LIB=<path>; used only for tuning runs)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    if not force and not needs_build():
+    target = out or LIB
+    if not force and out is None and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + srcs
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -100,7 +100,16 @@ __global__ void __launch_bounds__(128) setup_cameras_kernel(const T* __restrict_
 // ------------------------------------------------------------------------------------------
 // Splat.  CTA = 256 threads x kPpt points; blockIdx.y selects a group of `cams_per_block` cameras.
 // ------------------------------------------------------------------------------------------
-constexpr int kSplatThreads = 256;
+#ifndef P3D_SPLAT_THREADS
+#define P3D_SPLAT_THREADS 256
+#endif
+#ifndef P3D_PPTF
+#define P3D_PPTF 4
+#endif
+#ifndef P3D_MINBLOCKS
+#define P3D_MINBLOCKS 4
+#endif
+constexpr int kSplatThreads = P3D_SPLAT_THREADS;
 constexpr int kPpt = 2;
 
 template <int MODE>
@@ -191,7 +200,7 @@ splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label
 // Cameras whose box comes within max(1e-3, 2^-17 DZ) of the camera plane, or with non-finite / non-positive-f
 // parameters, or whose bound exceeds 0.25 px, get thr = -1: every point takes the exact path.
 // ------------------------------------------------------------------------------------------
-constexpr int kPptF = 4;
+constexpr int kPptF = P3D_PPTF;
 constexpr int kQueueCap = 64;        // per warp: at most 32 new entries on top of < 32 pending
 
 struct FastCam {                     // 16 floats per camera
@@ -245,10 +254,10 @@ __global__ void __launch_bounds__(64) fast_cams_kernel(const double* __restrict_
   if (k < K) make_fast_cam(cams + (size_t)k * 16, bbox, H, W, reinterpret_cast<FastCam*>(fast) + k);
 }
 
-constexpr int kFlushEvery = 16;      // cameras between queue flushes: 4 bits per camera in a 64-bit mask
+constexpr int kFlushEvery = 64 / kPptF; // cameras between queue flushes: kPptF bits per camera in a 64-bit mask
 
 template <int MODE>
-__global__ void __launch_bounds__(kSplatThreads, 4)
+__global__ void __launch_bounds__(kSplatThreads, P3D_MINBLOCKS)
 splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label, int64_t n,
                       const double* __restrict__ cams, int K, int cams_per_block, int H, int W,
                       uint32_t* __restrict__ zbuf, const float* __restrict__ fast) {
@@ -305,15 +314,20 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
     return qn - take;
   };
 
-  // push the undecided (point, camera) pairs recorded in `mask` (bit 4*cc + j <-> camera cbase + cc, point j);
-  // every round each lane pushes at most one entry, then full groups of 32 are drained: the queue never exceeds 63
-  auto flush = [&](unsigned long long mask, int cbase) {
+  // push the undecided (point, camera) pairs recorded in `mask`: nibble g (from the low end) belongs to camera
+  // clast - g, bit j of the nibble to point j.  Every round each lane pushes at most one entry, then full groups of 32
+  // are drained: the queue never exceeds 63.  Dead lanes (index >= n) carry NaN coordinates, are never decided and
+  // are dropped here.
+  auto flush = [&](unsigned long long mask, int clast) {
     while (__any_sync(0xffffffffu, mask != 0ull)) {
       if (mask) {
         const int b = __ffsll((long long)mask) - 1;
         mask &= mask - 1ull;
-        const int pos = atomicAdd(qn_ptr, 1);
-        q[pos] = make_uint2((uint32_t)(base + (int64_t)(b & 3) * kSplatThreads), (uint32_t)(cbase + (b >> 2)));
+        const int64_t idx = base + (int64_t)(b % kPptF) * kSplatThreads;
+        if (idx < n) {
+          const int pos = atomicAdd(qn_ptr, 1);
+          q[pos] = make_uint2((uint32_t)idx, (uint32_t)(clast - (b / kPptF)));
+        }
       }
       __syncwarp();
       int qn = *reinterpret_cast<volatile int*>(qn_ptr);
@@ -349,15 +363,19 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       const uint32_t iu = (uint32_t)(__float_as_int(su) - 0x4B400000), iv = (uint32_t)(__float_as_int(sv) - 0x4B400000);
       hit[j] = decided && iu < (uint32_t)W && iv < (uint32_t)H;
       addr[j] = zb + (iv * (uint32_t)W + iu);            // only dereferenced when hit
-      if (!decided && key[j] != 0) und |= 1u << j;
+      if (!decided) und |= 1u << j;
     }
-    parked |= (unsigned long long)und << (4 * (c & (kFlushEvery - 1)));
+    parked = (parked << kPptF) | (unsigned long long)und;
     // all early-out loads first (memory-level parallelism), then the reductions
     uint32_t cur[kPptF];
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
       cur[j] = 0xffffffffu;
+#ifdef P3D_EARLY_CA
+      if (hit[j]) cur[j] = __ldca(addr[j]);
+#else
       if (hit[j]) cur[j] = __ldcg(addr[j]);
+#endif
     }
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
@@ -368,11 +386,11 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       }
     }
     if ((c & (kFlushEvery - 1)) == kFlushEvery - 1) {
-      flush(parked, c - (kFlushEvery - 1));
+      flush(parked, c);
       parked = 0ull;
     }
   }
-  flush(parked, (nc - 1) & ~(kFlushEvery - 1));
+  flush(parked, nc - 1);
   __syncwarp();
   int qn = *reinterpret_cast<volatile int*>(qn_ptr);
   while (qn > 0) qn = drain32(qn);
@@ -427,60 +445,96 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ pts
 constexpr int kScoreThreads = 256;
 constexpr int kMaxParts = 32;
 
+// accumulate one pixel per lane into the warp's counters (all 32 lanes must call)
+template <int MODE>
+__device__ __forceinline__ void score_accumulate(uint32_t key, uint32_t g, bool ga, const uint8_t* __restrict__ pt_label,
+                                                 int P, unsigned int* acc, int lane) {
+  if (MODE == P3D_MODE_JOINT) {
+    const uint32_t lab = key ? (uint32_t)__ldg(pt_label + (key - 1)) : 0u;
+    uint32_t rem = __ballot_sync(0xffffffffu, lab != 0);
+    while (rem) {
+      const int leader = __ffs(rem) - 1;
+      const uint32_t l = __shfl_sync(0xffffffffu, lab, leader);
+      const uint32_t m = __ballot_sync(0xffffffffu, lab == l);
+      const uint32_t mi = __ballot_sync(0xffffffffu, lab == l && g == l);
+      if (lane == 0 && l <= (uint32_t)P) {
+        acc[(l - 1) * 2] += __popc(m);
+        acc[(l - 1) * 2 + 1] += __popc(mi);
+      }
+      rem &= ~m;
+    }
+  } else {
+    uint32_t present = __reduce_or_sync(0xffffffffu, key);
+    while (present) {
+      const int b = __ffs(present) - 1;
+      present &= present - 1;
+      const bool has = (key >> b) & 1u;
+      const uint32_t m = __ballot_sync(0xffffffffu, has);
+      const uint32_t mi = __ballot_sync(0xffffffffu, has && g == (uint32_t)(b + 1));
+      if (lane == 0 && b < P) {
+        acc[b * 2] += __popc(m);
+        acc[b * 2 + 1] += __popc(mi);
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, key != 0);
+    const uint32_t mi = __ballot_sync(0xffffffffu, key != 0 && ga);
+    if (lane == 0) {
+      acc[P * 2] += __popc(m);
+      acc[P * 2 + 1] += __popc(mi);
+    }
+  }
+}
+
+// One camera per blockIdx.y.  A thread reads 4 consecutive pixels (uint4 of keys, 4 GT bytes); warps whose 128 pixels
+// are all untouched skip after one vote; touched quads are cleared with one 16-byte store.  `vec` = HW % 4 == 0.
 template <int MODE>
 __global__ void __launch_bounds__(kScoreThreads)
 score_kernel(uint32_t* __restrict__ zbuf, const uint8_t* __restrict__ pt_label,
              const uint8_t* __restrict__ gt_label, const uint8_t* __restrict__ gt_any, int HW, int P,
-             unsigned long long* __restrict__ raw) {
+             unsigned long long* __restrict__ raw, int vec) {
   __shared__ unsigned int s_acc[kScoreThreads / 32][(kMaxParts + 1) * 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = (P + 1) * 2;
   for (int i = lane; i < rows; i += 32) s_acc[warp][i] = 0;
   __syncwarp();
   uint32_t* zb = zbuf + (size_t)blockIdx.y * HW;
-  const int stride = gridDim.x * kScoreThreads;
-  const int iters = (HW + stride - 1) / stride;
-  for (int it = 0; it < iters; ++it) {
-    const int pix = it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
-    const bool in = pix < HW;
-    const uint32_t key = in ? __ldcg(zb + pix) : 0u;
-    if (!__any_sync(0xffffffffu, key != 0)) continue;
-    if (key) zb[pix] = 0u;
-    const uint32_t g = in ? (uint32_t)__ldg(gt_label + pix) : 0u;
-    if (MODE == P3D_MODE_JOINT) {
-      const uint32_t lab = key ? (uint32_t)__ldg(pt_label + (key - 1)) : 0u;
-      uint32_t rem = __ballot_sync(0xffffffffu, lab != 0);
-      while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const uint32_t l = __shfl_sync(0xffffffffu, lab, leader);
-        const uint32_t m = __ballot_sync(0xffffffffu, lab == l);
-        const uint32_t mi = __ballot_sync(0xffffffffu, lab == l && g == l);
-        if (lane == 0 && l <= (uint32_t)P) {
-          s_acc[warp][(l - 1) * 2] += __popc(m);
-          s_acc[warp][(l - 1) * 2 + 1] += __popc(mi);
-        }
-        rem &= ~m;
+  unsigned int* acc = s_acc[warp];
+  if (vec) {
+    const int nq = HW >> 2;
+    const int stride = gridDim.x * kScoreThreads;
+    const int iters = (nq + stride - 1) / stride;
+    for (int it = 0; it < iters; ++it) {
+      const int qd = it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
+      const bool in = qd < nq;
+      uint4 k4 = make_uint4(0, 0, 0, 0);
+      if (in) k4 = __ldcg(reinterpret_cast<const uint4*>(zb) + qd);
+      const bool touched = (k4.x | k4.y | k4.z | k4.w) != 0;
+      if (!__any_sync(0xffffffffu, touched)) continue;
+      uint32_t g4 = 0, a4 = 0;
+      if (touched) {
+        reinterpret_cast<uint4*>(zb)[qd] = make_uint4(0, 0, 0, 0);
+        g4 = __ldg(reinterpret_cast<const uint32_t*>(gt_label) + qd);
+        if (MODE == P3D_MODE_PER_PART && gt_any) a4 = __ldg(reinterpret_cast<const uint32_t*>(gt_any) + qd);
       }
-    } else {
-      uint32_t present = __reduce_or_sync(0xffffffffu, key);
-      while (present) {
-        const int b = __ffs(present) - 1;
-        present &= present - 1;
-        const bool has = (key >> b) & 1u;
-        const uint32_t m = __ballot_sync(0xffffffffu, has);
-        const uint32_t mi = __ballot_sync(0xffffffffu, has && g == (uint32_t)(b + 1));
-        if (lane == 0 && b < P) {
-          s_acc[warp][b * 2] += __popc(m);
-          s_acc[warp][b * 2 + 1] += __popc(mi);
-        }
+      const uint32_t ks[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (!__any_sync(0xffffffffu, ks[s] != 0)) continue;
+        score_accumulate<MODE>(ks[s], (g4 >> (8 * s)) & 0xffu, ((a4 >> (8 * s)) & 0xffu) != 0, pt_label, P, acc, lane);
       }
-      const bool ga = in && gt_any != nullptr && __ldg(gt_any + pix) != 0;
-      const uint32_t m = __ballot_sync(0xffffffffu, key != 0);
-      const uint32_t mi = __ballot_sync(0xffffffffu, key != 0 && ga);
-      if (lane == 0) {
-        s_acc[warp][P * 2] += __popc(m);
-        s_acc[warp][P * 2 + 1] += __popc(mi);
-      }
+    }
+  } else {
+    const int stride = gridDim.x * kScoreThreads;
+    const int iters = (HW + stride - 1) / stride;
+    for (int it = 0; it < iters; ++it) {
+      const int pix = it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
+      const bool in = pix < HW;
+      const uint32_t key = in ? __ldcg(zb + pix) : 0u;
+      if (!__any_sync(0xffffffffu, key != 0)) continue;
+      if (key) zb[pix] = 0u;
+      const uint32_t g = in ? (uint32_t)__ldg(gt_label + pix) : 0u;
+      const bool ga = MODE == P3D_MODE_PER_PART && in && gt_any != nullptr && __ldg(gt_any + pix) != 0;
+      score_accumulate<MODE>(key, g, ga, pt_label, P, acc, lane);
     }
   }
   __syncthreads();
@@ -786,8 +840,8 @@ inline int batch_cameras(int K, int H, int W, size_t zbuf_budget) {
 
 inline size_t default_zbuf_budget() {
   const char* e = getenv("P3D_ZBUF_BUDGET_MB");
-  long mb = e ? atol(e) : 64;
-  if (mb < 1) mb = 64;
+  long mb = e ? atol(e) : 128;
+  if (mb < 1) mb = 128;
   return (size_t)mb << 20;
 }
 
@@ -862,16 +916,18 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
                     (sizeof(T) == 8 && n > 0) ? fast + (size_t)k0 * 16 : nullptr, stream);
       if (rc) return rc;
       if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
-      dim3 grid((unsigned)grid_for(HW, kScoreThreads, 2), (unsigned)kb);
+      const int vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(gt_label) & 3) == 0) &&
+                      (gt_any == nullptr || (reinterpret_cast<uintptr_t>(gt_any) & 3) == 0);
+      dim3 grid((unsigned)grid_for(vec ? HW / 4 : HW, kScoreThreads, 2), (unsigned)kb);
       // spread one camera's pixels over at most ~2 waves / kb CTAs
       int per_cam = (p3d::sm_count() * 8 + kb - 1) / kb;
       if ((int)grid.x > per_cam) grid.x = per_cam < 1 ? 1 : per_cam;
       if (mode == P3D_MODE_JOINT)
         score_kernel<P3D_MODE_JOINT><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, nullptr, HW, P,
-                                                                     raw + (size_t)k0 * (P + 1) * 2);
+                                                                     raw + (size_t)k0 * (P + 1) * 2, vec);
       else
         score_kernel<P3D_MODE_PER_PART><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, gt_any, HW, P,
-                                                                        raw + (size_t)k0 * (P + 1) * 2);
+                                                                        raw + (size_t)k0 * (P + 1) * 2, vec);
       P3D_LAUNCH_CHECK();
       g_last_launches += 2;
     }

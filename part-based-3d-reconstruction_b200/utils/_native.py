@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libp3d_b200.so"))
+LIB_PATH = os.environ.get("P3D_LIB") or os.path.normpath(os.path.join(_HERE, "..", "csrc", "libp3d_b200.so"))
 
 MODE_JOINT = 0
 MODE_PER_PART = 1
