@@ -170,3 +170,230 @@ def score_camera_candidates(voxel_grid, image, part_colors, parts, candidates, *
     the order of `parts`, best_index = first candidate with the greatest score)."""
     return CandidateScorer(voxel_grid, image, part_colors, parts, mode=mode, device=device,
                            dtype=dtype).score(candidates)
+
+
+# --------------------------------------------------------------------------------------------
+# launch_smart_aligner without the widgets: the three optimiser buttons as methods
+# --------------------------------------------------------------------------------------------
+_SLIDER_KEYS = ["cam_x", "cam_y", "cam_z", "target_x", "target_y", "target_z", "f", "cx", "cy"]
+
+
+class SmartAligner:
+    """Headless equivalent of launch_smart_aligner (camera_estimation.py:479-768).
+
+    Holds the same state as the widget version (nine sliders with the reference's ranges, `saved_params`, the
+    original init) and exposes the button callbacks as methods: run_random (:606-650), run_coord (:652-686),
+    run_powell (:688-725), save / load / reset (:728-739).  Every candidate is scored on the GPU; run_random and
+    each coordinate-descent round are scored as ONE batch (the reference's selection only depends on the scores,
+    strict `>`, first candidate wins ties), Powell stays sequential because scipy drives it.
+
+    Reference quirks that are reproduced because they change the result:
+      * slider values are clamped to the slider ranges whenever parameters are written back (:528-551);
+      * run_coord copies the parameter dict shallowly, so a rejected `-20` step on cam_pos/target is undone by the
+        following `+20` "trial", which therefore re-evaluates the current point and never tests `+20` (:661-668);
+      * run_random draws from the global np.random state in the order cam_pos(3), target(3), f, cx, cy (:621-625).
+    `scorer` may be any object with `.score(cand) -> (scores, counts, best)` (tests inject the oracle).
+    """
+
+    def __init__(self, voxel_grid, image, part_colors, parts_for_alignment=("plinth", "minarets"), init_params=None,
+                 lock_xy_equal=False, device=None, scorer=None, verbose=True):
+        if init_params is None:
+            raise NotImplementedError("auto_compute_initial_params_matching_bbox (camera_estimation.py:56-108) is outside "
+                                      "this package's scope: pass init_params")
+        self.H, self.W = int(image.shape[0]), int(image.shape[1])
+        self.lock_xy_equal = bool(lock_xy_equal)
+        self.verbose = verbose
+        self.scorer = scorer if scorer is not None else CandidateScorer(voxel_grid, image, part_colors,
+                                                                        list(parts_for_alignment), device=device)
+        self._ranges = {"cam_x": (-3000, 3000), "cam_y": (-3000, 3000), "cam_z": (-4000, 4000),
+                        "target_x": (-2000, 2000), "target_y": (-2000, 2000), "target_z": (-2000, 2000),
+                        "f": (100, 3000), "cx": (-self.W, 2 * self.W), "cy": (-self.H, 2 * self.H)}
+        self.sliders = {}
+        self.set_params(init_params)
+        self.orig_init = dict(init_params)
+        self.saved_params = {}
+        self.evaluations = 0
+
+    # ---- slider state ------------------------------------------------------------------------
+    def _set(self, key, value):
+        lo, hi = self._ranges[key]
+        self.sliders[key] = float(min(max(float(value), lo), hi))
+
+    def set_params(self, p):
+        for c, v in zip("xyz", p["cam_pos"]):
+            self._set(f"cam_{c}", v)
+        for c, v in zip("xyz", p["target"]):
+            self._set(f"target_{c}", v)
+        for k in ("f", "cx", "cy"):
+            self._set(k, p[k])
+
+    def get_params(self):
+        cam = np.array([self.sliders[f"cam_{c}"] for c in "xyz"])
+        tgt = np.array([self.sliders[f"target_{c}"] for c in "xyz"])
+        if self.lock_xy_equal:
+            cam[0], cam[1] = tgt[0], tgt[1]
+        return {"cam_pos": cam, "target": tgt, "f": self.sliders["f"], "cx": self.sliders["cx"],
+                "cy": self.sliders["cy"], "H": self.H, "W": self.W}
+
+    # ---- scoring -------------------------------------------------------------------------------
+    def iou_batch(self, param_dicts):
+        rows = np.stack([params_to_row(p) for p in param_dicts])
+        scores, _, _ = self.scorer.score(rows)
+        self.evaluations += len(param_dicts)
+        return np.asarray(scores, dtype=np.float64)
+
+    def iou(self, p):
+        return float(self.iou_batch([p])[0])
+
+    def evaluate(self, p):
+        """The `evaluate` closure (:597-603): negative mean IoU."""
+        return -self.iou(p)
+
+    # ---- optimisers ------------------------------------------------------------------------------
+    def run_random(self, steps=5):
+        base = self.get_params()
+        trials = []
+        for _ in range(int(steps)):
+            t = dict(base)
+            t["cam_pos"] = base["cam_pos"] + np.random.uniform(-1, 1, 3) * _STEP_SIZES[0:3]
+            t["target"] = base["target"] + np.random.uniform(-1, 1, 3) * _STEP_SIZES[3:6]
+            t["f"] = base["f"] + np.random.uniform(-1, 1) * _STEP_SIZES[6]
+            t["cx"] = base["cx"] + np.random.uniform(-1, 1) * _STEP_SIZES[7]
+            t["cy"] = base["cy"] + np.random.uniform(-1, 1) * _STEP_SIZES[8]
+            if self.lock_xy_equal:
+                t["cam_pos"][:2] = t["target"][:2]
+            trials.append(t)
+        scores = self.iou_batch([base] + trials)
+        best_iou, best_p = scores[0], base
+        for s, t in zip(scores[1:], trials):
+            if s > best_iou:
+                best_iou, best_p = s, t
+        self.set_params(best_p)
+        if self.verbose:
+            print(f"Random Done | Best IoU: {best_iou:.4f}")
+        return float(best_iou)
+
+    def _coord_round_trials(self, cam, tgt, scal):
+        """All trials of one coordinate-descent round assuming no improvement, with the reference's aliasing: the
+        cam_pos/target arrays are shared by every parameter dict, so each -20 / +20 pair is applied IN PLACE (and its
+        floating-point residue, if any, stays).  Returns the parameter snapshots as evaluated."""
+        out = []
+        for k in _SLIDER_KEYS:
+            for delta in (-20, 20):
+                sc = dict(scal)
+                if k.startswith("cam_") and not self.lock_xy_equal:
+                    cam["xyz".index(k[-1])] += delta
+                elif k.startswith("target_"):
+                    tgt["xyz".index(k[-1])] += delta
+                    if self.lock_xy_equal and k in ("target_x", "target_y"):
+                        cam["xyz".index(k[-1])] += delta
+                elif k in ("f", "cx", "cy"):
+                    sc[k] = sc[k] + delta
+                else:
+                    continue
+                out.append({"cam_pos": cam.copy(), "target": tgt.copy(), "f": sc["f"], "cx": sc["cx"], "cy": sc["cy"],
+                            "H": self.H, "W": self.W})
+        return out
+
+    def run_coord(self, steps=5):
+        state = self.get_params()
+        best_iou = self.iou(state)
+        cam, tgt = state["cam_pos"], state["target"]                 # the arrays every dict of the reference shares
+        scal = {k: state[k] for k in ("f", "cx", "cy")}
+        for _ in range(int(steps)):
+            trials = self._coord_round_trials(cam, tgt, scal)
+            if not trials:
+                break
+            scores = self.iou_batch(trials)
+            hit = next((i for i, s in enumerate(scores) if s > best_iou), None)
+            if hit is not None:                                       # first improvement ends the round (:679-683)
+                best_iou = float(scores[hit])
+                cam, tgt = trials[hit]["cam_pos"].copy(), trials[hit]["target"].copy()
+                scal = {k: trials[hit][k] for k in ("f", "cx", "cy")}
+        self.set_params({"cam_pos": cam, "target": tgt, **scal})
+        if self.verbose:
+            print(f"Coord Descent Done | Best IoU: {best_iou:.4f}")
+        return float(best_iou)
+
+    def _to_vector(self, p):
+        if self.lock_xy_equal:
+            return np.array([p["cam_pos"][2], p["target"][2], p["f"], p["cx"], p["cy"]])
+        return np.concatenate([p["cam_pos"], p["target"], [p["f"], p["cx"], p["cy"]]])
+
+    def _from_vector(self, x):
+        if self.lock_xy_equal:
+            tx, ty = self.sliders["target_x"], self.sliders["target_y"]
+            return {"cam_pos": np.array([tx, ty, x[0]]), "target": np.array([tx, ty, x[1]]), "f": x[2], "cx": x[3],
+                    "cy": x[4], "H": self.H, "W": self.W}
+        return {"cam_pos": x[:3], "target": x[3:6], "f": x[6], "cx": x[7], "cy": x[8], "H": self.H, "W": self.W}
+
+    def run_powell(self, maxiter=5):
+        from scipy.optimize import minimize
+        x0 = self._to_vector(self.get_params())
+        res = minimize(lambda x: self.evaluate(self._from_vector(x)), x0, method="Powell",
+                       options={"maxiter": int(maxiter), "maxfev": int(maxiter) * 10, "xtol": 1e-3, "ftol": 1e-3,
+                                "disp": bool(self.verbose)})
+        p = self._from_vector(res.x)
+        iou = self.iou(p)
+        self.set_params(p)
+        if self.verbose:
+            print(f"Powell Done | Best IoU: {iou:.4f}")
+        return iou
+
+    # ---- Save / Load / Init buttons --------------------------------------------------------------
+    def save(self):
+        self.saved_params.clear()
+        self.saved_params.update(self.get_params())
+        return self.saved_params
+
+    def load(self):
+        self.set_params(self.saved_params)
+
+    def reset(self):
+        self.set_params(self.orig_init)
+
+
+def launch_smart_aligner(voxel_grid, image, part_colors, parts_for_alignment=["plinth", "minarets"], init_params=None,
+                         lock_xy_equal=False, device=None):
+    """camera_estimation.py:479-768 without the ipywidgets UI: returns the `saved_params` dict like the reference and
+    attaches the SmartAligner that fills it (`saved_params.aligner`), so a notebook can drive
+    `.run_random() / .run_coord() / .run_powell() / .save()` where the buttons used to be."""
+    aligner = SmartAligner(voxel_grid, image, part_colors, parts_for_alignment, init_params, lock_xy_equal, device)
+
+    class _Saved(dict):
+        pass
+
+    saved = _Saved()
+    aligner.saved_params = saved
+    saved.aligner = aligner
+    return saved
+
+
+def partwise_projection_iou(voxel_grid, part_colors, image, cam_params, device=None):
+    """Scoring core of visualize_voxel_projection_iou (camera_estimation.py:381-403, 433-447): every part of
+    `part_colors` rendered on its own and compared with its colour in `image`, plus the combined binary IoU against
+    any(image != background).  Returns (dict part -> IoU for the parts that have voxels, combined IoU, counts)."""
+    parts = list(part_colors.keys())
+    scorer = CandidateScorer(voxel_grid, image, part_colors, parts, mode="per_part", device=device)
+    _, counts, _ = scorer.score(params_to_row(cam_params)[None])
+    labels_present = set(torch.unique(scorer.pt_label).cpu().tolist())
+    per_part = {}
+    for i, name in enumerate(parts):
+        if scorer.label_of[name] in labels_present:            # the reference skips parts without voxels (:383-385)
+            per_part[name] = iou_from_counts(counts[0, i, 0], counts[0, i, 1])
+    combined = iou_from_counts(counts[0, -1, 0], counts[0, -1, 1])
+    return per_part, combined, counts[0]
+
+
+def visualize_voxel_projection_iou(voxel_grid, part_colors, image, cam_params, mode="part_on_whole", save=False,
+                                   save_root="visualisation", device=None):
+    """camera_estimation.py:346-477.  The figures are out of scope; the numbers the figures are titled with are
+    printed instead: per-part IoU for the `part_*` modes, the combined binary IoU for `whole_on_whole`."""
+    per_part, combined, _ = partwise_projection_iou(voxel_grid, part_colors, image, cam_params, device=device)
+    if mode in ("part_on_whole", "part_on_part"):
+        for name, iou in per_part.items():
+            print(f"{name} | IoU: {iou:.3f}")
+    if mode == "whole_on_whole":
+        print("Visualizing combined binary projection vs. binary ground-truth...")
+        print(f"Combined Binary | IoU: {combined:.3f}")
+    return per_part, combined

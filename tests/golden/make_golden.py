@@ -276,9 +276,83 @@ def carve_golden():
     np.savez_compressed(os.path.join(HERE, "carve_golden.npz"), **out)
 
 
+
+
+def aligner_golden():
+    """Drive the live launch_smart_aligner (camera_estimation.py:479-768) through fake widgets and record where the
+    three optimisers end up."""
+    import _fake_widgets as fw
+    ce = ref.ce
+    ce.widgets = fw
+    ce.display = lambda *a, **k: None
+    ce.clear_output = lambda *a, **k: None
+    grid = np.load(os.path.join(ref.root, "results/1.Orthographic_Voxel_Carving/Taj_voxel_grid.npz"))["voxel_grid"]
+    grid = np.ascontiguousarray(grid[::2, ::2, ::2])               # 256x139x256: keeps the run short
+    front = ref.mu.load_mask(os.path.join(ref.root, "data"), "Taj", "front", int(np.max(grid.shape)))
+    kp = json.load(open(os.path.join(ref.root, "results/2.Perspective_Camera_Estimation/Taj_camera_params_kp.json")))["front"]
+    init = {"cam_pos": np.array(kp["cam_pos"]) / 2, "target": np.array(kp["target"]) / 2, "f": kp["f"] / 2,
+            "cx": kp["cx"] / 2, "cy": kp["cy"] / 2}
+    parts = ["front_minarets", "back_minarets"]
+    out = {"grid": grid, "image": front, "init": np.array([*init["cam_pos"], *init["target"], init["f"], init["cx"], init["cy"]])}
+
+    def snapshot(sliders):
+        return np.array([sliders[k].value for k in ["cam_x", "cam_y", "cam_z", "target_x", "target_y", "target_z", "f", "cx", "cy"]])
+
+    for lock in (False, True):
+        fw.Button.instances.clear()
+        captured = {}
+        orig_vbox = fw.VBox
+
+        def grab(children):
+            captured["layout"] = children
+            return orig_vbox(children)
+
+        fw.VBox = grab
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            saved = ce.launch_smart_aligner(grid, front, C.PART_COLORS, parts_for_alignment=parts,
+                                            init_params={k: (v.copy() if hasattr(v, "copy") else v) for k, v in init.items()},
+                                            lock_xy_equal=lock)
+        fw.VBox = orig_vbox
+        btn = {b.description: b for b in fw.Button.instances}
+        rows = captured["layout"]
+        sliders = {}
+        for row in rows[:4]:
+            for w in row.children:
+                sliders[w.description] = w
+        steps = {w.description: w for w in rows[5].children}
+        tag = "lock" if lock else "free"
+        np.random.seed(1234)
+        steps["Random Steps"].value = 12
+        with contextlib.redirect_stdout(buf):
+            btn["Random Search"].click()
+        out[f"{tag}_after_random"] = snapshot(sliders)
+        steps["Coord Steps"].value = 4
+        with contextlib.redirect_stdout(buf):
+            btn["Coordinate Descent"].click()
+        out[f"{tag}_after_coord"] = snapshot(sliders)
+        steps["Powell MaxIter"].value = 2
+        with contextlib.redirect_stdout(buf):
+            btn["Powell"].click()
+        out[f"{tag}_after_powell"] = snapshot(sliders)
+        with contextlib.redirect_stdout(buf):
+            btn["Save"].click()
+        out[f"{tag}_saved"] = np.array([*saved["cam_pos"], *saved["target"], saved["f"], saved["cx"], saved["cy"]])
+        out[f"{tag}_log"] = np.array("\n".join(l for l in buf.getvalue().split("\n") if "Done" in l))
+        print(tag, out[f"{tag}_log"])
+    np.savez_compressed(os.path.join(HERE, "aligner_golden.npz"), **out)
+
+
 if __name__ == "__main__":
-    copy_assets()
-    camera_golden()
-    carve_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz"):
-        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner"]
+    if "assets" in which:
+        copy_assets()
+    if "camera" in which:
+        camera_golden()
+    if "carve" in which:
+        carve_golden()
+    if "aligner" in which:
+        aligner_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz"):
+        if os.path.exists(os.path.join(HERE, f)):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
