@@ -315,14 +315,22 @@ def carve_bench(N, dev, peak):
     m_hw = torch.from_numpy(binm).to(dev)
     kout = torch.empty((N, N, N, 3), dtype=torch.uint8, device=dev)
     kms = None
-    if foldable:
+    bits = vc._fold_bits(table, N, N, (N, N, M.tobytes(), off.tobytes(), str(dev))) if foldable else None
+    if bits is not None:
+        wpr = (N + 31) // 32 + 2
+        mbits = torch.empty((N, wpr), dtype=torch.int32, device=dev)
+        nv.check(nv.lib.p3d_pack_mask_bits(nv.ptr(m_hw), N, N, nv.ptr(mbits), wpr, nv.stream_ptr()))
+
+        def launch():
+            nv.check(nv.lib.p3d_global_carve_fold_bits(N, N, N, nv.ptr(bits[0]), bits[1], nv.ptr(mbits), wpr, nv.ptr(ext), 1,
+                                                       nv.ptr(kout), nv.stream_ptr()))
         for _ in range(3):
-            nv.check(nv.lib.p3d_global_carve_fold(N, N, N, nv.ptr(table), nv.ptr(m_hw), nv.ptr(ext), 1, nv.ptr(kout), nv.stream_ptr()))
+            launch()
         torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
         for _ in range(10):
-            nv.check(nv.lib.p3d_global_carve_fold(N, N, N, nv.ptr(table), nv.ptr(m_hw), nv.ptr(ext), 1, nv.ptr(kout), nv.stream_ptr()))
+            launch()
         k1.record()
         torch.cuda.synchronize()
         kms = k0.elapsed_time(k1) / 10
@@ -332,7 +340,7 @@ def carve_bench(N, dev, peak):
            "occupied": int(torch.count_nonzero(out.view(-1, 3).any(dim=1)).item()),
            "kernel_gvoxel_s": round(kgvox, 2) if kgvox else None, "kernel_ms": round(kms, 4) if kms else None,
            "roofline": {"bound": "hbm", "achieved": round(3 * kgvox, 1) if kgvox else None, "peak": peak, "unit": "GB/s",
-                        "frac": round(3 * kgvox / peak, 4) if kgvox else None, "kernel": "global_fold_kernel<RGB>",
+                        "frac": round(3 * kgvox / peak, 4) if kgvox else None, "kernel": "global_fold_bits_kernel<RGB>",
                         "note": "3 B per output voxel (RGB grid written once, SURVEY 8d), kernel-only; "
                                 "global_carve_gvoxel_s is the whole Python call (mask upload, table lookup, launch)"}}
     del out, kout

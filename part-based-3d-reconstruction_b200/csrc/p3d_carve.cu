@@ -221,6 +221,122 @@ global_fold_kernel(int W, int H, int D, const int32_t* __restrict__ table, const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Bit-level fast path of the fused global_carve kernel.  When the fold table is "z-separable" -- every in-range
+// entry satisfies src0(x,z) = c - z for one constant c (checked by fold_analyse_kernel on the actual table, true
+// for the 90-degree pass) -- the 16 mask lookups of a thread are 16 consecutive bits of the bit-packed mask row,
+// read in reverse, and the 16 table lookups collapse to 16 bits of an "inside" bit matrix.
+//   inside_bits : (W, D/32) uint32, bit z%32 of word [x][z/32] = table[x][z] >= 0
+//   mask_bits   : (H, wpr) uint32 with one zero word of padding on each side: pixel x is bit (x+32)%32 of word
+//                 [y][(x+32)/32]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fold_analyse_kernel(const int32_t* __restrict__ table, int W, int D, uint32_t* __restrict__ inside_bits,
+                    int* __restrict__ info /* [0] = max(src0+z), [1] = min(src0+z) over in-range entries */) {
+  const int words = D >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per (x, word)
+  if (i >= W * words) return;
+  const int x = i / words, w = i - x * words;
+  uint32_t bits = 0;
+  int mx = -0x7fffffff, mn = 0x7fffffff;
+  for (int j = 0; j < 32; ++j) {
+    const int z = w * 32 + j;
+    const int32_t e = table[(size_t)x * D + z];
+    if (e >= 0) {
+      bits |= 1u << j;
+      const int c = (e >> 16) + z;
+      mx = max(mx, c);
+      mn = min(mn, c);
+    }
+  }
+  inside_bits[i] = bits;
+  if (bits) { atomicMax(info, mx); atomicMin(info + 1, mn); }
+}
+
+__global__ void __launch_bounds__(256)
+pack_mask_bits_kernel(const uint8_t* __restrict__ mask_hw, int H, int W, int wpr, uint32_t* __restrict__ bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per output word
+  if (i >= H * wpr) return;
+  const int y = i / wpr, w = i - y * wpr;
+  uint32_t v = 0;
+  const int x0 = (w - 1) * 32;                                  // one word of left padding
+  for (int j = 0; j < 32; ++j) {
+    const int x = x0 + j;
+    if (x >= 0 && x < W && mask_hw[(size_t)y * W + x]) v |= 1u << j;
+  }
+  bits[i] = v;
+}
+
+template <bool RGB>
+__global__ void __launch_bounds__(256)
+global_fold_bits_kernel(int W, int H, int D, const uint32_t* __restrict__ inside_bits, int c,
+                        const uint32_t* __restrict__ mask_bits, int wpr, const uint8_t* __restrict__ colour_hw,
+                        uint8_t* __restrict__ out) {
+  __shared__ uint4 stage[8][96];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t groups = (int64_t)W * H * D / 16;
+  const int64_t warp_groups = (groups + 31) / 32;
+  const int words = D >> 5;
+  for (int64_t wg = (int64_t)blockIdx.x * 8 + warp; wg < warp_groups; wg += (int64_t)gridDim.x * 8) {
+    const int64_t g = wg * 32 + lane;
+    uint32_t bits = 0, col = 0;
+    if (g < groups) {
+      const int64_t v0 = g * 16;
+      const int z0 = (int)(v0 % D);
+      const int64_t r = v0 / D;
+      const int y = (int)(r % H), x = (int)(r / H);
+      const uint32_t* mrow = mask_bits + (size_t)y * wpr;
+      const int xb = x + 32;
+      if ((__ldg(mrow + (xb >> 5)) >> (xb & 31)) & 1u) {
+        const uint32_t in16 = (__ldg(inside_bits + (size_t)x * words + (z0 >> 5)) >> (z0 & 31)) & 0xffffu;
+        // mask pixels c - z for z = z0 .. z0+15  ==  bits [lo, lo+16) of the row read backwards, lo = c - z0 - 15
+        const int lo = c - z0 - 15 + 32;                        // + padding; in [0, 32*wpr - 16] when in16 != 0
+        uint32_t m16 = 0;
+        if (in16 && lo >= 0 && (lo >> 5) + 1 < wpr) {
+          const uint32_t w0 = __ldg(mrow + (lo >> 5)), w1 = __ldg(mrow + (lo >> 5) + 1);
+          m16 = __funnelshift_r(w0, w1, lo & 31) & 0xffffu;
+        }
+        bits = in16 & (__brev(m16) >> 16);
+        if (RGB) {
+          const uint8_t* cc = colour_hw + ((size_t)y * W + x) * 3;
+          col = cc[0] | (cc[1] << 8) | (cc[2] << 16);
+        } else {
+          col = colour_hw[(size_t)y * W + x];
+        }
+      }
+    }
+    if (RGB) {
+      const uint32_t r8 = col & 0xff, g8 = (col >> 8) & 0xff, b8 = (col >> 16) & 0xff;
+      const uint32_t w0 = r8 | (g8 << 8) | (b8 << 16) | (r8 << 24);
+      const uint32_t w1 = g8 | (b8 << 8) | (r8 << 16) | (g8 << 24);
+      const uint32_t w2 = b8 | (r8 << 8) | (g8 << 16) | (b8 << 24);
+      uint32_t o[12];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) expand4((bits >> (4 * q)) & 0xfu, w0, w1, w2, o + 3 * q);
+      uint4* mine = &stage[warp][lane * 3];
+      mine[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      mine[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      mine[2] = make_uint4(o[8], o[9], o[10], o[11]);
+      __syncwarp();
+      uint4* dst = reinterpret_cast<uint4*>(out) + wg * 96;
+      const int64_t limit = groups * 3;
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        if (wg * 96 + p * 32 + lane < limit) __stcs(dst + p * 32 + lane, stage[warp][p * 32 + lane]);
+      __syncwarp();
+    } else if (g < groups) {
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t b = (bits >> (4 * q)) & 0xfu;
+        o[q] = (col * 0x01010101u) & ((b & 1u ? 0xffu : 0u) | (b & 2u ? 0xff00u : 0u) | (b & 4u ? 0xff0000u : 0u) |
+                                     (b & 8u ? 0xff000000u : 0u));
+      }
+      __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
 // Scalar path for any D.
 template <bool RGB>
 __global__ void __launch_bounds__(256)
@@ -698,6 +814,45 @@ P3D_API int p3d_mask_carve(const uint8_t* grid, int W, int H, int D, int channel
   P3D_REQUIRE(grid && mask_wh && out, "mask_carve: null pointer");
   mask_carve_kernel<<<grid_for(n * channels, 256, 16), 256, 0, p3d::as_stream(stream)>>>(grid, n, D, channels, mask_wh,
                                                                                       mask_channels, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_fold_analyse(const int32_t* table, int W, int D, uint32_t* inside_bits, int* info, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && D > 0 && D % 32 == 0, "fold_analyse: D must be a multiple of 32");
+  P3D_REQUIRE(table && inside_bits && info, "fold_analyse: null pointer");
+  cudaStream_t st = p3d::as_stream(stream);
+  const int init[2] = {-0x7fffffff, 0x7fffffff};
+  P3D_CUDA(cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int n = W * (D / 32);
+  fold_analyse_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, W, D, inside_bits, info);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_pack_mask_bits(const uint8_t* mask_hw, int H, int W, uint32_t* bits, int words_per_row,
+                               p3d_stream_t stream) {
+  P3D_REQUIRE(H > 0 && W > 0 && words_per_row >= (W + 31) / 32 + 2, "pack_mask_bits: words_per_row too small");
+  P3D_REQUIRE(mask_hw && bits, "pack_mask_bits: null pointer");
+  const int n = H * words_per_row;
+  pack_mask_bits_kernel<<<(n + 255) / 256, 256, 0, p3d::as_stream(stream)>>>(mask_hw, H, W, words_per_row, bits);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_global_carve_fold_bits(int W, int H, int D, const uint32_t* inside_bits, int c,
+                                       const uint32_t* mask_bits, int words_per_row, const uint8_t* colour_hw, int rgb,
+                                       uint8_t* out, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0, "global_carve_fold_bits: D must be a multiple of 32");
+  P3D_REQUIRE(words_per_row >= (W + 31) / 32 + 2, "global_carve_fold_bits: words_per_row too small");
+  P3D_REQUIRE(inside_bits && mask_bits && colour_hw && out, "global_carve_fold_bits: null pointer");
+  P3D_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "global_carve_fold_bits: out must be 16-byte aligned");
+  const int64_t n = (int64_t)W * H * D;
+  const int64_t warp_groups = (n / 16 + 31) / 32;
+  const int blocks = grid_for(warp_groups, 8, 32);
+  cudaStream_t st = p3d::as_stream(stream);
+  if (rgb) global_fold_bits_kernel<true><<<blocks, 256, 0, st>>>(W, H, D, inside_bits, c, mask_bits, words_per_row, colour_hw, out);
+  else global_fold_bits_kernel<false><<<blocks, 256, 0, st>>>(W, H, D, inside_bits, c, mask_bits, words_per_row, colour_hw, out);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

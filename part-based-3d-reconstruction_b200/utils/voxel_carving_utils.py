@@ -112,6 +112,26 @@ def _fold_table(n0, n2, M, off, dev):
     return res
 
 
+_FOLD_BITS_CACHE = {}
+
+
+def _fold_bits(table, W, D, cache_key):
+    """(inside_bits (W, D/32) int32 tensor, c) when the table is z-separable (src0 = c - z), else None.  Cached."""
+    hit = _FOLD_BITS_CACHE.get(cache_key)
+    if hit is not None:
+        return hit if hit[0] is not None else None
+    inside = torch.empty((W, D // 32), dtype=torch.int32, device=table.device)
+    info = torch.empty(2, dtype=torch.int32, device=table.device)
+    check(lib.p3d_fold_analyse(ptr(table), W, D, ptr(inside), ptr(info), stream_ptr()), "p3d_fold_analyse")
+    _launched()
+    mx, mn = (int(v) for v in info.cpu())
+    res = (inside, mx) if mx == mn else (None, None)
+    if len(_FOLD_BITS_CACHE) >= 16:
+        _FOLD_BITS_CACHE.pop(next(iter(_FOLD_BITS_CACHE)))
+    _FOLD_BITS_CACHE[cache_key] = res
+    return res if res[0] is not None else None
+
+
 def _process_device(vol, mask_wh, angle_interval):
     """process_voxel_grid on device tensors: vol (n0,n1,n2) u8, mask_wh (n0,n1) u8 -> carved (n0,n1,n2) u8."""
     n0, n1, n2 = vol.shape
@@ -385,9 +405,18 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
             if foldable:
                 m_hw = torch.from_numpy(np.ascontiguousarray(m_wh.T).astype(np.uint8)).to(dev)
                 out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
-                check(lib.p3d_global_carve_fold(W, H, D, ptr(table), ptr(m_hw), ptr(col), 1, ptr(out), stream_ptr()),
-                      "p3d_global_carve_fold")
-                _launched()
+                bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
+                if bits is not None:                      # z-separable table: bit-packed mask, 10x fewer loads
+                    wpr = (W + 31) // 32 + 2
+                    mbits = torch.empty((H, wpr), dtype=torch.int32, device=dev)
+                    check(lib.p3d_pack_mask_bits(ptr(m_hw), H, W, ptr(mbits), wpr, stream_ptr()), "p3d_pack_mask_bits")
+                    check(lib.p3d_global_carve_fold_bits(W, H, D, ptr(bits[0]), bits[1], ptr(mbits), wpr, ptr(col), 1,
+                                                         ptr(out), stream_ptr()), "p3d_global_carve_fold_bits")
+                    _launched(2)
+                else:
+                    check(lib.p3d_global_carve_fold(W, H, D, ptr(table), ptr(m_hw), ptr(col), 1, ptr(out),
+                                                    stream_ptr()), "p3d_global_carve_fold")
+                    _launched()
     if out is None:
         vol = torch.ones((W, H, D), dtype=torch.uint8, device=dev)
         carved = _process_device(vol, torch.from_numpy(m_wh.astype(np.uint8)).to(dev), angle_interval)
