@@ -322,7 +322,7 @@ def carve_bench(N, dev, peak):
         nv.check(nv.lib.p3d_pack_mask_bits(nv.ptr(m_hw), N, N, nv.ptr(mbits), wpr, nv.stream_ptr()))
 
         def launch():
-            nv.check(nv.lib.p3d_global_carve_fold_bits(N, N, N, nv.ptr(bits[0]), bits[1], nv.ptr(mbits), wpr, nv.ptr(ext), 1,
+            nv.check(nv.lib.p3d_global_carve_fold_bits(N, N, N, 0, N, nv.ptr(bits[0]), bits[1], nv.ptr(mbits), wpr, nv.ptr(ext), 1,
                                                        nv.ptr(kout), nv.stream_ptr()))
         for _ in range(3):
             launch()

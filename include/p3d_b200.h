@@ -192,11 +192,13 @@ int p3d_global_carve_fold(int W, int H, int D, const int32_t* table, const uint8
  * for the 90-degree pass).  p3d_fold_analyse packs table >= 0 into inside_bits (W, D/32) and writes
  * info = [max, min] of src0 + z over the in-range entries (separable iff max == min =: c).  p3d_pack_mask_bits packs
  * mask_hw (H,W) into rows of words_per_row >= ceil(W/32) + 2 words with one zero word of padding on each side.
- * D must be a multiple of 32 and out 16-byte aligned.  Same output bytes as p3d_global_carve_fold. */
+ * D must be a multiple of 32 and out 16-byte aligned.  Same output bytes as p3d_global_carve_fold.
+ * [x_begin, x_begin + x_count) selects an x-slab: out is then the (x_count,H,D[,3]) slab -- the unit of multi-GPU
+ * sharding (each output voxel depends only on the 2-D masks, so slabs need no exchange). */
 int p3d_fold_analyse(const int32_t* table, int W, int D, uint32_t* inside_bits, int* info, p3d_stream_t stream);
 int p3d_pack_mask_bits(const uint8_t* mask_hw, int H, int W, uint32_t* bits, int words_per_row,
                        p3d_stream_t stream);
-int p3d_global_carve_fold_bits(int W, int H, int D, const uint32_t* inside_bits, int c,
+int p3d_global_carve_fold_bits(int W, int H, int D, int x_begin, int x_count, const uint32_t* inside_bits, int c,
                                const uint32_t* mask_bits, int words_per_row, const uint8_t* colour_hw, int rgb,
                                uint8_t* out, p3d_stream_t stream);
 /* carve_voxel_grid_with_masks :76-97: out = where(mask, grid, 0).  grid (W,H,D[,3]) with channels = 1 or 3;

@@ -269,12 +269,12 @@ pack_mask_bits_kernel(const uint8_t* __restrict__ mask_hw, int H, int W, int wpr
 
 template <bool RGB>
 __global__ void __launch_bounds__(256)
-global_fold_bits_kernel(int W, int H, int D, const uint32_t* __restrict__ inside_bits, int c,
+global_fold_bits_kernel(int W, int H, int D, int x_begin, int x_count, const uint32_t* __restrict__ inside_bits, int c,
                         const uint32_t* __restrict__ mask_bits, int wpr, const uint8_t* __restrict__ colour_hw,
                         uint8_t* __restrict__ out) {
   __shared__ uint4 stage[8][96];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t groups = (int64_t)W * H * D / 16;
+  const int64_t groups = (int64_t)x_count * H * D / 16;
   const int64_t warp_groups = (groups + 31) / 32;
   const int words = D >> 5;
   for (int64_t wg = (int64_t)blockIdx.x * 8 + warp; wg < warp_groups; wg += (int64_t)gridDim.x * 8) {
@@ -284,7 +284,7 @@ global_fold_bits_kernel(int W, int H, int D, const uint32_t* __restrict__ inside
       const int64_t v0 = g * 16;
       const int z0 = (int)(v0 % D);
       const int64_t r = v0 / D;
-      const int y = (int)(r % H), x = (int)(r / H);
+      const int y = (int)(r % H), x = x_begin + (int)(r / H);
       const uint32_t* mrow = mask_bits + (size_t)y * wpr;
       const int xb = x + 32;
       if ((__ldg(mrow + (xb >> 5)) >> (xb & 31)) & 1u) {
@@ -840,19 +840,21 @@ P3D_API int p3d_pack_mask_bits(const uint8_t* mask_hw, int H, int W, uint32_t* b
   return P3D_OK;
 }
 
-P3D_API int p3d_global_carve_fold_bits(int W, int H, int D, const uint32_t* inside_bits, int c,
+P3D_API int p3d_global_carve_fold_bits(int W, int H, int D, int x_begin, int x_count, const uint32_t* inside_bits, int c,
                                        const uint32_t* mask_bits, int words_per_row, const uint8_t* colour_hw, int rgb,
                                        uint8_t* out, p3d_stream_t stream) {
   P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0, "global_carve_fold_bits: D must be a multiple of 32");
+  P3D_REQUIRE(x_begin >= 0 && x_count >= 0 && x_begin + x_count <= W, "global_carve_fold_bits: bad x slab");
+  if (x_count == 0) return P3D_OK;
   P3D_REQUIRE(words_per_row >= (W + 31) / 32 + 2, "global_carve_fold_bits: words_per_row too small");
   P3D_REQUIRE(inside_bits && mask_bits && colour_hw && out, "global_carve_fold_bits: null pointer");
   P3D_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "global_carve_fold_bits: out must be 16-byte aligned");
-  const int64_t n = (int64_t)W * H * D;
+  const int64_t n = (int64_t)x_count * H * D;
   const int64_t warp_groups = (n / 16 + 31) / 32;
   const int blocks = grid_for(warp_groups, 8, 32);
   cudaStream_t st = p3d::as_stream(stream);
-  if (rgb) global_fold_bits_kernel<true><<<blocks, 256, 0, st>>>(W, H, D, inside_bits, c, mask_bits, words_per_row, colour_hw, out);
-  else global_fold_bits_kernel<false><<<blocks, 256, 0, st>>>(W, H, D, inside_bits, c, mask_bits, words_per_row, colour_hw, out);
+  if (rgb) global_fold_bits_kernel<true><<<blocks, 256, 0, st>>>(W, H, D, x_begin, x_count, inside_bits, c, mask_bits, words_per_row, colour_hw, out);
+  else global_fold_bits_kernel<false><<<blocks, 256, 0, st>>>(W, H, D, x_begin, x_count, inside_bits, c, mask_bits, words_per_row, colour_hw, out);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

@@ -65,7 +65,7 @@ _SIGNATURES = {
     "p3d_global_carve_fold": ([_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp], _i32),
     "p3d_fold_analyse": ([_vp, _i32, _i32, _vp, _vp, _vp], _i32),
     "p3d_pack_mask_bits": ([_vp, _i32, _i32, _vp, _i32, _vp], _i32),
-    "p3d_global_carve_fold_bits": ([_i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp], _i32),
+    "p3d_global_carve_fold_bits": ([_i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp], _i32),
     "p3d_mask_carve": ([_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
     "p3d_colourise": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "p3d_part_carve_fold": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),

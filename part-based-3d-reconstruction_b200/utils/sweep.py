@@ -110,3 +110,27 @@ def score_candidates_sharded(scorer, candidates, group=None, gather_scores=False
         out = out.cpu().numpy()
         scores = np.concatenate([out[r, :h - l] for r, (l, h) in enumerate(sizes)])
     return best_score, best_index, scores, (lo, hi)
+
+
+def carve_sharded(carve_slab, W: int, group=None, gather: bool = False):
+    """Carve a (W,H,D,3) grid in x-slabs, one contiguous slab per rank (global_carve's output at [x,y,z] depends only
+    on the 2-D masks, so there is no exchange).  `carve_slab(x0, x1)` returns this rank's (x1-x0,H,D,3) uint8 tensor,
+    e.g. `lambda a, b: global_carve(binary, sem_ext, 90, return_tensor=True, x_range=(a, b))`.
+
+    Returns (slab, (x0, x1)), or with gather=True the full grid on every rank (one all-gather of equal-size padded
+    slabs; NCCL on GPUs, gloo on CPUs)."""
+    inited = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if inited else 1
+    rank = dist.get_rank(group) if inited else 0
+    x0, x1 = shard_range(W, world, rank)
+    slab = carve_slab(x0, x1)
+    if not gather or world == 1:
+        return slab, (x0, x1)
+    spans = [shard_range(W, world, r) for r in range(world)]
+    width = max(b - a for a, b in spans)
+    padded = slab.new_zeros((width,) + tuple(slab.shape[1:]))
+    padded[:x1 - x0] = slab
+    out = slab.new_empty((world * width,) + tuple(slab.shape[1:]))
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    full = torch.cat([out[r * width:r * width + (b - a)] for r, (a, b) in enumerate(spans)], dim=0)
+    return full, (0, W)

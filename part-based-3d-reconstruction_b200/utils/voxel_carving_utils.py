@@ -381,10 +381,13 @@ def recolor_backward_components(voxel_grid, color, new_color, k=4, sort_axis=2):
 
 
 def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=4, visualize=False,
-                 device=None, return_tensor=False):
+                 device=None, return_tensor=False, x_range=None):
     """voxel_carving_utils.py:269-298: start from a full (w,h,w) grid, carve it with the binary front mask under
     4-way symmetry (rotate-and-carve every `angle_interval` degrees), then colour every surviving voxel with
-    the semantic colour of its (x,y) pixel.  Returns the (W,H,D=W,3) uint8 grid."""
+    the semantic colour of its (x,y) pixel.  Returns the (W,H,D=W,3) uint8 grid.
+
+    Extension (keyword-only in spirit): `x_range=(x0, x1)` returns only the x-slab `[x0:x1]` of that grid -- the unit
+    of multi-GPU sharding (utils.sweep.carve_sharded); supported on the 90-degree fast path."""
     as_tensor = return_tensor or _is_tensor(binary_mask)
     dev = nv.require_cuda(device if device is not None else (binary_mask.device if _is_tensor(binary_mask) and binary_mask.is_cuda else None))
     bm = binary_mask.cpu().numpy() if _is_tensor(binary_mask) else np.asarray(binary_mask)
@@ -396,6 +399,9 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
     if tuple(col.shape) != (H, W, 3):
         raise ValueError(f"semantic_mask_exterior {tuple(col.shape)} does not match (H,W,3)=({H},{W},3)")
     m_wh = np.ascontiguousarray(_mask_to_wh(bm != 0, W, H))                          # (W,H) bool
+    x0, x1 = (0, W) if x_range is None else (int(x_range[0]), int(x_range[1]))
+    if not (0 <= x0 <= x1 <= W):
+        raise ValueError(f"x_range {x_range} outside [0, {W}]")
     out = None
     if angle_interval == 90:
         M0, off0 = _pass_transform((W, H, D), 0)
@@ -404,16 +410,18 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
             table, foldable = _fold_table(W, D, M, off, dev)
             if foldable:
                 m_hw = torch.from_numpy(np.ascontiguousarray(m_wh.T).astype(np.uint8)).to(dev)
-                out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
                 bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
                 if bits is not None:                      # z-separable table: bit-packed mask, 10x fewer loads
+                    out = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
                     wpr = (W + 31) // 32 + 2
                     mbits = torch.empty((H, wpr), dtype=torch.int32, device=dev)
                     check(lib.p3d_pack_mask_bits(ptr(m_hw), H, W, ptr(mbits), wpr, stream_ptr()), "p3d_pack_mask_bits")
-                    check(lib.p3d_global_carve_fold_bits(W, H, D, ptr(bits[0]), bits[1], ptr(mbits), wpr, ptr(col), 1,
-                                                         ptr(out), stream_ptr()), "p3d_global_carve_fold_bits")
+                    check(lib.p3d_global_carve_fold_bits(W, H, D, x0, x1 - x0, ptr(bits[0]), bits[1], ptr(mbits), wpr,
+                                                         ptr(col), 1, ptr(out), stream_ptr()), "p3d_global_carve_fold_bits")
                     _launched(2)
+                    x0, x1 = 0, out.shape[0]              # the slab has been applied
                 else:
+                    out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
                     check(lib.p3d_global_carve_fold(W, H, D, ptr(table), ptr(m_hw), ptr(col), 1, ptr(out),
                                                     stream_ptr()), "p3d_global_carve_fold")
                     _launched()
@@ -423,6 +431,8 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
         out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
         check(lib.p3d_colourise(ptr(carved), W, H, D, ptr(col), ptr(out), stream_ptr()), "p3d_colourise")
         _launched()
+    if (x0, x1) != (0, out.shape[0]):
+        out = out[x0:x1].contiguous()                     # general path: slab cut from the full grid
     if visualize:
         warnings.warn("visualize=True is ignored: plotting is outside this package's scope")
     return _ret(out, as_tensor)

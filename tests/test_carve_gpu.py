@@ -185,3 +185,17 @@ def test_global_carve_512_synthetic_vs_oracle(vc, oracle):
     got = vc.global_carve(binm, ext, 90)
     want = oracle.global_carve(binm, ext, 90)
     assert np.array_equal(got, want)
+
+
+def test_x_slabs_tile_the_full_grid(vc, carve_golden):
+    """global_carve(..., x_range) == the same rows of the full grid (the multi-GPU sharding unit), on the bit-packed
+    fast path (D % 32 == 0), the table path and the general-angle path."""
+    g = carve_golden
+    for key, interval in (("syn_sq64", 90), ("syn_rect40x64", 90), ("syn_rect33x48", 90), ("syn_rect40x64", 45)):
+        ext, binm = g[key + "_ext"], g[key + "_bin"]
+        full = vc.global_carve(binm, ext, interval)
+        W = full.shape[0]
+        for a, b in ((0, W), (0, 17), (17, 40), (40, W), (5, 5)):
+            assert np.array_equal(vc.global_carve(binm, ext, interval, x_range=(a, b)), full[a:b]), (key, a, b)
+    with pytest.raises(ValueError):
+        vc.global_carve(g["syn_sq64_bin"], g["syn_sq64_ext"], 90, x_range=(10, 99))

@@ -93,3 +93,29 @@ def test_sharded_sweep_gloo(tmp_path, world, K):
         z = np.load(tmp_path / f"r{r}.npz")
         assert int(z["best_i"]) == want_i and float(z["best_s"]) == full[want_i]
         assert np.array_equal(z["scores"], full)
+
+
+def _carve_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+    from oracle import oracle as orc
+    sw = pkg("utils.sweep")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "carve_golden.npz"))
+    binm, ext = g["syn_rect40x64_bin"], g["syn_rect40x64_ext"]
+    full = orc.global_carve(binm, ext, 90)                       # stands in for the CUDA slab kernel on CPU
+    got, span = sw.carve_sharded(lambda a, b: torch.from_numpy(full[a:b].copy()), full.shape[0], gather=True)
+    np.save(os.path.join(out_dir, f"c{rank}.npy"), got.numpy())
+    slab, (a, b) = sw.carve_sharded(lambda a, b: torch.from_numpy(full[a:b].copy()), full.shape[0])
+    assert (a, b) == sw.shard_range(full.shape[0], world, rank) and np.array_equal(slab.numpy(), full[a:b])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_carve_sharded_gloo(tmp_path, world, carve_golden):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_carve_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"c{r}.npy"), carve_golden["syn_rect40x64_global"])
