@@ -231,13 +231,13 @@ def run_ours(args):
     avg_launch_s = (splat_ms.value / max(1, splat_launches.value)) * 1e-3
     achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "splat_kernel<double,joint>",
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "splat_filtered_kernel<joint> (FP32 filter + exact FP64 queue)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch,
                 "cameras_per_launch": batch, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "splat_share_of_step": round(splat_ms.value / ms, 4),
                 "point_candidates_per_s": round(n_points * batch / avg_launch_s, 1) if avg_launch_s > 0 else None,
-                "note": "streaming model of SURVEY 8(d): dense u8 grid once per camera + 9 B/pixel; the kernel is "
-                        "FP64-issue bound, see DESIGN.md"}
+                "note": "effective GB/s under the streaming model of SURVEY 8(d) (dense u8 grid once per camera + 9 B/pixel); "
+                        "the kernel batches cameras per point pass and is instruction-issue bound, see DESIGN.md 4.1"}
 
     # ---- CPU baseline: NumPy port of the reference path on this box's host cores -----------------
     cpu = None

@@ -155,6 +155,24 @@ int p3d_best_pack(const double* scores, const int64_t* best, int64_t offset, int
                   p3d_stream_t stream);
 int p3d_best_select(const int64_t* pairs, int n, int64_t* out, p3d_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------- *
+ * Depth-buffer visibility evaluator       utils/eval_helpers_intra.py:134-190  (SURVEY 8 f1, next to the path)
+ *   p3d_depth_buffer_*  : compute_global_depth_buffer :134-161 -- zbuf (H,W) float32 = min Z of the points that project
+ *                         into each pixel with Z > 1e-6, +inf elsewhere.  cam = one (16) camera block from
+ *                         p3d_setup_cameras_*.  The f64 variant needs p3d_depth_workspace_bytes(H,W,8) of scratch
+ *                         (64-bit atomicMin on the double's bits), the f32 variant none.
+ *   p3d_part_visible_*  : project_part_visible :168-190 -- mask (H,W) uint8 = 1 where a point lies within eps of zbuf.
+ * --------------------------------------------------------------------------------------------- */
+size_t p3d_depth_workspace_bytes(int H, int W, int elem_bytes);
+int p3d_depth_buffer_f32(const float* pts, int64_t n, const float* cam, int H, int W, float* zbuf, void* workspace,
+                         size_t workspace_bytes, p3d_stream_t stream);
+int p3d_depth_buffer_f64(const float* pts, int64_t n, const double* cam, int H, int W, float* zbuf, void* workspace,
+                         size_t workspace_bytes, p3d_stream_t stream);
+int p3d_part_visible_f32(const float* pts, int64_t n, const float* cam, const float* zbuf, float eps, int H, int W,
+                         uint8_t* mask, p3d_stream_t stream);
+int p3d_part_visible_f64(const float* pts, int64_t n, const double* cam, const float* zbuf, double eps, int H, int W,
+                         uint8_t* mask, p3d_stream_t stream);
+
 /* Measurement hook: while enabled on the calling thread, p3d_sweep_* records a CUDA-event pair on the launch
  * stream around every splat launch; p3d_sweep_timing_read() waits for them, returns the summed splat
  * duration (ms) and the number of launches (host out-pointers), and resets the counters. */

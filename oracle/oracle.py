@@ -360,3 +360,49 @@ def partwise_carve(colored_voxel_grid, semantic_mask_exterior, semantic_mask_ful
         grid = recolor_backward_components(oriented, part_colors_np["front_minarets"],
                                            part_colors_np["back_minarets"], k=2, sort_axis=0)
     return grid
+
+
+# --------------------------------------------------------------------------- #
+# evaluation helper next to the path: depth-buffer visibility
+# --------------------------------------------------------------------------- #
+def _depth_fns():
+    L = lib()
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    for name, ft in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+        z = getattr(L, f"orc_depth_buffer_{name}")
+        v = getattr(L, f"orc_part_visible_{name}")
+        z.argtypes = [vp, i64, vp, vp, ft, ft, ft, i32, i32, vp]
+        v.argtypes = [vp, i64, vp, vp, ft, ft, ft, vp, ft, i32, i32, vp]
+        z.restype = v.restype = None
+    return L
+
+
+def _occupied_points(voxel_grid):
+    g = np.asarray(voxel_grid)
+    flat = np.flatnonzero((g > 0).any(-1))
+    a0, a1, a2 = np.unravel_index(flat, g.shape[:3])
+    return np.stack([a2, a1, a0], axis=1).astype(np.float32)
+
+
+def compute_global_depth_buffer(voxel_grid, cam, H, W):
+    """eval_helpers_intra.py:134-161 (min-Z buffer of every occupied voxel, float32, inf where empty)."""
+    pts = np.ascontiguousarray(_occupied_points(voxel_grid))
+    dt = _working_dtype(pts, cam["cam_pos"], cam["target"])
+    cp, tg = np.ascontiguousarray(cam["cam_pos"], dtype=dt), np.ascontiguousarray(cam["target"], dtype=dt)
+    zbuf = np.empty((H, W), np.float32)
+    fn = getattr(_depth_fns(), "orc_depth_buffer_f32" if dt == np.float32 else "orc_depth_buffer_f64")
+    fn(_p(pts), pts.shape[0], _p(cp), _p(tg), float(cam["f"]), float(cam["cx"]), float(cam["cy"]), int(H), int(W), _p(zbuf))
+    return zbuf
+
+
+def project_part_visible(pts3d, cam, zbuf, H, W, eps=1e-3):
+    """eval_helpers_intra.py:168-190 (pixels where a part point lies within eps of the global depth buffer)."""
+    pts = np.ascontiguousarray(pts3d, dtype=np.float32).reshape(-1, 3)
+    dt = _working_dtype(pts, cam["cam_pos"], cam["target"])
+    cp, tg = np.ascontiguousarray(cam["cam_pos"], dtype=dt), np.ascontiguousarray(cam["target"], dtype=dt)
+    zb = np.ascontiguousarray(zbuf, dtype=np.float32)
+    mask = np.empty((H, W), np.uint8)
+    fn = getattr(_depth_fns(), "orc_part_visible_f32" if dt == np.float32 else "orc_part_visible_f64")
+    fn(_p(pts), pts.shape[0], _p(cp), _p(tg), float(cam["f"]), float(cam["cx"]), float(cam["cy"]), _p(zb),
+       float(np.float32(eps)) if dt == np.float32 else float(eps), int(H), int(W), _p(mask))
+    return mask.astype(bool)

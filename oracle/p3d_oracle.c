@@ -232,3 +232,52 @@ ORC_API int orc_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* lab
   free(parent);
   return next;
 }
+
+/* ------------------------------------------------------------------------- *
+ * Depth-buffer visibility evaluator        utils/eval_helpers_intra.py:134-190
+ *   compute_global_depth_buffer: zbuf[v,u] = min Z over the points with Z > 1e-6 that round into the image
+ *   project_part_visible:        mask[v,u] = 1 if some point there has |Z - zbuf[v,u]| < eps
+ * Projection arithmetic as project_colored_voxels (same NumPy expressions), but points with Z <= 1e-6 are culled
+ * instead of clamped.  zbuf is float32 in the reference; with float64 cameras each accepted Z is rounded to float32
+ * on store, and the final value is float32(min Z) whatever the order (rounding is monotone).
+ * ------------------------------------------------------------------------- */
+#define DEFINE_DEPTH(NAME_Z, NAME_V, T, LOOKAT, FMA, RINT, FABS)                                     \
+  static int NAME_Z##_pix(const float* p, const T* cam_pos, const T* R, T f, T cx, T cy, int H,      \
+                          int W, T* zout) {                                                          \
+    T d0 = (T)p[0] - cam_pos[0], d1 = (T)p[1] - cam_pos[1], d2 = (T)p[2] - cam_pos[2];               \
+    T X = FMA(d2, R[2], FMA(d1, R[1], d0 * R[0]));                                                   \
+    T Y = FMA(d2, R[5], FMA(d1, R[4], d0 * R[3]));                                                   \
+    T Z = FMA(d2, R[8], FMA(d1, R[7], d0 * R[6]));                                                   \
+    if (!(Z > (T)1e-6)) return -1;                                                                   \
+    T q = X / Z; T u = q * f; u = u + cx;                                                            \
+    T r = Y / Z; r = -r; T v = r * f; v = v + cy;                                                    \
+    T ur = RINT(u), vr = RINT(v);                                                                    \
+    if (!(ur >= 0 && ur < (T)W && vr >= 0 && vr < (T)H)) return -1;                                  \
+    *zout = Z;                                                                                       \
+    return (int)vr * W + (int)ur;                                                                    \
+  }                                                                                                  \
+  ORC_API void NAME_Z(const float* pts, int64_t n, const T* cam_pos, const T* target, T f, T cx,     \
+                      T cy, int H, int W, float* zbuf) {                                             \
+    T R[9];                                                                                          \
+    LOOKAT(cam_pos, target, R);                                                                      \
+    for (int i = 0; i < H * W; ++i) zbuf[i] = INFINITY;                                              \
+    for (int64_t i = 0; i < n; ++i) {                                                                \
+      T z;                                                                                           \
+      int p = NAME_Z##_pix(pts + 3 * i, cam_pos, R, f, cx, cy, H, W, &z);                            \
+      if (p >= 0 && z < (T)zbuf[p]) zbuf[p] = (float)z;                                              \
+    }                                                                                                \
+  }                                                                                                  \
+  ORC_API void NAME_V(const float* pts, int64_t n, const T* cam_pos, const T* target, T f, T cx,     \
+                      T cy, const float* zbuf, T eps, int H, int W, uint8_t* mask) {                 \
+    T R[9];                                                                                          \
+    LOOKAT(cam_pos, target, R);                                                                      \
+    memset(mask, 0, (size_t)H * W);                                                                  \
+    for (int64_t i = 0; i < n; ++i) {                                                                \
+      T z;                                                                                           \
+      int p = NAME_Z##_pix(pts + 3 * i, cam_pos, R, f, cx, cy, H, W, &z);                            \
+      if (p >= 0) { T d = z - (T)zbuf[p]; if (FABS(d) < eps) mask[p] = 1; }                          \
+    }                                                                                                \
+  }
+
+DEFINE_DEPTH(orc_depth_buffer_f32, orc_part_visible_f32, float, orc_look_at_f32, fmaf, rintf, fabsf)
+DEFINE_DEPTH(orc_depth_buffer_f64, orc_part_visible_f64, double, orc_look_at_f64, fma, rint, fabs)

@@ -717,6 +717,77 @@ __global__ void __launch_bounds__(256) partwise_counts_rgb_kernel(const uint8_t*
     if (s_acc[i]) atomicAdd(counts + i, (unsigned long long)s_acc[i]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Depth-buffer visibility evaluator (utils/eval_helpers_intra.py:134-190).
+//   depth_buffer_kernel : zbuf[pixel] = min Z over points with Z > 1e-6 that round into the image.  Positive IEEE
+//                         floats order like their bit patterns, so the min is an integer atomicMin on the bits
+//                         (32-bit for float cameras, 64-bit for double cameras) -- order independent.
+//   part_visible_kernel : mask[pixel] = 1 when some point there has |Z - zbuf[pixel]| < eps.
+// Same operation order as exact_splat, but points behind the camera are culled, not clamped.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int depth_project(const float* __restrict__ p, const T* __restrict__ cam, int W, T fW, T fH,
+                                             T* zout) {
+  using F = Fp<T>;
+  const T d0 = F::sub((T)p[0], cam[0]), d1 = F::sub((T)p[1], cam[1]), d2 = F::sub((T)p[2], cam[2]);
+  const T X = F::fma(d2, cam[5], F::fma(d1, cam[4], F::mul(d0, cam[3])));
+  const T Y = F::fma(d2, cam[8], F::fma(d1, cam[7], F::mul(d0, cam[6])));
+  const T Z = F::fma(d2, cam[11], F::fma(d1, cam[10], F::mul(d0, cam[9])));
+  if (!(Z > (T)1e-6)) return -1;
+  const T u = F::add(F::mul(F::div(X, Z), cam[12]), cam[13]);
+  const T v = F::add(F::mul(-F::div(Y, Z), cam[12]), cam[14]);
+  const T ur = F::rint(u), vr = F::rint(v);
+  if (!(ur >= (T)0 && ur < fW && vr >= (T)0 && vr < fH)) return -1;
+  *zout = Z;
+  return (int)vr * W + (int)ur;
+}
+
+template <typename T, typename B>
+__global__ void __launch_bounds__(256) depth_buffer_kernel(const float* __restrict__ pts, int64_t n,
+                                                           const T* __restrict__ cam_g, int H, int W, B* __restrict__ zbits) {
+  __shared__ T cam[16];
+  if (threadIdx.x < 16) cam[threadIdx.x] = cam_g[threadIdx.x];
+  __syncthreads();
+  const T fW = (T)W, fH = (T)H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T z;
+    const int p = depth_project<T>(pts + 3 * i, cam, W, fW, fH, &z);
+    if (p < 0) continue;
+    B bits;
+    if (sizeof(T) == 4) bits = (B)__float_as_uint((float)z); else bits = (B)__double_as_longlong((double)z);
+    if (zbits[p] > bits) atomicMin(zbits + p, bits);
+  }
+}
+
+__global__ void __launch_bounds__(256) depth_fill_kernel(unsigned long long* __restrict__ z64, uint32_t* __restrict__ z32, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (z64) z64[i] = 0x7ff0000000000000ull;                  // +inf
+  else z32[i] = 0x7f800000u;
+}
+
+__global__ void __launch_bounds__(256) depth_narrow_kernel(const unsigned long long* __restrict__ z64, float* __restrict__ zbuf, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) zbuf[i] = (float)__longlong_as_double((long long)z64[i]);   // float32(min Z), round to nearest
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) part_visible_kernel(const float* __restrict__ pts, int64_t n,
+                                                           const T* __restrict__ cam_g, const float* __restrict__ zbuf, T eps,
+                                                           int H, int W, uint8_t* __restrict__ mask) {
+  __shared__ T cam[16];
+  if (threadIdx.x < 16) cam[threadIdx.x] = cam_g[threadIdx.x];
+  __syncthreads();
+  const T fW = (T)W, fH = (T)H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T z;
+    const int p = depth_project<T>(pts + 3 * i, cam, W, fW, fH, &z);
+    if (p < 0) continue;
+    const T d = Fp<T>::sub(z, (T)zbuf[p]);
+    if ((d < (T)0 ? -d : d) < eps) mask[p] = 1;
+  }
+}
+
 inline int grid_for(int64_t items, int threads, int waves) {
   int64_t blocks = (items + threads - 1) / threads;
   int64_t cap = (int64_t)p3d::sm_count() * waves;
@@ -1016,6 +1087,62 @@ P3D_API int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, 
 }
 
 P3D_API int p3d_sweep_last_launches(void) { return g_last_launches; }
+
+P3D_API size_t p3d_depth_workspace_bytes(int H, int W, int elem_bytes) {
+  if (H <= 0 || W <= 0) return 0;
+  return elem_bytes == 8 ? (size_t)H * W * sizeof(unsigned long long) : 0;
+}
+
+template <typename T>
+static int depth_buffer(const float* pts, int64_t n, const T* cam, int H, int W, float* zbuf, void* ws, size_t ws_bytes,
+                        p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && H > 0 && W > 0 && (int64_t)H * W < (1ll << 31), "depth_buffer: bad arguments");
+  P3D_REQUIRE(cam && zbuf && (pts || n == 0), "depth_buffer: null pointer");
+  cudaStream_t st = p3d::as_stream(stream);
+  const int HW = H * W;
+  if (sizeof(T) == 8) {
+    if (ws == nullptr || ws_bytes < (size_t)HW * 8) { p3d::set_error("depth_buffer: workspace too small"); return P3D_E_WORKSPACE; }
+    unsigned long long* z64 = static_cast<unsigned long long*>(ws);
+    depth_fill_kernel<<<(HW + 255) / 256, 256, 0, st>>>(z64, nullptr, HW);
+    if (n) depth_buffer_kernel<T, unsigned long long><<<grid_for(n, 256, 8), 256, 0, st>>>(pts, n, cam, H, W, z64);
+    depth_narrow_kernel<<<(HW + 255) / 256, 256, 0, st>>>(z64, zbuf, HW);
+  } else {
+    uint32_t* z32 = reinterpret_cast<uint32_t*>(zbuf);
+    depth_fill_kernel<<<(HW + 255) / 256, 256, 0, st>>>(nullptr, z32, HW);
+    if (n) depth_buffer_kernel<T, uint32_t><<<grid_for(n, 256, 8), 256, 0, st>>>(pts, n, cam, H, W, z32);
+  }
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+template <typename T>
+static int part_visible(const float* pts, int64_t n, const T* cam, const float* zbuf, T eps, int H, int W, uint8_t* mask,
+                        p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && H > 0 && W > 0 && (int64_t)H * W < (1ll << 31), "part_visible: bad arguments");
+  P3D_REQUIRE(cam && zbuf && mask && (pts || n == 0), "part_visible: null pointer");
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(mask, 0, (size_t)H * W, st));
+  if (n) part_visible_kernel<T><<<grid_for(n, 256, 8), 256, 0, st>>>(pts, n, cam, zbuf, eps, H, W, mask);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_depth_buffer_f32(const float* pts, int64_t n, const float* cam, int H, int W, float* zbuf, void* ws,
+                                 size_t ws_bytes, p3d_stream_t stream) {
+  return depth_buffer<float>(pts, n, cam, H, W, zbuf, ws, ws_bytes, stream);
+}
+P3D_API int p3d_depth_buffer_f64(const float* pts, int64_t n, const double* cam, int H, int W, float* zbuf, void* ws,
+                                 size_t ws_bytes, p3d_stream_t stream) {
+  return depth_buffer<double>(pts, n, cam, H, W, zbuf, ws, ws_bytes, stream);
+}
+P3D_API int p3d_part_visible_f32(const float* pts, int64_t n, const float* cam, const float* zbuf, float eps, int H, int W,
+                                 uint8_t* mask, p3d_stream_t stream) {
+  return part_visible<float>(pts, n, cam, zbuf, eps, H, W, mask, stream);
+}
+P3D_API int p3d_part_visible_f64(const float* pts, int64_t n, const double* cam, const float* zbuf, double eps, int H, int W,
+                                 uint8_t* mask, p3d_stream_t stream) {
+  return part_visible<double>(pts, n, cam, zbuf, eps, H, W, mask, stream);
+}
 
 P3D_API int p3d_best_pack(const double* scores, const int64_t* best, int64_t offset, int64_t* pair,
                           p3d_stream_t stream) {

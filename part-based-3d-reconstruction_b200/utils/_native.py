@@ -57,6 +57,11 @@ _SIGNATURES = {
     "p3d_sweep_last_launches": ([], _i32),
     "p3d_best_pack": ([_vp, _vp, _i64, _vp, _vp], _i32),
     "p3d_best_select": ([_vp, _i32, _vp, _vp], _i32),
+    "p3d_depth_workspace_bytes": ([_i32, _i32, _i32], _sz),
+    "p3d_depth_buffer_f32": ([_vp, _i64, _vp, _i32, _i32, _vp, _vp, _sz, _vp], _i32),
+    "p3d_depth_buffer_f64": ([_vp, _i64, _vp, _i32, _i32, _vp, _vp, _sz, _vp], _i32),
+    "p3d_part_visible_f32": ([_vp, _i64, _vp, _vp, ctypes.c_float, _i32, _i32, _vp, _vp], _i32),
+    "p3d_part_visible_f64": ([_vp, _i64, _vp, _vp, ctypes.c_double, _i32, _i32, _vp, _vp], _i32),
     "p3d_sweep_timing_enable": ([_i32], _i32),
     "p3d_sweep_timing_read": ([_vp, _vp], _i32),
     "p3d_resample_carve": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),

@@ -343,8 +343,34 @@ def aligner_golden():
     np.savez_compressed(os.path.join(HERE, "aligner_golden.npz"), **out)
 
 
+def depth_golden():
+    """compute_global_depth_buffer / project_part_visible of the live utils/eval_helpers_intra.py (:134-190) on the
+    half-resolution Taj grid stored in aligner_golden.npz, float32 cameras (as load_camera_json makes them) and float64."""
+    import importlib
+    eh = importlib.import_module("utils.eval_helpers_intra")
+    grid = np.load(os.path.join(HERE, "aligner_golden.npz"))["grid"]
+    cams = json.load(open(os.path.join(ref.root, "results/2.Perspective_Camera_Estimation/Taj_camera_params_final.json")))
+    H, W = 139, 256
+    out = {}
+    for view in ("front", "drone"):
+        c = cams[view]
+        for dt in (np.float32, np.float64):
+            cam = {"cam_pos": (np.array(c["cam_pos"]) / 2).astype(dt), "target": (np.array(c["target"]) / 2).astype(dt),
+                   "f": c["f"] / 2, "cx": c["cx"] / 2, "cy": c["cy"] / 2}
+            key = f"{view}_{np.dtype(dt).name}"
+            z = eh.compute_global_depth_buffer(grid, cam, H, W)
+            out[key + "_cam"] = np.array([*cam["cam_pos"], *cam["target"], cam["f"], cam["cx"], cam["cy"]], dtype=np.float64)
+            out[key + "_zbuf"] = z
+            for tag, parts in (("min", ["front_minarets", "back_minarets"]), ("dome", ["dome"])):
+                pts, _ = ref.vu.get_voxel_points_by_parts(grid, C.PART_COLORS, parts)
+                out[f"{key}_{tag}_visible"] = np.packbits(eh.project_part_visible(pts, cam, z, H, W))
+                out[f"{key}_{tag}_loose"] = np.packbits(eh.project_part_visible(pts, cam, z, H, W, eps=0.75))
+            print(key, "finite", int(np.isfinite(z).sum()))
+    np.savez_compressed(os.path.join(HERE, "depth_golden.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner"]
+    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth"]
     if "assets" in which:
         copy_assets()
     if "camera" in which:
@@ -353,6 +379,8 @@ if __name__ == "__main__":
         carve_golden()
     if "aligner" in which:
         aligner_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz"):
+    if "depth" in which:
+        depth_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz"):
         if os.path.exists(os.path.join(HERE, f)):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
