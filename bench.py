@@ -343,7 +343,34 @@ def carve_bench(N, dev, peak):
                         "frac": round(3 * kgvox / peak, 4) if kgvox else None, "kernel": "global_fold_bits_kernel<RGB>",
                         "note": "3 B per output voxel (RGB grid written once, SURVEY 8d), kernel-only; "
                                 "global_carve_gvoxel_s is the whole Python call (mask upload, table lookup, launch)"}}
-    del out, kout
+    # part_carve (all six notebook groups at 90 degrees) on that grid: 6 B per voxel (read RGB + write RGB)
+    jobs90 = [(["full_building"], 90), (["chhatris"], 90), (["plinth"], 90), (["front_minarets"], 90),
+              (["small_minarets"], 90), (["dome"], 90)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pc = vc.part_carve(out, ext, jobs90)
+    torch.cuda.synchronize()
+    pc_call_ms = (time.perf_counter() - t0) * 1e3
+    launch_pc = vc._LAST_PART_CARVE_LAUNCH
+    if launch_pc is not None:
+        for _ in range(2):
+            launch_pc()
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(10):
+            launch_pc()
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / 10
+        res["part_carve"] = {"kernel_ms": round(pms, 4), "kernel_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2),
+                             "call_ms": round(pc_call_ms, 3), "occupied": int(torch.count_nonzero(pc.view(-1, 3).any(dim=1)).item()),
+                             "roofline": {"bound": "hbm", "achieved": round(6 * N ** 3 / (pms * 1e-3) / 1e9, 1), "peak": peak,
+                                          "unit": "GB/s", "frac": round(6 * N ** 3 / (pms * 1e-3) / 1e9 / peak, 4),
+                                          "kernel": "occ_bits_x + pack_group_bits + part_fold_bits",
+                                          "note": "6 B per voxel (SURVEY 8d: read RGB + write RGB); the x-packed occupancy "
+                                                  "pre-pass re-reads the grid once, so real traffic is ~9 B/voxel"}}
+    del out, kout, pc
     data = os.path.join(ROOT, "tests", "golden", "data")
     try:
         sem, sem_ext, binary = mu.load_and_prepare_masks(data, "Bibi", "front", 256, cfg.PART_COLORS_NP, cfg.INTERIOR_PARTS)

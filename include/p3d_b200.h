@@ -208,7 +208,8 @@ int p3d_global_carve_fold(int W, int H, int D, const int32_t* table, const uint8
                           const uint8_t* colour_hw, int rgb, uint8_t* out, p3d_stream_t stream);
 /* Bit-level form of p3d_global_carve_fold for z-separable tables (src0(x,z) = c - z on every in-range entry; true
  * for the 90-degree pass).  p3d_fold_analyse packs table >= 0 into inside_bits (W, D/32) and writes
- * info = [max, min] of src0 + z over the in-range entries (separable iff max == min =: c).  p3d_pack_mask_bits packs
+ * info (4 ints) = [max, min] of src0 + z and [max, min] of src2 - x over the in-range entries (z-separable iff
+ * info[0] == info[1] =: c).  p3d_pack_mask_bits packs
  * mask_hw (H,W) into rows of words_per_row >= ceil(W/32) + 2 words with one zero word of padding on each side.
  * D must be a multiple of 32 and out 16-byte aligned.  Same output bytes as p3d_global_carve_fold.
  * [x_begin, x_begin + x_count) selects an x-slab: out is then the (x_count,H,D[,3]) slab -- the unit of multi-GPU
@@ -231,6 +232,14 @@ int p3d_colourise(const uint8_t* carved, int W, int H, int D, const uint8_t* col
  * bit g set when pixel (y,x) is in group g's mask AND in that mask after _mask_to_wh (square quirk). */
 int p3d_part_carve_fold(const uint8_t* grid, int W, int H, int D, const int32_t* table,
                         const uint32_t* group_mask_hw, uint8_t* out, p3d_stream_t stream);
+
+/* Bit-level form of p3d_part_carve_fold for z-separable tables with src0 = c - z and src2 = x + c2 (p3d_fold_analyse:
+ * info[0] == info[1] =: c, info[2] == info[3] =: c2).  Needs D % 32 == 0, 16-byte aligned grids and
+ * p3d_part_carve_bits_workspace_bytes() of scratch (x-packed occupancy bits + per-group mask bits). */
+size_t p3d_part_carve_bits_workspace_bytes(int W, int H, int D, int n_groups);
+int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, const uint32_t* inside_bits, int c, int c2,
+                             const uint32_t* group_mask_hw, int n_groups, uint8_t* out, void* workspace,
+                             size_t workspace_bytes, p3d_stream_t stream);
 
 /* Building blocks of the general-angle part_carve and of left_right_guided_carve :163-210. */
 int p3d_crop_occupancy(const uint8_t* grid, int W, int H, int D, int x0, int y0, int z0, int w, int h, int d,

@@ -232,25 +232,28 @@ global_fold_kernel(int W, int H, int D, const int32_t* __restrict__ table, const
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fold_analyse_kernel(const int32_t* __restrict__ table, int W, int D, uint32_t* __restrict__ inside_bits,
-                    int* __restrict__ info /* [0] = max(src0+z), [1] = min(src0+z) over in-range entries */) {
+                    int* __restrict__ info /* over in-range entries: [0] = max(src0+z), [1] = min(src0+z),
+                                              [2] = max(src2-x), [3] = min(src2-x) */) {
   const int words = D >> 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per (x, word)
   if (i >= W * words) return;
   const int x = i / words, w = i - x * words;
   uint32_t bits = 0;
-  int mx = -0x7fffffff, mn = 0x7fffffff;
+  int mx = -0x7fffffff, mn = 0x7fffffff, mx2 = -0x7fffffff, mn2 = 0x7fffffff;
   for (int j = 0; j < 32; ++j) {
     const int z = w * 32 + j;
     const int32_t e = table[(size_t)x * D + z];
     if (e >= 0) {
       bits |= 1u << j;
-      const int c = (e >> 16) + z;
+      const int c = (e >> 16) + z, c2 = (e & 0xffff) - x;
       mx = max(mx, c);
       mn = min(mn, c);
+      mx2 = max(mx2, c2);
+      mn2 = min(mn2, c2);
     }
   }
   inside_bits[i] = bits;
-  if (bits) { atomicMax(info, mx); atomicMin(info + 1, mn); }
+  if (bits) { atomicMax(info, mx); atomicMin(info + 1, mn); atomicMax(info + 2, mx2); atomicMin(info + 3, mn2); }
 }
 
 __global__ void __launch_bounds__(256)
@@ -334,6 +337,117 @@ global_fold_bits_kernel(int W, int H, int D, int x_begin, int x_count, const uin
       }
       __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4(o[0], o[1], o[2], o[3]));
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bit-level fast path of the fused part_carve kernel (all groups at 90 degrees, z-separable table with
+// src0 = c - z and src2 = x + c2).
+//   occ_bits_x_kernel      : occx[y][z][1 + x/32] bit x%32 = any(grid[x,y,z,:] > 0)   (bits packed along x, one zero
+//                            word of padding on each side), via a 32x32 ballot transpose
+//   pack_group_bits_kernel : gbits[g][y][1 + x/32] bit x%32 = bit g of the group image gm[y][x]
+//   part_fold_bits_kernel  : thread = 16 voxels of one z-row: three 16-byte loads, a handful of word loads for the
+//                            16 source-occupancy / source-group bits (read backwards), three 16-byte stores
+//   keep(x,y,z) = grid[x,y,z] != 0 && inside(x,z) && occ[c-z, y, x+c2] && OR_g (g in gm[y][x] && g in gm[y][c-z])
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rgb16_occupancy(const uint4& a, const uint4& b, const uint4& c) {
+  const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                         // 4 voxels = 3 words
+    const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+    if (w0 & 0x00ffffffu) bits |= 1u << (4 * q);
+    if ((w0 & 0xff000000u) | (w1 & 0x0000ffffu)) bits |= 2u << (4 * q);
+    if ((w1 & 0xffff0000u) | (w2 & 0x000000ffu)) bits |= 4u << (4 * q);
+    if (w2 & 0xffffff00u) bits |= 8u << (4 * q);
+  }
+  return bits;
+}
+
+__global__ void __launch_bounds__(256)
+occ_bits_x_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, int xwp, uint32_t* __restrict__ occx) {
+  const int lane = threadIdx.x & 31;
+  const int xt_n = (W + 31) >> 5, zt_n = D >> 5;
+  const int64_t tasks = (int64_t)H * zt_n * xt_n;
+  for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < tasks; t += (int64_t)gridDim.x * 8) {
+    const int xt = (int)(t % xt_n);
+    const int64_t r = t / xt_n;
+    const int zt = (int)(r % zt_n), y = (int)(r / zt_n);
+    const int x = xt * 32 + lane, z0 = zt * 32;
+    uint32_t mine = 0;
+    if (x < W) {
+      const uint4* p = reinterpret_cast<const uint4*>(grid + (((size_t)x * H + y) * D + z0) * 3);
+      const uint4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3), a4 = __ldg(p + 4), a5 = __ldg(p + 5);
+      mine = rgb16_occupancy(a0, a1, a2) | (rgb16_occupancy(a3, a4, a5) << 16);
+    }
+    uint32_t keep = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const uint32_t wj = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
+      if (lane == j) keep = wj;
+    }
+    occx[((size_t)y * D + z0 + lane) * xwp + 1 + xt] = keep;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_group_bits_kernel(const uint32_t* __restrict__ gm_hw, int H, int W, int n_groups, int xwp, uint32_t* __restrict__ gbits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per (g, y, word)
+  if (i >= n_groups * H * xwp) return;
+  const int w = i % xwp;
+  const int y = (i / xwp) % H, g = i / (xwp * H);
+  uint32_t v = 0;
+  const int x0 = (w - 1) * 32;
+  for (int j = 0; j < 32; ++j) {
+    const int x = x0 + j;
+    if (x >= 0 && x < W && ((gm_hw[(size_t)y * W + x] >> g) & 1u)) v |= 1u << j;
+  }
+  gbits[i] = v;
+}
+
+// 16 bits [lo, lo+16) of a padded bit row, returned in REVERSE order (bit j = row bit lo+15-j); 0 when out of range
+__device__ __forceinline__ uint32_t rev16_bits(const uint32_t* __restrict__ row, int lo, int xwp) {
+  if (lo < 0 || (lo >> 5) + 1 >= xwp) return 0u;
+  const uint32_t w0 = __ldg(row + (lo >> 5)), w1 = __ldg(row + (lo >> 5) + 1);
+  return __brev(__funnelshift_r(w0, w1, lo & 31) & 0xffffu) >> 16;
+}
+
+__global__ void __launch_bounds__(256)
+part_fold_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const uint32_t* __restrict__ inside_bits,
+                      int c, int c2, const uint32_t* __restrict__ gm_hw, const uint32_t* __restrict__ gbits,
+                      const uint32_t* __restrict__ occx, int xwp, uint8_t* __restrict__ out) {
+  const int64_t groups = (int64_t)W * H * D / 16;
+  const int words = D >> 5;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v0 = g * 16;
+    const int z0 = (int)(v0 % D);
+    const int64_t r = v0 / D;
+    const int y = (int)(r % H), x = (int)(r / H);
+    const uint4* src = reinterpret_cast<const uint4*>(grid + v0 * 3);
+    uint4 a = __ldg(src), b = __ldg(src + 1), cc = __ldg(src + 2);
+    uint32_t keep = rgb16_occupancy(a, b, cc);
+    const uint32_t self = keep ? __ldg(gm_hw + (size_t)y * W + x) : 0u;
+    if (self == 0u) keep = 0u;
+    if (keep) keep &= (__ldg(inside_bits + (size_t)x * words + (z0 >> 5)) >> (z0 & 31)) & 0xffffu;
+    const int lo = c - z0 - 15 + 32;                              // padded bit index of source x' = c - z0 - 15
+    const int sz = x + c2;
+    if (keep) keep &= (sz >= 0 && sz < D) ? rev16_bits(occx + ((size_t)y * D + sz) * xwp, lo, xwp) : 0u;
+    if (keep) {
+      uint32_t grp = 0, rem = self;
+      while (rem) {
+        const int gi = __ffs(rem) - 1;
+        rem &= rem - 1;
+        grp |= rev16_bits(gbits + ((size_t)gi * H + y) * xwp, lo, xwp);
+      }
+      keep &= grp;
+    }
+    uint32_t m[12];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) expand4((keep >> (4 * q)) & 0xfu, 0xffffffffu, 0xffffffffu, 0xffffffffu, m + 3 * q);
+    uint4* dst = reinterpret_cast<uint4*>(out + v0 * 3);
+    dst[0] = make_uint4(a.x & m[0], a.y & m[1], a.z & m[2], a.w & m[3]);
+    dst[1] = make_uint4(b.x & m[4], b.y & m[5], b.z & m[6], b.w & m[7]);
+    dst[2] = make_uint4(cc.x & m[8], cc.y & m[9], cc.z & m[10], cc.w & m[11]);
   }
 }
 
@@ -822,7 +936,7 @@ P3D_API int p3d_fold_analyse(const int32_t* table, int W, int D, uint32_t* insid
   P3D_REQUIRE(W > 0 && D > 0 && D % 32 == 0, "fold_analyse: D must be a multiple of 32");
   P3D_REQUIRE(table && inside_bits && info, "fold_analyse: null pointer");
   cudaStream_t st = p3d::as_stream(stream);
-  const int init[2] = {-0x7fffffff, 0x7fffffff};
+  const int init[4] = {-0x7fffffff, 0x7fffffff, -0x7fffffff, 0x7fffffff};
   P3D_CUDA(cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, st));
   const int n = W * (D / 32);
   fold_analyse_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, W, D, inside_bits, info);
@@ -876,6 +990,39 @@ P3D_API int p3d_part_carve_fold(const uint8_t* grid, int W, int H, int D, const 
   P3D_REQUIRE(W > 0 && H > 0 && D > 0, "part_carve_fold: bad shape");
   P3D_REQUIRE(grid && table && group_mask_hw && out && grid != out, "part_carve_fold: null or aliased pointers");
   part_fold_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(grid, W, H, D, table, group_mask_hw, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API size_t p3d_part_carve_bits_workspace_bytes(int W, int H, int D, int n_groups) {
+  if (W <= 0 || H <= 0 || D <= 0 || n_groups < 0) return 0;
+  const size_t xwp = (size_t)(W + 31) / 32 + 2;
+  return p3d_align_up((size_t)H * D * xwp * 4, 256) + p3d_align_up((size_t)n_groups * H * xwp * 4, 256);
+}
+
+P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, const uint32_t* inside_bits, int c, int c2,
+                                     const uint32_t* group_mask_hw, int n_groups, uint8_t* out, void* workspace,
+                                     size_t workspace_bytes, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0 && n_groups >= 1 && n_groups <= 32, "part_carve_fold_bits: bad shape");
+  P3D_REQUIRE(grid && inside_bits && group_mask_hw && out && workspace && grid != out, "part_carve_fold_bits: null/aliased");
+  P3D_REQUIRE(((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "part_carve_fold_bits: grids must be 16-byte aligned");
+  if (workspace_bytes < p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups)) {
+    p3d::set_error("part_carve_fold_bits: workspace too small");
+    return P3D_E_WORKSPACE;
+  }
+  const int xwp = (W + 31) / 32 + 2;
+  uint32_t* occx = static_cast<uint32_t*>(workspace);
+  uint32_t* gbits = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(workspace) + p3d_align_up((size_t)H * D * xwp * 4, 256));
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(occx, 0, (size_t)H * D * xwp * 4, st));           // padding words
+  const int64_t tasks = (int64_t)H * (D / 32) * ((W + 31) / 32);
+  occ_bits_x_kernel<<<grid_for(tasks, 8, 32), 256, 0, st>>>(grid, W, H, D, xwp, occx);
+  const int ng = n_groups * H * xwp;
+  pack_group_bits_kernel<<<(ng + 255) / 256, 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
+  const int64_t n16 = (int64_t)W * H * D / 16;
+  part_fold_bits_kernel<<<grid_for(n16, 256, 16), 256, 0, st>>>(grid, W, H, D, inside_bits, c, c2, group_mask_hw, gbits,
+                                                               occx, xwp, out);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

@@ -113,19 +113,21 @@ def _fold_table(n0, n2, M, off, dev):
 
 
 _FOLD_BITS_CACHE = {}
+_LAST_PART_CARVE_LAUNCH = None
 
 
 def _fold_bits(table, W, D, cache_key):
-    """(inside_bits (W, D/32) int32 tensor, c) when the table is z-separable (src0 = c - z), else None.  Cached."""
+    """(inside_bits (W, D/32) int32 tensor, c, c2 | None) when the table is z-separable (src0 = c - z; c2 is set when
+    additionally src2 = x + c2), else None.  Cached."""
     hit = _FOLD_BITS_CACHE.get(cache_key)
     if hit is not None:
         return hit if hit[0] is not None else None
     inside = torch.empty((W, D // 32), dtype=torch.int32, device=table.device)
-    info = torch.empty(2, dtype=torch.int32, device=table.device)
+    info = torch.empty(4, dtype=torch.int32, device=table.device)
     check(lib.p3d_fold_analyse(ptr(table), W, D, ptr(inside), ptr(info), stream_ptr()), "p3d_fold_analyse")
     _launched()
-    mx, mn = (int(v) for v in info.cpu())
-    res = (inside, mx) if mx == mn else (None, None)
+    mx, mn, mx2, mn2 = (int(v) for v in info.cpu())
+    res = (inside, mx, mx2 if mx2 == mn2 else None) if mx == mn else (None, None, None)
     if len(_FOLD_BITS_CACHE) >= 16:
         _FOLD_BITS_CACHE.pop(next(iter(_FOLD_BITS_CACHE)))
     _FOLD_BITS_CACHE[cache_key] = res
@@ -140,7 +142,8 @@ def _process_device(vol, mask_wh, angle_interval):
     for angle in tqdm(range(0, 91, angle_interval), desc="90 Carving", leave=True, disable=None):
         M, off = _pass_transform((n0, n1, n2), angle)
         out = torch.empty_like(cur)
-        table, foldable = _fold_table(n0, n2, M, off, dev)
+        # an index fold is only possible at multiples of 90 degrees; other angles go straight to the resample kernel
+        table, foldable = _fold_table(n0, n2, M, off, dev) if angle % 90 == 0 else (None, False)
         if foldable:
             check(lib.p3d_fold_gather(ptr(cur), n0, n1, n2, ptr(table), ptr(mask_wh), ptr(out), stream_ptr()),
                   "p3d_fold_gather")
@@ -152,13 +155,35 @@ def _process_device(vol, mask_wh, angle_interval):
     return cur
 
 
+class _PackedMask:
+    """A (H,W,3) uint8 semantic mask with its channels packed into one 32-bit key per pixel, so that every colour
+    test is a single integer compare (host side, O(H*W) per colour)."""
+
+    def __init__(self, semantic_mask):
+        sem = semantic_mask.cpu().numpy() if _is_tensor(semantic_mask) else np.asarray(semantic_mask)
+        self.sem = sem
+        self.shape = sem.shape
+        self.packed = None
+        if sem.dtype == np.uint8 and sem.ndim == 3 and sem.shape[2] == 3:
+            self.packed = (sem[..., 0].astype(np.uint32) | (sem[..., 1].astype(np.uint32) << 8)
+                           | (sem[..., 2].astype(np.uint32) << 16))
+
+    def match(self, colours):
+        """any over colours of all(mask == colour, axis=-1)  (voxel_carving_utils.py:143-146, :170)."""
+        out = np.zeros(self.shape[:2], bool)
+        for c in colours:
+            if self.packed is None:
+                out |= np.all(self.sem == np.asarray(c), axis=-1)
+                continue
+            r, g, b = (int(v) for v in np.asarray(c).reshape(3))
+            if 0 <= r < 256 and 0 <= g < 256 and 0 <= b < 256:
+                out |= self.packed == np.uint32(r | (g << 8) | (b << 16))
+        return out
+
+
 def _mask2d_bool(semantic_mask, colours):
-    """any over colours of all(semantic_mask == colour, axis=-1) on the host (2-D, O(H*W))."""
-    sem = semantic_mask.cpu().numpy() if _is_tensor(semantic_mask) else np.asarray(semantic_mask)
-    out = np.zeros(sem.shape[:2], bool)
-    for c in colours:
-        out |= np.all(sem == np.asarray(c), axis=-1)
-    return out
+    pm = semantic_mask if isinstance(semantic_mask, _PackedMask) else _PackedMask(semantic_mask)
+    return pm.match(colours)
 
 
 def _colour_args(colour):
@@ -230,6 +255,7 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
     grid = _to_dev_u8(colored_grid, dev, "colored_grid")
     W, H, D, _ = grid.shape
     jobs = []
+    semantic_mask = semantic_mask if isinstance(semantic_mask, _PackedMask) else _PackedMask(semantic_mask)
     for names, angle in group_jobs:
         m2d = _mask2d_bool(semantic_mask, [PART_COLORS[n] for n in names])          # (H,W)
         if not m2d.any():
@@ -248,9 +274,22 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
                 gm |= (m & mm).astype(np.uint32) << np.uint32(g)
             gm_hw = torch.from_numpy(np.ascontiguousarray(gm.T).view(np.int32)).to(dev)
             out = torch.empty_like(grid)
-            check(lib.p3d_part_carve_fold(ptr(grid), W, H, D, ptr(table), ptr(gm_hw), ptr(out), stream_ptr()),
-                  "p3d_part_carve_fold")
-            _launched()
+            bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
+            if bits is not None and bits[2] is not None:       # z-separable table: bit-packed occupancy / group masks
+                ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+                def launch(grid=grid, out=out, ws=ws, gm_hw=gm_hw, bits=bits, n=len(jobs)):
+                    check(lib.p3d_part_carve_fold_bits(ptr(grid), W, H, D, ptr(bits[0]), bits[1], bits[2], ptr(gm_hw), n,
+                                                       ptr(out), ptr(ws), ws_bytes, stream_ptr()), "p3d_part_carve_fold_bits")
+                    _launched(3)
+                launch()
+                global _LAST_PART_CARVE_LAUNCH
+                _LAST_PART_CARVE_LAUNCH = launch              # bench.py re-issues it to time the kernels alone
+            else:
+                check(lib.p3d_part_carve_fold(ptr(grid), W, H, D, ptr(table), ptr(gm_hw), ptr(out), stream_ptr()),
+                      "p3d_part_carve_fold")
+                _launched()
     if out is None:
         out = torch.zeros_like(grid)
         for m, angle in jobs:
@@ -308,10 +347,10 @@ def left_right_guided_carve(colored_grid, semantic_mask, target_color, angle=60,
         return _ret(carved, as_tensor)
     labels, n, bbox, _ = _label_components(_colour_mask(grid, target_color))
     print(f"[{target_color}] 3D components: {n}")
+    log = []                                   # (bbox line, device count) per component: printed after ONE sync
     for i in range(1, n + 1):
         x0, y0, z0 = (int(v) for v in bbox[i - 1, 0:3])
         x1, y1, z1 = (int(v) + 1 for v in bbox[i - 1, 3:6])
-        print(f"  - Component {i}: bbox ({x0},{y0},{z0}) → ({x1},{y1},{z1})")
         w, h, d = x1 - x0, y1 - y0, z1 - z0
         crop2d = mask2d[y0:y1, x0:x1]
         m_wh = _to_dev_u8(np.ascontiguousarray(_mask_to_wh(crop2d, w, h)), dev)
@@ -319,12 +358,17 @@ def left_right_guided_carve(colored_grid, semantic_mask, target_color, angle=60,
         check(lib.p3d_crop_occupancy(ptr(grid), W, H, D, x0, y0, z0, w, h, d, None, ptr(occ), stream_ptr()),
               "p3d_crop_occupancy")
         kept = _process_device(occ, m_wh, angle)
-        print(f"    carved voxels: {int(torch.count_nonzero(kept).item())}")
+        log.append((f"  - Component {i}: bbox ({x0},{y0},{z0}) → ({x1},{y1},{z1})", torch.count_nonzero(kept)))
         check(lib.p3d_paste_component(ptr(grid), ptr(labels), i, ptr(kept), W, H, D, x0, y0, z0, w, h, d, ptr(carved),
                                       stream_ptr()), "p3d_paste_component")
         _launched(2)
-        if visualize:
-            warnings.warn("visualize=True is ignored: plotting is outside this package's scope")
+    if log:
+        counts = torch.stack([c for _, c in log]).cpu().tolist()
+        for (line, _), c in zip(log, counts):
+            print(line)
+            print(f"    carved voxels: {int(c)}")
+    if visualize:
+        warnings.warn("visualize=True is ignored: plotting is outside this package's scope")
     return _ret(carved, as_tensor)
 
 
@@ -447,6 +491,8 @@ def partwise_carve(colored_voxel_grid, semantic_mask_exterior, semantic_mask_ful
     dev = nv.require_cuda(colored_voxel_grid.device if as_tensor and colored_voxel_grid.is_cuda else None)
     grid = _to_dev_u8(colored_voxel_grid, dev, "colored_voxel_grid")
 
+    semantic_mask_exterior = _PackedMask(semantic_mask_exterior)
+    semantic_mask_full = _PackedMask(semantic_mask_full)
     grid = part_carve(grid, semantic_mask_exterior, group_jobs, visualize=False)     # fresh tensor from here on
     for part, angle in part_symmetry.items():
         grid = left_right_guided_carve(colored_grid=grid, semantic_mask=semantic_mask_exterior,
