@@ -242,6 +242,7 @@ __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, co
     bv = 2.0 * eps * dxv / zmin + ((double)H + 2.0 + fabs(cam[14])) * b1 + 1e-7;
   }
   ok = ok && bu <= 0.25 && bv <= 0.25 && b1 * 2.0 * (double)(W > H ? W : H) <= 0.25;
+  ok = ok && W < (1 << 21) && H < (1 << 21);                                     // range of the magic-number rounding
   fc.thr_u = ok ? __double2float_rd(0.5 - bu) : -1.f;
   fc.thr_v = ok ? __double2float_rd(0.5 - bv) : -1.f;
   *out = fc;

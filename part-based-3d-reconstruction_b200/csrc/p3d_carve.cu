@@ -844,6 +844,71 @@ mask_carve_kernel(const uint8_t* __restrict__ grid, int64_t n_vox, int D, int C,
   }
 }
 
+// Vector form for W % 32 == 0 and D % 32 == 0: 16-byte loads along z and 16-byte stores along x.
+__global__ void __launch_bounds__(192)
+reorient_vec_kernel(const uint8_t* __restrict__ in, int W, int H, int D, uint8_t* __restrict__ out) {
+  __shared__ __align__(16) uint8_t tile[32][96 + 16];    // [x][z*3 + c], padded rows
+  const int y = blockIdx.y;
+  const int tiles_z = D >> 5;
+  const int x0 = (blockIdx.x / tiles_z) << 5, z0 = (blockIdx.x % tiles_z) << 5;
+  const int t = threadIdx.x;
+  {
+    const int xr = t / 6, part = t - xr * 6;              // 32 rows x 6 uint4
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)(x0 + xr) * H + y) * D + z0) * 3) + part);
+    *reinterpret_cast<uint4*>(&tile[xr][part * 16]) = v;
+  }
+  __syncthreads();
+  {
+    const int zr = t / 6, part = t - zr * 6;              // output row z0+zr: 96 bytes = x-major RGB
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ob = part * 16 + q * 4 + b;             // output byte within the 96-byte row
+        const int xr = ob / 3, c = ob - xr * 3;
+        acc |= (uint32_t)tile[xr][zr * 3 + c] << (8 * b);
+      }
+      w[q] = acc;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)(z0 + zr) * H + (H - 1 - y)) * W + x0) * 3) + part;
+    __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
+  }
+}
+
+// axis-2 extrusion, one WARP per masked column: the z-row is scanned 32 voxels (96 contiguous bytes) at a time.
+__global__ void __launch_bounds__(256)
+extrude_z_kernel(uint8_t* __restrict__ grid, int W, int H, int D, const uint8_t* __restrict__ mask_hw, int sign, int depth,
+                 uint32_t colour) {
+  const int lane = threadIdx.x & 31;
+  const int ncol = W * H;
+  for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < ncol; t += gridDim.x * 8) {
+    const int x = t / H, y = t - x * H;
+    if (!mask_hw[(size_t)y * W + x]) continue;
+    uint8_t* col = grid + 3 * ((size_t)x * H + y) * D;
+    int start = sign > 0 ? 0 : D - 1;                     // argmax of an all-False column
+    for (int base = 0; base < D; base += 32) {
+      const int k = base + lane;                          // k-th voxel from the scanning end
+      const int idx = sign > 0 ? k : D - 1 - k;
+      const bool occ = k < D && rgb_nonzero(col + 3 * (size_t)idx);
+      const uint32_t m = __ballot_sync(0xffffffffu, occ);
+      if (m) {
+        const int first = base + __ffs(m) - 1;
+        start = sign > 0 ? first : D - 1 - first;
+        break;
+      }
+    }
+    const uint8_t r = colour & 0xff, g = (colour >> 8) & 0xff, b = (colour >> 16) & 0xff;
+    for (int dd = lane; dd < depth; dd += 32) {
+      const int idx = start + sign * dd;
+      if (idx < 0 || idx >= D) continue;
+      uint8_t* p = col + 3 * (size_t)idx;
+      p[0] = r; p[1] = g; p[2] = b;
+    }
+  }
+}
+
 int check_affine(const double* M, const double* off, Affine* A) {
   P3D_REQUIRE(M && off, "affine: null matrix/offset (host pointers)");
   for (int i = 0; i < 9; ++i) A->M[i] = M[i];
@@ -1143,8 +1208,11 @@ P3D_API int p3d_extrude(uint8_t* grid_rgb, int W, int H, int D, const uint8_t* m
   else P3D_REQUIRE(mask_h == H && mask_w == D, "extrude: mask (%d,%d) does not match (H,D)=(%d,%d)", mask_h, mask_w, H, D);
   const int ncol = axis == 2 ? W * H : H * D;
   const uint32_t colour = (uint32_t)((r & 0xff) | ((g & 0xff) << 8) | ((b & 0xff) << 16));
-  extrude_kernel<<<(ncol + 127) / 128, 128, 0, p3d::as_stream(stream)>>>(grid_rgb, W, H, D, mask_hw, mask_w, axis, sign,
-                                                                      depth, colour);
+  if (axis == 2)
+    extrude_z_kernel<<<grid_for(ncol, 8, 16), 256, 0, p3d::as_stream(stream)>>>(grid_rgb, W, H, D, mask_hw, sign, depth, colour);
+  else
+    extrude_kernel<<<(ncol + 127) / 128, 128, 0, p3d::as_stream(stream)>>>(grid_rgb, W, H, D, mask_hw, mask_w, axis, sign,
+                                                                        depth, colour);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -1155,7 +1223,10 @@ P3D_API int p3d_reorient(const uint8_t* in, int W, int H, int D, uint8_t* out, p
   P3D_REQUIRE(in && out && in != out, "reorient: null or aliased pointers");
   P3D_REQUIRE(H <= 65535, "reorient: H too large");
   dim3 grid((unsigned)(((W + 31) / 32) * ((D + 31) / 32)), (unsigned)H);
-  reorient_kernel<<<grid, 256, 0, p3d::as_stream(stream)>>>(in, W, H, D, out);
+  const bool vec = W % 32 == 0 && D % 32 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) reorient_vec_kernel<<<grid, 192, 0, p3d::as_stream(stream)>>>(in, W, H, D, out);
+  else reorient_kernel<<<grid, 256, 0, p3d::as_stream(stream)>>>(in, W, H, D, out);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
