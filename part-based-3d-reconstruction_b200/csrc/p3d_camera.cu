@@ -255,6 +255,31 @@ __global__ void __launch_bounds__(64) fast_cams_kernel(const double* __restrict_
   if (k < K) make_fast_cam(cams + (size_t)k * 16, bbox, H, W, reinterpret_cast<FastCam*>(fast) + k);
 }
 
+// Packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2): one issue slot for two lanes' worth of IEEE-rn FP32 operations.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+#ifndef P3D_SCALAR_FILTER
+#define P3D_PACKED 1
+#endif
+constexpr int kPackCamFloats = 32;   // per camera in shared memory: every coefficient duplicated into an f32x2
 constexpr int kFlushEvery = 64 / kPptF; // cameras between queue flushes: kPptF bits per camera in a 64-bit mask
 
 template <int MODE>
@@ -264,15 +289,19 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
                       uint32_t* __restrict__ zbuf, const float* __restrict__ fast) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_cam = reinterpret_cast<double*>(smem_raw);                                   // nc x 16 doubles
-  FastCam* s_fast = reinterpret_cast<FastCam*>(s_cam + (size_t)cams_per_block * 16);      // nc x FastCam
-  uint2* s_queue = reinterpret_cast<uint2*>(s_fast + cams_per_block);                     // 8 warps x kQueueCap
+  float* s_fast = reinterpret_cast<float*>(s_cam + (size_t)cams_per_block * 16);          // nc x kPackCamFloats
+  uint2* s_queue = reinterpret_cast<uint2*>(s_fast + (size_t)cams_per_block * kPackCamFloats);   // 8 warps x kQueueCap
   int* s_qn = reinterpret_cast<int*>(s_queue + (kSplatThreads / 32) * kQueueCap);          // 8 counters
 
   const int c0 = blockIdx.y * cams_per_block;
   const int nc = min(cams_per_block, K - c0);
   for (int i = threadIdx.x; i < nc * 16; i += kSplatThreads) {
     s_cam[i] = cams[(size_t)c0 * 16 + i];
-    reinterpret_cast<float*>(s_fast)[i] = fast[(size_t)c0 * 16 + i];
+    // FastCam (16 floats) -> duplicated pairs: A[3],TA, B[3],TB, C[3],TC, cx, cy at 2e / 2e+1; thr_u, thr_v at 28, 29
+    const float v = fast[(size_t)c0 * 16 + i];
+    const int cc = i >> 4, e = i & 15;
+    float* dst = s_fast + cc * kPackCamFloats;
+    if (e < 14) { dst[2 * e] = v; dst[2 * e + 1] = v; } else { dst[28 + (e - 14)] = v; }
   }
   if (threadIdx.x < kSplatThreads / 32) s_qn[threadIdx.x] = 0;
   __syncthreads();
@@ -301,6 +330,16 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
   const double dW = (double)W, dH = (double)H;
   const uint32_t HW = (uint32_t)H * (uint32_t)W;
   const float kMagic = 12582912.f;                         // 1.5 * 2^23: (x + m) - m == rint(x) for |x| < 2^22
+#ifdef P3D_PACKED
+  static_assert(kPptF % 2 == 0, "packed path pairs points");
+  f32x2 PX[kPptF / 2], PY[kPptF / 2], PZ[kPptF / 2];
+#pragma unroll
+  for (int jp = 0; jp < kPptF / 2; ++jp) {
+    PX[jp] = pack2(px[2 * jp], px[2 * jp + 1]);
+    PY[jp] = pack2(py[2 * jp], py[2 * jp + 1]);
+    PZ[jp] = pack2(pz[2 * jp], pz[2 * jp + 1]);
+  }
+#endif
 
   // exact FP64 projection of the newest `take` queue entries (one per lane)
   auto drain32 = [&](int qn) -> int {
@@ -343,13 +382,46 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
 
   unsigned long long parked = 0ull;
   for (int c = 0; c < nc; ++c) {
-    const float4* fcv = reinterpret_cast<const float4*>(s_fast + c);
-    const float4 vA = fcv[0], vB = fcv[1], vC = fcv[2], vD = fcv[3];
     uint32_t* zb = zbuf + (size_t)(c0 + c) * HW;
     asm volatile("" : "+l"(zb));                          // keep the per-camera base in registers
     uint32_t* addr[kPptF];
     bool hit[kPptF];
     uint32_t und = 0;
+    const float* fc = s_fast + c * kPackCamFloats;
+    const float thr_u = fc[28], thr_v = fc[29];
+#ifdef P3D_PACKED
+    const ulonglong2* fc2 = reinterpret_cast<const ulonglong2*>(fc);
+    const ulonglong2 a01 = fc2[0], a23 = fc2[1], b01 = fc2[2], b23 = fc2[3], c01 = fc2[4], c23 = fc2[5], d01 = fc2[6];
+    const f32x2 kM2 = pack2(kMagic, kMagic), kNegM2 = pack2(-kMagic, -kMagic), kNeg1 = pack2(-1.f, -1.f);
+#pragma unroll
+    for (int jp = 0; jp < kPptF / 2; ++jp) {              // points 2jp and 2jp+1 share each FFMA2 / FADD2
+      const f32x2 X = fma2(PZ[jp], a23.x, fma2(PY[jp], a01.y, fma2(PX[jp], a01.x, a23.y)));
+      const f32x2 Y = fma2(PZ[jp], b23.x, fma2(PY[jp], b01.y, fma2(PX[jp], b01.x, b23.y)));
+      const f32x2 Z = fma2(PZ[jp], c23.x, fma2(PY[jp], c01.y, fma2(PX[jp], c01.x, c23.y)));
+      float z0, z1, r0, r1;
+      unpack2(Z, z0, z1);
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(z0));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(z1));
+      const f32x2 R = pack2(r0, r1);
+      const f32x2 U = fma2(X, R, d01.x), V = fma2(Y, R, d01.y);
+      const f32x2 SU = add2(U, kM2), SV = add2(V, kM2);
+      const f32x2 DU = fma2(add2(SU, kNegM2), kNeg1, U), DV = fma2(add2(SV, kNegM2), kNeg1, V);   // u - rint(u)
+      float du[2], dv[2], su[2], sv[2];
+      unpack2(DU, du[0], du[1]); unpack2(DV, dv[0], dv[1]); unpack2(SU, su[0], su[1]); unpack2(SV, sv[0], sv[1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * jp + h;
+        const bool decided = fabsf(du[h]) < thr_u && fabsf(dv[h]) < thr_v;                        // false for NaN
+        const uint32_t iu = (uint32_t)(__float_as_int(su[h]) - 0x4B400000), iv = (uint32_t)(__float_as_int(sv[h]) - 0x4B400000);
+        hit[j] = decided && iu < (uint32_t)W && iv < (uint32_t)H;
+        addr[j] = zb + (iv * (uint32_t)W + iu);          // only dereferenced when hit
+        if (!decided) und |= 1u << j;
+      }
+    }
+#else
+    const float4 vA = make_float4(fc[0], fc[2], fc[4], fc[6]), vB = make_float4(fc[8], fc[10], fc[12], fc[14]);
+    const float4 vC = make_float4(fc[16], fc[18], fc[20], fc[22]);
+    const float4 vD = make_float4(fc[24], fc[26], thr_u, thr_v);
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
       const float X = fmaf(pz[j], vA.z, fmaf(py[j], vA.y, fmaf(px[j], vA.x, vA.w)));
@@ -366,6 +438,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       addr[j] = zb + (iv * (uint32_t)W + iu);            // only dereferenced when hit
       if (!decided) und |= 1u << j;
     }
+#endif
     parked = (parked << kPptF) | (unsigned long long)und;
     // all early-out loads first (memory-level parallelism), then the reductions
     uint32_t cur[kPptF];
@@ -882,7 +955,7 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   dim3 grid((unsigned)tiles, (unsigned)((K + cpb - 1) / cpb));
   cudaStream_t st = p3d::as_stream(stream);
   if (filtered) {
-    const size_t smem = (size_t)cpb * (16 * sizeof(double) + sizeof(FastCam)) +
+    const size_t smem = (size_t)cpb * (16 * sizeof(double) + kPackCamFloats * sizeof(float)) +
                         (size_t)(kSplatThreads / 32) * (kQueueCap * sizeof(uint2) + sizeof(int));
     const double* dc = reinterpret_cast<const double*>(cams);
     if (mode == P3D_MODE_JOINT)
