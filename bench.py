@@ -230,8 +230,15 @@ def run_ours(args):
     alg_per_launch = batch * (G * 1 + 9 * H * W)
     avg_launch_s = (splat_ms.value / max(1, splat_launches.value)) * 1e-3
     achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
+    traffic = None
+    try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same batch size only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_splat_traffic.json")))
+        if int(tj["cameras_per_launch"]) == batch and N == 512 and H == 1024 and args.parts == "all":
+            traffic = int(tj["traffic_bytes_per_launch"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "splat_filtered_kernel<joint> (FP32 filter + exact FP64 queue)",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "splat_filtered_kernel<joint> (FP32 filter + exact FP64 queue)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch,
                 "cameras_per_launch": batch, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "splat_share_of_step": round(splat_ms.value / ms, 4),
