@@ -279,6 +279,10 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 #ifndef P3D_SCALAR_FILTER
 #define P3D_PACKED 1
 #endif
+#ifndef P3D_CAM_UNROLL
+#define P3D_CAM_UNROLL 1
+#endif
+constexpr int kCamUnroll = P3D_CAM_UNROLL;   // camera-loop unroll factor (tuning knob; 1 measured best)
 constexpr int kPackCamFloats = 32;   // per camera in shared memory: every coefficient duplicated into an f32x2
 constexpr int kFlushEvery = 64 / kPptF; // cameras between queue flushes: kPptF bits per camera in a 64-bit mask
 
@@ -381,6 +385,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
   };
 
   unsigned long long parked = 0ull;
+#pragma unroll kCamUnroll
   for (int c = 0; c < nc; ++c) {
     uint32_t* zb = zbuf + (size_t)(c0 + c) * HW;
     asm volatile("" : "+l"(zb));                          // keep the per-camera base in registers
