@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-carve", action="store_true", help="skip the secondary carving measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of configs 2 and 3")
     return ap.parse_args()
 
 
@@ -271,6 +272,8 @@ def run_ours(args):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    if world == 1 and not args.no_extra:
+        out["other_configs"] = extra_configs(dev, not args.no_cpu_baseline)
     if world == 1 and not args.no_carve:
         del scorer
         torch.cuda.empty_cache()
@@ -401,6 +404,72 @@ def carve_bench(N, dev, peak):
     except Exception as exc:      # the real mask is a test asset; never fail the headline bench because of it
         res["bibi256_pipeline"] = {"error": repr(exc)}
     return res
+
+
+def extra_configs(dev, with_cpu):
+    """BASELINE.json configs 2 and 3 as side measurements (not the headline): the real Taj grid + front mask with the
+    stored final camera (minaret parts as in notebook 2, and all parts), and the synthetic 256^3 / 4096-candidate case."""
+    import torch
+    syn = importlib.import_module(PKG + ".synthetic")
+    ce = importlib.import_module(PKG + ".utils.camera_estimation")
+    cfg = importlib.import_module(PKG + ".utils.config")
+    mu = importlib.import_module(PKG + ".utils.mask_utils")
+    out = {}
+
+    def rate(scorer, cand, reps=3):
+        cd = torch.from_numpy(cand).to(dev)
+        scorer.score_device(cd)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            scorer.score_device(cd)
+        e1.record()
+        torch.cuda.synchronize()
+        return len(cand) * reps / (e0.elapsed_time(e1) * 1e-3)
+
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    try:
+        grid = np.load(os.path.join(data, "results", "1.Orthographic_Voxel_Carving", "Taj_voxel_grid.npz"))["voxel_grid"]
+        cams = json.load(open(os.path.join(data, "results", "2.Perspective_Camera_Estimation", "Taj_camera_params_final.json")))
+        front = mu.load_mask(data, "Taj", "front", int(max(grid.shape)))
+        c = cams["front"]
+        base = np.array([*c["cam_pos"], *c["target"], c["f"], c["cx"], c["cy"]])
+        cand = syn.candidates(base, 4096)
+        gdev = torch.from_numpy(grid).to(dev)
+        for tag, parts in (("minarets", ["front_minarets", "back_minarets"]), ("all_parts", syn.PART_NAMES)):
+            sc = ce.CandidateScorer(gdev, front, cfg.PART_COLORS, parts)
+            entry = {"points": sc.n_points, "mask": list(front.shape[:2]), "candidates": len(cand),
+                     "value": round(rate(sc, cand), 1), "unit": UNIT}
+            if with_cpu and tag == "minarets":
+                from oracle import np_port
+                pts = sc.pts.cpu().numpy()
+                lut = np.zeros((256, 3), np.uint8)
+                lut[1:1 + len(sc.colours)] = np.array(sc.colours, np.uint8)
+                cols = lut[sc.pt_label.cpu().numpy()]
+                sel = {p: cfg.PART_COLORS[p] for p in parts}
+                seg = np.zeros_like(front)
+                for col in sel.values():
+                    seg[np.all(front == col, axis=-1)] = col
+                dt, _ = np_port.timed_sweep(pts, cols, seg, sel, cand[:64], front.shape[0], front.shape[1], processes=1)
+                entry["cpu_baseline"] = {"value": round(64 / dt, 2), "unit": UNIT, "cores": 1, "kind": "port",
+                                         "sample": "first 64 candidates, NumPy port, 1 process"}
+            out["taj_front_" + tag] = entry
+        del gdev
+    except Exception as exc:
+        out["taj"] = {"error": repr(exc)}
+    try:
+        N, H, W = 256, 1024, 1024
+        rgb = torch.from_numpy(syn.label_lut()).to(dev)[syn.monument_labels(N, dev).long()]
+        base = syn.base_camera(N, H, W)
+        full = ce.CandidateScorer(rgb, torch.zeros((H, W, 3), dtype=torch.uint8, device=dev), cfg.PART_COLORS, syn.PART_NAMES)
+        gt = full.render(ce.row_to_params(base + HIDDEN_DELTA))
+        sc = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, syn.PART_NAMES)
+        out["synthetic_256_4096cand"] = {"points": sc.n_points, "mask": [H, W], "candidates": 4096,
+                                         "value": round(rate(sc, syn.candidates(base, 4096), reps=2), 1), "unit": UNIT}
+    except Exception as exc:
+        out["synthetic_256_4096cand"] = {"error": repr(exc)}
+    return out
 
 
 def carve_cpu_baseline():
