@@ -90,13 +90,15 @@ int p3d_setup_cameras_f32(const float* cand, int K, float* cams, p3d_stream_t st
  *   joint    : zbuf[k][v*W+u] = max(zbuf, i+1)        (last write wins == largest index wins)
  *   per-part : zbuf[k][v*W+u] |= 1 << (pt_label[i]-1) (pt_label required, values 1..32)
  * zbuf (K,H,W) uint32 must be zero on entry.  n < 2^32-1.
- * fast (f64 entry point only; may be NULL): the (K,16) float blocks written by p3d_fast_cameras_f64 for these
- * cameras, this image size and the bounding box of `pts`.  With it the kernel decides most pixels in FP32 under a
- * proven error bound and re-projects only the undecided points in FP64 -- the z-buffer is bit-identical either
- * way; without it every point takes the FP64 path.
+ * fast, bbox (f64 entry point only; both may be NULL): the (K,16) float blocks written by p3d_fast_cameras_f64 for
+ * these cameras, this image size and the bounding box `bbox` of `pts` (p3d_points_bbox; the kernel re-centres the
+ * points on the middle of the box).  With them the kernel decides most pixels in FP32 under a proven error bound and
+ * re-projects only the undecided points in FP64 -- the z-buffer is bit-identical either way; without them every
+ * point takes the FP64 path.
  * --------------------------------------------------------------------------------------------- */
 int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K,
-                  int H, int W, int mode, uint32_t* zbuf, const float* fast, p3d_stream_t stream);
+                  int H, int W, int mode, uint32_t* zbuf, const float* fast, const float* bbox,
+                  p3d_stream_t stream);
 int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K,
                   int H, int W, int mode, uint32_t* zbuf, p3d_stream_t stream);
 

@@ -186,17 +186,22 @@ splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label
 // shared-memory queue and drained 32 at a time, so the FP64 pass runs with full warps instead of diverging.
 // The result is bit-identical to splat_kernel<double> (tests/test_camera_gpu.py).
 //
-// FP32 form (per camera constants computed in FP64 and rounded once):  with A_j = f R_0j, B_j = -f R_1j, C_j = R_2j,
-// T_A = -f e.R_0, T_B = f e.R_1, T_C = -e.R_2:
-//   X' = fma(p2,A2, fma(p1,A1, fma(p0,A0, T_A)))   (= f X),   Y' likewise (= -f Y),   Z = fma chain with C, T_C
+// FP32 form.  Points are first re-centred on the middle c of the list's bounding box, q = fl(p - c) (one rounding; exact
+// for voxel indices), which halves the magnitudes the roundings act on.  Per camera, computed in FP64 and rounded once:
+// A_j = f R_0j, B_j = -f R_1j, C_j = R_2j, T_A = f (c - e).R_0, T_B = -f (c - e).R_1, T_C = (c - e).R_2:
+//   X' = fma(q2,A2, fma(q1,A1, fma(q0,A0, T_A)))   (= f X),   Y' likewise (= -f Y),   Z = fma chain with C, T_C
 //   r = rcp.approx(Z) ;  u = fma(X', r, cx) ;  v = fma(Y', r, cy)
-// Error model (eps = 2^-24, |R| <= 1, S_p = sum_k max|p_k| over the bounding box of the point list):
-//   |Z32 - Z| <= eps DZ,  DZ = 4.04 (S_p + |T_C|)        |X'32 - f X| <= eps DX,  DX = 4.04 (f S_p + |T_A|)
-//   |u32 - u_ref| <= eps [ DX/Zmin + (|u32| + |cx|) (DZ/Zmin + 6) ]          (Zmin = min of Z over the box, FP64)
-// The kernel uses twice that plus 1e-7, evaluated at |u| = W + 2:  thr_u = 0.5 - Bmax_u.  A coordinate is decided
-// when |u32 - rint(u32)| < thr_u; decided + in range -> pixel; decided + out of range -> dropped; else exact path.
-// (Out-of-range decisions stay valid far from the image because the camera is only "fast" when
-//  b1 * 2 max(W,H) <= 0.25 and Bmax <= 0.25, so |u32 - u_ref| < 1 wherever |u32| <= 2W and < |u32|/2 beyond.)
+// Error model (eps = 2^-24, |R| <= 1, S = sum_k max|p_k - c_k| over the box, Zmin = min of Z over the box in FP64).
+// Roundings: q (1), each coefficient (1), T (1), three fma results (3 x the running magnitude <= f S + |T_A|):
+//   |X'32 - f X| <= eps DX,  DX = 5.05 f S + 4.04 |T_A|            |Z32 - Z| <= eps DZ,  DZ = 5.05 S + 4.04 |T_C|
+// rcp.approx is within 1 ulp (2 eps); the final fma rounds once (eps |u|); cx is rounded to FP32 (eps |cx|):
+//   |u32 - u_ref| <= eps [ DX/Zmin + |u - cx| (DZ/Zmin + 2) + |cx| + |u| ]
+// evaluated over the padded image, |u| <= W + 2 and |u - cx| <= Ud = max(|cx + 2|, |W + 2 - cx|) + 1; the kernel uses
+// Bmax_u = 1.25 x that (second-order terms, FP64 noise of the reference itself) + 1e-7 and thr_u = 0.5 - Bmax_u.  A
+// coordinate is decided when |u32 - rint(u32)| < thr_u; decided + in range -> pixel; decided + out of range -> dropped;
+// else exact path.  (Out-of-range decisions stay valid beyond the padded image because the bound grows with slope
+// b1 = 1.25 eps (DZ/Zmin + 3) per pixel of |u32|, and the camera is only "fast" when b1 * 2 max(W,H) <= 0.25 and
+// Bmax <= 0.25: the true coordinate cannot come back across the image border.)
 // Cameras whose box comes within max(1e-3, 2^-17 DZ) of the camera plane, or with non-finite / non-positive-f
 // parameters, or whose bound exceeds 0.25 px, get thr = -1: every point takes the exact path.
 // ------------------------------------------------------------------------------------------
@@ -207,6 +212,11 @@ struct FastCam {                     // 16 floats per camera
   float A[3], TA, B[3], TB, C[3], TC, cx, cy, thr_u, thr_v;
 };
 
+// centre of the bounding box used by the FP32 filter; the same expression in fast_cams_kernel and the splat
+__device__ __forceinline__ float bbox_centre(const float* __restrict__ bbox, int k) {
+  return __fmul_rn(0.5f, __fadd_rn(bbox[k], bbox[3 + k]));
+}
+
 __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, const float* __restrict__ bbox, int H,
                                               int W, FastCam* out) {
   FastCam fc;
@@ -216,30 +226,34 @@ __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, co
   const double f = cam[12];
   double sp = 0.0, zmin = 0.0, zabs = 0.0, ta = 0.0, tb = 0.0, tc = 0.0;
   for (int k = 0; k < 3; ++k) {
-    const double lo = (double)bbox[k], hi = (double)bbox[3 + k];
+    const double lo = (double)bbox[k], hi = (double)bbox[3 + k], c = (double)bbox_centre(bbox, k);
     ok = ok && (fabs(lo) < 1e30) && (fabs(hi) < 1e30) && lo <= hi;
-    sp += fmax(fabs(lo), fabs(hi));
+    sp += fmax(fabs(lo - c), fabs(hi - c));
     const double a = (lo - cam[k]) * cam[9 + k], b = (hi - cam[k]) * cam[9 + k];
     zmin += fmin(a, b);
     zabs += fmax(fabs(a), fabs(b));
     fc.A[k] = (float)(f * cam[3 + k]);
     fc.B[k] = (float)(-f * cam[6 + k]);
     fc.C[k] = (float)cam[9 + k];
-    ta -= f * cam[k] * cam[3 + k];
-    tb += f * cam[k] * cam[6 + k];
-    tc -= cam[k] * cam[9 + k];
+    ta += f * (c - cam[k]) * cam[3 + k];
+    tb -= f * (c - cam[k]) * cam[6 + k];
+    tc += (c - cam[k]) * cam[9 + k];
   }
   fc.TA = (float)ta; fc.TB = (float)tb; fc.TC = (float)tc;
   fc.cx = (float)cam[13]; fc.cy = (float)cam[14];
   const double eps = 5.9604644775390625e-08;                                    // 2^-24
-  const double dz = 4.04 * (sp + fabs(tc)), dxu = 4.04 * (f * sp + fabs(ta)), dxv = 4.04 * (f * sp + fabs(tb));
+  sp *= 1.0000002;                                                              // |q| <= (1 + eps) |p - c|
+  const double dz = 5.05 * sp + 4.04 * fabs(tc);
+  const double dxu = 5.05 * f * sp + 4.04 * fabs(ta), dxv = 5.05 * f * sp + 4.04 * fabs(tb);
   zmin -= 1e-9 * zabs;
   ok = ok && f > 1e-3 && zmin > fmax(1e-3, dz * 7.62939453125e-06);              // 2^-17
   double bu = 1.0, bv = 1.0, b1 = 1.0;
   if (ok) {
-    b1 = 2.0 * eps * (dz / zmin + 6.0);
-    bu = 2.0 * eps * dxu / zmin + ((double)W + 2.0 + fabs(cam[13])) * b1 + 1e-7;
-    bv = 2.0 * eps * dxv / zmin + ((double)H + 2.0 + fabs(cam[14])) * b1 + 1e-7;
+    const double cx = cam[13], cy = cam[14], dW = (double)W, dH = (double)H;
+    const double ud = fmax(fabs(cx + 2.0), fabs(dW + 2.0 - cx)) + 1.0, vd = fmax(fabs(cy + 2.0), fabs(dH + 2.0 - cy)) + 1.0;
+    b1 = 1.25 * eps * (dz / zmin + 3.0);
+    bu = 1.25 * eps * (dxu / zmin + ud * (dz / zmin + 2.0) + fabs(cx) + dW + 2.0) + 1e-7;
+    bv = 1.25 * eps * (dxv / zmin + vd * (dz / zmin + 2.0) + fabs(cy) + dH + 2.0) + 1e-7;
   }
   ok = ok && bu <= 0.25 && bv <= 0.25 && b1 * 2.0 * (double)(W > H ? W : H) <= 0.25;
   ok = ok && W < (1 << 21) && H < (1 << 21);                                     // range of the magic-number rounding
@@ -290,12 +304,11 @@ template <int MODE>
 __global__ void __launch_bounds__(kSplatThreads, P3D_MINBLOCKS)
 splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label, int64_t n,
                       const double* __restrict__ cams, int K, int cams_per_block, int H, int W,
-                      uint32_t* __restrict__ zbuf, const float* __restrict__ fast) {
+                      uint32_t* __restrict__ zbuf, const float* __restrict__ fast, const float* __restrict__ bbox) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_cam = reinterpret_cast<double*>(smem_raw);                                   // nc x 16 doubles
   float* s_fast = reinterpret_cast<float*>(s_cam + (size_t)cams_per_block * 16);          // nc x kPackCamFloats
   uint2* s_queue = reinterpret_cast<uint2*>(s_fast + (size_t)cams_per_block * kPackCamFloats);   // 8 warps x kQueueCap
-  int* s_qn = reinterpret_cast<int*>(s_queue + (kSplatThreads / 32) * kQueueCap);          // 8 counters
 
   const int c0 = blockIdx.y * cams_per_block;
   const int nc = min(cams_per_block, K - c0);
@@ -307,30 +320,34 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
     float* dst = s_fast + cc * kPackCamFloats;
     if (e < 14) { dst[2 * e] = v; dst[2 * e + 1] = v; } else { dst[28 + (e - 14)] = v; }
   }
-  if (threadIdx.x < kSplatThreads / 32) s_qn[threadIdx.x] = 0;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint2* q = s_queue + warp * kQueueCap;
-  int* qn_ptr = s_qn + warp;
+  int qn = 0;                                              // entries pending in the warp's queue (warp-uniform)
+  const float ctr0 = bbox_centre(bbox, 0), ctr1 = bbox_centre(bbox, 1), ctr2 = bbox_centre(bbox, 2);
 
   const int64_t tile = (int64_t)gridDim.x - 1 - blockIdx.x;
   const int64_t base = tile * (kSplatThreads * kPptF) + threadIdx.x;
   float px[kPptF], py[kPptF], pz[kPptF];
   uint32_t key[kPptF];
+  unsigned long long live = 0ull;                          // parked-mask bits of the points that exist (index < n)
 #pragma unroll
   for (int j = 0; j < kPptF; ++j) {
     const int64_t i = base + (int64_t)j * kSplatThreads;
     key[j] = 0;
-    px[j] = py[j] = pz[j] = __int_as_float(0x7fc00000);     // NaN: dead lanes never decide and never park (key 0)
+    px[j] = py[j] = pz[j] = __int_as_float(0x7fc00000);     // NaN: dead lanes never decide (and are never parked)
     if (i < n) {
-      px[j] = __ldg(pts + 3 * i + 0);
-      py[j] = __ldg(pts + 3 * i + 1);
-      pz[j] = __ldg(pts + 3 * i + 2);
+      px[j] = __fsub_rn(__ldg(pts + 3 * i + 0), ctr0);      // re-centred coordinates of the FP32 filter
+      py[j] = __fsub_rn(__ldg(pts + 3 * i + 1), ctr1);
+      pz[j] = __fsub_rn(__ldg(pts + 3 * i + 2), ctr2);
+      live |= 1ull << j;
       if (MODE == P3D_MODE_JOINT) key[j] = (uint32_t)(i + 1);
       else key[j] = 1u << ((uint32_t)__ldg(pt_label + i) - 1u);
     }
   }
+#pragma unroll
+  for (int g = kPptF; g < 64; g <<= 1) live |= live << g;
   const double dW = (double)W, dH = (double)H;
   const uint32_t HW = (uint32_t)H * (uint32_t)W;
   const float kMagic = 12582912.f;                         // 1.5 * 2^23: (x + m) - m == rint(x) for |x| < 2^22
@@ -345,8 +362,8 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
   }
 #endif
 
-  // exact FP64 projection of the newest `take` queue entries (one per lane)
-  auto drain32 = [&](int qn) -> int {
+  // exact FP64 projection of the newest 32 (or all remaining) queue entries, one per lane
+  auto drain32 = [&]() {
     const int take = qn < 32 ? qn : 32;
     if (lane < take) {
       const uint2 e = q[qn - take + lane];                  // (point index, camera)
@@ -355,32 +372,29 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       exact_splat<double, MODE>((double)__ldg(pp), (double)__ldg(pp + 1), (double)__ldg(pp + 2), k, s_cam + e.y * 16,
                                 zbuf + (size_t)(c0 + e.y) * HW, W, dW, dH);
     }
-    return qn - take;
+    qn -= take;
+    __syncwarp();
   };
 
-  // push the undecided (point, camera) pairs recorded in `mask`: nibble g (from the low end) belongs to camera
-  // clast - g, bit j of the nibble to point j.  Every round each lane pushes at most one entry, then full groups of 32
-  // are drained: the queue never exceeds 63.  Dead lanes (index >= n) carry NaN coordinates, are never decided and
-  // are dropped here.
+  // push the undecided (point, camera) pairs recorded in `mask`: group g of kPptF bits (from the low end) belongs to
+  // camera clast - g, bit j of the group to point j.  Every round each lane pushes at most one entry -- slots come
+  // from a ballot, the count stays in a register -- then a full group of 32 is drained: the queue never exceeds 63.
   auto flush = [&](unsigned long long mask, int clast) {
-    while (__any_sync(0xffffffffu, mask != 0ull)) {
-      if (mask) {
-        const int b = __ffsll((long long)mask) - 1;
+    mask &= live;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (;;) {
+      const bool has = mask != 0ull;
+      const uint32_t m = __ballot_sync(0xffffffffu, has);
+      if (m == 0u) break;
+      if (has) {
+        const uint32_t b = (uint32_t)(__ffsll((long long)mask) - 1);
         mask &= mask - 1ull;
-        const int64_t idx = base + (int64_t)(b % kPptF) * kSplatThreads;
-        if (idx < n) {
-          const int pos = atomicAdd(qn_ptr, 1);
-          q[pos] = make_uint2((uint32_t)idx, (uint32_t)(clast - (b / kPptF)));
-        }
+        const uint32_t idx = (uint32_t)base + (b % (uint32_t)kPptF) * (uint32_t)kSplatThreads;
+        q[qn + __popc(m & lt)] = make_uint2(idx, (uint32_t)clast - b / (uint32_t)kPptF);
       }
+      qn += __popc(m);
       __syncwarp();
-      int qn = *reinterpret_cast<volatile int*>(qn_ptr);
-      if (qn >= 32) {
-        qn = drain32(qn);
-        __syncwarp();
-        if (lane == 0) *qn_ptr = qn;
-      }
-      __syncwarp();
+      if (qn >= 32) drain32();
     }
   };
 
@@ -470,9 +484,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
     }
   }
   flush(parked, nc - 1);
-  __syncwarp();
-  int qn = *reinterpret_cast<volatile int*>(qn_ptr);
-  while (qn > 0) qn = drain32(qn);
+  while (qn > 0) drain32();
 }
 
 // Bounding box of a point list: bbox = (min x, min y, min z, max x, max y, max z); NaNs are ignored.
@@ -944,7 +956,7 @@ int fast_cameras(const double* cams, int K, const float* bbox, int H, int W, flo
 
 template <typename T>
 int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, int K, int H, int W, int mode,
-          uint32_t* zbuf, const float* fast, p3d_stream_t stream) {
+          uint32_t* zbuf, const float* fast, const float* bbox, p3d_stream_t stream) {
   P3D_REQUIRE(n >= 0 && K >= 0 && H > 0 && W > 0, "splat: n=%lld K=%d H=%d W=%d", (long long)n, K, H, W);
   P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
   P3D_REQUIRE(n < 0xffffffffll, "splat: n=%lld does not fit 32-bit keys", (long long)n);
@@ -952,7 +964,7 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   if (n == 0 || K == 0) return P3D_OK;
   P3D_REQUIRE(pts && cams && zbuf, "splat: null pointer");
   P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: per-part mode needs pt_label");
-  const bool filtered = sizeof(T) == 8 && fast != nullptr && !splat_exact_only();
+  const bool filtered = sizeof(T) == 8 && fast != nullptr && bbox != nullptr && !splat_exact_only();
   const int ppt = filtered ? kPptF : kPpt;
   const int64_t tiles = (n + kSplatThreads * ppt - 1) / (kSplatThreads * ppt);
   P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
@@ -961,12 +973,12 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   cudaStream_t st = p3d::as_stream(stream);
   if (filtered) {
     const size_t smem = (size_t)cpb * (16 * sizeof(double) + kPackCamFloats * sizeof(float)) +
-                        (size_t)(kSplatThreads / 32) * (kQueueCap * sizeof(uint2) + sizeof(int));
+                        (size_t)(kSplatThreads / 32) * (kQueueCap * sizeof(uint2));
     const double* dc = reinterpret_cast<const double*>(cams);
     if (mode == P3D_MODE_JOINT)
-      splat_filtered_kernel<P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast);
+      splat_filtered_kernel<P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
     else
-      splat_filtered_kernel<P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast);
+      splat_filtered_kernel<P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
   } else {
     const size_t smem = (size_t)cpb * 16 * sizeof(T);
     if (mode == P3D_MODE_JOINT)
@@ -1063,7 +1075,7 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
       rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, mode, zbuf,
-                    (sizeof(T) == 8 && n > 0) ? fast + (size_t)k0 * 16 : nullptr, stream);
+                    (sizeof(T) == 8 && n > 0) ? fast + (size_t)k0 * 16 : nullptr, bbox, stream);
       if (rc) return rc;
       if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
       const int vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(gt_label) & 3) == 0) &&
@@ -1112,12 +1124,13 @@ P3D_API int p3d_fast_cameras_f64(const double* cams, int K, const float* bbox, i
 }
 
 P3D_API int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K, int H,
-                          int W, int mode, uint32_t* zbuf, const float* fast, p3d_stream_t stream) {
-  return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, fast, stream);
+                          int W, int mode, uint32_t* zbuf, const float* fast, const float* bbox,
+                          p3d_stream_t stream) {
+  return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, fast, bbox, stream);
 }
 P3D_API int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K, int H,
                           int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
-  return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, nullptr, stream);
+  return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, nullptr, nullptr, stream);
 }
 
 P3D_API int p3d_resolve_rgb(const uint32_t* zbuf, const uint8_t* pt_rgb, int64_t n_pixels, uint8_t* img,

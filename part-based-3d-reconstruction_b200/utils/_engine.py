@@ -110,7 +110,7 @@ def splat(pts: torch.Tensor, pt_label, cams: torch.Tensor, H: int, W: int, mode:
                   "p3d_fast_cameras_f64")
             _launched(1)
         check(lib.p3d_splat_f64(ptr(pts), ptr(pt_label), n, ptr(cams), K, H, W, mode, ptr(zbuf), ptr(fast),
-                                stream_ptr()), "p3d_splat_f64")
+                                ptr(bbox if fast is not None else None), stream_ptr()), "p3d_splat_f64")
     else:
         check(lib.p3d_splat_f32(ptr(pts), ptr(pt_label), n, ptr(cams), K, H, W, mode, ptr(zbuf), stream_ptr()),
               "p3d_splat_f32")

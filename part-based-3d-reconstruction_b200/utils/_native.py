@@ -45,7 +45,7 @@ _SIGNATURES = {
     "p3d_points_fill": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp], _i32),
     "p3d_setup_cameras_f64": ([_vp, _i32, _vp, _vp], _i32),
     "p3d_setup_cameras_f32": ([_vp, _i32, _vp, _vp], _i32),
-    "p3d_splat_f64": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "p3d_splat_f64": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),
     "p3d_points_bbox": ([_vp, _i64, _vp, _vp], _i32),
     "p3d_fast_cameras_f64": ([_vp, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
     "p3d_splat_f32": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
