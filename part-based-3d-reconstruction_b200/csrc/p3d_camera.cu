@@ -297,7 +297,7 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 #define P3D_CAM_UNROLL 1
 #endif
 constexpr int kCamUnroll = P3D_CAM_UNROLL;   // camera-loop unroll factor (tuning knob; 1 measured best)
-constexpr int kPackCamFloats = 32;   // per camera in shared memory: every coefficient duplicated into an f32x2
+constexpr int kPackCamFloats = 16;   // per camera in shared memory: one FastCam (FFMA2 broadcasts a scalar operand)
 constexpr int kFlushEvery = 64 / kPptF; // cameras between queue flushes: kPptF bits per camera in a 64-bit mask
 
 template <int MODE>
@@ -314,11 +314,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
   const int nc = min(cams_per_block, K - c0);
   for (int i = threadIdx.x; i < nc * 16; i += kSplatThreads) {
     s_cam[i] = cams[(size_t)c0 * 16 + i];
-    // FastCam (16 floats) -> duplicated pairs: A[3],TA, B[3],TB, C[3],TC, cx, cy at 2e / 2e+1; thr_u, thr_v at 28, 29
-    const float v = fast[(size_t)c0 * 16 + i];
-    const int cc = i >> 4, e = i & 15;
-    float* dst = s_fast + cc * kPackCamFloats;
-    if (e < 14) { dst[2 * e] = v; dst[2 * e + 1] = v; } else { dst[28 + (e - 14)] = v; }
+    s_fast[i] = fast[(size_t)c0 * 16 + i];                 // FastCam: A[3],TA, B[3],TB, C[3],TC, cx, cy, thr_u, thr_v
   }
   __syncthreads();
 
@@ -406,23 +402,27 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
     uint32_t* addr[kPptF];
     bool hit[kPptF];
     uint32_t und = 0;
-    const float* fc = s_fast + c * kPackCamFloats;
-    const float thr_u = fc[28], thr_v = fc[29];
+    const float4* fc4 = reinterpret_cast<const float4*>(s_fast + c * kPackCamFloats);
+    const float4 vA = fc4[0], vB = fc4[1], vC = fc4[2], vD = fc4[3];
+    const float thr_u = vD.z, thr_v = vD.w;
 #ifdef P3D_PACKED
-    const ulonglong2* fc2 = reinterpret_cast<const ulonglong2*>(fc);
-    const ulonglong2 a01 = fc2[0], a23 = fc2[1], b01 = fc2[2], b23 = fc2[3], c01 = fc2[4], c23 = fc2[5], d01 = fc2[6];
+    // pack2(a, a) costs nothing: FFMA2 takes a scalar register as a broadcast operand
     const f32x2 kM2 = pack2(kMagic, kMagic), kNegM2 = pack2(-kMagic, -kMagic), kNeg1 = pack2(-1.f, -1.f);
+    const f32x2 A0 = pack2(vA.x, vA.x), A1 = pack2(vA.y, vA.y), A2 = pack2(vA.z, vA.z), TA = pack2(vA.w, vA.w);
+    const f32x2 B0 = pack2(vB.x, vB.x), B1 = pack2(vB.y, vB.y), B2 = pack2(vB.z, vB.z), TB = pack2(vB.w, vB.w);
+    const f32x2 C0 = pack2(vC.x, vC.x), C1 = pack2(vC.y, vC.y), C2 = pack2(vC.z, vC.z), TC = pack2(vC.w, vC.w);
+    const f32x2 CX = pack2(vD.x, vD.x), CY = pack2(vD.y, vD.y);
 #pragma unroll
     for (int jp = 0; jp < kPptF / 2; ++jp) {              // points 2jp and 2jp+1 share each FFMA2 / FADD2
-      const f32x2 X = fma2(PZ[jp], a23.x, fma2(PY[jp], a01.y, fma2(PX[jp], a01.x, a23.y)));
-      const f32x2 Y = fma2(PZ[jp], b23.x, fma2(PY[jp], b01.y, fma2(PX[jp], b01.x, b23.y)));
-      const f32x2 Z = fma2(PZ[jp], c23.x, fma2(PY[jp], c01.y, fma2(PX[jp], c01.x, c23.y)));
+      const f32x2 X = fma2(PZ[jp], A2, fma2(PY[jp], A1, fma2(PX[jp], A0, TA)));
+      const f32x2 Y = fma2(PZ[jp], B2, fma2(PY[jp], B1, fma2(PX[jp], B0, TB)));
+      const f32x2 Z = fma2(PZ[jp], C2, fma2(PY[jp], C1, fma2(PX[jp], C0, TC)));
       float z0, z1, r0, r1;
       unpack2(Z, z0, z1);
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(z0));
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(z1));
       const f32x2 R = pack2(r0, r1);
-      const f32x2 U = fma2(X, R, d01.x), V = fma2(Y, R, d01.y);
+      const f32x2 U = fma2(X, R, CX), V = fma2(Y, R, CY);
       const f32x2 SU = add2(U, kM2), SV = add2(V, kM2);
       const f32x2 DU = fma2(add2(SU, kNegM2), kNeg1, U), DV = fma2(add2(SV, kNegM2), kNeg1, V);   // u - rint(u)
       float du[2], dv[2], su[2], sv[2];
@@ -438,9 +438,6 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       }
     }
 #else
-    const float4 vA = make_float4(fc[0], fc[2], fc[4], fc[6]), vB = make_float4(fc[8], fc[10], fc[12], fc[14]);
-    const float4 vC = make_float4(fc[16], fc[18], fc[20], fc[22]);
-    const float4 vD = make_float4(fc[24], fc[26], thr_u, thr_v);
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
       const float X = fmaf(pz[j], vA.z, fmaf(py[j], vA.y, fmaf(px[j], vA.x, vA.w)));
