@@ -101,13 +101,13 @@ __global__ void __launch_bounds__(128) setup_cameras_kernel(const T* __restrict_
 // Splat.  CTA = 256 threads x kPpt points; blockIdx.y selects a group of `cams_per_block` cameras.
 // ------------------------------------------------------------------------------------------
 #ifndef P3D_SPLAT_THREADS
-#define P3D_SPLAT_THREADS 256
+#define P3D_SPLAT_THREADS 128
 #endif
 #ifndef P3D_PPTF
 #define P3D_PPTF 4
 #endif
 #ifndef P3D_MINBLOCKS
-#define P3D_MINBLOCKS 4
+#define P3D_MINBLOCKS 8
 #endif
 constexpr int kSplatThreads = P3D_SPLAT_THREADS;
 constexpr int kPpt = 2;
@@ -395,10 +395,9 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
   };
 
   unsigned long long parked = 0ull;
+  uint32_t* zb = zbuf + (size_t)c0 * HW;                   // this camera's z-buffer: advanced once per pass
 #pragma unroll kCamUnroll
-  for (int c = 0; c < nc; ++c) {
-    uint32_t* zb = zbuf + (size_t)(c0 + c) * HW;
-    asm volatile("" : "+l"(zb));                          // keep the per-camera base in registers
+  for (int c = 0; c < nc; ++c, zb += HW) {
     uint32_t* addr[kPptF];
     bool hit[kPptF];
     uint32_t und = 0;
@@ -457,10 +456,9 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
 #endif
     parked = (parked << kPptF) | (unsigned long long)und;
     // all early-out loads first (memory-level parallelism), then the reductions
-    uint32_t cur[kPptF];
+    uint32_t cur[kPptF];                                   // only meaningful (and only read) where hit[j]
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
-      cur[j] = 0xffffffffu;
 #ifdef P3D_EARLY_CA
       if (hit[j]) cur[j] = __ldca(addr[j]);
 #else
@@ -470,9 +468,9 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
       if (MODE == P3D_MODE_JOINT) {
-        if (cur[j] < key[j]) atomicMax(addr[j], key[j]);
+        if (hit[j] && cur[j] < key[j]) atomicMax(addr[j], key[j]);
       } else {
-        if ((cur[j] & key[j]) != key[j]) atomicOr(addr[j], key[j]);     // cur == ~0 when no load was issued
+        if (hit[j] && (cur[j] & key[j]) != key[j]) atomicOr(addr[j], key[j]);
       }
     }
     if ((c & (kFlushEvery - 1)) == kFlushEvery - 1) {
