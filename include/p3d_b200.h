@@ -175,6 +175,43 @@ int p3d_part_visible_f32(const float* pts, int64_t n, const float* cam, const fl
 int p3d_part_visible_f64(const float* pts, int64_t n, const double* cam, const float* zbuf, double eps, int H, int W,
                          uint8_t* mask, p3d_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------- *
+ * Stage 3: part-wise deformation with a fixed camera      utils/deformation_estimation.py  
+ * pts (n,3) float32 = voxel coordinates [x,y,z] of ONE part (get_voxel_points_by_parts); `stride` keeps every
+ * stride-th point (project_fast :35-38).  deform = (scale_y, shift_y, scale_xz, shift_xz) doubles;
+ * pix2vox = (W/W_img, H/H_img, D/W_img) doubles (:76-78).  All pointers are device pointers.
+ *   p3d_deform_centres : sums (4) int64 = exact coordinate sums + number of non-integer coordinates (must be 0);
+ *                        centres (9) doubles = per axis the mean for jitter offset 0, +0.25, -0.25 (:72, :87-96).
+ *   p3d_deform_points  : deform_coords :70-98 before np.unique -- out (7, m, 3) int64, m = ceil(n/stride).
+ *   p3d_pack_label_bits: bits[w] bit b = (labels[32w+b] == label), the ground-truth mask of one part.
+ *   p3d_deform_sweep_* : for each of D candidates: deform, bounds-test in the (A0,A1,A2) grid (:111-115), project
+ *                        through `cam` (one block of p3d_setup_cameras_f64/_f32 -- the working dtype of the
+ *                        reference's projection follows the camera arrays; f64: fast/bbox = its
+ *                        p3d_fast_cameras_f64 block for the box (0,0,0)-(A2-1,A1-1,A0-1)), and compare the covered
+ *                        pixels with gt_bits:
+ *                        counts (D,2) int64 = |proj & gt|, |proj | gt| (compute_partwise_iou for one part);
+ *                        nvalid (D) int64 = (point, jitter) pairs inside the grid.  cov: (D, ceil(H*W/32)) uint32
+ *                        scratch, zero on entry and on return.
+ *   p3d_deform_scatter : save_deformed_grid :288-311 for one part -- grid_rgb (A0,A1,A2,3)[z][y][x] = (r,g,b) at
+ *                        every valid deformed coordinate; nvalid (1) int64 may be NULL.
+ * --------------------------------------------------------------------------------------------- */
+int p3d_deform_centres(const float* pts, int64_t n, int64_t stride, int64_t* sums, double* centres,
+                       p3d_stream_t stream);
+int p3d_deform_points(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deform,
+                      const double* pix2vox, int64_t* out, p3d_stream_t stream);
+int p3d_pack_label_bits(const uint8_t* labels, int64_t n, int label, uint32_t* bits, p3d_stream_t stream);
+int p3d_deform_sweep_f64(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deforms,
+                         int D, const double* pix2vox, int A0, int A1, int A2, const double* cam, const float* fast,
+                         const float* bbox, const uint32_t* gt_bits, int H, int W, uint32_t* cov, int64_t* counts,
+                         int64_t* nvalid, p3d_stream_t stream);
+int p3d_deform_sweep_f32(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deforms,
+                         int D, const double* pix2vox, int A0, int A1, int A2, const float* cam,
+                         const uint32_t* gt_bits, int H, int W, uint32_t* cov, int64_t* counts, int64_t* nvalid,
+                         p3d_stream_t stream);
+int p3d_deform_scatter(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deform,
+                       const double* pix2vox, int A0, int A1, int A2, int r, int g, int b, uint8_t* grid_rgb,
+                       int64_t* nvalid, p3d_stream_t stream);
+
 /* Measurement hook: while enabled on the calling thread, p3d_sweep_* records a CUDA-event pair on the launch
  * stream around every splat launch; p3d_sweep_timing_read() waits for them, returns the summed splat
  * duration (ms) and the number of launches (host out-pointers), and resets the counters. */

@@ -406,3 +406,66 @@ def project_part_visible(pts3d, cam, zbuf, H, W, eps=1e-3):
     fn(_p(pts), pts.shape[0], _p(cp), _p(tg), float(cam["f"]), float(cam["cx"]), float(cam["cy"]), _p(zb),
        float(np.float32(eps)) if dt == np.float32 else float(eps), int(H), int(W), _p(mask))
     return mask.astype(bool)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 3: part-wise deformation with a fixed camera (utils/deformation_estimation.py)
+# ------------------------------------------------------------------------------------------------
+DEFORM_OFFSETS = np.array([[0, 0, 0], [0.25, 0, 0], [-0.25, 0, 0], [0, 0.25, 0], [0, -0.25, 0],
+                           [0, 0, 0.25], [0, 0, -0.25]])                    # deformation_estimation.py:87-92
+
+
+def deform_coords(coords, image_shape, voxel_shape, deform):
+    """`deform_coords` closure, deformation_estimation.py:70-103: seven jittered copies of the part's voxel coordinates,
+    each scaled/shifted about ITS OWN mean, rounded half-even to integers; rows made unique (lexicographic x, y, z)."""
+    H_img, W_img = image_shape
+    D, H, W = voxel_shape
+    px, py, pz = W / float(W_img), H / float(H_img), D / float(W_img)      # :76-78 (z uses the image WIDTH)
+    out = []
+    for off in DEFORM_OFFSETS:
+        c = coords + off                                                    # :95 (float64: offsets are float64)
+        centre = c.mean(axis=0, keepdims=True)                              # :72
+        c = c - centre
+        c[:, 0] = c[:, 0] * deform["scale_xz"] + deform["shift_xz"] * px * np.sign(c[:, 0])   # :79
+        c[:, 1] = c[:, 1] * deform["scale_y"] - deform["shift_y"] * py                          # :80
+        c[:, 2] = c[:, 2] * deform["scale_xz"] + deform["shift_xz"] * pz * np.sign(c[:, 2])   # :81
+        out.append(np.round(c + centre).astype(int))                        # :82
+    return np.unique(np.vstack(out), axis=0)                                # :100-102
+
+
+def deform_valid(coords_def, voxel_shape):
+    """Bounds test shared by update / save_params / save_deformed_grid (deformation_estimation.py:111-115)."""
+    return ((coords_def[:, 0] >= 0) & (coords_def[:, 0] < voxel_shape[2]) &
+            (coords_def[:, 1] >= 0) & (coords_def[:, 1] < voxel_shape[1]) &
+            (coords_def[:, 2] >= 0) & (coords_def[:, 2] < voxel_shape[0]))
+
+
+def deform_part_iou(voxel_grid, part_labels, image, cam_params, part, deform):
+    """`save_params` (deformation_estimation.py:263-284): IoU of ONE part after deformation, fixed camera.
+    Returns (iou, number of valid deformed voxels); with no voxel left inside the grid the projection is empty and the
+    IoU is 0/|gt| = 0.0, as in the reference."""
+    coords, colors = get_voxel_points_by_parts(voxel_grid, part_labels, [part])
+    cd = deform_coords(coords.copy(), image.shape[:2], voxel_grid.shape[:3], deform)
+    cd = cd[deform_valid(cd, voxel_grid.shape[:3])]
+    cols = np.repeat(colors, repeats=max(1, int(len(cd) / len(colors)) + 1), axis=0)[:len(cd)]   # :274
+    proj = project_colored_voxels(cd.astype(np.float32), cols, cam_params["cam_pos"], cam_params["target"],
+                                  cam_params["f"], cam_params["cx"], cam_params["cy"], image.shape[0], image.shape[1])
+    iou, _ = compute_partwise_iou(proj, image, {part: part_labels[part]})
+    return float(iou[part]), len(cd)
+
+
+def deformed_grid(voxel_grid, part_labels, image, saved_params):
+    """`save_deformed_grid` (deformation_estimation.py:288-311): parts WITH saved parameters re-drawn at their deformed
+    coordinates into an empty grid, in `part_labels` order (later parts overwrite earlier ones)."""
+    out = np.zeros_like(voxel_grid, dtype=np.uint8)
+    for part in part_labels:
+        if part not in saved_params:
+            continue
+        coords, colors = get_voxel_points_by_parts(voxel_grid, part_labels, [part])
+        cd = deform_coords(coords.copy(), image.shape[:2], voxel_grid.shape[:3], saved_params[part]["deform"])
+        cd = cd[deform_valid(cd, voxel_grid.shape[:3])]
+        if cd.size == 0:
+            continue
+        cols = np.repeat(colors, repeats=max(1, int(len(cd) / len(colors)) + 1), axis=0)[:len(cd)]
+        out[cd[:, 2], cd[:, 1], cd[:, 0]] = cols.astype(np.uint8)
+    return out

@@ -62,6 +62,14 @@ _SIGNATURES = {
     "p3d_depth_buffer_f64": ([_vp, _i64, _vp, _i32, _i32, _vp, _vp, _sz, _vp], _i32),
     "p3d_part_visible_f32": ([_vp, _i64, _vp, _vp, ctypes.c_float, _i32, _i32, _vp, _vp], _i32),
     "p3d_part_visible_f64": ([_vp, _i64, _vp, _vp, ctypes.c_double, _i32, _i32, _vp, _vp], _i32),
+    "p3d_deform_centres": ([_vp, _i64, _i64, _vp, _vp, _vp], _i32),
+    "p3d_deform_points": ([_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp], _i32),
+    "p3d_pack_label_bits": ([_vp, _i64, _i32, _vp, _vp], _i32),
+    "p3d_deform_sweep_f64": ([_vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
+                              _vp, _vp, _vp], _i32),
+    "p3d_deform_sweep_f32": ([_vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp,
+                              _vp], _i32),
+    "p3d_deform_scatter": ([_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "p3d_sweep_timing_enable": ([_i32], _i32),
     "p3d_sweep_timing_read": ([_vp, _vp], _i32),
     "p3d_resample_carve": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),

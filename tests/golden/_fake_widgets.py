@@ -1,4 +1,4 @@
-"""Minimal stand-in for ipywidgets so that the LIVE reference's launch_smart_aligner can be driven headlessly by
+"""Minimal stand-in for ipywidgets so that the LIVE reference's launch_smart_aligner / launch_deform_viewer can be driven headlessly by
 make_golden.py: sliders clamp like ipywidgets' bounded floats, buttons remember their callbacks."""
 
 
@@ -30,6 +30,27 @@ class FloatSlider(_Bounded):
 
 class IntSlider(_Bounded):
     _cast = staticmethod(int)
+
+
+class Dropdown:
+    def __init__(self, options=(), description="", value=None):
+        self.options, self.description = list(options), description
+        self._observers = []
+        self._value = self.options[0] if value is None and self.options else value
+
+    @property
+    def value(self):
+        return self._value
+
+    @value.setter
+    def value(self, v):
+        old, self._value = self._value, v
+        if v != old:
+            for cb in self._observers:
+                cb({"new": v, "old": old})
+
+    def observe(self, cb, names=None):
+        self._observers.append(cb)
 
 
 class Button:

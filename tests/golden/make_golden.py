@@ -343,6 +343,84 @@ def aligner_golden():
     np.savez_compressed(os.path.join(HERE, "aligner_golden.npz"), **out)
 
 
+def deform_golden():
+    """Drive the live launch_deform_viewer_fixed_camera (deformation_estimation.py:15-356) through fake widgets: for a
+    few (part, slider) settings record the IoU its "Save Params" button stores and the grid its "Save Deformed Grid"
+    button builds -- once with float64 camera arrays and once with float32 ones (notebook 3 converts the camera JSON
+    with dtype=float32, which switches the projection to float32).  Same half-resolution Taj grid / front mask /
+    camera as aligner_golden.npz."""
+    import _fake_widgets as fw
+    import utils.deformation_estimation as de
+    de.widgets = fw
+    de.display = lambda *a, **k: None
+    de.clear_output = lambda *a, **k: None
+    de.visualize_voxel_projection_iou = lambda *a, **k: None      # figures only (deformation_estimation.py:137)
+    ag = np.load(os.path.join(HERE, "aligner_golden.npz"))
+    grid, front, row = ag["grid"], ag["image"], ag["free_saved"]
+    part_labels = {k: v for k, v in C.PART_COLORS.items() if k != "background"}
+    out = {"cam": row}
+    buf = io.StringIO()
+
+    def run(tag, cam, parts, settings):
+        fw.Button.instances.clear()
+        captured = {}
+        orig_vbox = fw.VBox
+
+        def grab(children):
+            captured["layout"] = children
+            return orig_vbox(children)
+
+        fw.VBox = grab
+        with contextlib.redirect_stdout(buf):
+            saved, storage = de.launch_deform_viewer_fixed_camera(grid, part_labels, front, cam, parts)
+        fw.VBox = orig_vbox
+        btn = {b.description: b for b in fw.Button.instances}
+        rows = captured["layout"]
+        drop = rows[0]
+        sl = {w.description: w for r in rows[1:3] for w in r.children}
+        names, deforms, ious = [], [], []
+        with contextlib.redirect_stdout(buf):
+            for part in parts:
+                drop.value = part
+                for (sy, dy, sxz, dxz) in settings[part]:
+                    sl["scale_y"].value, sl["shift_y"].value = sy, dy
+                    sl["scale_xz"].value, sl["shift_xz"].value = sxz, dxz
+                    btn["Save Params"].click()
+                    names.append(part); deforms.append([sy, dy, sxz, dxz]); ious.append(saved[part]["iou"])
+            for part in parts:                                  # keep the first setting of every part for the grid
+                sy, dy, sxz, dxz = settings[part][0]
+                saved[part] = {"deform": {"scale_y": sy, "shift_y": dy, "scale_xz": sxz, "shift_xz": dxz}, "iou": 0.0}
+            btn["Save Deformed Grid"].click()
+        g = storage["grid"]
+        nz = np.flatnonzero(g.any(-1))
+        out.update({f"{tag}_parts": np.array(names), f"{tag}_deforms": np.array(deforms), f"{tag}_ious": np.array(ious),
+                    f"{tag}_grid_sha": np.array(sha(g)), f"{tag}_grid_nz": nz.astype(np.int64),
+                    f"{tag}_grid_rgb": g.reshape(-1, 3)[nz]})
+        print(tag, list(zip(names, ious)), "grid occupied", len(nz))
+        return btn
+
+    cam64 = {"cam_pos": row[0:3].copy(), "target": row[3:6].copy(), "f": float(row[6]), "cx": float(row[7]), "cy": float(row[8])}
+    btn = run("f64", cam64, ["front_minarets", "dome", "plinth", "chhatris"],
+              {"front_minarets": [(1.0, 0.0, 1.0, 0.0), (1.07, -6.0, 0.93, 4.0), (0.81, 11.0, 1.26, -9.0)],
+               "dome": [(1.13, 5.0, 1.1, 3.0), (0.9, -12.0, 0.77, 0.0)],
+               "plinth": [(1.5, 0.0, 0.6, -21.0)],
+               "chhatris": [(0.5, 100.0, 2.0, 100.0), (1.0, -100.0, 1.0, 0.0)]})    # last ones leave few / no voxels inside
+    cam32 = {"cam_pos": row[0:3].astype(np.float32), "target": row[3:6].astype(np.float32), "f": float(row[6]),
+             "cx": float(row[7]), "cy": float(row[8])}
+    run("f32", cam32, ["back_minarets", "dome"],
+        {"back_minarets": [(1.0, 0.0, 1.0, 0.0), (0.95, 3.0, 1.11, -5.0)], "dome": [(1.02, -2.0, 0.97, 1.0)]})
+    # deform_coords itself (closure): recover it from the callback's closure cells
+    fn = btn["Save Params"]._cb
+    cells = dict(zip(fn.__code__.co_freevars, fn.__closure__))
+    deform_coords = cells["deform_coords"].cell_contents
+    pts, _ = ref.vu.get_voxel_points_by_parts(grid, part_labels, ["back_minarets"])
+    d0 = {"scale_y": 1.21, "shift_y": 7.0, "scale_xz": 0.88, "shift_xz": -13.0}
+    cd = deform_coords(pts.copy(), front.shape[:2], grid.shape[:3], d0)
+    out.update(coords_part=np.array("back_minarets"), coords_deform=np.array([1.21, 7.0, 0.88, -13.0]), coords_def=cd.astype(np.int32))
+    np.savez_compressed(os.path.join(HERE, "deform_golden.npz"), **out)
+    print("coords", cd.shape)
+
+
 def depth_golden():
     """compute_global_depth_buffer / project_part_visible of the live utils/eval_helpers_intra.py (:134-190) on the
     half-resolution Taj grid stored in aligner_golden.npz, float32 cameras (as load_camera_json makes them) and float64."""
@@ -370,7 +448,7 @@ def depth_golden():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth"]
+    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth", "deform"]
     if "assets" in which:
         copy_assets()
     if "camera" in which:
@@ -381,6 +459,8 @@ if __name__ == "__main__":
         aligner_golden()
     if "depth" in which:
         depth_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz"):
+    if "deform" in which:
+        deform_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz"):
         if os.path.exists(os.path.join(HERE, f)):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

