@@ -296,10 +296,25 @@ int p3d_colour_mask(const uint8_t* grid_rgb, int64_t n, int r, int g, int b, uin
 size_t p3d_label6_workspace_bytes(int64_t n_voxels);
 int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components,
                void* workspace, size_t workspace_bytes, p3d_stream_t stream);
+/* skimage.measure.label(mask) for a 2-D image (8-connectivity, ids in raster order of the first pixel):
+ * camera_estimation.py:263 (extract_minaret_masks_by_label).  Workspace: p3d_label6_workspace_bytes(H*W). */
+int p3d_label8_2d(const uint8_t* mask, int H, int W, int32_t* labels, int32_t* n_components, void* workspace,
+                  size_t workspace_bytes, p3d_stream_t stream);
 /* Per component: bbox (n,6) int32 = min0,min1,min2,max0,max1,max2 (inclusive) and sums (n,4) int64 =
  * voxel count and coordinate sums per axis (:184-185, :258-259). */
 int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, int n_components, int32_t* bbox,
                         int64_t* sums, p3d_stream_t stream);
+/* Top/bottom keypoints (camera_estimation.py:329-344): per component and end e (0 = min, 1 = max of the coordinate
+ * along `axis`, read from bbox of p3d_component_stats), sums (n,2,4) int64 = count and coordinate sums of the voxels
+ * AT that extreme. */
+int p3d_component_extremes(const int32_t* labels, int n0, int n1, int n2, int n_components, int axis,
+                           const int32_t* bbox, int64_t* sums, p3d_stream_t stream);
+/* mask[i] = (labels[i] == id): one component as a 0/1 volume (np.argwhere(labeled == cid), camera_estimation.py:184). */
+int p3d_label_equals(const int32_t* labels, int64_t n, int32_t id, uint8_t* mask, p3d_stream_t stream);
+/* extract_top_bottom_voxel_points (camera_estimation.py:329-335) for a coordinate list (n,3) int32: minmax (2) int32 =
+ * range of column `axis`; sums (2,4) int64 = count and column sums of the rows at the minimum / maximum. */
+int p3d_coords_extremes(const int32_t* coords, int64_t n, int axis, int32_t* minmax, int64_t* sums,
+                        p3d_stream_t stream);
 /* recolor_backward_components :263-265: voxels of components with recolour[id-1] != 0 get the colour. */
 int p3d_recolour_components(const int32_t* labels, const uint8_t* recolour, int64_t n, int r, int g, int b,
                             uint8_t* grid_rgb, p3d_stream_t stream);

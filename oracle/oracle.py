@@ -469,3 +469,149 @@ def deformed_grid(voxel_grid, part_labels, image, saved_params):
         cols = np.repeat(colors, repeats=max(1, int(len(cd) / len(colors)) + 1), axis=0)[:len(cd)]
         out[cd[:, 2], cd[:, 1], cd[:, 0]] = cols.astype(np.uint8)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 2 initialisation chain (utils/camera_estimation.py:20-344): bbox init, minaret key points, key-point fit
+# ------------------------------------------------------------------------------------------------
+def initial_params_matching_bbox(voxel_grid, image, part_colors, parts_for_alignment, fov_deg=30):
+    """auto_compute_initial_params_matching_bbox, camera_estimation.py:56-108 (dtypes as NumPy promotes them there:
+    the voxel box is float32, the camera offset float64)."""
+    H_img, W_img = image.shape[:2]
+    pts, _ = get_voxel_points_by_parts(voxel_grid, part_colors, parts_for_alignment)
+    seg = mask_parts_from_image(image, part_colors, parts_for_alignment)
+    lo, hi = pts.min(axis=0), pts.max(axis=0)                                 # :65-66 float32
+    centre = (lo + hi) / 2
+    size = np.linalg.norm(hi - lo)                                            # :68 float32 scalar
+    ys, xs = np.where(np.any(seg > 0, axis=-1))                               # :71-72
+    img_lo, img_hi = np.array([xs.min(), ys.min()]), np.array([xs.max(), ys.max()])
+    img_width = np.linalg.norm(img_hi - img_lo)                               # :76
+    cam_pos = centre + np.array([0, 0, -size * 2.0])                          # :80
+    f = H_img / (2 * np.tan(np.deg2rad(fov_deg) / 2))                         # :85
+    approx = (size * f) / (size * 2.0)                                        # :88
+    scale = img_width / approx                                                # :91
+    return {"cam_pos": cam_pos, "target": centre, "f": f * scale, "cx": W_img / 2, "cy": H_img / 2}, scale
+
+
+def label8_2d(mask):
+    """skimage.measure.label(mask) for a 2-D image: 8-connectivity, ids in raster order of the first pixel
+    (camera_estimation.py:263); restated with scipy.ndimage.label and a full 3x3 structure."""
+    import scipy.ndimage
+    return scipy.ndimage.label(np.asarray(mask) != 0, structure=np.ones((3, 3), int))
+
+
+def minaret_voxels_by_label(voxel_grid, minaret_colors):
+    """extract_minaret_voxels_by_label, camera_estimation.py:176-207: the four tallest (extent along axis 1)
+    6-connected components of the minaret colours, named LM1/LM2/RM1/RM2 by centroid."""
+    comps = []
+    for colour in minaret_colors:
+        lab, n = label6(_colour_eq(voxel_grid, colour))
+        for cid in range(1, n + 1):
+            coords = np.argwhere(lab == cid)
+            if coords.size == 0:
+                continue
+            comps.append((coords.mean(axis=0), np.ptp(coords[:, 1]), coords))   # :187-189 (ndarray.ptp in NumPy 1.x)
+    if len(comps) < 4:
+        raise ValueError(f"Expected ≥4 minarets, found {len(comps)}")
+    top4 = sorted(comps, key=lambda c: -c[1])[:4]                             # stable: ties keep discovery order
+    cen = np.stack([c[0] for c in top4])
+    order = np.argsort(cen[:, 0])
+    left = sorted(order[:2], key=lambda i: cen[i, 2])
+    right = sorted(order[2:], key=lambda i: cen[i, 2])
+    return {"LM1": top4[left[0]][2], "LM2": top4[left[1]][2], "RM1": top4[right[0]][2], "RM2": top4[right[1]][2]}
+
+
+def minaret_masks_by_label(image, minaret_colors, min_area=50):
+    """extract_minaret_masks_by_label, camera_estimation.py:247-323."""
+    rgb = image[:, :, :3]
+    regions = []
+    for ci, colour in enumerate(minaret_colors):
+        lab, n = label8_2d(_colour_eq(rgb, colour))
+        for cid in range(1, n + 1):
+            yy, xx = np.nonzero(lab == cid)
+            if len(yy) < min_area:
+                continue
+            regions.append({"color_idx": ci, "centroid": (yy.mean(), xx.mean()), "mask": (lab == cid).astype(np.uint8)})
+    if len(regions) < 2:
+        raise ValueError("Not enough minarets for camera alignment")
+    regions.sort(key=lambda r: r["centroid"][1])                              # left -> right (:279)
+    mid = len(regions) // 2
+
+    def front_back(side):
+        if len(side) == 1:
+            return side[0], None
+        side = sorted(side, key=lambda r: (r["color_idx"], r["centroid"][0]))
+        return side[0], side[1]
+
+    (lm1, lm2), (rm1, rm2) = front_back(regions[:mid]), front_back(regions[mid:])
+    out = {}
+    for key, reg in (("LM1", lm1), ("RM1", rm1), ("LM2", lm2), ("RM2", rm2)):  # insertion order of :317-320
+        if reg:
+            out[key] = reg["mask"]
+    return out
+
+
+def top_bottom_voxel_points(voxel_parts):
+    """extract_top_bottom_voxel_points, camera_estimation.py:329-335."""
+    out = {}
+    for name, vox in voxel_parts.items():
+        y = vox[:, 1]
+        out[f"{name}_bottom"] = vox[y == y.min()].mean(axis=0)
+        out[f"{name}_top"] = vox[y == y.max()].mean(axis=0)
+    return out
+
+
+def top_bottom_image_points(mask_parts):
+    """extract_top_bottom_image_points, camera_estimation.py:338-344."""
+    out = {}
+    for name, m in mask_parts.items():
+        yy, xx = np.nonzero(m)
+        out[f"{name}_top"] = (xx[yy == yy.min()].mean(), yy.min())
+        out[f"{name}_bottom"] = (xx[yy == yy.max()].mean(), yy.max())
+    return out
+
+
+def minaret_kps_for_view(voxel_grid, mask_img, minaret_colors):
+    """extract_minaret_kps_for_view, camera_estimation.py:20-50."""
+    vparts, mparts = minaret_voxels_by_label(voxel_grid, minaret_colors), minaret_masks_by_label(mask_img, minaret_colors)
+    common = [k for k in vparts if k in mparts]
+    if len(common) < 2:
+        raise ValueError("Not enough visible minarets")
+    vk, ik = top_bottom_voxel_points({k: vparts[k] for k in common}), top_bottom_image_points({k: mparts[k] for k in common})
+    vsel, isel = {}, {}
+    for k in vk:
+        m = k.split("_")[0]
+        if ("1" in m) or ("2" in m and "top" in k):
+            vsel[k], isel[k] = vk[k], ik[k]
+    if len(vsel) < 2:
+        raise ValueError("Not enough keypoints after filtering")
+    return vsel, isel
+
+
+def project_point(pt3d, cam_pos, target, f, cx, cy):
+    """camera_geometry.py:17-27 (un-rounded pixel coordinates of one point)."""
+    R = look_at_rotation(np.asarray(cam_pos), np.asarray(target))
+    X, Y, Z = (np.asarray(pt3d) - np.asarray(cam_pos)) @ R.T
+    Z = max(Z, 1e-8)
+    return np.array([(X / Z) * f + cx, -(Y / Z) * f + cy])
+
+
+def optimize_camera_with_keypoints(voxel_kps, image_kps, image, init_params, loss_type="L2"):
+    """camera_estimation.py:110-170: L-BFGS-B on the 9 camera parameters, squared (or absolute) reprojection error of
+    the key points.  Returns (params, final loss)."""
+    from scipy.optimize import minimize
+    H, W = image.shape[:2]
+    keys = list(image_kps.keys())
+
+    def loss(x):
+        total = 0
+        for k in keys:
+            d = project_point(voxel_kps[k], x[0:3], x[3:6], x[6], x[7], x[8]) - image_kps[k]
+            total += (np.abs(d) if loss_type == "L1" else d ** 2).sum()
+        return total
+
+    x0 = [*init_params["cam_pos"], *init_params["target"], init_params["f"], init_params["cx"], init_params["cy"]]
+    bounds = [(-W, 2 * W), (-H, 2 * H), (-2000, 100), (-W, 2 * W), (-H, 2 * H), (-2000, 100), (10, 2000), (0, W), (0, H)]
+    res = minimize(loss, x0, bounds=bounds, method="L-BFGS-B")
+    x = res.x
+    return {"cam_pos": np.array(x[0:3]), "target": np.array(x[3:6]), "f": x[6], "cx": x[7], "cy": x[8]}, res.fun

@@ -632,6 +632,22 @@ ccl_merge_kernel(const uint8_t* __restrict__ mask, int n0, int n1, int n2, int32
   }
 }
 
+// 8-connected 2-D variant (skimage.measure.label's default for images, camera_estimation.py:263): W, N, NW, NE.
+__global__ void __launch_bounds__(256)
+ccl_merge8_kernel(const uint8_t* __restrict__ mask, int H, int W, int32_t* __restrict__ parent) {
+  const int64_t n = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!mask[i]) continue;
+    const int x = (int)(i % W), y = (int)(i / W);
+    if (x > 0 && mask[i - 1]) uf_union(parent, (int32_t)i, (int32_t)(i - 1));
+    if (y > 0) {
+      if (mask[i - W]) uf_union(parent, (int32_t)i, (int32_t)(i - W));
+      if (x > 0 && mask[i - W - 1]) uf_union(parent, (int32_t)i, (int32_t)(i - W - 1));
+      if (x + 1 < W && mask[i - W + 1]) uf_union(parent, (int32_t)i, (int32_t)(i - W + 1));
+    }
+  }
+}
+
 // parent[i] <- root(i); is_root[i] = (root == i)
 __global__ void __launch_bounds__(256)
 ccl_flatten_kernel(int64_t n, int32_t* __restrict__ parent, uint8_t* __restrict__ is_root) {
@@ -759,6 +775,73 @@ component_stats_kernel(const int32_t* __restrict__ labels, int n0, int n1, int n
     atomicAdd(s + 0, 1ull); atomicAdd(s + 1, (unsigned long long)a);
     atomicAdd(s + 2, (unsigned long long)b); atomicAdd(s + 3, (unsigned long long)c);
   }
+}
+
+// per component and end (0 = minimum, 1 = maximum of the coordinate along `axis`, taken from bbox): voxel count and
+// coordinate sums of the voxels AT that extreme -- the top/bottom keypoints of camera_estimation.py:329-344.
+__global__ void __launch_bounds__(256)
+component_extremes_kernel(const int32_t* __restrict__ labels, int n0, int n1, int n2, int axis,
+                          const int32_t* __restrict__ bbox, unsigned long long* __restrict__ sums /* [comp][2][4] */) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t l = labels[i];
+    if (l <= 0) continue;
+    int c[3];
+    c[2] = (int)(i % n2);
+    const int64_t r = i / n2;
+    c[1] = (int)(r % n1);
+    c[0] = (int)(r / n1);
+    const int32_t* bb = bbox + (size_t)(l - 1) * 6;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (c[axis] != bb[3 * e + axis]) continue;
+      unsigned long long* s = sums + ((size_t)(l - 1) * 2 + e) * 4;
+      atomicAdd(s + 0, 1ull); atomicAdd(s + 1, (unsigned long long)c[0]);
+      atomicAdd(s + 2, (unsigned long long)c[1]); atomicAdd(s + 3, (unsigned long long)c[2]);
+    }
+  }
+}
+
+// mask[i] = (labels[i] == id): one component as a 0/1 volume (np.argwhere(labeled == cid), camera_estimation.py:184)
+__global__ void __launch_bounds__(256)
+label_equals_kernel(const int32_t* __restrict__ labels, int64_t n, int32_t id, uint8_t* __restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = labels[i] == id;
+}
+
+// coordinate lists (n,3) int32: range of one column, then count / column sums of the rows at either end of that range
+__global__ void __launch_bounds__(256)
+coords_minmax_kernel(const int32_t* __restrict__ coords, int64_t n, int axis, int32_t* __restrict__ mm) {
+  int lo = 0x7fffffff, hi = (int)0x80000000;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = coords[3 * i + axis];
+    lo = min(lo, v); hi = max(hi, v);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+
+__global__ void __launch_bounds__(256)
+coords_extreme_sums_kernel(const int32_t* __restrict__ coords, int64_t n, int axis, const int32_t* __restrict__ mm,
+                           long long* __restrict__ sums /* [2][4] = count, sum of columns 0..2 */) {
+  const int lo = mm[0], hi = mm[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = coords[3 * i + axis];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (v != (e ? hi : lo)) continue;
+      unsigned long long* s = reinterpret_cast<unsigned long long*>(sums) + e * 4;
+      atomicAdd(s + 0, 1ull);
+      for (int k = 0; k < 3; ++k) atomicAdd(s + 1 + k, (unsigned long long)(long long)coords[3 * i + k]);
+    }
+  }
+}
+
+__global__ void coords_mm_init_kernel(int32_t* mm) {
+  if (threadIdx.x == 0) { mm[0] = 0x7fffffff; mm[1] = (int)0x80000000; }
 }
 
 __global__ void __launch_bounds__(256) bbox_init_kernel(int32_t* __restrict__ bbox, int ncomp) {
@@ -1143,8 +1226,8 @@ P3D_API size_t p3d_label6_workspace_bytes(int64_t n) {
   return p3d_align_up((size_t)n * 4, 256) + p3d_align_up((size_t)n, 256) + p3d_align_up((size_t)(tiles + 1) * 4, 256);
 }
 
-P3D_API int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components,
-                       void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+static int label_components(const uint8_t* mask, int n0, int n1, int n2, bool eight2d, int32_t* labels,
+                            int32_t* n_components, void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
   P3D_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0 && n_components, "label6: bad arguments");
   const int64_t n = (int64_t)n0 * n1 * n2;
   cudaStream_t st = p3d::as_stream(stream);
@@ -1163,7 +1246,8 @@ P3D_API int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* lab
   const int blocks = grid_for(n, 256, 16);
   int32_t* parent = labels;                              // labels doubles as the union-find forest
   ccl_init_kernel<<<blocks, 256, 0, st>>>(mask, n, parent);
-  ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, n0, n1, n2, parent);
+  if (eight2d) ccl_merge8_kernel<<<blocks, 256, 0, st>>>(mask, n1, n2, parent);
+  else ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, n0, n1, n2, parent);
   ccl_flatten_kernel<<<blocks, 256, 0, st>>>(n, parent, is_root);
   root_count_kernel<<<tiles, kRankThreads, 0, st>>>(is_root, n, tiles_buf);
   root_scan_kernel<<<1, 1024, 0, st>>>(tiles_buf, tiles, n_components);
@@ -1172,6 +1256,16 @@ P3D_API int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* lab
   ccl_relabel_kernel<<<blocks, 256, 0, st>>>(parent, rank_of, n, labels);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
+}
+
+P3D_API int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components,
+                       void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  return label_components(mask, n0, n1, n2, false, labels, n_components, workspace, workspace_bytes, stream);
+}
+
+P3D_API int p3d_label8_2d(const uint8_t* mask, int H, int W, int32_t* labels, int32_t* n_components, void* workspace,
+                          size_t workspace_bytes, p3d_stream_t stream) {
+  return label_components(mask, 1, H, W, true, labels, n_components, workspace, workspace_bytes, stream);
 }
 
 P3D_API int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, int n_components, int32_t* bbox,
@@ -1185,6 +1279,44 @@ P3D_API int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, i
   P3D_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_components * 4 * sizeof(int64_t), st));
   component_stats_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(labels, n0, n1, n2, bbox,
                                                              reinterpret_cast<unsigned long long*>(sums));
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_component_extremes(const int32_t* labels, int n0, int n1, int n2, int n_components, int axis,
+                                   const int32_t* bbox, int64_t* sums, p3d_stream_t stream) {
+  P3D_REQUIRE(n_components >= 0 && axis >= 0 && axis < 3, "component_extremes: bad arguments");
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  if (n_components == 0 || n == 0) return P3D_OK;
+  P3D_REQUIRE(labels && bbox && sums, "component_extremes: null pointer");
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_components * 8 * sizeof(int64_t), st));
+  component_extremes_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(labels, n0, n1, n2, axis, bbox,
+                                                                reinterpret_cast<unsigned long long*>(sums));
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_label_equals(const int32_t* labels, int64_t n, int32_t id, uint8_t* mask, p3d_stream_t stream) {
+  if (n <= 0) return P3D_OK;
+  P3D_REQUIRE(labels && mask, "label_equals: null pointer");
+  label_equals_kernel<<<grid_for(n, 256, 16), 256, 0, p3d::as_stream(stream)>>>(labels, n, id, mask);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_coords_extremes(const int32_t* coords, int64_t n, int axis, int32_t* minmax, int64_t* sums,
+                                p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && axis >= 0 && axis < 3 && minmax && sums, "coords_extremes: bad arguments");
+  cudaStream_t st = p3d::as_stream(stream);
+  coords_mm_init_kernel<<<1, 32, 0, st>>>(minmax);
+  P3D_CUDA(cudaMemsetAsync(sums, 0, 8 * sizeof(int64_t), st));
+  if (n > 0) {
+    P3D_REQUIRE(coords, "coords_extremes: null coordinates");
+    coords_minmax_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(coords, n, axis, minmax);
+    coords_extreme_sums_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(coords, n, axis, minmax,
+                                                                   reinterpret_cast<long long*>(sums));
+  }
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

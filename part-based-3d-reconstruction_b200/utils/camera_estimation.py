@@ -2,8 +2,12 @@
 
 Reference functions covered: compute_partwise_iou (:770-787), the `evaluate` / `quick_overlay_proj`
 closures of launch_smart_aligner (:552-572, :597-603) as a batched scorer, the three optimiser loops
-(:606-725) as a headless `SmartAligner`, and the scoring core of visualize_voxel_projection_iou
-(:381-403, :433-447).  The ipywidgets UI itself is not reproduced.
+(:606-725) as a headless `SmartAligner`, the scoring core of visualize_voxel_projection_iou
+(:381-403, :433-447), and the initialisation chain of notebook 2:
+auto_compute_initial_params_matching_bbox (:56-108), extract_minaret_voxels_by_label (:176-207),
+extract_minaret_masks_by_label (:247-323), extract_top_bottom_voxel_points / _image_points (:329-344),
+extract_minaret_kps_for_view (:20-50) and optimize_camera_with_keypoints (:110-170).
+The ipywidgets UI itself is not reproduced.
 """
 from __future__ import annotations
 
@@ -14,7 +18,7 @@ from . import _engine as eng
 from . import _native as nv
 from .camera_geometry import candidate_row
 from .mask_utils import image_labels
-from .voxel_utils import device_points_by_parts
+from .voxel_utils import device_points_by_parts, grid_to_device
 
 _STEP_SIZES = np.array([50, 50, 100, 50, 50, 100, 50, 20, 20], dtype=np.float64)   # camera_estimation.py:611-617
 
@@ -197,9 +201,9 @@ class SmartAligner:
 
     def __init__(self, voxel_grid, image, part_colors, parts_for_alignment=("plinth", "minarets"), init_params=None,
                  lock_xy_equal=False, device=None, scorer=None, verbose=True):
-        if init_params is None:
-            raise NotImplementedError("auto_compute_initial_params_matching_bbox (camera_estimation.py:56-108) is outside "
-                                      "this package's scope: pass init_params")
+        if init_params is None:                                   # camera_estimation.py:525-526
+            init_params = auto_compute_initial_params_matching_bbox(voxel_grid, image, part_colors,
+                                                                    list(parts_for_alignment), device=device)
         self.H, self.W = int(image.shape[0]), int(image.shape[1])
         self.lock_xy_equal = bool(lock_xy_equal)
         self.verbose = verbose
@@ -397,3 +401,251 @@ def visualize_voxel_projection_iou(voxel_grid, part_colors, image, cam_params, m
         print("Visualizing combined binary projection vs. binary ground-truth...")
         print(f"Combined Binary | IoU: {combined:.3f}")
     return per_part, combined
+
+
+# --------------------------------------------------------------------------------------------
+# initialisation chain of notebook 2 (camera_estimation.py:20-344)
+# --------------------------------------------------------------------------------------------
+def _mask_bbox_2d(mask_u8: torch.Tensor):
+    """(x_min, y_min, x_max, y_max, count) of the non-zero pixels of an (H,W) u8 device mask."""
+    H, W = mask_u8.shape
+    lab = mask_u8.to(torch.int32).contiguous()
+    bbox = torch.empty((1, 6), dtype=torch.int32, device=mask_u8.device)
+    sums = torch.empty((1, 4), dtype=torch.int64, device=mask_u8.device)
+    nv.check(nv.lib.p3d_component_stats(nv.ptr(lab), 1, H, W, 1, nv.ptr(bbox), nv.ptr(sums), nv.stream_ptr()),
+             "p3d_component_stats")
+    eng._launched(2)
+    b, n = bbox.cpu().numpy()[0], int(sums[0, 0].item())
+    return int(b[2]), int(b[1]), int(b[5]), int(b[4]), n
+
+
+def auto_compute_initial_params_matching_bbox(voxel_grid, image, part_colors, parts_for_alignment, fov_deg=30,
+                                              device=None):
+    """camera_estimation.py:56-108: camera on the -z side of the selected parts' bounding box, focal length scaled so
+    that the box diagonal matches the diagonal of the mask's bounding box.  The two bounding boxes are reduced on the
+    GPU; the scalar arithmetic keeps the reference's NumPy dtypes (float32 voxel box, float64 focal length)."""
+    dev = nv.require_cuda(device)
+    with torch.cuda.device(dev):
+        img = nv.to_device(image, torch.uint8, dev)
+        H_img, W_img = int(img.shape[0]), int(img.shape[1])
+        pts, _, colours, _ = device_points_by_parts(voxel_grid, part_colors, list(parts_for_alignment), dev)
+        if pts.shape[0] == 0:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        box = eng.points_bbox(pts).cpu().numpy()
+        x0, y0, x1, y1, n = _mask_bbox_2d((image_labels(img, colours, dev) != 0).to(torch.uint8))
+        if n == 0:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    bbox_min, bbox_max = box[0:3].astype(np.float32), box[3:6].astype(np.float32)
+    voxel_center = (bbox_min + bbox_max) / 2
+    voxel_size = np.linalg.norm(bbox_max - bbox_min)
+    img_bbox_width = np.linalg.norm(np.array([x1, y1]) - np.array([x0, y0]))
+    cam_pos = voxel_center + np.array([0, 0, -voxel_size * 2.0])
+    f = H_img / (2 * np.tan(np.deg2rad(fov_deg) / 2))
+    scale_factor = img_bbox_width / ((voxel_size * f) / (voxel_size * 2.0))
+    f_adjusted = f * scale_factor
+    print(f"Estimated scale factor: {scale_factor:.4f}")
+    print(f"Adjusted focal length: {f_adjusted:.2f}")
+    return {"cam_pos": cam_pos, "target": voxel_center, "f": f_adjusted, "cx": W_img / 2, "cy": H_img / 2}
+
+
+def _component_coords(labels: torch.Tensor, cid: int) -> np.ndarray:
+    """np.argwhere(labeled == cid): (n,3) int64 [a0,a1,a2] in raster order."""
+    mask = torch.empty(labels.shape, dtype=torch.uint8, device=labels.device)
+    nv.check(nv.lib.p3d_label_equals(nv.ptr(labels), labels.numel(), int(cid), nv.ptr(mask), nv.stream_ptr()),
+             "p3d_label_equals")
+    eng._launched(1)
+    pts, _ = eng.compact_points(mask)
+    return pts.cpu().numpy()[:, ::-1].astype(np.int64)
+
+
+def extract_minaret_voxels_by_label(voxel_grid, minaret_colors, device=None):
+    """camera_estimation.py:176-207: the four tallest (extent along axis 1) 6-connected components of the minaret
+    colours, as coordinate arrays named LM1/LM2 (left, front/back) and RM1/RM2."""
+    from .voxel_carving_utils import _colour_mask, _label_components
+    dev = nv.require_cuda(device)
+    comps = []
+    with torch.cuda.device(dev):
+        grid = grid_to_device(voxel_grid, dev)
+        for colour in minaret_colors:
+            labels, n, bbox, sums = _label_components(_colour_mask(grid, colour))
+            for cid in range(1, n + 1):
+                cnt = sums[cid - 1, 0]
+                centroid = sums[cid - 1, 1:4].astype(np.float64) / cnt           # coords.mean(axis=0): exact sums
+                height = int(bbox[cid - 1, 4] - bbox[cid - 1, 1])                # coords[:, 1].ptp()
+                comps.append((centroid, height, labels, cid))
+        if len(comps) < 4:
+            raise ValueError(f"Expected ≥4 minarets, found {len(comps)}")
+        top4 = sorted(comps, key=lambda c: -c[1])[:4]
+        centroids = np.stack([c[0] for c in top4])
+        coord_sets = [_component_coords(c[2], c[3]) for c in top4]
+    order_x = np.argsort(centroids[:, 0])
+    left, right = order_x[:2], order_x[2:]
+    left = sorted(left, key=lambda i: centroids[i, 2])
+    right = sorted(right, key=lambda i: centroids[i, 2])
+    return {"LM1": coord_sets[left[0]], "LM2": coord_sets[left[1]], "RM1": coord_sets[right[0]], "RM2": coord_sets[right[1]]}
+
+
+def _label_image8(mask_u8: torch.Tensor):
+    """skimage.measure.label for an (H,W) mask (8-connectivity): (labels int32, n, bbox (n,6), sums (n,4))."""
+    H, W = mask_u8.shape
+    dev = mask_u8.device
+    labels = torch.empty((1, H, W), dtype=torch.int32, device=dev)
+    ncomp = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(nv.lib.p3d_label6_workspace_bytes(H * W))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    nv.check(nv.lib.p3d_label8_2d(nv.ptr(mask_u8), H, W, nv.ptr(labels), nv.ptr(ncomp), nv.ptr(ws), ws_bytes,
+                                  nv.stream_ptr()), "p3d_label8_2d")
+    eng._launched(7)
+    n = int(ncomp.item())
+    bbox = torch.empty((max(n, 1), 6), dtype=torch.int32, device=dev)
+    sums = torch.empty((max(n, 1), 4), dtype=torch.int64, device=dev)
+    nv.check(nv.lib.p3d_component_stats(nv.ptr(labels), 1, H, W, n, nv.ptr(bbox), nv.ptr(sums), nv.stream_ptr()),
+             "p3d_component_stats")
+    eng._launched(2 if n else 0)
+    return labels, n, bbox.cpu().numpy()[:n], sums.cpu().numpy()[:n]
+
+
+def extract_minaret_masks_by_label(image, minaret_colors, min_area=50, device=None):
+    """camera_estimation.py:247-323: 8-connected regions of the minaret colours with at least `min_area` pixels, split
+    left/right by centroid column, front/back by colour order then centroid row; (H,W) uint8 masks."""
+    dev = nv.require_cuda(device)
+    regions = []
+    with torch.cuda.device(dev):
+        img = nv.to_device(image, torch.uint8, dev)[:, :, :3].contiguous()
+        H, W = int(img.shape[0]), int(img.shape[1])
+        for color_idx, colour in enumerate(minaret_colors):
+            c = tuple(int(v) for v in np.asarray(colour).reshape(3))
+            labels, n, _, sums = _label_image8(image_labels(img, [c], dev))
+            for cid in range(1, n + 1):
+                area = int(sums[cid - 1, 0])
+                if area < min_area:
+                    continue
+                regions.append({"color_idx": color_idx, "centroid": (sums[cid - 1, 2] / area, sums[cid - 1, 3] / area),
+                                "area": area, "label": cid, "labels": labels})
+        if len(regions) < 2:
+            raise ValueError("Not enough minarets for camera alignment")
+        regions.sort(key=lambda r: r["centroid"][1])
+        mid = len(regions) // 2
+
+        def pick_front_back(side):
+            if len(side) == 1:
+                return side[0], None
+            side = sorted(side, key=lambda r: (r["color_idx"], r["centroid"][0]))
+            return side[0], side[1]
+
+        (LM1, LM2), (RM1, RM2) = pick_front_back(regions[:mid]), pick_front_back(regions[mid:])
+
+        def region_to_mask(region):
+            m = torch.empty((H, W), dtype=torch.uint8, device=dev)
+            nv.check(nv.lib.p3d_label_equals(nv.ptr(region["labels"]), H * W, region["label"], nv.ptr(m), nv.stream_ptr()),
+                     "p3d_label_equals")
+            eng._launched(1)
+            return m.cpu().numpy()
+
+        out = {}
+        for key, region in (("LM1", LM1), ("RM1", RM1), ("LM2", LM2), ("RM2", RM2)):
+            if region:
+                out[key] = region_to_mask(region)
+    return out
+
+
+def _coords_extremes(coords_i32: torch.Tensor, axis: int):
+    mm = torch.empty(2, dtype=torch.int32, device=coords_i32.device)
+    sums = torch.empty((2, 4), dtype=torch.int64, device=coords_i32.device)
+    nv.check(nv.lib.p3d_coords_extremes(nv.ptr(coords_i32), coords_i32.shape[0], axis, nv.ptr(mm), nv.ptr(sums),
+                                        nv.stream_ptr()), "p3d_coords_extremes")
+    eng._launched(3)
+    return mm.cpu().numpy(), sums.cpu().numpy()
+
+
+def extract_top_bottom_voxel_points(voxel_parts, device=None):
+    """camera_estimation.py:329-335: mean coordinate of the voxels at the lowest / highest axis-1 value."""
+    dev = nv.require_cuda(device)
+    out = {}
+    for name, vox in voxel_parts.items():
+        v = np.asarray(vox)
+        if v.shape[0] == 0:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        _, sums = _coords_extremes(torch.from_numpy(np.ascontiguousarray(v, dtype=np.int32)).to(dev), 1)
+        out[f"{name}_bottom"] = sums[0, 1:4].astype(np.float64) / sums[0, 0]
+        out[f"{name}_top"] = sums[1, 1:4].astype(np.float64) / sums[1, 0]
+    return out
+
+
+def extract_top_bottom_image_points(mask_parts, device=None):
+    """camera_estimation.py:338-344: (mean column of the mask's first row, that row) and the same for its last row."""
+    dev = nv.require_cuda(device)
+    out = {}
+    with torch.cuda.device(dev):
+        for name, mask in mask_parts.items():
+            m = nv.to_device((np.asarray(mask) != 0).astype(np.uint8), torch.uint8, dev).to(torch.int32).contiguous()
+            H, W = m.shape
+            bbox = torch.empty((1, 6), dtype=torch.int32, device=dev)
+            sums = torch.empty((1, 4), dtype=torch.int64, device=dev)
+            ext = torch.empty((1, 2, 4), dtype=torch.int64, device=dev)
+            nv.check(nv.lib.p3d_component_stats(nv.ptr(m), 1, H, W, 1, nv.ptr(bbox), nv.ptr(sums), nv.stream_ptr()),
+                     "p3d_component_stats")
+            nv.check(nv.lib.p3d_component_extremes(nv.ptr(m), 1, H, W, 1, 1, nv.ptr(bbox), nv.ptr(ext), nv.stream_ptr()),
+                     "p3d_component_extremes")
+            eng._launched(3)
+            if int(sums[0, 0].item()) == 0:
+                raise ValueError("zero-size array to reduction operation minimum which has no identity")
+            b, e = bbox.cpu().numpy()[0], ext.cpu().numpy()[0]
+            out[f"{name}_top"] = (e[0, 3] / e[0, 0], b[1].astype(np.int64))
+            out[f"{name}_bottom"] = (e[1, 3] / e[1, 0], b[4].astype(np.int64))
+    return out
+
+
+def extract_minaret_kps_for_view(voxel_grid, mask_img, minaret_colors, back_top_only=False, device=None):
+    """camera_estimation.py:20-50: matching 3-D / 2-D key points of the minarets visible in this view (front minarets:
+    top and bottom; back minarets: top only)."""
+    voxel_parts = extract_minaret_voxels_by_label(voxel_grid, minaret_colors, device=device)
+    mask_parts = extract_minaret_masks_by_label(mask_img, minaret_colors, device=device)
+    common = [k for k in voxel_parts if k in mask_parts]       # the reference's list(set & set) has no defined order
+    if len(common) < 2:
+        raise ValueError("Not enough visible minarets")
+    voxel_kps = extract_top_bottom_voxel_points({k: voxel_parts[k] for k in common}, device=device)
+    image_kps = extract_top_bottom_image_points({k: mask_parts[k] for k in common}, device=device)
+    voxel_sel, image_sel = {}, {}
+    for k in voxel_kps:
+        m = k.split("_")[0]
+        if ("1" in m) or ("2" in m and "top" in k):
+            voxel_sel[k] = voxel_kps[k]
+            image_sel[k] = image_kps[k]
+    if len(voxel_sel) < 2:
+        raise ValueError("Not enough keypoints after filtering")
+    return voxel_sel, image_sel
+
+
+def optimize_camera_with_keypoints(voxel_keypoints_dict, image_keypoints_dict, image, init_params, loss_type="L2",
+                                   verbose=True):
+    """camera_estimation.py:110-170: L-BFGS-B (scipy, on the host like the reference: 9 unknowns, <= 8 key points) on the
+    squared / absolute reprojection error; the look-at rotation of every evaluation comes from the device kernel the
+    sweep uses (camera_geometry.project)."""
+    from scipy.optimize import minimize
+    from .camera_geometry import project
+    H, W = np.asarray(image).shape[:2] if not isinstance(image, torch.Tensor) else image.shape[:2]
+    keys = list(image_keypoints_dict.keys())
+
+    def loss_fn(x):
+        cam_pos, target = np.array([x[0], x[1], x[2]]), np.array([x[3], x[4], x[5]])
+        total = 0
+        for k in keys:
+            proj_pt = project(voxel_keypoints_dict[k], cam_pos, target, x[6], x[7], x[8])
+            gt_pt = image_keypoints_dict[k]
+            error = np.abs(proj_pt - gt_pt) if loss_type == "L1" else (proj_pt - gt_pt) ** 2
+            total += error.sum()
+        return total
+
+    x0 = [*init_params["cam_pos"], *init_params["target"], init_params["f"], init_params["cx"], init_params["cy"]]
+    bounds = [(-W, 2 * W), (-H, 2 * H), (-2000, 100), (-W, 2 * W), (-H, 2 * H), (-2000, 100), (10, 2000), (0, W), (0, H)]
+    result = minimize(loss_fn, x0, bounds=bounds, method="L-BFGS-B")
+    x = result.x
+    final_params = {"cam_pos": np.array([x[0], x[1], x[2]]), "target": np.array([x[3], x[4], x[5]]), "f": x[6],
+                    "cx": x[7], "cy": x[8]}
+    if verbose:
+        print("\n\U0001F4F7 Optimized Camera Parameters:")
+        for k, v in final_params.items():
+            print(f"{k}: {v}")
+        print(f"\U0001F4C9 Final Reprojection Loss: {result.fun:.2f}")
+    return final_params

@@ -421,6 +421,73 @@ def deform_golden():
     print("coords", cd.shape)
 
 
+def init_golden():
+    """Camera initialisation chain of the live reference (camera_estimation.py:20-344) on the half-resolution Taj grid
+    and front mask: bbox init, minaret extraction (3-D and 2-D), top/bottom key points, key-point L-BFGS-B fit.
+    Two shims, needed only because of this container's library versions (the reference's own code is unmodified):
+      * ndarray.ptp() was removed in NumPy 2 (camera_estimation.py:189): np.argwhere is wrapped to return an ndarray
+        subclass that still has it;
+      * scikit-image is not installed: `label2d` / `regionprops` (camera_estimation.py:8, 246, 263-266) are replaced by
+        scipy.ndimage.label with a full 3x3 structure (skimage's default 8-connectivity, same raster-order ids) and a
+        minimal regionprops (area, centroid = mean row/col, label)."""
+    import types
+    ce = ref.ce
+
+    class _Arr(np.ndarray):
+        def ptp(self, *a, **k):
+            return np.ptp(np.asarray(self), *a, **k)
+
+    npx = types.ModuleType("numpy_with_ptp")
+    npx.__dict__.update(np.__dict__)
+    npx.argwhere = lambda m: np.argwhere(m).view(_Arr)
+    ce.np = npx
+
+    def label2d(mask):
+        return scipy.ndimage.label(np.asarray(mask) != 0, structure=np.ones((3, 3), int))[0]
+
+    class _Region:
+        def __init__(self, lab, cid):
+            yy, xx = np.nonzero(lab == cid)
+            self.area, self.centroid, self.label = len(yy), (yy.mean(), xx.mean()), cid
+
+    ce.label2d = label2d
+    ce.regionprops = lambda lab: [_Region(lab, c) for c in range(1, int(lab.max()) + 1)]
+
+    ag = np.load(os.path.join(HERE, "aligner_golden.npz"))
+    grid, front = ag["grid"], ag["image"]
+    parts = ["front_minarets", "back_minarets"]
+    colours = [C.PART_COLORS[p] for p in parts]
+    out = {}
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        init = ce.auto_compute_initial_params_matching_bbox(grid, front, C.PART_COLORS, parts)
+    out["init_row"] = np.array([*init["cam_pos"], *init["target"], init["f"], init["cx"], init["cy"]], dtype=np.float64)
+    out["init_dtypes"] = np.array([str(np.asarray(init[k]).dtype) for k in ("cam_pos", "target", "f", "cx", "cy")])
+    out["init_log"] = np.array(buf.getvalue())
+    vparts = ce.extract_minaret_voxels_by_label(grid, colours)
+    mparts = ce.extract_minaret_masks_by_label(front, colours)
+    for k, v in vparts.items():
+        out[f"vox_{k}_sha"] = np.array(sha(np.asarray(v).astype(np.int64)))
+        out[f"vox_{k}_n"] = np.array(len(v))
+    for k, v in mparts.items():
+        out[f"mask_{k}"] = np.packbits(v.astype(bool))
+    out["mask_keys"] = np.array(list(mparts.keys()))
+    vk = ce.extract_top_bottom_voxel_points(vparts)
+    ik = ce.extract_top_bottom_image_points(mparts)
+    out["vk_keys"], out["vk"] = np.array(list(vk.keys())), np.array([vk[k] for k in vk], dtype=np.float64)
+    out["ik_keys"], out["ik"] = np.array(list(ik.keys())), np.array([ik[k] for k in ik], dtype=np.float64)
+    vsel, isel = ce.extract_minaret_kps_for_view(grid, front, colours)
+    out["sel_keys"] = np.array(list(vsel.keys()))
+    out["sel_v"], out["sel_i"] = np.array([vsel[k] for k in vsel], dtype=np.float64), np.array([isel[k] for k in isel], dtype=np.float64)
+    for loss in ("L2", "L1"):
+        with contextlib.redirect_stdout(buf):
+            fit = ce.optimize_camera_with_keypoints(vsel, isel, front, init, loss_type=loss)
+        out[f"fit_{loss}"] = np.array([*fit["cam_pos"], *fit["target"], fit["f"], fit["cx"], fit["cy"]], dtype=np.float64)
+    # a drone-like second view: the same chain on the transposed-free 'drone' mask of the reference data
+    np.savez_compressed(os.path.join(HERE, "init_golden.npz"), **out)
+    print("init", out["init_row"], out["init_dtypes"], "sel", list(out["sel_keys"]), "fit", out["fit_L2"])
+
+
 def depth_golden():
     """compute_global_depth_buffer / project_part_visible of the live utils/eval_helpers_intra.py (:134-190) on the
     half-resolution Taj grid stored in aligner_golden.npz, float32 cameras (as load_camera_json makes them) and float64."""
@@ -448,7 +515,7 @@ def depth_golden():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth", "deform"]
+    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth", "deform", "init"]
     if "assets" in which:
         copy_assets()
     if "camera" in which:
@@ -461,6 +528,8 @@ if __name__ == "__main__":
         depth_golden()
     if "deform" in which:
         deform_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz"):
+    if "init" in which:
+        init_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz"):
         if os.path.exists(os.path.join(HERE, f)):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
