@@ -218,6 +218,24 @@ int p3d_deform_scatter(const float* pts, int64_t n, int64_t stride, const double
 int p3d_sweep_timing_enable(int on);
 int p3d_sweep_timing_read(double* splat_ms, int* n_launches);
 
+/* voxel_grid_to_points for RGB grids      utils/voxel_utils.py:35-51   (inspection without a CPU round trip)
+ *   p3d_strided_occupancy  : mask (ceil(A0/s), ceil(A1/s), ceil(A2/s)) u8 = any(grid[::s, ::s, ::s], axis=-1)
+ *   p3d_gather_scale_points: for the compacted points of that mask (p3d_points_fill: [x,y,z] on the sub-sampled
+ *                            lattice) rgb[i] = grid[z*s][y*s][x*s] and pts[i] *= s (in place). */
+int p3d_strided_occupancy(const uint8_t* grid_rgb, int A0, int A1, int A2, int stride, uint8_t* mask,
+                          p3d_stream_t stream);
+int p3d_gather_scale_points(const uint8_t* grid_rgb, int A0, int A1, int A2, int stride, float* pts, int64_t n,
+                            uint8_t* rgb, p3d_stream_t stream);
+
+/* compute_binary_gt                      utils/eval_helpers_intra.py:274-285
+ *   p3d_colour_presence: present (p3d_colour_presence_bytes() = 2 MiB, one bit per 24-bit colour r | g<<8 | b<<16)
+ *                        = the non-black colours occurring in grid_rgb (n voxels).
+ *   p3d_colour_lookup  : mask[p] = image colour p is marked in `present`. */
+size_t p3d_colour_presence_bytes(void);
+int p3d_colour_presence(const uint8_t* grid_rgb, int64_t n, uint32_t* present, p3d_stream_t stream);
+int p3d_colour_lookup(const uint8_t* image_rgb, int64_t n, const uint32_t* present, uint8_t* mask,
+                      p3d_stream_t stream);
+
 /* ============================================================================================= *
  * Stage 1: orthographic semantic voxel carving            utils/voxel_carving_utils.py
  * Grids are (W,H,D) uint8 occupancy or (W,H,D,3) uint8 RGB.  2-D masks are passed already oriented:

@@ -397,6 +397,8 @@ def compute_global_depth_buffer(voxel_grid, cam, H, W):
 
 def project_part_visible(pts3d, cam, zbuf, H, W, eps=1e-3):
     """eval_helpers_intra.py:168-190 (pixels where a part point lies within eps of the global depth buffer)."""
+    if np.asarray(pts3d).dtype != np.float32:
+        return _project_part_visible_np(np.asarray(pts3d), cam, zbuf, H, W, eps)
     pts = np.ascontiguousarray(pts3d, dtype=np.float32).reshape(-1, 3)
     dt = _working_dtype(pts, cam["cam_pos"], cam["target"])
     cp, tg = np.ascontiguousarray(cam["cam_pos"], dtype=dt), np.ascontiguousarray(cam["target"], dtype=dt)
@@ -406,6 +408,91 @@ def project_part_visible(pts3d, cam, zbuf, H, W, eps=1e-3):
     fn(_p(pts), pts.shape[0], _p(cp), _p(tg), float(cam["f"]), float(cam["cx"]), float(cam["cy"]), _p(zb),
        float(np.float32(eps)) if dt == np.float32 else float(eps), int(H), int(W), _p(mask))
     return mask.astype(bool)
+
+
+def _project_part_visible_np(pts3d, cam, zbuf, H, W, eps):
+    """The same function for non-float32 points (the int64 argwhere coordinates notebook 4 passes, :516-526): NumPy
+    promotes `pts3d - cam_pos` to float64 while the rotation stays the float32 look-at of the float32 camera arrays."""
+    R = look_at_rotation(cam["cam_pos"], cam["target"])
+    pc = (pts3d - cam["cam_pos"]) @ R.T
+    X, Y, Z = pc.T
+    ok = Z > 1e-6
+    X, Y, Z = X[ok], Y[ok], Z[ok]
+    ui = np.round((X / Z) * cam["f"] + cam["cx"]).astype(int)
+    vi = np.round(-(Y / Z) * cam["f"] + cam["cy"]).astype(int)
+    inside = (ui >= 0) & (ui < W) & (vi >= 0) & (vi < H)
+    ui, vi, Z = ui[inside], vi[inside], Z[inside]
+    mask = np.zeros((H, W), bool)
+    hit = np.abs(Z - zbuf[vi, ui]) < eps
+    mask[vi[hit], ui[hit]] = True
+    return mask
+
+
+def iou_bool(a, b):
+    """eval_helpers_intra.py:268-271."""
+    inter, union = np.logical_and(a, b).sum(), np.logical_or(a, b).sum()
+    return inter / union if union > 0 else np.nan
+
+
+def compute_binary_gt(mask_img, voxel_grid):
+    """eval_helpers_intra.py:274-285."""
+    g = np.asarray(voxel_grid).reshape(-1, 3).astype(np.uint32)
+    codes = np.unique(g[:, 0] | (g[:, 1] << 8) | (g[:, 2] << 16))
+    m = np.asarray(mask_img).astype(np.uint32)
+    mc = m[..., 0] | (m[..., 1] << 8) | (m[..., 2] << 16)
+    return np.isin(mc, codes[codes != 0])
+
+
+def minaret_kp_errors(voxel_grid, mask_img, cams, minaret_colors, back_top_only):
+    """Numbers behind run_minaret_kp_evaluation (eval_helpers_intra.py:346-393): {tag: {minaret: mean error in px}}."""
+    vk = top_bottom_voxel_points(minaret_voxels_by_label(voxel_grid, minaret_colors))
+    ik = top_bottom_image_points(minaret_masks_by_label(mask_img, minaret_colors))
+    out = {}
+    for tag, cam in cams.items():
+        pk = {k: project_point(p, cam["cam_pos"], cam["target"], cam["f"], cam["cx"], cam["cy"]) for k, p in vk.items()}
+        out[tag] = {}
+        for m in ("LM1", "RM1", "LM2", "RM2"):
+            errs = [np.linalg.norm(np.array(ik[f"{m}_top"]) - np.array(pk[f"{m}_top"]))]
+            if not (m in ("LM2", "RM2") and back_top_only):
+                errs.append(np.linalg.norm(np.array(ik[f"{m}_bottom"]) - np.array(pk[f"{m}_bottom"])))
+            out[tag][m] = np.mean(errs)
+    return out
+
+
+def minaret_visible_ious(voxel_grid, mask_img, cams, minaret_colors):
+    """Numbers behind run_minaret_iou_evaluation (eval_helpers_intra.py:500-527): {minaret: {tag: IoU}}."""
+    H, W = mask_img.shape[:2]
+    vp, mp = minaret_voxels_by_label(voxel_grid, minaret_colors), minaret_masks_by_label(mask_img, minaret_colors)
+    names = ("LM1", "RM1", "LM2", "RM2")
+    out = {m: {} for m in names}
+    for tag, cam in cams.items():
+        zbuf = compute_global_depth_buffer(voxel_grid, cam, H, W)
+        pr_all = project_part_visible(np.vstack([vp[m] for m in names]), cam, zbuf, H, W)
+        for m in names:
+            out[m][tag] = iou_bool(mp[m].astype(bool) & pr_all, project_part_visible(vp[m], cam, zbuf, H, W))
+    return out
+
+
+def part_minaret_binary_ious(voxel_init, voxel_def, mask_img, cam, part_colors):
+    """Numbers behind run_part_minaret_binary_iou (eval_helpers_intra.py:625-722): {row: (init, deformed) | None}."""
+    H, W = mask_img.shape[:2]
+    z_i, z_d = compute_global_depth_buffer(voxel_init, cam, H, W), compute_global_depth_buffer(voxel_def, cam, H, W)
+    out = {}
+    for part in ("dome", "chhatris", "main_door", "windows", "plinth"):
+        gt = np.any(mask_parts_from_image(mask_img, part_colors, [part]) > 0, axis=-1)
+        p_i, p_d = get_voxel_points_by_parts(voxel_init, part_colors, [part])[0], get_voxel_points_by_parts(voxel_def, part_colors, [part])[0]
+        if gt.sum() == 0 or p_i.shape[0] == 0:
+            out[part] = None
+            continue
+        out[part] = (iou_bool(gt, project_part_visible(p_i, cam, z_i, H, W)), iou_bool(gt, project_part_visible(p_d, cam, z_d, H, W)))
+    mins = ["front_minarets", "back_minarets"]
+    p_min = get_voxel_points_by_parts(voxel_init, part_colors, mins)[0]
+    gt = np.any(mask_parts_from_image(mask_img, part_colors, mins) > 0, axis=-1)
+    out["minarets"] = (iou_bool(gt, project_part_visible(p_min, cam, z_i, H, W)), iou_bool(gt, project_part_visible(p_min, cam, z_d, H, W)))
+    gt = compute_binary_gt(mask_img, voxel_init)
+    out["whole"] = (iou_bool(gt, project_part_visible(_occupied_points(voxel_init), cam, z_i, H, W)),
+                    iou_bool(gt, project_part_visible(_occupied_points(voxel_def), cam, z_d, H, W)))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -615,3 +702,16 @@ def optimize_camera_with_keypoints(voxel_kps, image_kps, image, init_params, los
     res = minimize(loss, x0, bounds=bounds, method="L-BFGS-B")
     x = res.x
     return {"cam_pos": np.array(x[0:3]), "target": np.array(x[3:6]), "f": x[6], "cx": x[7], "cy": x[8]}, res.fun
+
+
+# ------------------------------------------------------------------------------------------------
+# hand-off helpers
+# ------------------------------------------------------------------------------------------------
+def voxel_grid_to_points(grid, stride=2):
+    """voxel_utils.py:35-51, RGB branch: strided non-black voxels as float32 [a2,a1,a0]*stride, their colours, and the
+    reference's (shape[1], shape[0], shape[2]) tuple."""
+    g = np.asarray(grid)
+    ds = g[::stride, ::stride, ::stride]
+    a0, a1, a2 = np.nonzero(ds.any(axis=-1))
+    pts = np.stack([a2, a1, a0], axis=1).astype(np.float32) * stride
+    return pts, ds[a0, a1, a2], (g.shape[1], g.shape[0], g.shape[2])

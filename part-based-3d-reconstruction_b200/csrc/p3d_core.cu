@@ -336,3 +336,112 @@ P3D_API int p3d_points_fill(const uint8_t* labels, int A0, int A1, int A2, const
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// voxel_grid_to_points (utils/voxel_utils.py:35-51): strided occupancy of an RGB grid and the colours of the kept
+// voxels.  mask[(a,b,c)] = any(grid[a*s, b*s, c*s, :]) on the sub-sampled lattice; colours are gathered at the
+// compacted points afterwards.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) strided_occupancy_kernel(const uint8_t* __restrict__ grid, int A1, int A2, int stride,
+                                                                int B0, int B1, int B2, uint8_t* __restrict__ mask) {
+  const int64_t n = (int64_t)B0 * B1 * B2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % B2);
+    const int64_t r = i / B2;
+    const int b = (int)(r % B1), a = (int)(r / B1);
+    const uint8_t* p = grid + ((((size_t)a * stride) * A1 + (size_t)b * stride) * A2 + (size_t)c * stride) * 3;
+    mask[i] = (p[0] | p[1] | p[2]) != 0;
+  }
+}
+
+// rgb[i] = grid[z*s][y*s][x*s] for pts[i] = (x, y, z) on the sub-sampled lattice; pts are scaled by s in place
+__global__ void __launch_bounds__(256) gather_scale_points_kernel(const uint8_t* __restrict__ grid, int A1, int A2, int stride,
+                                                                  float* __restrict__ pts, int64_t n,
+                                                                  uint8_t* __restrict__ rgb) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)pts[3 * i], y = (int)pts[3 * i + 1], z = (int)pts[3 * i + 2];
+    const uint8_t* p = grid + ((((size_t)z * stride) * A1 + (size_t)y * stride) * A2 + (size_t)x * stride) * 3;
+    rgb[3 * i] = p[0]; rgb[3 * i + 1] = p[1]; rgb[3 * i + 2] = p[2];
+    pts[3 * i] = __fmul_rn((float)x, (float)stride);
+    pts[3 * i + 1] = __fmul_rn((float)y, (float)stride);
+    pts[3 * i + 2] = __fmul_rn((float)z, (float)stride);
+  }
+}
+
+}  // namespace
+
+P3D_API int p3d_strided_occupancy(const uint8_t* grid_rgb, int A0, int A1, int A2, int stride, uint8_t* mask,
+                                  p3d_stream_t stream) {
+  P3D_REQUIRE(A0 >= 0 && A1 >= 0 && A2 >= 0 && stride >= 1, "strided_occupancy: bad arguments");
+  const int B0 = (A0 + stride - 1) / stride, B1 = (A1 + stride - 1) / stride, B2 = (A2 + stride - 1) / stride;
+  const int64_t n = (int64_t)B0 * B1 * B2;
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(grid_rgb && mask, "strided_occupancy: null pointer");
+  strided_occupancy_kernel<<<stream_grid(n, 256), 256, 0, p3d::as_stream(stream)>>>(grid_rgb, A1, A2, stride, B0, B1, B2, mask);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_gather_scale_points(const uint8_t* grid_rgb, int A0, int A1, int A2, int stride, float* pts, int64_t n,
+                                    uint8_t* rgb, p3d_stream_t stream) {
+  P3D_REQUIRE(A0 >= 0 && A1 >= 0 && A2 >= 0 && stride >= 1 && n >= 0, "gather_scale_points: bad arguments");
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(grid_rgb && pts && rgb, "gather_scale_points: null pointer");
+  gather_scale_points_kernel<<<stream_grid(n, 256), 256, 0, p3d::as_stream(stream)>>>(grid_rgb, A1, A2, stride, pts, n, rgb);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compute_binary_gt (utils/eval_helpers_intra.py:274-285): pixels whose colour occurs (as a non-black voxel colour)
+// in the grid.  Pass 1 marks the 24-bit colours present in the grid in a 2 MiB bitmap, pass 2 looks every pixel up.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) colour_presence_kernel(const uint8_t* __restrict__ rgb, int64_t n,
+                                                              uint32_t* __restrict__ present) {
+  uint32_t last = 0;                                       // runs of one colour set their bit once
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = rgb[3 * i] | (rgb[3 * i + 1] << 8) | (rgb[3 * i + 2] << 16);
+    if (c == 0 || c == last) continue;
+    last = c;
+    const uint32_t bit = 1u << (c & 31u);
+    if ((present[c >> 5] & bit) == 0u) atomicOr(present + (c >> 5), bit);
+  }
+}
+
+__global__ void __launch_bounds__(256) colour_lookup_kernel(const uint8_t* __restrict__ rgb, int64_t n,
+                                                            const uint32_t* __restrict__ present,
+                                                            uint8_t* __restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = rgb[3 * i] | (rgb[3 * i + 1] << 8) | (rgb[3 * i + 2] << 16);
+    mask[i] = c != 0 && ((present[c >> 5] >> (c & 31u)) & 1u);
+  }
+}
+
+}  // namespace
+
+P3D_API size_t p3d_colour_presence_bytes(void) { return (size_t)1 << 21; }
+
+P3D_API int p3d_colour_presence(const uint8_t* grid_rgb, int64_t n, uint32_t* present, p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && present, "colour_presence: bad arguments");
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(present, 0, p3d_colour_presence_bytes(), st));
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(grid_rgb, "colour_presence: null grid");
+  colour_presence_kernel<<<stream_grid(n, 256), 256, 0, st>>>(grid_rgb, n, present);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_colour_lookup(const uint8_t* image_rgb, int64_t n, const uint32_t* present, uint8_t* mask,
+                              p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0, "colour_lookup: bad arguments");
+  if (n == 0) return P3D_OK;
+  P3D_REQUIRE(image_rgb && present && mask, "colour_lookup: null pointer");
+  colour_lookup_kernel<<<stream_grid(n, 256), 256, 0, p3d::as_stream(stream)>>>(image_rgb, n, present, mask);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}

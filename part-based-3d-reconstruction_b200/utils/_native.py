@@ -43,6 +43,11 @@ _SIGNATURES = {
     "p3d_points_workspace_bytes": ([_i64], _sz),
     "p3d_points_count": ([_vp, _i64, _vp, _vp, _sz, _vp], _i32),
     "p3d_points_fill": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp], _i32),
+    "p3d_strided_occupancy": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_gather_scale_points": ([_vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp], _i32),
+    "p3d_colour_presence_bytes": ([], _sz),
+    "p3d_colour_presence": ([_vp, _i64, _vp, _vp], _i32),
+    "p3d_colour_lookup": ([_vp, _i64, _vp, _vp, _vp], _i32),
     "p3d_setup_cameras_f64": ([_vp, _i32, _vp, _vp], _i32),
     "p3d_setup_cameras_f32": ([_vp, _i32, _vp, _vp], _i32),
     "p3d_splat_f64": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),

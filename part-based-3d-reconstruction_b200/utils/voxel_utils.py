@@ -51,3 +51,29 @@ def get_voxel_points_by_parts(grid, part_colors, part_names, device=None):
     pal = nv.palette_tensor(colours, pts.device)
     cols = eng.labels_to_rgb(pt_label, eng.make_lut(pal))
     return pts.cpu().numpy(), cols.cpu().numpy()
+
+
+def voxel_grid_to_points(grid, axis="z", colormap="viridis", stride=2, device=None):
+    """voxel_utils.py:35-51 for RGB grids: every `stride`-th voxel along each axis that is not black, as
+    (pts float32 (N,3) = [a2, a1, a0] * stride, colors uint8 (N,3), (H, W, D)) with the reference's shape tuple
+    (it unpacks `W, H, D = grid.shape[:3]` and returns `(H, W, D)`).  Scalar grids are coloured through a matplotlib
+    colormap in the reference (a viewer concern) and are not handled here."""
+    dev = nv.require_cuda(device)
+    g = grid if isinstance(grid, torch.Tensor) else np.asarray(grid)
+    if g.ndim != 4 or g.shape[3] != 3:
+        raise NotImplementedError("voxel_grid_to_points: only (A0,A1,A2,3) RGB grids (the scalar branch needs matplotlib)")
+    stride = int(stride)
+    with torch.cuda.device(dev):
+        t = grid_to_device(g, dev)
+        A0, A1, A2 = (int(v) for v in t.shape[:3])
+        B = [(a + stride - 1) // stride for a in (A0, A1, A2)]
+        mask = torch.empty(B, dtype=torch.uint8, device=dev)
+        nv.check(nv.lib.p3d_strided_occupancy(nv.ptr(t), A0, A1, A2, stride, nv.ptr(mask), nv.stream_ptr()),
+                 "p3d_strided_occupancy")
+        eng._launched(1)
+        pts, _ = eng.compact_points(mask)
+        cols = torch.empty((pts.shape[0], 3), dtype=torch.uint8, device=dev)
+        nv.check(nv.lib.p3d_gather_scale_points(nv.ptr(t), A0, A1, A2, stride, nv.ptr(pts), pts.shape[0], nv.ptr(cols),
+                                                nv.stream_ptr()), "p3d_gather_scale_points")
+        eng._launched(1 if pts.shape[0] else 0)
+        return pts.cpu().numpy(), cols.cpu().numpy(), (A1, A0, A2)

@@ -488,6 +488,86 @@ def init_golden():
     print("init", out["init_row"], out["init_dtypes"], "sel", list(out["sel_keys"]), "fit", out["fit_L2"])
 
 
+def handoff_golden():
+    """voxel_grid_to_points of the live reference (voxel_utils.py:35-51, RGB branch) on the half-resolution Taj grid."""
+    grid = np.load(os.path.join(HERE, "aligner_golden.npz"))["grid"]
+    out = {}
+    for stride in (1, 2, 3):
+        pts, cols, shp = ref.vu.voxel_grid_to_points(grid, stride=stride)
+        out[f"s{stride}_pts_sha"], out[f"s{stride}_cols_sha"] = np.array(sha(pts)), np.array(sha(cols))
+        out[f"s{stride}_n"], out[f"s{stride}_shape"] = np.array(len(pts)), np.array(shp)
+        out[f"s{stride}_dtypes"] = np.array([str(pts.dtype), str(cols.dtype)])
+    np.savez_compressed(os.path.join(HERE, "handoff_golden.npz"), **out)
+    print("handoff", {k: (int(v) if v.ndim == 0 and v.dtype.kind == "i" else None) for k, v in out.items() if k.endswith("_n")})
+
+
+def build_table_scene(tmp, cams_json):
+    """Directory layout notebook 4 expects (nb4 cell 3), filled with the half-resolution Taj scene: the grid of
+    aligner_golden.npz, the deformed grid of deform_golden.npz, the original front-mask PNG and the given cameras."""
+    ag = np.load(os.path.join(HERE, "aligner_golden.npz"))
+    dg = np.load(os.path.join(HERE, "deform_golden.npz"))
+    grid = ag["grid"]
+    deformed = np.zeros((int(np.prod(grid.shape[:3])), 3), np.uint8)
+    deformed[dg["f64_grid_nz"]] = dg["f64_grid_rgb"]
+    dirs = {k: os.path.join(tmp, k) for k in ("voxels", "deformed", "cams", "data")}
+    for d in dirs.values():
+        os.makedirs(d, exist_ok=True)
+    os.makedirs(os.path.join(dirs["data"], "Taj", "masks"), exist_ok=True)
+    np.savez_compressed(os.path.join(dirs["voxels"], "Taj_voxel_grid.npz"), voxel_grid=grid)
+    np.savez_compressed(os.path.join(dirs["deformed"], "Taj_deformed_voxel_grid.npz"), voxel_grid=deformed.reshape(grid.shape))
+    shutil.copy(os.path.join(DATA, "Taj", "masks", "Taj_front_mask.png"), os.path.join(dirs["data"], "Taj", "masks"))
+    for tag, cam in cams_json.items():
+        json.dump(cam, open(os.path.join(dirs["cams"], f"Taj_camera_params_{tag}.json"), "w"))
+    return dirs
+
+
+def tables_golden():
+    """The three table drivers of notebook 4 (eval_helpers_intra.py:287-748) run live, visualize=False, on the
+    half-resolution Taj scene (the reference's depth buffer is a Python loop over every voxel).  Same two library shims
+    as init_golden (ndarray.ptp, skimage label/regionprops)."""
+    import tempfile
+    import types
+    ce = ref.ce
+
+    class _Arr(np.ndarray):
+        def ptp(self, *a, **k):
+            return np.ptp(np.asarray(self), *a, **k)
+
+    npx = types.ModuleType("numpy_with_ptp")
+    npx.__dict__.update(np.__dict__)
+    npx.argwhere = lambda m: np.argwhere(m).view(_Arr)
+    ce.np = npx
+
+    class _Region:
+        def __init__(self, lab, cid):
+            yy, xx = np.nonzero(lab == cid)
+            self.area, self.centroid, self.label = len(yy), (yy.mean(), xx.mean()), cid
+
+    ce.label2d = lambda mask: scipy.ndimage.label(np.asarray(mask) != 0, structure=np.ones((3, 3), int))[0]
+    ce.regionprops = lambda lab: [_Region(lab, c) for c in range(1, int(lab.max()) + 1)]
+    import utils.eval_helpers_intra as eh
+
+    cams = {}
+    for tag in ("init", "kp", "final"):
+        c = json.load(open(os.path.join(ref.root, "results/2.Perspective_Camera_Estimation", f"Taj_camera_params_{tag}.json")))["front"]
+        cams[tag] = {"front": {"cam_pos": [v / 2 for v in c["cam_pos"]], "target": [v / 2 for v in c["target"]],
+                               "f": c["f"] / 2, "cx": c["cx"] / 2, "cy": c["cy"] / 2}}
+    out = {"cams_json": np.array(json.dumps(cams))}
+    with tempfile.TemporaryDirectory() as tmp:
+        d = build_table_scene(tmp, cams)
+        common = dict(monuments=["Taj"], view="front", root_masks=d["data"], cam_dir=d["cams"], part_colors=C.PART_COLORS, visualize=False)
+        for name, fn, extra in (("kp", eh.run_minaret_kp_evaluation, {"root_voxels": d["voxels"]}),
+                                ("iou", eh.run_minaret_iou_evaluation, {"root_voxels": d["voxels"]}),
+                                ("part", eh.run_part_minaret_binary_iou, {"root_voxels": d["voxels"], "deformed_voxels": d["deformed"]})):
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                df = fn(**common, **extra)
+            out[f"{name}_df"] = np.array(df.to_json())
+            out[f"{name}_log"] = np.array(buf.getvalue())
+            print(name, df.to_dict())
+    np.savez_compressed(os.path.join(HERE, "tables_golden.npz"), **out)
+
+
 def depth_golden():
     """compute_global_depth_buffer / project_part_visible of the live utils/eval_helpers_intra.py (:134-190) on the
     half-resolution Taj grid stored in aligner_golden.npz, float32 cameras (as load_camera_json makes them) and float64."""
@@ -515,7 +595,7 @@ def depth_golden():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth", "deform", "init"]
+    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth", "deform", "init", "handoff", "tables"]
     if "assets" in which:
         copy_assets()
     if "camera" in which:
@@ -530,6 +610,10 @@ if __name__ == "__main__":
         deform_golden()
     if "init" in which:
         init_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz"):
+    if "handoff" in which:
+        handoff_golden()
+    if "tables" in which:
+        tables_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz", "handoff_golden.npz", "tables_golden.npz"):
         if os.path.exists(os.path.join(HERE, f)):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
