@@ -283,7 +283,7 @@ def run_ours(args):
                 out["carve"]["cpu_baseline"] = carve_cpu_baseline()
             except Exception as exc:
                 out["carve"]["cpu_baseline"] = {"error": repr(exc)}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -559,7 +559,7 @@ def run_reference(args):
     value = per_step * args.steps / total
     sample = (f"{per_step} candidates per step (bounded sample of the {TOTAL_CANDIDATES}-candidate sweep) on the same "
               f"{N}^3 grid / {H}x{W} mask, candidate-parallel over {procs} host processes")
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -572,7 +572,22 @@ def run_reference(args):
     }))
 
 
+def _emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints there (NCCL's version banner, ...)
+    was re-routed to stderr by _quiet_stdout()."""
+    _REAL_STDOUT.write(line + "\n")
+    _REAL_STDOUT.flush()
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
