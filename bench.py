@@ -455,6 +455,43 @@ def extra_configs(dev, with_cpu):
                 entry["cpu_baseline"] = {"value": round(64 / dt, 2), "unit": UNIT, "cores": 1, "kind": "port",
                                          "sample": "first 64 candidates, NumPy port, 1 process"}
             out["taj_front_" + tag] = entry
+        # notebook 3's part-wise deformation sweep on the same grid: dome, fixed final camera
+        try:
+            de = importlib.import_module(PKG + ".utils.deformation_estimation")
+            import contextlib
+            import io
+            cam = {"cam_pos": np.array(c["cam_pos"]), "target": np.array(c["target"]), "f": c["f"], "cx": c["cx"], "cy": c["cy"]}
+            labels = {k: v for k, v in cfg.PART_COLORS.items() if k != "background"}
+            with contextlib.redirect_stdout(io.StringIO()):
+                viewer = de.DeformViewer(gdev, labels, front, cam, ["dome"])
+            rng = np.random.default_rng(7)
+            D = 4096
+            rows = np.column_stack([rng.uniform(0.8, 1.2, D), rng.uniform(-60, 60, D), rng.uniform(0.8, 1.2, D), rng.uniform(-60, 60, D)])
+            viewer.score("dome", rows[:64])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ious, _, _ = viewer.score("dome", rows)
+            e1.record()
+            torch.cuda.synchronize()
+            secs = e0.elapsed_time(e1) * 1e-3
+            n_dome = viewer.part_points("dome").n
+            entry = {"part": "dome", "points": n_dome, "jitters": 7, "deformations": D, "value": round(D / secs, 1),
+                     "unit": "deformations/s", "point_jitter_deformations_per_s": round(D * 7 * n_dome / secs, 1),
+                     "best_iou": float(ious.max()),
+                     "note": "deform (FP64, reference op order) + bounds + projection through the fixed final camera + coverage "
+                             "bitmap + IoU per deformation; host rows in, host IoUs out"}
+            if with_cpu:
+                from oracle import oracle as orc
+                t0 = time.perf_counter()
+                ref_iou, _ = orc.deform_part_iou(grid, labels, front, cam, "dome", de.row_to_deform(rows[0]))
+                dt = time.perf_counter() - t0
+                entry["cpu_baseline"] = {"value": round(1 / dt, 4), "unit": "deformations/s", "cores": 1, "kind": "port",
+                                         "sample": "1 deformation through oracle/ (NumPy restatement incl. np.unique)",
+                                         "iou_matches": bool(ref_iou == ious[0])}
+            out["taj_front_deform_dome"] = entry
+        except Exception as exc:
+            out["taj_front_deform_dome"] = {"error": repr(exc)}
         del gdev
     except Exception as exc:
         out["taj"] = {"error": repr(exc)}

@@ -80,6 +80,20 @@ __device__ __forceinline__ DeformParams load_deform(const double* __restrict__ d
 
 __device__ __forceinline__ double np_sign(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : v); }   // NaN / 0 -> itself
 
+// One coordinate of one jittered copy: axis k (0 = x, 1 = y, 2 = z) of a point whose coordinate is v, jitter slot o
+// (0: offset 0, 1: +0.25, 2: -0.25).  A jitter only moves ONE axis, so the other two coordinates of that copy equal
+// those of the un-jittered copy -- the sweep evaluates 3 + 6 axis values per point instead of 7 x 3.
+__device__ __forceinline__ double deform_axis(double v, int k, int o, const double* __restrict__ centres,
+                                              const DeformParams& q) {
+  const double off = o == 0 ? 0.0 : (o == 1 ? 0.25 : -0.25);
+  const double ctr = centres[3 * k + o];
+  const double c = __dsub_rn(__dadd_rn(v, off), ctr);                     // v + off is exact
+  double t;
+  if (k == 1) t = __dsub_rn(__dmul_rn(c, q.sy), q.ky);
+  else t = __dadd_rn(__dmul_rn(c, q.sxz), __dmul_rn(k == 0 ? q.kx : q.kz, np_sign(c)));
+  return rint(__dadd_rn(t, ctr));
+}
+
 // One jittered copy of one point -> deformed coordinates as doubles holding integers (before the int cast).
 __device__ __forceinline__ void deform_one(const double p[3], int j, const double* __restrict__ centres,
                                            const DeformParams& q, double out[3]) {
@@ -170,16 +184,12 @@ __global__ void __launch_bounds__(kDeformThreads) deform_splat_kernel(
     uint32_t* cv = cov + (size_t)(d0 + dd) * words;
     int count = 0;
     if (live) {
-      for (int j = 0; j < kJitters; ++j) {
-        double o[3];
-        deform_one(p, j, s_ctr, q, o);
-        // bounds in the grid: x < A2, y < A1, z < A0 (deformation_estimation.py:111-115); NaN fails every test
-        if (!(o[0] >= 0.0 && o[0] < fA2 && o[1] >= 0.0 && o[1] < fA1 && o[2] >= 0.0 && o[2] < fA0)) continue;
-        ++count;
+      // splat one deformed voxel (already known to lie inside the grid)
+      auto splat_voxel = [&](double ox, double oy, double oz) {
         bool hit, decided = false;
         uint32_t pix = 0;
         if (kFilter) {   // FP32 filter (same arithmetic and thresholds as splat_filtered_kernel)
-          const float qx = __fsub_rn((float)o[0], ctr0), qy = __fsub_rn((float)o[1], ctr1), qz = __fsub_rn((float)o[2], ctr2);
+          const float qx = __fsub_rn((float)ox, ctr0), qy = __fsub_rn((float)oy, ctr1), qz = __fsub_rn((float)oz, ctr2);
           const float X = __fmaf_rn(qz, fc.A[2], __fmaf_rn(qy, fc.A[1], __fmaf_rn(qx, fc.A[0], fc.TA)));
           const float Y = __fmaf_rn(qz, fc.B[2], __fmaf_rn(qy, fc.B[1], __fmaf_rn(qx, fc.B[0], fc.TB)));
           const float Z = __fmaf_rn(qz, fc.C[2], __fmaf_rn(qy, fc.C[1], __fmaf_rn(qx, fc.C[0], fc.TC)));
@@ -193,11 +203,43 @@ __global__ void __launch_bounds__(kDeformThreads) deform_splat_kernel(
           hit = decided && iu < (uint32_t)W && iv < (uint32_t)H;
           pix = iv * (uint32_t)W + iu;
         }
-        if (!decided) hit = exact_pixel<T>((T)o[0], (T)o[1], (T)o[2], s_cam, W, tW, tH, pix);   // the reference's sequence
+        if (!decided) hit = exact_pixel<T>((T)ox, (T)oy, (T)oz, s_cam, W, tW, tH, pix);   // the reference's sequence
         if (hit) {
           const uint32_t bit = 1u << (pix & 31u);
           uint32_t* w = cv + (pix >> 5);
           if ((__ldcg(w) & bit) == 0u) atomicOr(w, bit);
+        }
+      };
+      // bounds in the grid: x < A2, y < A1, z < A0 (deformation_estimation.py:111-115); NaN fails every test
+      const double lim[3] = {fA2, fA1, fA0};
+      double o0[3];
+      bool in0[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        o0[k] = deform_axis(p[k], k, 0, s_ctr, q);
+        in0[k] = o0[k] >= 0.0 && o0[k] < lim[k];
+      }
+      if (in0[0] && in0[1] && in0[2]) {                        // jitter 0
+        ++count;
+        splat_voxel(o0[0], o0[1], o0[2]);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {                            // jitters 1..6: axis k moved by +0.25 / -0.25
+        const bool others = in0[(k + 1) % 3] && in0[(k + 2) % 3];
+        if (!others) continue;
+        double prev = o0[k];
+        bool prev_done = in0[k];                               // a voxel equal to an already splatted one adds no pixel
+#pragma unroll
+        for (int o = 1; o <= 2; ++o) {
+          const double v = deform_axis(p[k], k, o, s_ctr, q);
+          if (!(v >= 0.0 && v < lim[k])) continue;
+          ++count;
+          if ((v == o0[k] && in0[k]) || (v == prev && prev_done)) continue;
+          double c3[3] = {o0[0], o0[1], o0[2]};
+          c3[k] = v;
+          splat_voxel(c3[0], c3[1], c3[2]);
+          prev = v;
+          prev_done = true;
         }
       }
     }
