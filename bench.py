@@ -227,7 +227,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (splat) --------------------------------------------------
     peak, peak_src = peaks()
     G = N ** 3
-    batch = max(1, min(B, 64, (int(os.environ.get('P3D_ZBUF_BUDGET_MB', '128')) << 20) // (H * W * 4)))
+    batch = -(-B * args.steps // max(1, splat_launches.value))       # cameras per splat launch, from the launch count
     alg_per_launch = batch * (G * 1 + 9 * H * W)
     avg_launch_s = (splat_ms.value / max(1, splat_launches.value)) * 1e-3
     achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
@@ -506,6 +506,24 @@ def extra_configs(dev, with_cpu):
                                          "value": round(rate(sc, syn.candidates(base, 4096), reps=2), 1), "unit": UNIT}
     except Exception as exc:
         out["synthetic_256_4096cand"] = {"error": repr(exc)}
+    try:        # BASELINE.json configs[4] on one GPU: 1024^3 grid, 2048x2048 masks (front + aerial views)
+        N, H, W = 1024, 2048, 2048
+        del rgb, full, sc
+        torch.cuda.empty_cache()
+        rgb = torch.from_numpy(syn.label_lut()).to(dev)[syn.monument_labels(N, dev).long()]
+        entry = {"mask": [H, W], "candidates": 256, "unit": UNIT}
+        for view in ("front", "aerial"):
+            base = syn.base_camera(N, H, W, view)
+            full = ce.CandidateScorer(rgb, torch.zeros((H, W, 3), dtype=torch.uint8, device=dev), cfg.PART_COLORS, syn.PART_NAMES)
+            gt = full.render(ce.row_to_params(base + HIDDEN_DELTA))
+            del full
+            sc = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, syn.PART_NAMES)
+            entry["points"] = sc.n_points
+            entry[view] = round(rate(sc, syn.candidates(base, 256), reps=2), 1)
+            del sc
+        out["synthetic_1024_2048mask"] = entry
+    except Exception as exc:
+        out["synthetic_1024_2048mask"] = {"error": repr(exc)}
     return out
 
 

@@ -844,10 +844,15 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   return P3D_OK;
 }
 
-// cameras per batch: keep the batch's z-buffers within an L2-sized budget
+// cameras per batch: keep the batch's z-buffers within an L2-sized budget, but never fewer than 16 cameras per launch
+// while that stays under 1 GiB -- a launch streams the whole point list once, so few cameras per launch cost more than
+// an L2-overflowing z-buffer does (measured at 1024^3 / 2048^2: 8 cameras 3.5 k cand/s, 16 cameras 4.0 k, 32: 3.8 k).
 inline int batch_cameras(int K, int H, int W, size_t zbuf_budget) {
   const size_t per = (size_t)H * W * sizeof(uint32_t);
   int64_t c = (int64_t)(zbuf_budget / per);
+  int64_t floor16 = (int64_t)(((size_t)1 << 30) / per);
+  if (floor16 > 16) floor16 = 16;
+  if (c < floor16) c = floor16;
   if (c > 64) c = 64;
   if (c > K) c = K;
   if (c < 1) c = 1;
