@@ -112,6 +112,27 @@ def score_candidates_sharded(scorer, candidates, group=None, gather_scores=False
     return best_score, best_index, scores, (lo, hi)
 
 
+def score_deformations_sharded(viewer, part, deforms, stride=1, group=None):
+    """Notebook 3's deformation sweep across GPUs: the (D,4) deformation rows are split into contiguous
+    blocks, every rank scores its block with `viewer.score(part, rows, stride)` (no data-path collective) and one
+    16-byte all-gather picks the first deformation with the greatest IoU -- the strict `>` loop of the reference's
+    auto-align (deformation_estimation.py:195-197).  Returns (best_iou, best_global_index, local_ious, (lo, hi))."""
+    rows = np.ascontiguousarray(deforms, dtype=np.float64).reshape(-1, 4)
+    D = rows.shape[0]
+    inited = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if inited else 1
+    rank = dist.get_rank(group) if inited else 0
+    lo, hi = shard_range(D, world, rank)
+    if hi > lo:
+        ious = np.asarray(viewer.score(part, rows[lo:hi], stride=stride)[0], dtype=np.float64)
+        k = int(np.argmax(ious))                                  # first index of the maximum
+        local = (float(ious[k]), lo + k)
+    else:
+        ious, local = np.zeros(0), (-np.inf, -1)
+    best_iou, best_index = all_gather_best(local[0], local[1], group)
+    return best_iou, best_index, ious, (lo, hi)
+
+
 def carve_sharded(carve_slab, W: int, group=None, gather: bool = False):
     """Carve a (W,H,D,3) grid in x-slabs, one contiguous slab per rank (global_carve's output at [x,y,z] depends only
     on the 2-D masks, so there is no exchange).  `carve_slab(x0, x1)` returns this rank's (x1-x0,H,D,3) uint8 tensor,

@@ -119,3 +119,54 @@ def test_carve_sharded_gloo(tmp_path, world, carve_golden):
     mp.spawn(_carve_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"c{r}.npy"), carve_golden["syn_rect40x64_global"])
+
+
+class OracleDeformViewer:
+    """Same `score` interface as DeformViewer, computed by the oracle on a tiny scene."""
+
+    def __init__(self):
+        from oracle import oracle as orc
+        self.orc = orc
+        g = np.zeros((12, 14, 12, 3), np.uint8)
+        g[3:9, 2:11, 4:9] = orc.PART_COLORS["dome"]
+        self.grid = g
+        self.image = np.zeros((32, 32, 3), np.uint8)
+        self.image[6:24, 10:22] = orc.PART_COLORS["dome"]
+        self.cam = {"cam_pos": np.array([6.0, 7.0, -30.0]), "target": np.array([6.0, 7.0, 6.0]), "f": 40.0, "cx": 16.0, "cy": 16.0}
+
+    def score(self, part, rows, stride=1):
+        ious = [self.orc.deform_part_iou(self.grid, {part: self.orc.PART_COLORS[part]}, self.image, self.cam, part,
+                                         {"scale_y": r[0], "shift_y": r[1], "scale_xz": r[2], "shift_xz": r[3]})[0] for r in rows]
+        return np.array(ious), None, None
+
+
+def make_deforms(D):
+    rng = np.random.default_rng(4)
+    rows = np.column_stack([rng.uniform(0.7, 1.4, D), rng.uniform(-6, 6, D), rng.uniform(0.7, 1.4, D), rng.uniform(-6, 6, D)])
+    if D > 4:
+        rows[D - 1] = rows[2]                  # equal IoUs in different shards
+    return rows
+
+
+def _deform_worker(rank, world, port, D, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sw = pkg("utils.sweep")
+    best_iou, best_i, ious, (lo, hi) = sw.score_deformations_sharded(OracleDeformViewer(), "dome", make_deforms(D))
+    np.savez(os.path.join(out_dir, f"d{rank}.npz"), best_iou=best_iou, best_i=best_i, ious=ious, lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,D", [(2, 9), (3, 7)])
+def test_sharded_deformation_sweep_gloo(tmp_path, world, D):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_deform_worker, args=(world, port, D, str(tmp_path)), nprocs=world, join=True)
+    full = OracleDeformViewer().score("dome", make_deforms(D))[0]
+    want = int(np.argmax(full))
+    got = np.concatenate([np.load(tmp_path / f"d{r}.npz")["ious"] for r in range(world)])
+    assert np.array_equal(got, full)
+    for r in range(world):
+        z = np.load(tmp_path / f"d{r}.npz")
+        assert int(z["best_i"]) == want and float(z["best_iou"]) == full[want]
