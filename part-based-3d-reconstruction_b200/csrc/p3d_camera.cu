@@ -71,6 +71,18 @@ __global__ void __launch_bounds__(128) setup_cameras_kernel(const T* __restrict_
 #define P3D_MINBLOCKS 8
 #endif
 constexpr int kSplatThreads = P3D_SPLAT_THREADS;
+// Internal third mode of the sweep: joint visibility with the point's label carried in the key,
+// key = (index + 1) << 5 | (label - 1).  The order of keys is the order of indices, so the winner is unchanged, and
+// the score kernel reads the label out of the z-buffer instead of gathering pt_label[index] (n < 2^27, labels <= 32).
+constexpr int kModeJointPacked = 2;
+constexpr int kLabelBits = 5;
+template <int MODE>
+__device__ __forceinline__ uint32_t make_key(int64_t i, const uint8_t* __restrict__ pt_label) {
+  if (MODE == P3D_MODE_JOINT) return (uint32_t)(i + 1);
+  const uint32_t lab = (uint32_t)__ldg(pt_label + i) - 1u;
+  if (MODE == kModeJointPacked) return ((uint32_t)(i + 1) << kLabelBits) | lab;
+  return 1u << lab;
+}
 constexpr int kPpt = 2;
 
 template <typename T, int MODE>
@@ -99,8 +111,7 @@ splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label
       px[j] = (T)__ldg(pts + 3 * i + 0);
       py[j] = (T)__ldg(pts + 3 * i + 1);
       pz[j] = (T)__ldg(pts + 3 * i + 2);
-      if (MODE == P3D_MODE_JOINT) key[j] = (uint32_t)(i + 1);
-      else key[j] = 1u << ((uint32_t)__ldg(pt_label + i) - 1u);
+      key[j] = make_key<MODE>(i, pt_label);
     }
   }
   const T fW = (T)W, fH = (T)H;
@@ -197,8 +208,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       py[j] = __fsub_rn(__ldg(pts + 3 * i + 1), ctr1);
       pz[j] = __fsub_rn(__ldg(pts + 3 * i + 2), ctr2);
       live |= 1ull << j;
-      if (MODE == P3D_MODE_JOINT) key[j] = (uint32_t)(i + 1);
-      else key[j] = 1u << ((uint32_t)__ldg(pt_label + i) - 1u);
+      key[j] = make_key<MODE>(i, pt_label);
     }
   }
 #pragma unroll
@@ -223,7 +233,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
     if (lane < take) {
       const uint2 e = q[qn - take + lane];                  // (point index, camera)
       const float* pp = pts + 3 * (size_t)e.x;
-      const uint32_t k = MODE == P3D_MODE_JOINT ? e.x + 1u : 1u << ((uint32_t)__ldg(pt_label + e.x) - 1u);
+      const uint32_t k = make_key<MODE>((int64_t)e.x, pt_label);
       exact_splat<double, MODE>((double)__ldg(pp), (double)__ldg(pp + 1), (double)__ldg(pp + 2), k, s_cam + e.y * 16,
                                 zbuf + (size_t)(c0 + e.y) * HW, W, dW, dH);
     }
@@ -326,7 +336,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
     }
 #pragma unroll
     for (int j = 0; j < kPptF; ++j) {
-      if (MODE == P3D_MODE_JOINT) {
+      if (MODE != P3D_MODE_PER_PART) {
         if (hit[j] && cur[j] < key[j]) atomicMax(addr[j], key[j]);
       } else {
         if (hit[j] && (cur[j] & key[j]) != key[j]) atomicOr(addr[j], key[j]);
@@ -394,8 +404,9 @@ constexpr int kMaxParts = 32;
 template <int MODE>
 __device__ __forceinline__ void score_accumulate(uint32_t key, uint32_t g, bool ga, const uint8_t* __restrict__ pt_label,
                                                  int P, unsigned int* acc, int lane) {
-  if (MODE == P3D_MODE_JOINT) {
-    const uint32_t lab = key ? (uint32_t)__ldg(pt_label + (key - 1)) : 0u;
+  if (MODE != P3D_MODE_PER_PART) {
+    const uint32_t lab = MODE == kModeJointPacked ? (key ? (key & ((1u << kLabelBits) - 1u)) + 1u : 0u)
+                                                  : (key ? (uint32_t)__ldg(pt_label + (key - 1)) : 0u);
     uint32_t rem = __ballot_sync(0xffffffffu, lab != 0);
     while (rem) {
       const int leader = __ffs(rem) - 1;
@@ -812,12 +823,13 @@ template <typename T>
 int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, int K, int H, int W, int mode,
           uint32_t* zbuf, const float* fast, const float* bbox, p3d_stream_t stream) {
   P3D_REQUIRE(n >= 0 && K >= 0 && H > 0 && W > 0, "splat: n=%lld K=%d H=%d W=%d", (long long)n, K, H, W);
-  P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
+  P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART || mode == kModeJointPacked, "splat: mode=%d", mode);
   P3D_REQUIRE(n < 0xffffffffll, "splat: n=%lld does not fit 32-bit keys", (long long)n);
+  P3D_REQUIRE(mode != kModeJointPacked || n < (1ll << (32 - kLabelBits)) - 1, "splat: n=%lld does not fit packed keys", (long long)n);
   P3D_REQUIRE((int64_t)H * W < (1ll << 31), "splat: image too large");
   if (n == 0 || K == 0) return P3D_OK;
   P3D_REQUIRE(pts && cams && zbuf, "splat: null pointer");
-  P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: per-part mode needs pt_label");
+  P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: this mode needs pt_label");
   const bool filtered = sizeof(T) == 8 && fast != nullptr && bbox != nullptr && !splat_exact_only();
   const int ppt = filtered ? kPptF : kPpt;
   const int64_t tiles = (n + kSplatThreads * ppt - 1) / (kSplatThreads * ppt);
@@ -831,12 +843,16 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
     const double* dc = reinterpret_cast<const double*>(cams);
     if (mode == P3D_MODE_JOINT)
       splat_filtered_kernel<P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
+    else if (mode == kModeJointPacked)
+      splat_filtered_kernel<kModeJointPacked><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
     else
       splat_filtered_kernel<P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
   } else {
     const size_t smem = (size_t)cpb * 16 * sizeof(T);
     if (mode == P3D_MODE_JOINT)
       splat_kernel<T, P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
+    else if (mode == kModeJointPacked)
+      splat_kernel<T, kModeJointPacked><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
     else
       splat_kernel<T, P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, cams, K, cpb, H, W, zbuf);
   }
@@ -928,12 +944,15 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
     if (rc) return rc;
     g_last_launches += 3;
   }
+  // joint mode: carry the label in the key whenever it fits (P3D_NO_PACKED_KEYS=1 keeps the gather, for A/B runs)
+  static const bool no_packed = getenv("P3D_NO_PACKED_KEYS") != nullptr;
+  const int smode = (mode == P3D_MODE_JOINT && !no_packed && n < (1ll << (32 - kLabelBits)) - 1) ? kModeJointPacked : mode;
   for (int k0 = 0; k0 < K; k0 += L.batch) {
     const int kb = K - k0 < L.batch ? K - k0 : L.batch;
     if (n > 0) {
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
-      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, mode, zbuf,
+      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, smode, zbuf,
                     (sizeof(T) == 8 && n > 0) ? fast + (size_t)k0 * 16 : nullptr, bbox, stream);
       if (rc) return rc;
       if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
@@ -943,7 +962,10 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
       // spread one camera's pixels over at most ~2 waves / kb CTAs
       int per_cam = (p3d::sm_count() * 8 + kb - 1) / kb;
       if ((int)grid.x > per_cam) grid.x = per_cam < 1 ? 1 : per_cam;
-      if (mode == P3D_MODE_JOINT)
+      if (smode == kModeJointPacked)
+        score_kernel<kModeJointPacked><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, nullptr, HW, P,
+                                                                       raw + (size_t)k0 * (P + 1) * 2, vec);
+      else if (mode == P3D_MODE_JOINT)
         score_kernel<P3D_MODE_JOINT><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, nullptr, HW, P,
                                                                      raw + (size_t)k0 * (P + 1) * 2, vec);
       else
@@ -985,10 +1007,12 @@ P3D_API int p3d_fast_cameras_f64(const double* cams, int K, const float* bbox, i
 P3D_API int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K, int H,
                           int W, int mode, uint32_t* zbuf, const float* fast, const float* bbox,
                           p3d_stream_t stream) {
+  P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
   return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, fast, bbox, stream);
 }
 P3D_API int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K, int H,
                           int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
+  P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
   return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, nullptr, nullptr, stream);
 }
 

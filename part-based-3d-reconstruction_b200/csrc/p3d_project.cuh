@@ -52,7 +52,7 @@ template <> struct Fp<float> {
 template <int MODE>
 __device__ __forceinline__ void zbuf_update(uint32_t* p, uint32_t key) {
   const uint32_t cur = __ldcg(p);
-  if (MODE == P3D_MODE_JOINT) {
+  if (MODE != P3D_MODE_PER_PART) {
     if (cur < key) atomicMax(p, key);
   } else {
     if ((cur & key) == 0) atomicOr(p, key);
