@@ -217,7 +217,10 @@ class DeformViewer:
     def update(self):
         """:105-145 without the figure: prints (and returns) the IoU of the current part at the current sliders."""
         part, deform = self.sliders["part"], self.current_deform()
-        ious, _, nvalid = self.score(part, [deform])
+        try:
+            ious, _, nvalid = self.score(part, [deform])
+        except ZeroDivisionError:                 # a part without voxels deforms to nothing in the reference (:116-120)
+            ious, nvalid = np.zeros(1), np.zeros(1, np.int64)
         if nvalid[0] == 0:
             if self.verbose:
                 print("No deformed voxels within bounds. Adjust sliders.")
@@ -263,10 +266,7 @@ class DeformViewer:
         deform = self.saved_params[part]["deform"] if part in self.saved_params else _IDENTITY
         for k in _KEYS:
             self.set_sliders(**{k: deform[k]})
-        try:
-            return self.update()
-        except ZeroDivisionError:                                             # part without voxels: nothing to show
-            return None
+        return self.update()
 
     # ---- the (commented-out) grid search, batched --------------------------------------------------------
     def project_fast_iou(self, part, deforms, stride=8):

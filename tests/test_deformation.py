@@ -162,3 +162,31 @@ def test_auto_align_selection(oracle, scene, g):
     assert v.current_deform() == {k: min(max(best[k], lo), hi) for k, (lo, hi) in de._RANGES.items()}
     # sequential re-evaluation of the refinement winner at stride 4 gives the same number
     assert v.iou("front_minarets", best, stride=4) == best_iou or v.iou("front_minarets", best, stride=6) == best_iou
+
+
+@pytest.mark.gpu
+def test_deformation_edge_cases(oracle, scene, g):
+    """Absent part (the reference divides by len(colors) == 0), stride beyond the part, empty batch, a float32 camera
+    through the batched path, and the sharded helper on one rank."""
+    de = pkg("utils.deformation_estimation")
+    sw = pkg("utils.sweep")
+    grid, image = scene
+    labels = part_labels(oracle)
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        v = de.DeformViewer(grid, labels, image, cam_of(g["cam"], np.float32), ["small_minarets", "dome"])   # Taj has no small minarets
+        assert v.update() is None
+        with pytest.raises(ZeroDivisionError):
+            v.save_params()
+        v.set_sliders(part="dome")
+    ident = {"scale_y": 1.0, "shift_y": 0.0, "scale_xz": 1.0, "shift_xz": 0.0}
+    n = v.part_points("dome").n
+    ious, counts, nvalid = v.score("dome", [ident], stride=n + 5)             # a single voxel survives the sub-sampling
+    assert nvalid[0] == 7 and counts[0, 0] <= 1
+    ious, counts, nvalid = v.score("dome", np.zeros((0, 4)))
+    assert ious.shape == (0,) and counts.shape == (0, 2)
+    rows = np.array([[1.0, 0.0, 1.0, 0.0], [1.1, 3.0, 0.9, -2.0], [1.0, 0.0, 1.0, 0.0]])
+    best_iou, best_i, local, span = sw.score_deformations_sharded(v, "dome", rows)
+    assert span == (0, 3) and best_i == int(np.argmax(local)) and best_iou == local[best_i]
+    pts, cols = oracle.get_voxel_points_by_parts(grid, labels, ["dome"])
+    want, _ = oracle.deform_part_iou(grid, labels, image, cam_of(g["cam"], np.float32), "dome", deform_of(rows[1]))
+    assert local[1] == want

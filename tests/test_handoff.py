@@ -59,3 +59,16 @@ def test_io_round_trips(tmp_path, grid):
     out = io.save_camera_params(tmp_path / "cams" / "Taj_camera_params_final.json", cams64)
     assert json.load(open(out)) == json.load(open(ref_json))             # lossless through float64
     assert io.to_json_safe({"a": (np.float32(1.5), np.arange(2))}) == {"a": [1.5, [0, 1]]}
+
+
+@pytest.mark.gpu
+def test_voxel_grid_to_points_edge_cases(oracle):
+    vu = pkg("utils.voxel_utils")
+    empty = np.zeros((5, 4, 6, 3), np.uint8)
+    pts, cols, shp = vu.voxel_grid_to_points(empty, stride=2)
+    assert pts.shape == (0, 3) and cols.shape == (0, 3) and shp == (4, 5, 6)
+    rng = np.random.default_rng(1)
+    g = (rng.random((7, 9, 5, 3)) < 0.2).astype(np.uint8) * rng.integers(1, 255, (7, 9, 5, 3), dtype=np.uint8)
+    for stride in (1, 2, 4, 16):                                           # 16 > every extent: only voxel (0,0,0) is sampled
+        got, want = vu.voxel_grid_to_points(g, stride=stride), oracle.voxel_grid_to_points(g, stride=stride)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] == want[2]
