@@ -219,6 +219,14 @@ def run_ours(args):
     h2d = B * 9 * 8
     d2h = B * 8 + B * cn.shape[1] * 2 * 8 + 8
 
+    # ---- N > 1: global_carve of the same N^3 grid sharded by x-slab (no exchange), max over ranks ----------
+    carve_multi = None
+    if world > 1 and not args.no_carve:
+        try:
+            carve_multi = carve_sharded_bench(N, dev, world, rank, dist)
+        except Exception as exc:
+            carve_multi = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -274,6 +282,8 @@ def run_ours(args):
         out["cpu_baseline"] = cpu
     if world == 1 and not args.no_extra:
         out["other_configs"] = extra_configs(dev, not args.no_cpu_baseline)
+    if carve_multi is not None:
+        out["carve"] = carve_multi
     if world == 1 and not args.no_carve:
         del scorer
         torch.cuda.empty_cache()
@@ -286,6 +296,45 @@ def run_ours(args):
     _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def carve_sharded_bench(N, dev, world, rank, dist):
+    """global_carve of the synthetic monument's front silhouette at N^3, one x-slab per rank (utils.sweep.carve_sharded:
+    masks replicated, no data-path collective).  Strong scaling: the grid is fixed, the slab shrinks with N."""
+    import torch
+    syn = importlib.import_module(PKG + ".synthetic")
+    vc = importlib.import_module(PKG + ".utils.voxel_carving_utils")
+    cfg = importlib.import_module(PKG + ".utils.config")
+    sw = importlib.import_module(PKG + ".utils.sweep")
+    lab = syn.monument_labels(N, dev)
+    front = torch.flip(lab.max(dim=0).values, dims=[0]).cpu().numpy()
+    del lab
+    lut = syn.label_lut()
+    lut[0] = cfg.PART_COLORS["background"]
+    ext = torch.from_numpy(lut[front]).to(dev)
+    binm = (front > 0).astype(np.uint8)
+    carve = lambda a, b: vc.global_carve(binm, ext, 90, return_tensor=True, x_range=(a, b))
+    for _ in range(3):
+        slab, span = sw.carve_sharded(carve, N)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        slab, span = sw.carve_sharded(carve, N)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    occ = torch.count_nonzero(slab.view(-1, 3).any(dim=1)).to(torch.float64).reshape(1)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(occ, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    return {"global_carve_sharded_gvoxel_s": round(N ** 3 / (ms * 1e-3) / 1e9, 2), "grid": N, "ms_per_call": round(ms, 4),
+            "n_gpus": world, "scaling": "strong", "occupied": int(occ.item()), "slab_of_rank0": list(span),
+            "note": "whole Python call per rank (mask upload, table lookup, slab kernel), x-slab per rank, max over ranks; "
+                    "no collective on the data path"}
 
 
 def carve_bench(N, dev, peak):
