@@ -795,6 +795,7 @@ inline int pick_cams_per_block(int64_t tiles, int K) {
   if (groups > K) groups = K;
   int cpb = (K + groups - 1) / groups;
   if (cpb < 4) cpb = K < 4 ? K : 4;
+  if (cpb > 64) cpb = 64;                                  // 192 B of shared memory per camera: keep 8 CTAs per SM
   return cpb;
 }
 
@@ -869,7 +870,8 @@ inline int batch_cameras(int K, int H, int W, size_t zbuf_budget) {
   int64_t floor16 = (int64_t)(((size_t)1 << 30) / per);
   if (floor16 > 16) floor16 = 16;
   if (c < floor16) c = floor16;
-  if (c > 64) c = 64;
+  static const int max_batch = [] { const char* e = getenv("P3D_MAX_BATCH"); int v = e ? atoi(e) : 256; return v > 0 ? v : 256; }();
+  if (c > max_batch) c = max_batch;
   if (c > K) c = K;
   if (c < 1) c = 1;
   return (int)c;
