@@ -50,3 +50,21 @@ def project_colored_voxels(pts3d, colors, cam_pos, target, f, cx, cy, H, W, devi
     zbuf = eng.splat(pts, None, cams, H, W, nv.MODE_JOINT)
     img = eng.resolve_rgb(zbuf[0], cols)
     return img if return_tensor else img.cpu().numpy()
+
+
+def visualize_reprojection(image, voxel_keypoints_dict, image_keypoints_dict, cam_params, title="Reprojection"):
+    """projection_utils.py:26-67 without the matplotlib figure: the printed key-point comparison table."""
+    from .camera_geometry import project
+    projected = {name: tuple(project(pt3d, cam_params["cam_pos"], cam_params["target"], cam_params["f"], cam_params["cx"],
+                                     cam_params["cy"])) for name, pt3d in voxel_keypoints_dict.items()}
+    print(f"\n{'Keypoint':<6} | {'GT (x, y)':<30} | {'Projected (x, y)':<30} | Error (L2)")
+    print("-" * 80)
+    total_err = 0
+    for name in image_keypoints_dict:
+        gt = np.array(image_keypoints_dict[name])
+        pr = np.array(projected[name])
+        err = np.linalg.norm(gt - pr)
+        total_err += err
+        print(f"{name:<6} | {tuple(np.round(gt, 2))!s:<30} | {tuple(np.round(pr, 2))!s:<30} | {err:.2f}")
+    avg_err = total_err / len(image_keypoints_dict)
+    print(f"\nAverage Reprojection Error: {avg_err:.2f} pixels")

@@ -77,3 +77,11 @@ def voxel_grid_to_points(grid, axis="z", colormap="viridis", stride=2, device=No
                                                 nv.stream_ptr()), "p3d_gather_scale_points")
         eng._launched(1 if pts.shape[0] else 0)
         return pts.cpu().numpy(), cols.cpu().numpy(), (A1, A0, A2)
+
+
+def meshify_colored_voxel_grid(colored_voxel_grid, stride=1):
+    """voxel_utils.py:53-95 (marching cubes + nearest-voxel colouring for the plotly viewer) is not part of this
+    package: scikit-image's Lewiner marching cubes, whose vertex/face order the output is defined by, is a viewer
+    dependency outside the geometry hot path.  Importable so that notebook 1's import cell works."""
+    raise NotImplementedError("meshify_colored_voxel_grid is a viewer helper outside this package's scope; "
+                              "use voxel_grid_to_points(grid, stride=...) to export points for inspection")

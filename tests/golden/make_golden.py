@@ -483,7 +483,10 @@ def init_golden():
         with contextlib.redirect_stdout(buf):
             fit = ce.optimize_camera_with_keypoints(vsel, isel, front, init, loss_type=loss)
         out[f"fit_{loss}"] = np.array([*fit["cam_pos"], *fit["target"], fit["f"], fit["cx"], fit["cy"]], dtype=np.float64)
-    # a drone-like second view: the same chain on the transposed-free 'drone' mask of the reference data
+    rbuf = io.StringIO()                                   # visualize_reprojection's printed table (projection_utils.py:26-67)
+    with contextlib.redirect_stdout(rbuf):
+        ref.pu.visualize_reprojection(front, vsel, isel, init, title="Front | Initial Reprojection")
+    out["reproj_log"] = np.array(rbuf.getvalue())
     np.savez_compressed(os.path.join(HERE, "init_golden.npz"), **out)
     print("init", out["init_row"], out["init_dtypes"], "sel", list(out["sel_keys"]), "fit", out["fit_L2"])
 

@@ -143,3 +143,13 @@ def test_aligner_default_init_uses_bbox_init(g, scene, oracle):
         saved = ce.launch_smart_aligner(grid, image, oracle.PART_COLORS, parts_for_alignment=PARTS)
     p = saved.aligner.get_params()
     assert np.allclose(row_of(p), g["init_row"])
+
+
+@pytest.mark.gpu
+def test_visualize_reprojection_prints_reference_table(g, scene):
+    pu = pkg("utils.projection_utils")
+    vsel, isel = golden_selection(g)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        pu.visualize_reprojection(scene[1], vsel, isel, init_of(g), title="Front | Initial Reprojection")
+    assert buf.getvalue() == str(g["reproj_log"])
