@@ -90,23 +90,27 @@ int p3d_setup_cameras_f32(const float* cand, int K, float* cams, p3d_stream_t st
  *   joint    : zbuf[k][v*W+u] = max(zbuf, i+1)        (last write wins == largest index wins)
  *   per-part : zbuf[k][v*W+u] |= 1 << (pt_label[i]-1) (pt_label required, values 1..32)
  * zbuf (K,H,W) uint32 must be zero on entry.  n < 2^32-1.
- * fast, bbox (f64 entry point only; both may be NULL): the (K,16) float blocks written by p3d_fast_cameras_f64 for
- * these cameras, this image size and the bounding box `bbox` of `pts` (p3d_points_bbox; the kernel re-centres the
- * points on the middle of the box).  With them the kernel decides most pixels in FP32 under a proven error bound and
- * re-projects only the undecided points in FP64 -- the z-buffer is bit-identical either way; without them every
- * point takes the FP64 path.
+ * fast, bbox (both may be NULL): the (K,16) float blocks written by p3d_fast_cameras_f64 / _f32 for these cameras,
+ * this image size and the bounding box `bbox` of `pts` (p3d_points_bbox; the kernel re-centres the points on the
+ * middle of the box).  With them the kernel decides most pixels with a cheap FP32 evaluation under a proven error
+ * bound and re-projects only the undecided points with the reference's exact sequence (float64 or float32, by entry
+ * point) -- the z-buffer is bit-identical either way; without them every point takes the exact path.
  * --------------------------------------------------------------------------------------------- */
 int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K,
                   int H, int W, int mode, uint32_t* zbuf, const float* fast, const float* bbox,
                   p3d_stream_t stream);
 int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K,
-                  int H, int W, int mode, uint32_t* zbuf, p3d_stream_t stream);
+                  int H, int W, int mode, uint32_t* zbuf, const float* fast, const float* bbox,
+                  p3d_stream_t stream);
 
 /* bbox (6 floats, device) = min x,y,z, max x,y,z of pts (n,3); NaN coordinates are ignored. */
 int p3d_points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream);
-/* FP32 companion blocks of K f64 cameras: pre-scaled rows, translation terms and the per-camera rounding
- * thresholds derived from an FP32 error bound over the box (see csrc/p3d_camera.cu).  fast: (K,16) floats. */
+/* FP32 companion blocks of K cameras: pre-scaled rows, translation terms and the per-camera rounding thresholds
+ * derived from an FP32 error bound over the box (see csrc/p3d_project.cuh); the _f32 variant adds the rounding error of
+ * the float32 reference sequence itself to the bound.  fast: (K,16) floats. */
 int p3d_fast_cameras_f64(const double* cams, int K, const float* bbox, int H, int W, float* fast,
+                         p3d_stream_t stream);
+int p3d_fast_cameras_f32(const float* cams, int K, const float* bbox, int H, int W, float* fast,
                          p3d_stream_t stream);
 
 /* project_colored_voxels (image)       utils/projection_utils.py:20-23

@@ -153,11 +153,16 @@ splat_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label
 constexpr int kPptF = P3D_PPTF;
 constexpr int kQueueCap = 64;        // per warp: at most 32 new entries on top of < 32 pending
 
-__global__ void __launch_bounds__(64) fast_cams_kernel(const double* __restrict__ cams, int K,
+template <typename T>
+__global__ void __launch_bounds__(64) fast_cams_kernel(const T* __restrict__ cams, int K,
                                                         const float* __restrict__ bbox, int H, int W,
                                                         float* __restrict__ fast) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < K) make_fast_cam(cams + (size_t)k * 16, bbox, H, W, reinterpret_cast<FastCam*>(fast) + k);
+  if (k >= K) return;
+  double cam[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) cam[i] = (double)cams[(size_t)k * 16 + i];       // float32 blocks widen exactly
+  make_fast_cam(cam, bbox, H, W, reinterpret_cast<FastCam*>(fast) + k, sizeof(T) == 4);
 }
 
 #ifndef P3D_SCALAR_FILTER
@@ -170,13 +175,13 @@ constexpr int kCamUnroll = P3D_CAM_UNROLL;   // camera-loop unroll factor (tunin
 constexpr int kPackCamFloats = 16;   // per camera in shared memory: one FastCam (FFMA2 broadcasts a scalar operand)
 constexpr int kFlushEvery = 64 / kPptF; // cameras between queue flushes: kPptF bits per camera in a 64-bit mask
 
-template <int MODE>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kSplatThreads, P3D_MINBLOCKS)
 splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ pt_label, int64_t n,
-                      const double* __restrict__ cams, int K, int cams_per_block, int H, int W,
+                      const T* __restrict__ cams, int K, int cams_per_block, int H, int W,
                       uint32_t* __restrict__ zbuf, const float* __restrict__ fast, const float* __restrict__ bbox) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_cam = reinterpret_cast<double*>(smem_raw);                                   // nc x 16 doubles
+  T* s_cam = reinterpret_cast<T*>(smem_raw);                                             // nc x 16 camera scalars
   float* s_fast = reinterpret_cast<float*>(s_cam + (size_t)cams_per_block * 16);          // nc x kPackCamFloats
   uint2* s_queue = reinterpret_cast<uint2*>(s_fast + (size_t)cams_per_block * kPackCamFloats);   // 8 warps x kQueueCap
 
@@ -213,7 +218,7 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
   }
 #pragma unroll
   for (int g = kPptF; g < 64; g <<= 1) live |= live << g;
-  const double dW = (double)W, dH = (double)H;
+  const T dW = (T)W, dH = (T)H;
   const uint32_t HW = (uint32_t)H * (uint32_t)W;
   const float kMagic = 12582912.f;                         // 1.5 * 2^23: (x + m) - m == rint(x) for |x| < 2^22
 #ifdef P3D_PACKED
@@ -234,8 +239,8 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       const uint2 e = q[qn - take + lane];                  // (point index, camera)
       const float* pp = pts + 3 * (size_t)e.x;
       const uint32_t k = make_key<MODE>((int64_t)e.x, pt_label);
-      exact_splat<double, MODE>((double)__ldg(pp), (double)__ldg(pp + 1), (double)__ldg(pp + 2), k, s_cam + e.y * 16,
-                                zbuf + (size_t)(c0 + e.y) * HW, W, dW, dH);
+      exact_splat<T, MODE>((T)__ldg(pp), (T)__ldg(pp + 1), (T)__ldg(pp + 2), k, s_cam + e.y * 16,
+                           zbuf + (size_t)(c0 + e.y) * HW, W, dW, dH);
     }
     qn -= take;
     __syncwarp();
@@ -811,11 +816,12 @@ int points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream) {
   return P3D_OK;
 }
 
-int fast_cameras(const double* cams, int K, const float* bbox, int H, int W, float* fast, p3d_stream_t stream) {
+template <typename T>
+int fast_cameras(const T* cams, int K, const float* bbox, int H, int W, float* fast, p3d_stream_t stream) {
   P3D_REQUIRE(K >= 0 && H > 0 && W > 0, "fast_cameras: bad arguments");
   if (K == 0) return P3D_OK;
   P3D_REQUIRE(cams && bbox && fast, "fast_cameras: null pointer");
-  fast_cams_kernel<<<(K + 63) / 64, 64, 0, p3d::as_stream(stream)>>>(cams, K, bbox, H, W, fast);
+  fast_cams_kernel<T><<<(K + 63) / 64, 64, 0, p3d::as_stream(stream)>>>(cams, K, bbox, H, W, fast);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -831,7 +837,7 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   if (n == 0 || K == 0) return P3D_OK;
   P3D_REQUIRE(pts && cams && zbuf, "splat: null pointer");
   P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: this mode needs pt_label");
-  const bool filtered = sizeof(T) == 8 && fast != nullptr && bbox != nullptr && !splat_exact_only();
+  const bool filtered = fast != nullptr && bbox != nullptr && !splat_exact_only();
   const int ppt = filtered ? kPptF : kPpt;
   const int64_t tiles = (n + kSplatThreads * ppt - 1) / (kSplatThreads * ppt);
   P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
@@ -839,15 +845,15 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   dim3 grid((unsigned)tiles, (unsigned)((K + cpb - 1) / cpb));
   cudaStream_t st = p3d::as_stream(stream);
   if (filtered) {
-    const size_t smem = (size_t)cpb * (16 * sizeof(double) + kPackCamFloats * sizeof(float)) +
+    const size_t smem = (size_t)cpb * (16 * sizeof(T) + kPackCamFloats * sizeof(float)) +
                         (size_t)(kSplatThreads / 32) * (kQueueCap * sizeof(uint2));
-    const double* dc = reinterpret_cast<const double*>(cams);
+    const T* dc = cams;
     if (mode == P3D_MODE_JOINT)
-      splat_filtered_kernel<P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
+      splat_filtered_kernel<T, P3D_MODE_JOINT><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
     else if (mode == kModeJointPacked)
-      splat_filtered_kernel<kModeJointPacked><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
+      splat_filtered_kernel<T, kModeJointPacked><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
     else
-      splat_filtered_kernel<P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
+      splat_filtered_kernel<T, P3D_MODE_PER_PART><<<grid, kSplatThreads, smem, st>>>(pts, pt_label, n, dc, K, cpb, H, W, zbuf, fast, bbox);
   } else {
     const size_t smem = (size_t)cpb * 16 * sizeof(T);
     if (mode == P3D_MODE_JOINT)
@@ -939,10 +945,10 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
                                                       gt_area);
   P3D_LAUNCH_CHECK();
   g_last_launches += 2;
-  if (n > 0 && sizeof(T) == 8) {
+  if (n > 0) {
     rc = points_bbox(pts, n, bbox, stream);
     if (rc) return rc;
-    rc = fast_cameras(reinterpret_cast<const double*>(cams), K, bbox, H, W, fast, stream);
+    rc = fast_cameras<T>(cams, K, bbox, H, W, fast, stream);
     if (rc) return rc;
     g_last_launches += 3;
   }
@@ -955,7 +961,7 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
       rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, smode, zbuf,
-                    (sizeof(T) == 8 && n > 0) ? fast + (size_t)k0 * 16 : nullptr, bbox, stream);
+                    n > 0 ? fast + (size_t)k0 * 16 : nullptr, bbox, stream);
       if (rc) return rc;
       if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
       const int vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(gt_label) & 3) == 0) &&
@@ -1003,7 +1009,11 @@ P3D_API int p3d_points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream
 
 P3D_API int p3d_fast_cameras_f64(const double* cams, int K, const float* bbox, int H, int W, float* fast,
                                  p3d_stream_t stream) {
-  return fast_cameras(cams, K, bbox, H, W, fast, stream);
+  return fast_cameras<double>(cams, K, bbox, H, W, fast, stream);
+}
+P3D_API int p3d_fast_cameras_f32(const float* cams, int K, const float* bbox, int H, int W, float* fast,
+                                 p3d_stream_t stream) {
+  return fast_cameras<float>(cams, K, bbox, H, W, fast, stream);
 }
 
 P3D_API int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cams, int K, int H,
@@ -1013,9 +1023,10 @@ P3D_API int p3d_splat_f64(const float* pts, const uint8_t* pt_label, int64_t n, 
   return splat<double>(pts, pt_label, n, cams, K, H, W, mode, zbuf, fast, bbox, stream);
 }
 P3D_API int p3d_splat_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cams, int K, int H,
-                          int W, int mode, uint32_t* zbuf, p3d_stream_t stream) {
+                          int W, int mode, uint32_t* zbuf, const float* fast, const float* bbox,
+                          p3d_stream_t stream) {
   P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "splat: mode=%d", mode);
-  return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, nullptr, nullptr, stream);
+  return splat<float>(pts, pt_label, n, cams, K, H, W, mode, zbuf, fast, bbox, stream);
 }
 
 P3D_API int p3d_resolve_rgb(const uint32_t* zbuf, const uint8_t* pt_rgb, int64_t n_pixels, uint8_t* img,

@@ -102,18 +102,24 @@ __device__ __forceinline__ float bbox_centre(const float* __restrict__ bbox, int
   return __fmul_rn(0.5f, __fadd_rn(bbox[k], bbox[3 + k]));
 }
 
+// ref_f32: the exact path is the reference's FLOAT32 sequence (float32 camera arrays) instead of the float64 one.  Its
+// own rounding error against the real-arithmetic value of the same (float32-valued) camera block is added to the bound:
+//   d = fl(p - e) (1 rounding), X = fma(d2,R2, fma(d1,R1, fl(d0 R0))) (3 roundings)  =>  |X32 - X| <= 4 eps Md,
+//   Md = sum_k max|p_k - e_k| over the box; the same for Z;  u = fl(fl(fl(X/Z) f) + cx)  =>
+//   |u_ref32 - u| <= eps [ 4 f Md / Zmin + |u - cx| (4 Md / Zmin + 2) + |u| ]            (Zmin lowered by 4 eps Md)
 __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, const float* __restrict__ bbox, int H,
-                                              int W, FastCam* out) {
+                                              int W, FastCam* out, bool ref_f32 = false) {
   FastCam fc;
   bool ok = true;
   for (int k = 0; k < 15; ++k) ok = ok && (fabs(cam[k]) < 1e30);                 // false for NaN / Inf
   for (int k = 3; k < 12; ++k) ok = ok && (fabs(cam[k]) <= 1.0001);
   const double f = cam[12];
-  double sp = 0.0, zmin = 0.0, zabs = 0.0, ta = 0.0, tb = 0.0, tc = 0.0;
+  double sp = 0.0, zmin = 0.0, zabs = 0.0, ta = 0.0, tb = 0.0, tc = 0.0, md = 0.0;
   for (int k = 0; k < 3; ++k) {
     const double lo = (double)bbox[k], hi = (double)bbox[3 + k], c = (double)bbox_centre(bbox, k);
     ok = ok && (fabs(lo) < 1e30) && (fabs(hi) < 1e30) && lo <= hi;
     sp += fmax(fabs(lo - c), fabs(hi - c));
+    md += fmax(fabs(lo - cam[k]), fabs(hi - cam[k]));
     const double a = (lo - cam[k]) * cam[9 + k], b = (hi - cam[k]) * cam[9 + k];
     zmin += fmin(a, b);
     zabs += fmax(fabs(a), fabs(b));
@@ -131,7 +137,9 @@ __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, co
   const double dz = 5.05 * sp + 4.04 * fabs(tc);
   const double dxu = 5.05 * f * sp + 4.04 * fabs(ta), dxv = 5.05 * f * sp + 4.04 * fabs(tb);
   zmin -= 1e-9 * zabs;
-  ok = ok && f > 1e-3 && zmin > fmax(1e-3, dz * 7.62939453125e-06);              // 2^-17
+  const double refx = ref_f32 ? 4.05 * md : 0.0;                                 // rounding of the float32 reference chain
+  if (ref_f32) zmin -= eps * refx;
+  ok = ok && f > 1e-3 && zmin > fmax(1e-3, (dz + refx) * 7.62939453125e-06);     // 2^-17
   double bu = 1.0, bv = 1.0, b1 = 1.0;
   if (ok) {
     const double cx = cam[13], cy = cam[14], dW = (double)W, dH = (double)H;
@@ -139,6 +147,11 @@ __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, co
     b1 = 1.25 * eps * (dz / zmin + 3.0);
     bu = 1.25 * eps * (dxu / zmin + ud * (dz / zmin + 2.0) + fabs(cx) + dW + 2.0) + 1e-7;
     bv = 1.25 * eps * (dxv / zmin + vd * (dz / zmin + 2.0) + fabs(cy) + dH + 2.0) + 1e-7;
+    if (ref_f32) {
+      b1 += 1.25 * eps * (refx / zmin + 3.0);
+      bu += 1.25 * eps * (f * refx / zmin + ud * (refx / zmin + 2.02) + dW + 2.0);
+      bv += 1.25 * eps * (f * refx / zmin + vd * (refx / zmin + 2.02) + dH + 2.0);
+    }
   }
   ok = ok && bu <= 0.25 && bv <= 0.25 && b1 * 2.0 * (double)(W > H ? W : H) <= 0.25;
   ok = ok && W < (1 << 21) && H < (1 << 21);                                     // range of the magic-number rounding

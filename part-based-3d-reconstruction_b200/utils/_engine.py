@@ -100,20 +100,17 @@ def splat(pts: torch.Tensor, pt_label, cams: torch.Tensor, H: int, W: int, mode:
     K = cams.shape[0]
     zbuf = torch.zeros((K, H, W), dtype=torch.int32, device=pts.device)
     n = pts.shape[0]
-    if _elem(cams.dtype) == "f64":
-        fast = None
-        if n and K:
-            if bbox is None:
-                bbox = points_bbox(pts)
-            fast = torch.empty((K, 16), dtype=torch.float32, device=pts.device)
-            check(lib.p3d_fast_cameras_f64(ptr(cams), K, ptr(bbox), H, W, ptr(fast), stream_ptr()),
-                  "p3d_fast_cameras_f64")
-            _launched(1)
-        check(lib.p3d_splat_f64(ptr(pts), ptr(pt_label), n, ptr(cams), K, H, W, mode, ptr(zbuf), ptr(fast),
-                                ptr(bbox if fast is not None else None), stream_ptr()), "p3d_splat_f64")
-    else:
-        check(lib.p3d_splat_f32(ptr(pts), ptr(pt_label), n, ptr(cams), K, H, W, mode, ptr(zbuf), stream_ptr()),
-              "p3d_splat_f32")
+    el = _elem(cams.dtype)
+    fast = None
+    if n and K:
+        if bbox is None:
+            bbox = points_bbox(pts)
+        fast = torch.empty((K, 16), dtype=torch.float32, device=pts.device)
+        check(getattr(lib, f"p3d_fast_cameras_{el}")(ptr(cams), K, ptr(bbox), H, W, ptr(fast), stream_ptr()),
+              "p3d_fast_cameras")
+        _launched(1)
+    check(getattr(lib, f"p3d_splat_{el}")(ptr(pts), ptr(pt_label), n, ptr(cams), K, H, W, mode, ptr(zbuf), ptr(fast),
+                                          ptr(bbox if fast is not None else None), stream_ptr()), "p3d_splat")
     _launched(1 if (K and n) else 0)
     return zbuf
 

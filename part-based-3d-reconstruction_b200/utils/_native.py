@@ -53,7 +53,8 @@ _SIGNATURES = {
     "p3d_splat_f64": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),
     "p3d_points_bbox": ([_vp, _i64, _vp, _vp], _i32),
     "p3d_fast_cameras_f64": ([_vp, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
-    "p3d_splat_f32": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_fast_cameras_f32": ([_vp, _i32, _vp, _i32, _i32, _vp, _vp], _i32),
+    "p3d_splat_f32": ([_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),
     "p3d_resolve_rgb": ([_vp, _vp, _i64, _vp, _vp], _i32),
     "p3d_partwise_counts_rgb": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp], _i32),
     "p3d_sweep_workspace_bytes": ([_i32, _i32, _i32, _i32, _i32], _sz),

@@ -111,7 +111,7 @@ def test_sweep_512_properties():
 @pytest.mark.gpu
 def test_filtered_splat_equals_exact_over_many_cameras():
     """The FP32 filter's proven bound under stress: z-buffers of the filtered kernel and of the exact FP64 kernel are
-    identical for 320 perturbed cameras at full 512^3 size -- front and aerial views, a square and an odd-sized image,
+    identical for 320 perturbed cameras (each as float64 and as float32) at full 512^3 size -- front and aerial views, a square and an odd-sized image,
     principal points inside and far outside the image (each camera decides ~2.2e7 points; ~1e5 of them sit within the
     bound of a rounding boundary and must take the FP64 path)."""
     import os
@@ -128,13 +128,14 @@ def test_filtered_splat_equals_exact_over_many_cameras():
         cand = syn.candidates(syn.base_camera(N, H, W, view), K, seed=int(rng.integers(1 << 30)))
         cand[K // 2:, 7] += rng.uniform(-3 * W, 3 * W, K - K // 2)           # cx far outside the image for half of them
         cand[K // 2:, 8] += rng.uniform(-2 * H, 2 * H, K - K // 2)
-        for k0 in range(0, K, 32):
-            cams = eng.setup_cameras(torch.from_numpy(cand[k0:k0 + 32]).to(dev))
-            os.environ["P3D_SPLAT_EXACT"] = "1"
-            try:
-                ref = eng.splat(pts, pt_label, cams, H, W, bbox=bbox)
-            finally:
-                os.environ["P3D_SPLAT_EXACT"] = "0"
-            got = eng.splat(pts, pt_label, cams, H, W, bbox=bbox)
-            assert torch.equal(ref, got), (H, W, view, k0)
-            del ref, got
+        for dt in (np.float64, np.float32):                  # float32 cameras: the exact path is the reference's float32 sequence
+            for k0 in range(0, K, 32):
+                cams = eng.setup_cameras(torch.from_numpy(cand[k0:k0 + 32].astype(dt)).to(dev))
+                os.environ["P3D_SPLAT_EXACT"] = "1"
+                try:
+                    ref = eng.splat(pts, pt_label, cams, H, W, bbox=bbox)
+                finally:
+                    os.environ["P3D_SPLAT_EXACT"] = "0"
+                got = eng.splat(pts, pt_label, cams, H, W, bbox=bbox)
+                assert torch.equal(ref, got), (H, W, view, k0, dt)
+                del ref, got
