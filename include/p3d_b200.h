@@ -190,9 +190,9 @@ int p3d_part_visible_f64(const float* pts, int64_t n, const double* cam, const f
  *   p3d_pack_label_bits: bits[w] bit b = (labels[32w+b] == label), the ground-truth mask of one part.
  *   p3d_deform_sweep_* : for each of D candidates: deform, bounds-test in the (A0,A1,A2) grid (:111-115), project
  *                        through `cam` (one block of p3d_setup_cameras_f64/_f32 -- the working dtype of the
- *                        reference's projection follows the camera arrays; f64: fast/bbox = its
- *                        p3d_fast_cameras_f64 block for the box (0,0,0)-(A2-1,A1-1,A0-1)), and compare the covered
- *                        pixels with gt_bits:
+ *                        reference's projection follows the camera arrays; fast/bbox = its p3d_fast_cameras_f64/_f32
+ *                        block for the box (0,0,0)-(A2-1,A1-1,A0-1), or both NULL = exact path only), and compare the
+ *                        covered pixels with gt_bits:
  *                        counts (D,2) int64 = |proj & gt|, |proj | gt| (compute_partwise_iou for one part);
  *                        nvalid (D) int64 = (point, jitter) pairs inside the grid.  cov: (D, ceil(H*W/32)) uint32
  *                        scratch, zero on entry and on return.
@@ -209,9 +209,9 @@ int p3d_deform_sweep_f64(const float* pts, int64_t n, int64_t stride, const doub
                          const float* bbox, const uint32_t* gt_bits, int H, int W, uint32_t* cov, int64_t* counts,
                          int64_t* nvalid, p3d_stream_t stream);
 int p3d_deform_sweep_f32(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deforms,
-                         int D, const double* pix2vox, int A0, int A1, int A2, const float* cam,
-                         const uint32_t* gt_bits, int H, int W, uint32_t* cov, int64_t* counts, int64_t* nvalid,
-                         p3d_stream_t stream);
+                         int D, const double* pix2vox, int A0, int A1, int A2, const float* cam, const float* fast,
+                         const float* bbox, const uint32_t* gt_bits, int H, int W, uint32_t* cov, int64_t* counts,
+                         int64_t* nvalid, p3d_stream_t stream);
 int p3d_deform_scatter(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deform,
                        const double* pix2vox, int A0, int A1, int A2, int r, int g, int b, uint8_t* grid_rgb,
                        int64_t* nvalid, p3d_stream_t stream);

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kDeformThreads) deform_splat_kernel(
   __shared__ T s_cam[16];
   __shared__ double s_ctr[9];
   __shared__ FastCam s_fast;
-  constexpr bool kFilter = sizeof(T) == 8;
+  const bool kFilter = fast != nullptr;                   // FP32 filter block present (either exact dtype)
   if (threadIdx.x < 16) s_cam[threadIdx.x] = cam[threadIdx.x];
   if (threadIdx.x < 9) s_ctr[threadIdx.x] = centres[threadIdx.x];
   if (kFilter && threadIdx.x < 16) reinterpret_cast<float*>(&s_fast)[threadIdx.x] = fast[threadIdx.x];
@@ -368,7 +368,7 @@ int deform_sweep(const float* pts, int64_t n, int64_t stride, const double* cent
   P3D_REQUIRE((int64_t)H * W < (1ll << 31) && W < (1 << 21) && H < (1 << 21), "deform_sweep: image too large");
   if (D == 0) return P3D_OK;
   P3D_REQUIRE(centres && deforms && pix2vox && cam && gt_bits && cov && counts && nvalid, "deform_sweep: null pointer");
-  P3D_REQUIRE(sizeof(T) == 4 || (fast && bbox), "deform_sweep: the f64 entry point needs the FP32 companion block");
+  P3D_REQUIRE((fast == nullptr) == (bbox == nullptr), "deform_sweep: fast and bbox go together");
   cudaStream_t st = p3d::as_stream(stream);
   const int64_t m = (n + stride - 1) / stride;
   const int64_t words = ((int64_t)H * W + 31) / 32;
@@ -400,10 +400,10 @@ P3D_API int p3d_deform_sweep_f64(const float* pts, int64_t n, int64_t stride, co
 }
 P3D_API int p3d_deform_sweep_f32(const float* pts, int64_t n, int64_t stride, const double* centres,
                                  const double* deforms, int D, const double* pix2vox, int A0, int A1, int A2,
-                                 const float* cam, const uint32_t* gt_bits, int H, int W, uint32_t* cov, int64_t* counts,
-                                 int64_t* nvalid, p3d_stream_t stream) {
-  return deform_sweep<float>(pts, n, stride, centres, deforms, D, pix2vox, A0, A1, A2, cam, nullptr, nullptr, gt_bits, H, W,
-                             cov, counts, nvalid, stream);
+                                 const float* cam, const float* fast, const float* bbox, const uint32_t* gt_bits, int H,
+                                 int W, uint32_t* cov, int64_t* counts, int64_t* nvalid, p3d_stream_t stream) {
+  return deform_sweep<float>(pts, n, stride, centres, deforms, D, pix2vox, A0, A1, A2, cam, fast, bbox, gt_bits, H, W, cov,
+                             counts, nvalid, stream);
 }
 
 P3D_API int p3d_deform_scatter(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deform,

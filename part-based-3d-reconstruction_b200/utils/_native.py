@@ -73,8 +73,8 @@ _SIGNATURES = {
     "p3d_pack_label_bits": ([_vp, _i64, _i32, _vp, _vp], _i32),
     "p3d_deform_sweep_f64": ([_vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
                               _vp, _vp, _vp], _i32),
-    "p3d_deform_sweep_f32": ([_vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp,
-                              _vp], _i32),
+    "p3d_deform_sweep_f32": ([_vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
+                              _vp, _vp, _vp], _i32),
     "p3d_deform_scatter": ([_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "p3d_sweep_timing_enable": ([_i32], _i32),
     "p3d_sweep_timing_read": ([_vp, _vp], _i32),

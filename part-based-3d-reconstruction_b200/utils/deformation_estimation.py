@@ -124,14 +124,13 @@ class DeformViewer:
         self.cam_params = cam_params
         cand = torch.from_numpy(row[None]).to(self.device)
         self.cam = eng.setup_cameras(cand)
-        self.fast = self.bbox = None
-        if not f32:
-            D, H, W = self.voxel_shape
-            self.bbox = torch.tensor([0, 0, 0, W - 1, H - 1, D - 1, 0, 0], dtype=torch.float32, device=self.device)
-            self.fast = torch.empty((1, 16), dtype=torch.float32, device=self.device)
-            nv.check(nv.lib.p3d_fast_cameras_f64(nv.ptr(self.cam), 1, nv.ptr(self.bbox), self.H, self.W, nv.ptr(self.fast),
-                                                 nv.stream_ptr()), "p3d_fast_cameras_f64")
-            eng._launched(1)
+        D, H, W = self.voxel_shape                         # FP32 filter block over the whole grid box (every valid voxel)
+        self.bbox = torch.tensor([0, 0, 0, W - 1, H - 1, D - 1, 0, 0], dtype=torch.float32, device=self.device)
+        self.fast = torch.empty((1, 16), dtype=torch.float32, device=self.device)
+        fn = nv.lib.p3d_fast_cameras_f32 if f32 else nv.lib.p3d_fast_cameras_f64
+        nv.check(fn(nv.ptr(self.cam), 1, nv.ptr(self.bbox), self.H, self.W, nv.ptr(self.fast), nv.stream_ptr()),
+                 "p3d_fast_cameras")
+        eng._launched(1)
 
     # ---- per-part device state -----------------------------------------------------------------------
     def part_points(self, part, stride=1) -> _PartPoints:
@@ -180,17 +179,10 @@ class DeformViewer:
             A0, A1, A2 = self.voxel_shape
             for d0 in range(0, D, batch):
                 nd = min(batch, D - d0)
-                if self.cam_dtype == np.float64:
-                    rc = nv.lib.p3d_deform_sweep_f64(nv.ptr(pp.pts), pp.n, pp.stride, nv.ptr(pp.centres),
-                                                     nv.ptr(dev_rows[d0:]), nd, nv.ptr(self.p2v), A0, A1, A2,
-                                                     nv.ptr(self.cam), nv.ptr(self.fast), nv.ptr(self.bbox), nv.ptr(gt),
-                                                     self.H, self.W, nv.ptr(self._cov), nv.ptr(counts[d0:]),
-                                                     nv.ptr(nvalid[d0:]), nv.stream_ptr())
-                else:
-                    rc = nv.lib.p3d_deform_sweep_f32(nv.ptr(pp.pts), pp.n, pp.stride, nv.ptr(pp.centres),
-                                                     nv.ptr(dev_rows[d0:]), nd, nv.ptr(self.p2v), A0, A1, A2,
-                                                     nv.ptr(self.cam), nv.ptr(gt), self.H, self.W, nv.ptr(self._cov),
-                                                     nv.ptr(counts[d0:]), nv.ptr(nvalid[d0:]), nv.stream_ptr())
+                fn = nv.lib.p3d_deform_sweep_f64 if self.cam_dtype == np.float64 else nv.lib.p3d_deform_sweep_f32
+                rc = fn(nv.ptr(pp.pts), pp.n, pp.stride, nv.ptr(pp.centres), nv.ptr(dev_rows[d0:]), nd, nv.ptr(self.p2v),
+                        A0, A1, A2, nv.ptr(self.cam), nv.ptr(self.fast), nv.ptr(self.bbox), nv.ptr(gt), self.H, self.W,
+                        nv.ptr(self._cov), nv.ptr(counts[d0:]), nv.ptr(nvalid[d0:]), nv.stream_ptr())
                 nv.check(rc, "p3d_deform_sweep")
                 eng._launched(2)
             c = counts.cpu().numpy()
