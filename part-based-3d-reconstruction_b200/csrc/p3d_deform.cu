@@ -157,13 +157,15 @@ __global__ void __launch_bounds__(kDeformThreads) deform_splat_kernel(
   __shared__ T s_cam[16];
   __shared__ double s_ctr[9];
   __shared__ FastCam s_fast;
+  __shared__ DeformParams s_def[kDeformPerBlock];
   const bool kFilter = fast != nullptr;                   // FP32 filter block present (either exact dtype)
   if (threadIdx.x < 16) s_cam[threadIdx.x] = cam[threadIdx.x];
   if (threadIdx.x < 9) s_ctr[threadIdx.x] = centres[threadIdx.x];
   if (kFilter && threadIdx.x < 16) reinterpret_cast<float*>(&s_fast)[threadIdx.x] = fast[threadIdx.x];
-  __syncthreads();
   const int d0 = blockIdx.y * kDeformPerBlock;
   const int nd = min(kDeformPerBlock, D - d0);
+  if (threadIdx.x < nd) s_def[threadIdx.x] = load_deform(deforms + (size_t)(d0 + threadIdx.x) * 4, pix2vox);
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kDeformThreads + threadIdx.x;
   const bool live = i < m;
   double p[3] = {0.0, 0.0, 0.0};
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kDeformThreads) deform_splat_kernel(
   const double fA0 = (double)A0, fA1 = (double)A1, fA2 = (double)A2;
   const float kMagic = 12582912.f;
   for (int dd = 0; dd < nd; ++dd) {
-    const DeformParams q = load_deform(deforms + (size_t)(d0 + dd) * 4, pix2vox);
+    const DeformParams q = s_def[dd];
     uint32_t* cv = cov + (size_t)(d0 + dd) * words;
     int count = 0;
     if (live) {
