@@ -426,9 +426,11 @@ def carve_bench(N, dev, peak):
                              "call_ms": round(pc_call_ms, 3), "occupied": int(torch.count_nonzero(pc.view(-1, 3).any(dim=1)).item()),
                              "roofline": {"bound": "hbm", "achieved": round(6 * N ** 3 / (pms * 1e-3) / 1e9, 1), "peak": peak,
                                           "unit": "GB/s", "frac": round(6 * N ** 3 / (pms * 1e-3) / 1e9 / peak, 4),
-                                          "kernel": "occ_bits_x + pack_group_bits + part_fold_bits",
-                                          "note": "6 B per voxel (SURVEY 8d: read RGB + write RGB); the x-packed occupancy "
-                                                  "pre-pass re-reads the grid once, so real traffic is ~9 B/voxel"}}
+                                          "kernel": "pack_group_bits + part_copy_bits + part_clear",
+                                          "note": "6 B per voxel (SURVEY 8d: read RGB + write RGB); copy-then-clear: pass A "
+                                                  "writes the output from voxel-local terms and packs occupancy/alive bits "
+                                                  "(~0.25 B/voxel), pass B reads bits only and rewrites the runs whose "
+                                                  "rotated source is empty (none for this 4-way-symmetric grid)"}}
     del out, kout, pc
     data = os.path.join(ROOT, "tests", "golden", "data")
     try:

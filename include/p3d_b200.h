@@ -296,7 +296,9 @@ int p3d_part_carve_fold(const uint8_t* grid, int W, int H, int D, const int32_t*
 
 /* Bit-level form of p3d_part_carve_fold for z-separable tables with src0 = c - z and src2 = x + c2 (p3d_fold_analyse:
  * info[0] == info[1] =: c, info[2] == info[3] =: c2).  Needs D % 32 == 0, 16-byte aligned grids and
- * p3d_part_carve_bits_workspace_bytes() of scratch (x-packed occupancy bits + per-group mask bits). */
+ * p3d_part_carve_bits_workspace_bytes() of scratch (z-packed occupancy and "alive" bits + per-group mask bits).
+ * Two passes: the output is first written from the voxel-local terms, then the runs whose rotated source voxel is
+ * empty are cleared (none for an already 4-way-symmetric grid). */
 size_t p3d_part_carve_bits_workspace_bytes(int W, int H, int D, int n_groups);
 int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, const uint32_t* inside_bits, int c, int c2,
                              const uint32_t* group_mask_hw, int n_groups, uint8_t* out, void* workspace,

@@ -342,13 +342,11 @@ global_fold_bits_kernel(int W, int H, int D, int x_begin, int x_count, const uin
 
 // ------------------------------------------------------------------------------------------
 // Bit-level fast path of the fused part_carve kernel (all groups at 90 degrees, z-separable table with
-// src0 = c - z and src2 = x + c2).
-//   occ_bits_x_kernel      : occx[y][z][1 + x/32] bit x%32 = any(grid[x,y,z,:] > 0)   (bits packed along x, one zero
-//                            word of padding on each side), via a 32x32 ballot transpose
-//   pack_group_bits_kernel : gbits[g][y][1 + x/32] bit x%32 = bit g of the group image gm[y][x]
-//   part_fold_bits_kernel  : thread = 16 voxels of one z-row: three 16-byte loads, a handful of word loads for the
-//                            16 source-occupancy / source-group bits (read backwards), three 16-byte stores
+// src0 = c - z and src2 = x + c2):
 //   keep(x,y,z) = grid[x,y,z] != 0 && inside(x,z) && occ[c-z, y, x+c2] && OR_g (g in gm[y][x] && g in gm[y][c-z])
+//   pack_group_bits_kernel : gbits[g][y][1 + x/32] bit x%32 = bit g of the group image gm[y][x]  (one zero word of
+//                            padding on each side)
+//   part_copy_bits_kernel / part_clear_kernel : the copy-then-clear pair described below
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rgb16_occupancy(const uint4& a, const uint4& b, const uint4& c) {
   const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
@@ -362,32 +360,6 @@ __device__ __forceinline__ uint32_t rgb16_occupancy(const uint4& a, const uint4&
     if (w2 & 0xffffff00u) bits |= 8u << (4 * q);
   }
   return bits;
-}
-
-__global__ void __launch_bounds__(256)
-occ_bits_x_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, int xwp, uint32_t* __restrict__ occx) {
-  const int lane = threadIdx.x & 31;
-  const int xt_n = (W + 31) >> 5, zt_n = D >> 5;
-  const int64_t tasks = (int64_t)H * zt_n * xt_n;
-  for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < tasks; t += (int64_t)gridDim.x * 8) {
-    const int xt = (int)(t % xt_n);
-    const int64_t r = t / xt_n;
-    const int zt = (int)(r % zt_n), y = (int)(r / zt_n);
-    const int x = xt * 32 + lane, z0 = zt * 32;
-    uint32_t mine = 0;
-    if (x < W) {
-      const uint4* p = reinterpret_cast<const uint4*>(grid + (((size_t)x * H + y) * D + z0) * 3);
-      const uint4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3), a4 = __ldg(p + 4), a5 = __ldg(p + 5);
-      mine = rgb16_occupancy(a0, a1, a2) | (rgb16_occupancy(a3, a4, a5) << 16);
-    }
-    uint32_t keep = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const uint32_t wj = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
-      if (lane == j) keep = wj;
-    }
-    occx[((size_t)y * D + z0 + lane) * xwp + 1 + xt] = keep;
-  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -412,42 +384,123 @@ __device__ __forceinline__ uint32_t rev16_bits(const uint32_t* __restrict__ row,
   return __brev(__funnelshift_r(w0, w1, lo & 31) & 0xffffu) >> 16;
 }
 
-__global__ void __launch_bounds__(256)
-part_fold_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const uint32_t* __restrict__ inside_bits,
-                      int c, int c2, const uint32_t* __restrict__ gm_hw, const uint32_t* __restrict__ gbits,
-                      const uint32_t* __restrict__ occx, int xwp, uint8_t* __restrict__ out) {
-  const int64_t groups = (int64_t)W * H * D / 16;
-  const int words = D >> 5;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t v0 = g * 16;
-    const int z0 = (int)(v0 % D);
-    const int64_t r = v0 / D;
-    const int y = (int)(r % H), x = (int)(r / H);
-    const uint4* src = reinterpret_cast<const uint4*>(grid + v0 * 3);
-    uint4 a = __ldg(src), b = __ldg(src + 1), cc = __ldg(src + 2);
-    uint32_t keep = rgb16_occupancy(a, b, cc);
-    const uint32_t self = keep ? __ldg(gm_hw + (size_t)y * W + x) : 0u;
-    if (self == 0u) keep = 0u;
-    if (keep) keep &= (__ldg(inside_bits + (size_t)x * words + (z0 >> 5)) >> (z0 & 31)) & 0xffffu;
-    const int lo = c - z0 - 15 + 32;                              // padded bit index of source x' = c - z0 - 15
-    const int sz = x + c2;
-    if (keep) keep &= (sz >= 0 && sz < D) ? rev16_bits(occx + ((size_t)y * D + sz) * xwp, lo, xwp) : 0u;
-    if (keep) {
-      uint32_t grp = 0, rem = self;
-      while (rem) {
-        const int gi = __ffs(rem) - 1;
-        rem &= rem - 1;
-        grp |= rev16_bits(gbits + ((size_t)gi * H + y) * xwp, lo, xwp);
-      }
-      keep &= grp;
-    }
-    uint32_t m[12];
+// ------------------------------------------------------------------------------------------
+// Copy-then-clear (about 6.3 bytes of traffic per voxel; a separate occupancy pre-pass made it 9).  The source
+// occupancy occ[c-z, y, x+c2] is a transposed access, so it needs a pass over the grid before it can be used; instead
+// of spending that pass on occupancy bits alone, pass A already writes the output with every term that is local to
+// the voxel (own occupancy, inside bits, group masks) and records the z-packed occupancy bits of the input and the
+// z-packed "alive" bits of what it wrote.  Pass B then only reads bits: alive & ~source-occupancy tells it which
+// voxels still have to be cleared (none at all for a grid that is already 4-way symmetric, e.g. the output of
+// global_carve) and it rewrites just those 96-byte runs.
+// ------------------------------------------------------------------------------------------
+// 32 bits [lo, lo+32) of a zero-padded bit row, in REVERSE order (bit j = row bit lo+31-j); words outside the row read 0
+__device__ __forceinline__ uint32_t rev32_bits(const uint32_t* __restrict__ row, int lo, int xwp) {
+  const int w = lo >> 5;                                   // arithmetic shift: negative lo -> negative word index
+  const uint32_t w0 = (w >= 0 && w < xwp) ? __ldg(row + w) : 0u;
+  const uint32_t w1 = (w + 1 >= 0 && w + 1 < xwp) ? __ldg(row + w + 1) : 0u;
+  return __brev(__funnelshift_r(w0, w1, lo & 31));
+}
+
+__device__ __forceinline__ void mask96(uint4 (&v)[6], uint32_t keep) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(v);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) expand4((keep >> (4 * q)) & 0xfu, 0xffffffffu, 0xffffffffu, 0xffffffffu, m + 3 * q);
-    uint4* dst = reinterpret_cast<uint4*>(out + v0 * 3);
-    dst[0] = make_uint4(a.x & m[0], a.y & m[1], a.z & m[2], a.w & m[3]);
-    dst[1] = make_uint4(b.x & m[4], b.y & m[5], b.z & m[6], b.w & m[7]);
-    dst[2] = make_uint4(cc.x & m[8], cc.y & m[9], cc.z & m[10], cc.w & m[11]);
+  for (int q = 0; q < 8; ++q) {
+    uint32_t o[3];
+    expand4((keep >> (4 * q)) & 0xfu, w[3 * q], w[3 * q + 1], w[3 * q + 2], o);
+    w[3 * q] = o[0]; w[3 * q + 1] = o[1]; w[3 * q + 2] = o[2];
+  }
+}
+
+// pass A: thread = 16 voxels of one z-row (coalesced 48-byte loads and stores, like part_fold_bits_kernel); lane pairs
+// merge their 16 occupancy / alive bits into z-packed words occz / alive [x][y][z/32].
+__global__ void __launch_bounds__(256)
+part_copy_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const uint32_t* __restrict__ inside_bits,
+                      int c, const uint32_t* __restrict__ gm_hw, const uint32_t* __restrict__ gbits, int xwp,
+                      uint32_t* __restrict__ occz, uint32_t* __restrict__ alive, uint8_t* __restrict__ out) {
+  const int64_t groups = (int64_t)W * H * D / 16;          // even: D % 32 == 0
+  const int words = D >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t wb = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wb < groups; wb += stride) {
+    const int64_t g = wb + lane;
+    const bool in = g < groups;
+    uint32_t occ = 0, keep = 0;
+    if (in) {
+      const int64_t v0 = g * 16;
+      const int z0 = (int)(v0 % D);
+      const int64_t r = v0 / D;
+      const int y = (int)(r % H), x = (int)(r / H);
+      const uint4* src = reinterpret_cast<const uint4*>(grid + v0 * 3);
+      const uint4 a = __ldg(src), b = __ldg(src + 1), cc = __ldg(src + 2);
+      occ = keep = rgb16_occupancy(a, b, cc);
+      const uint32_t self = keep ? __ldg(gm_hw + (size_t)y * W + x) : 0u;
+      if (self == 0u) keep = 0u;
+      if (keep) keep &= (__ldg(inside_bits + (size_t)x * words + (z0 >> 5)) >> (z0 & 31)) & 0xffffu;
+      if (keep) {
+        const int lo = c - z0 - 15 + 32;                    // padded bit index of source x' = c - z0 - 15
+        uint32_t grp = 0, rem = self;
+        while (rem) {
+          const int gi = __ffs(rem) - 1;
+          rem &= rem - 1;
+          grp |= rev16_bits(gbits + ((size_t)gi * H + y) * xwp, lo, xwp);
+        }
+        keep &= grp;
+      }
+      uint32_t m[12];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) expand4((keep >> (4 * q)) & 0xfu, 0xffffffffu, 0xffffffffu, 0xffffffffu, m + 3 * q);
+      uint4* dst = reinterpret_cast<uint4*>(out + v0 * 3);
+      dst[0] = make_uint4(a.x & m[0], a.y & m[1], a.z & m[2], a.w & m[3]);
+      dst[1] = make_uint4(b.x & m[4], b.y & m[5], b.z & m[6], b.w & m[7]);
+      dst[2] = make_uint4(cc.x & m[8], cc.y & m[9], cc.z & m[10], cc.w & m[11]);
+    }
+    const uint32_t occ_hi = __shfl_xor_sync(0xffffffffu, occ, 1), keep_hi = __shfl_xor_sync(0xffffffffu, keep, 1);
+    if (in && !(lane & 1)) {                                // even lane: z0 is a multiple of 32
+      occz[g >> 1] = occ | (occ_hi << 16);                  // (g * 16) / 32 == ((x * H + y) * D + z0) / 32
+      alive[g >> 1] = keep | (keep_hi << 16);
+    }
+  }
+}
+
+// pass B: warp = (y, z-tile, x-tile), lane = one x.  The source occupancy of output (x, y, z0 + j) is
+// occ[c - z0 - j, y, x + c2]: for a fixed j the 32 lanes need 32 consecutive bits of ONE z-packed row, so the warp
+// fetches that row segment with two uniform word loads and every lane picks its bit.  Only runs with alive voxels
+// whose source is empty are rewritten.
+__global__ void __launch_bounds__(256)
+part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict__ occz,
+                  const uint32_t* __restrict__ alive, uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int xt_n = (W + 31) >> 5, words = D >> 5;
+  const int64_t tasks = (int64_t)H * words * xt_n;
+  for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < tasks; t += (int64_t)gridDim.x * 8) {
+    const int xt = (int)(t % xt_n);
+    const int64_t r = t / xt_n;
+    const int zt = (int)(r % words), y = (int)(r / words);
+    const int x = xt * 32 + lane, z0 = zt * 32;
+    const uint32_t a = x < W ? __ldg(alive + ((size_t)x * H + y) * words + zt) : 0u;
+    if (!__any_sync(0xffffffffu, a != 0u)) continue;
+    const int sz0 = xt * 32 + c2;                           // source z of lane 0; lane l needs bit sz0 + l
+    uint32_t src = 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int sx = c - z0 - j;                            // source x of output z = z0 + j (uniform across the warp)
+      uint32_t seg = 0;
+      if (sx >= 0 && sx < W) {
+        const uint32_t* row = occz + ((size_t)sx * H + y) * words;
+        const int w = sz0 >> 5;                             // arithmetic shift; bits outside [0, D) read 0
+        const uint32_t w0 = (w >= 0 && w < words) ? __ldg(row + w) : 0u;
+        const uint32_t w1 = (w + 1 >= 0 && w + 1 < words) ? __ldg(row + w + 1) : 0u;
+        seg = __funnelshift_r(w0, w1, sz0 & 31);
+      }
+      src |= ((seg >> lane) & 1u) << j;
+    }
+    const uint32_t clear = a & ~src;
+    if (clear == 0u) continue;
+    uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)x * H + y) * D + z0) * 3);
+    uint4 v[6] = {dst[0], dst[1], dst[2], dst[3], dst[4], dst[5]};
+    mask96(v, a & src);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) dst[q] = v[q];
   }
 }
 
@@ -1145,7 +1198,8 @@ P3D_API int p3d_part_carve_fold(const uint8_t* grid, int W, int H, int D, const 
 P3D_API size_t p3d_part_carve_bits_workspace_bytes(int W, int H, int D, int n_groups) {
   if (W <= 0 || H <= 0 || D <= 0 || n_groups < 0) return 0;
   const size_t xwp = (size_t)(W + 31) / 32 + 2;
-  return p3d_align_up((size_t)H * D * xwp * 4, 256) + p3d_align_up((size_t)n_groups * H * xwp * 4, 256);
+  const size_t zbits = p3d_align_up((size_t)W * H * ((size_t)(D + 31) / 32) * 4, 256);
+  return 2 * zbits + p3d_align_up((size_t)n_groups * H * xwp * 4, 256);
 }
 
 P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, const uint32_t* inside_bits, int c, int c2,
@@ -1160,17 +1214,19 @@ P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, c
     return P3D_E_WORKSPACE;
   }
   const int xwp = (W + 31) / 32 + 2;
-  uint32_t* occx = static_cast<uint32_t*>(workspace);
-  uint32_t* gbits = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(workspace) + p3d_align_up((size_t)H * D * xwp * 4, 256));
+  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)(D / 32) * 4, 256);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint32_t* occz = reinterpret_cast<uint32_t*>(ws);
+  uint32_t* alive = reinterpret_cast<uint32_t*>(ws + zbits);
+  uint32_t* gbits = reinterpret_cast<uint32_t*>(ws + 2 * zbits);
   cudaStream_t st = p3d::as_stream(stream);
-  P3D_CUDA(cudaMemsetAsync(occx, 0, (size_t)H * D * xwp * 4, st));           // padding words
-  const int64_t tasks = (int64_t)H * (D / 32) * ((W + 31) / 32);
-  occ_bits_x_kernel<<<grid_for(tasks, 8, 32), 256, 0, st>>>(grid, W, H, D, xwp, occx);
   const int ng = n_groups * H * xwp;
   pack_group_bits_kernel<<<(ng + 255) / 256, 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
   const int64_t n16 = (int64_t)W * H * D / 16;
-  part_fold_bits_kernel<<<grid_for(n16, 256, 16), 256, 0, st>>>(grid, W, H, D, inside_bits, c, c2, group_mask_hw, gbits,
-                                                               occx, xwp, out);
+  part_copy_bits_kernel<<<grid_for(n16, 256, 16), 256, 0, st>>>(grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp,
+                                                              occz, alive, out);
+  const int64_t tasks = (int64_t)H * (D / 32) * ((W + 31) / 32);
+  part_clear_kernel<<<grid_for(tasks, 8, 32), 256, 0, st>>>(W, H, D, c, c2, occz, alive, out);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

@@ -199,3 +199,30 @@ def test_x_slabs_tile_the_full_grid(vc, carve_golden):
             assert np.array_equal(vc.global_carve(binm, ext, interval, x_range=(a, b)), full[a:b]), (key, a, b)
     with pytest.raises(ValueError):
         vc.global_carve(g["syn_sq64_bin"], g["syn_sq64_ext"], 90, x_range=(10, 99))
+
+
+def test_part_carve_on_asymmetric_grids_vs_oracle(vc, oracle):
+    """The clear pass of the bit-level part_carve (runs whose rotated source voxel is empty) only has work on grids
+    that are NOT 4-way symmetric; global_carve's output never is.  Random sparse RGB grids with holes, every group at
+    90 degrees, W = D multiples of 32 (bit path) and one odd width (table path), against the oracle."""
+    rng = np.random.default_rng(77)
+    names = ["full_building", "plinth", "dome", "front_minarets"]
+    jobs = [([n], 90) for n in names]
+    for (W, H), uniform in (((64, 40), False), ((64, 40), True), ((96, 33), True), ((32, 32), False), ((32, 32), True),
+                            ((48, 20), True)):
+        sem = np.empty((H, W, 3), np.uint8)
+        sem[:] = oracle.PART_COLORS["background"]
+        lab = rng.integers(0, len(names) + 1, (H, W))
+        if uniform:                      # one part almost everywhere: the group term passes, the occupancy term decides
+            lab[:] = 2
+            lab[:, :3] = 0
+            lab[H // 2:, W // 2:] = 3
+        for k, n in enumerate(names):
+            sem[lab == k + 1] = oracle.PART_COLORS[n]
+        grid = np.zeros((W, H, W, 3), np.uint8)
+        occ = rng.random((W, H, W)) < 0.55
+        grid[occ] = sem.transpose(1, 0, 2)[:, :, None, :].repeat(W, axis=2)[occ]     # column colour where occupied
+        got = vc.part_carve(grid, sem, jobs)
+        want = oracle.part_carve(grid, sem, jobs)
+        assert np.array_equal(got, want), (W, H)
+        assert 0 < np.count_nonzero(want.any(-1)) < np.count_nonzero(grid.any(-1))   # the carve removed something
