@@ -364,17 +364,17 @@ __device__ __forceinline__ uint32_t rgb16_occupancy(const uint4& a, const uint4&
 
 __global__ void __launch_bounds__(256)
 pack_group_bits_kernel(const uint32_t* __restrict__ gm_hw, int H, int W, int n_groups, int xwp, uint32_t* __restrict__ gbits) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per (g, y, word)
-  if (i >= n_groups * H * xwp) return;
-  const int w = i % xwp;
-  const int y = (i / xwp) % H, g = i / (xwp * H);
-  uint32_t v = 0;
-  const int x0 = (w - 1) * 32;
-  for (int j = 0; j < 32; ++j) {
-    const int x = x0 + j;
-    if (x >= 0 && x < W && ((gm_hw[(size_t)y * W + x] >> g) & 1u)) v |= 1u << j;
+  const int lane = threadIdx.x & 31;
+  const int64_t tasks = (int64_t)H * xwp;                   // one warp per (y, word): 32 pixels, one ballot per group
+  for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < tasks; t += (int64_t)gridDim.x * 8) {
+    const int w = (int)(t % xwp), y = (int)(t / xwp);
+    const int x = (w - 1) * 32 + lane;
+    const uint32_t m = (x >= 0 && x < W) ? __ldg(gm_hw + (size_t)y * W + x) : 0u;
+    for (int g = 0; g < n_groups; ++g) {
+      const uint32_t v = __ballot_sync(0xffffffffu, (m >> g) & 1u);
+      if (lane == 0) gbits[((size_t)g * H + y) * xwp + w] = v;
+    }
   }
-  gbits[i] = v;
 }
 
 // 16 bits [lo, lo+16) of a padded bit row, returned in REVERSE order (bit j = row bit lo+15-j); 0 when out of range
@@ -479,20 +479,23 @@ part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict
     const int x = xt * 32 + lane, z0 = zt * 32;
     const uint32_t a = x < W ? __ldg(alive + ((size_t)x * H + y) * words + zt) : 0u;
     if (!__any_sync(0xffffffffu, a != 0u)) continue;
-    const int sz0 = xt * 32 + c2;                           // source z of lane 0; lane l needs bit sz0 + l
+    // lane l fetches row j = l: 32 bits occ[c - z0 - l, y, sz0 .. sz0 + 31] (two words of the z-packed row), then a
+    // 32x32 ballot transpose hands lane b the column b: bit j = occ[c - z0 - j, y, sz0 + b], its own source bits
+    const int sz0 = xt * 32 + c2;                           // source z of lane 0
+    const int sx = c - z0 - lane;
+    uint32_t seg = 0;
+    if (sx >= 0 && sx < W) {
+      const uint32_t* row = occz + ((size_t)sx * H + y) * words;
+      const int w = sz0 >> 5;                               // arithmetic shift; bits outside [0, D) read 0
+      const uint32_t w0 = (w >= 0 && w < words) ? __ldg(row + w) : 0u;
+      const uint32_t w1 = (w + 1 >= 0 && w + 1 < words) ? __ldg(row + w + 1) : 0u;
+      seg = __funnelshift_r(w0, w1, sz0 & 31);
+    }
     uint32_t src = 0;
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {
-      const int sx = c - z0 - j;                            // source x of output z = z0 + j (uniform across the warp)
-      uint32_t seg = 0;
-      if (sx >= 0 && sx < W) {
-        const uint32_t* row = occz + ((size_t)sx * H + y) * words;
-        const int w = sz0 >> 5;                             // arithmetic shift; bits outside [0, D) read 0
-        const uint32_t w0 = (w >= 0 && w < words) ? __ldg(row + w) : 0u;
-        const uint32_t w1 = (w + 1 >= 0 && w + 1 < words) ? __ldg(row + w + 1) : 0u;
-        seg = __funnelshift_r(w0, w1, sz0 & 31);
-      }
-      src |= ((seg >> lane) & 1u) << j;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t col = __ballot_sync(0xffffffffu, (seg >> b) & 1u);
+      if (lane == b) src = col;
     }
     const uint32_t clear = a & ~src;
     if (clear == 0u) continue;
@@ -1220,8 +1223,7 @@ P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, c
   uint32_t* alive = reinterpret_cast<uint32_t*>(ws + zbits);
   uint32_t* gbits = reinterpret_cast<uint32_t*>(ws + 2 * zbits);
   cudaStream_t st = p3d::as_stream(stream);
-  const int ng = n_groups * H * xwp;
-  pack_group_bits_kernel<<<(ng + 255) / 256, 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
+  pack_group_bits_kernel<<<grid_for((int64_t)H * xwp, 8, 32), 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
   const int64_t n16 = (int64_t)W * H * D / 16;
   part_copy_bits_kernel<<<grid_for(n16, 256, 16), 256, 0, st>>>(grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp,
                                                               occz, alive, out);
