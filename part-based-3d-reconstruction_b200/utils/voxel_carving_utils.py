@@ -12,6 +12,8 @@ from __future__ import annotations
 import ctypes
 import warnings
 
+import functools
+
 import numpy as np
 import torch
 
@@ -73,7 +75,20 @@ def _rotation_matrix_inv(angle):
     return np.linalg.inv(R)
 
 
+@functools.lru_cache(maxsize=64)
+def _pass_transform_cached(shape, angle):
+    M, off = _pass_transform_uncached(shape, angle)
+    M.setflags(write=False)
+    off.setflags(write=False)
+    return M, off
+
+
 def _pass_transform(shape, angle):
+    """Inverse rotation and offset of one process_voxel_grid pass; pure in (shape, angle), hence cached."""
+    return _pass_transform_cached(tuple(int(v) for v in shape), angle)
+
+
+def _pass_transform_uncached(shape, angle):
     """Matrix and offset handed to scipy.ndimage.affine_transform at :116-123."""
     M = np.ascontiguousarray(_rotation_matrix_inv(angle), dtype=np.float64)
     ctr = np.array(shape) / 2
@@ -442,7 +457,9 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
     col = _to_dev_u8(semantic_mask_exterior, dev, "semantic_mask_exterior")
     if tuple(col.shape) != (H, W, 3):
         raise ValueError(f"semantic_mask_exterior {tuple(col.shape)} does not match (H,W,3)=({H},{W},3)")
-    m_wh = np.ascontiguousarray(_mask_to_wh(bm != 0, W, H))                          # (W,H) bool
+    # (W,H) mask of the reference (:279-283).  W, H come from binary_mask itself, so _mask_to_wh always takes its
+    # (H,W) -> .T branch here and the (H,W) form the fold kernels want is simply `bm != 0`.
+    m_hw_np = bm != 0
     x0, x1 = (0, W) if x_range is None else (int(x_range[0]), int(x_range[1]))
     if not (0 <= x0 <= x1 <= W):
         raise ValueError(f"x_range {x_range} outside [0, {W}]")
@@ -453,7 +470,8 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
         if np.array_equal(M0, np.eye(3)) and not off0.any():
             table, foldable = _fold_table(W, D, M, off, dev)
             if foldable:
-                m_hw = torch.from_numpy(np.ascontiguousarray(m_wh.T).astype(np.uint8)).to(dev)
+                m_hw = torch.from_numpy(m_hw_np.view(np.uint8) if m_hw_np.flags.c_contiguous else
+                                        np.ascontiguousarray(m_hw_np).view(np.uint8)).to(dev)
                 bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
                 if bits is not None:                      # z-separable table: bit-packed mask, 10x fewer loads
                     out = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
@@ -471,6 +489,7 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
                     _launched()
     if out is None:
         vol = torch.ones((W, H, D), dtype=torch.uint8, device=dev)
+        m_wh = np.ascontiguousarray(_mask_to_wh(m_hw_np, W, H))                       # (W,H) bool
         carved = _process_device(vol, torch.from_numpy(m_wh.astype(np.uint8)).to(dev), angle_interval)
         out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
         check(lib.p3d_colourise(ptr(carved), W, H, D, ptr(col), ptr(out), stream_ptr()), "p3d_colourise")
