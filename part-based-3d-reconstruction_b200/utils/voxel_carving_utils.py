@@ -275,7 +275,7 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
         m2d = _mask2d_bool(semantic_mask, [PART_COLORS[n] for n in names])          # (H,W)
         if not m2d.any():
             continue
-        jobs.append((np.ascontiguousarray(m2d.T), angle))                           # m: (W,H) bool
+        jobs.append((m2d, angle))                                                   # (H,W) bool; m = m2d.T is the reference's (W,H)
     out = None
     if jobs and all(a == 90 for _, a in jobs) and len(jobs) <= 32 and D == W:
         M, off = _pass_transform((W, H, D), 90)
@@ -283,11 +283,13 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
         M0, off0 = _pass_transform((W, H, D), 0)
         identity0 = np.array_equal(M0, np.eye(3)) and not off0.any()
         if foldable and identity0:
-            gm = np.zeros((W, H), np.uint32)
-            for g, (m, _) in enumerate(jobs):
-                mm = _mask_to_wh(m, W, H)                                            # square quirk: m.T
-                gm |= (m & mm).astype(np.uint32) << np.uint32(g)
-            gm_hw = torch.from_numpy(np.ascontiguousarray(gm.T).view(np.int32)).to(dev)
+            # group image in (H,W): bit g where pixel is in m AND in _mask_to_wh(m) -- m itself for W != H, m.T for a
+            # square image (the quirk), i.e. m2d & m2d.T there
+            gm = np.zeros((H, W), np.uint32)
+            for g, (m2d, _) in enumerate(jobs):
+                sel = (m2d & m2d.T) if W == H else m2d
+                gm |= sel.astype(np.uint32) << np.uint32(g)
+            gm_hw = torch.from_numpy(gm.view(np.int32)).to(dev)
             out = torch.empty_like(grid)
             bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
             if bits is not None and bits[2] is not None:       # z-separable table: bit-packed occupancy / group masks
@@ -307,7 +309,8 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
                 _launched()
     if out is None:
         out = torch.zeros_like(grid)
-        for m, angle in jobs:
+        for m2d, angle in jobs:
+            m = np.ascontiguousarray(m2d.T)                                          # (W,H) bool
             sel = torch.from_numpy(m.astype(np.uint8)).to(dev)                       # (W,H)
             occ = torch.empty((W, H, D), dtype=torch.uint8, device=dev)
             check(lib.p3d_crop_occupancy(ptr(grid), W, H, D, 0, 0, 0, W, H, D, ptr(sel), ptr(occ), stream_ptr()),
