@@ -253,6 +253,13 @@ int p3d_colour_lookup(const uint8_t* image_rgb, int64_t n, const uint32_t* prese
 int p3d_resample_carve(const uint8_t* vol_in, int n0, int n1, int n2, const double* M, const double* off,
                        const uint8_t* mask_wh, uint8_t* vol_out, p3d_stream_t stream);
 
+/* n_passes consecutive passes of the above (the cumulative rotations of process_voxel_grid :111-124 at angles that are
+ * not index folds), ping-ponging between buf_a (holds the input) and buf_b; Ms (n_passes,9) / offs (n_passes,3) are HOST
+ * arrays; *result_in_b (host) = 1 when the result ended up in buf_b. */
+int p3d_resample_carve_passes(uint8_t* buf_a, uint8_t* buf_b, int n0, int n1, int n2, const double* Ms,
+                              const double* offs, int n_passes, const uint8_t* mask_wh, int* result_in_b,
+                              p3d_stream_t stream);
+
 /* For a transform that leaves axis 1 alone: table (n0,n2) int32 = (src0 << 16 | src2) of the nearest source
  * voxel, -1 where scipy's bounds rule rejects the point; flag[0] != 0 when some in-range coordinate is not
  * within 1e-9 of an integer, i.e. the pass is NOT a pure index fold and needs p3d_resample_carve. */

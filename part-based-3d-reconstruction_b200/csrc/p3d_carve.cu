@@ -1074,6 +1074,29 @@ P3D_API int p3d_resample_carve(const uint8_t* vol_in, int n0, int n1, int n2, co
   return P3D_OK;
 }
 
+P3D_API int p3d_resample_carve_passes(uint8_t* buf_a, uint8_t* buf_b, int n0, int n1, int n2, const double* Ms,
+                                      const double* offs, int n_passes, const uint8_t* mask_wh, int* result_in_b,
+                                      p3d_stream_t stream) {
+  P3D_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0 && n_passes >= 0 && result_in_b, "resample_carve_passes: bad arguments");
+  *result_in_b = 0;
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  if (n == 0 || n_passes == 0) return P3D_OK;
+  P3D_REQUIRE(buf_a && buf_b && buf_a != buf_b && Ms && offs, "resample_carve_passes: null or aliased volumes");
+  cudaStream_t st = p3d::as_stream(stream);
+  uint8_t* src = buf_a;
+  uint8_t* dst = buf_b;
+  for (int p = 0; p < n_passes; ++p) {
+    Affine A;
+    int rc = check_affine(Ms + 9 * p, offs + 3 * p, &A);
+    if (rc) return rc;
+    resample_carve_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(src, n0, n1, n2, A, mask_wh, dst);
+    uint8_t* t = src; src = dst; dst = t;
+  }
+  P3D_LAUNCH_CHECK();
+  *result_in_b = src == buf_b;
+  return P3D_OK;
+}
+
 P3D_API int p3d_fold_table(int n0, int n2, const double* M, const double* off, int32_t* table, int* flag,
                            p3d_stream_t stream) {
   P3D_REQUIRE(n0 > 0 && n2 > 0 && n0 < 32768 && n2 < 65536 && (int64_t)n0 * n2 < (1ll << 31), "fold_table: bad shape");

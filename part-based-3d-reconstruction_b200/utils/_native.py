@@ -79,6 +79,7 @@ _SIGNATURES = {
     "p3d_sweep_timing_enable": ([_i32], _i32),
     "p3d_sweep_timing_read": ([_vp, _vp], _i32),
     "p3d_resample_carve": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "p3d_resample_carve_passes": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp], _i32),
     "p3d_fold_table": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "p3d_fold_gather": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp], _i32),
     "p3d_global_carve_fold": ([_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp], _i32),

@@ -150,24 +150,42 @@ def _fold_bits(table, W, D, cache_key):
 
 
 def _process_device(vol, mask_wh, angle_interval):
-    """process_voxel_grid on device tensors: vol (n0,n1,n2) u8, mask_wh (n0,n1) u8 -> carved (n0,n1,n2) u8."""
+    """process_voxel_grid on device tensors: vol (n0,n1,n2) u8, mask_wh (n0,n1) u8 -> carved (n0,n1,n2) u8.
+    Index folds (multiples of 90 degrees, when the table says so) run one by one; every run of consecutive resample
+    passes in between goes to the library as ONE call that ping-pongs between two buffers."""
     n0, n1, n2 = vol.shape
     dev = vol.device
     cur = vol
+    pending = []                                            # (M, off) of the resample passes not yet issued
+
+    def flush(cur):
+        if not pending:
+            return cur
+        a = cur if cur is not vol else cur.clone()          # never write into the caller's volume
+        b = torch.empty_like(a)
+        Ms = np.ascontiguousarray(np.stack([m for m, _ in pending]), dtype=np.float64)
+        offs = np.ascontiguousarray(np.stack([o for _, o in pending]), dtype=np.float64)
+        in_b = ctypes.c_int(0)
+        check(lib.p3d_resample_carve_passes(ptr(a), ptr(b), n0, n1, n2, _dptr(Ms), _dptr(offs), len(pending), ptr(mask_wh),
+                                            ctypes.byref(in_b), stream_ptr()), "p3d_resample_carve_passes")
+        _launched(len(pending))
+        pending.clear()
+        return b if in_b.value else a
+
     for angle in tqdm(range(0, 91, angle_interval), desc="90 Carving", leave=True, disable=None):
         M, off = _pass_transform((n0, n1, n2), angle)
-        out = torch.empty_like(cur)
         # an index fold is only possible at multiples of 90 degrees; other angles go straight to the resample kernel
         table, foldable = _fold_table(n0, n2, M, off, dev) if angle % 90 == 0 else (None, False)
         if foldable:
+            cur = flush(cur)
+            out = torch.empty_like(cur)
             check(lib.p3d_fold_gather(ptr(cur), n0, n1, n2, ptr(table), ptr(mask_wh), ptr(out), stream_ptr()),
                   "p3d_fold_gather")
+            _launched()
+            cur = out
         else:
-            check(lib.p3d_resample_carve(ptr(cur), n0, n1, n2, _dptr(M), _dptr(off), ptr(mask_wh), ptr(out),
-                                         stream_ptr()), "p3d_resample_carve")
-        _launched()
-        cur = out
-    return cur
+            pending.append((M, off))
+    return flush(cur)
 
 
 class _PackedMask:
