@@ -148,7 +148,7 @@ constexpr int kDeformPerBlock = 8;       // candidates handled by one CTA
 
 // T = working dtype of the reference's projection: double for float64 camera arrays (notebook 2 JSON -> float64),
 // float for float32 camera arrays (notebook 3 converts them with to_numpy(dtype=float32)).
-template <typename T>
+template <typename T, bool kFilter>
 __global__ void __launch_bounds__(kDeformThreads) deform_splat_kernel(
     const float* __restrict__ pts, int64_t m, int64_t stride, const double* __restrict__ centres,
     const double* __restrict__ deforms, int D, const double* __restrict__ pix2vox, int A0, int A1, int A2,
@@ -158,7 +158,6 @@ __global__ void __launch_bounds__(kDeformThreads) deform_splat_kernel(
   __shared__ double s_ctr[9];
   __shared__ FastCam s_fast;
   __shared__ DeformParams s_def[kDeformPerBlock];
-  const bool kFilter = fast != nullptr;                   // FP32 filter block present (either exact dtype)
   if (threadIdx.x < 16) s_cam[threadIdx.x] = cam[threadIdx.x];
   if (threadIdx.x < 9) s_ctr[threadIdx.x] = centres[threadIdx.x];
   if (kFilter && threadIdx.x < 16) reinterpret_cast<float*>(&s_fast)[threadIdx.x] = fast[threadIdx.x];
@@ -381,9 +380,14 @@ int deform_sweep(const float* pts, int64_t n, int64_t stride, const double* cent
     const int64_t tiles = (m + kDeformThreads - 1) / kDeformThreads;
     P3D_REQUIRE(tiles < (1ll << 31), "deform_sweep: too many tiles");
     dim3 grid((unsigned)tiles, (unsigned)((D + kDeformPerBlock - 1) / kDeformPerBlock));
-    deform_splat_kernel<T><<<grid, kDeformThreads, 0, st>>>(pts, m, stride, centres, deforms, D, pix2vox, A0, A1, A2, cam,
-                                                            fast, bbox, H, W, cov, words,
-                                                            reinterpret_cast<unsigned long long*>(nvalid));
+    if (fast)                                              // FP32 filter block present (either exact dtype)
+      deform_splat_kernel<T, true><<<grid, kDeformThreads, 0, st>>>(pts, m, stride, centres, deforms, D, pix2vox, A0, A1, A2,
+                                                                    cam, fast, bbox, H, W, cov, words,
+                                                                    reinterpret_cast<unsigned long long*>(nvalid));
+    else
+      deform_splat_kernel<T, false><<<grid, kDeformThreads, 0, st>>>(pts, m, stride, centres, deforms, D, pix2vox, A0, A1, A2,
+                                                                     cam, fast, bbox, H, W, cov, words,
+                                                                     reinterpret_cast<unsigned long long*>(nvalid));
     P3D_LAUNCH_CHECK();
   }
   dim3 sgrid(grid_for(words, 256, 2), (unsigned)D);
