@@ -250,3 +250,47 @@ def test_filtered_splat_is_bit_identical_to_exact_fp64(mods, taj, monkeypatch):
     monkeypatch.setenv("P3D_SPLAT_EXACT", "0")
     got = mods.eng.splat(pts, pt_label, cams, 1024, 1024, mods.nv.MODE_JOINT).cpu()
     assert torch.equal(ref, got)
+
+
+def test_randomised_sweeps_vs_oracle(mods, oracle):
+    """Differential test over the rarely exercised corners of the sweep: odd image sizes (scalar score path), one to
+    nine parts, parts without voxels or without pixels, tiny point lists, K from 1 to 300 (several z-buffer batches and
+    camera groups), float64 and float32 candidates -- counts and scores against the oracle."""
+    ce = pkg("utils.camera_estimation")
+    rng = np.random.default_rng(2024)
+    names = [k for k in oracle.PART_COLORS if k != "background"]
+    for trial in range(14):
+        A0, A1, A2 = (int(v) for v in rng.integers(3, 22, 3))
+        H, W = (int(v) for v in rng.integers(5, 70, 2))
+        parts = list(rng.choice(names, size=int(rng.integers(1, 10)), replace=False))
+        grid = np.zeros((A0, A1, A2, 3), np.uint8)
+        lab = rng.integers(0, len(parts) + 2, (A0, A1, A2))
+        for k, n in enumerate(parts[:-1] if len(parts) > 2 else parts):        # sometimes a selected part has no voxels
+            grid[lab == k + 1] = oracle.PART_COLORS[n]
+        image = np.zeros((H, W, 3), np.uint8)
+        ilab = rng.integers(0, len(parts) + 1, (H, W))
+        for k, n in enumerate(parts[1:] if len(parts) > 2 else parts):        # ... or no pixels in the image
+            image[ilab == k + 1] = oracle.PART_COLORS[n]
+        K = int(rng.choice([1, 2, 7, 33, 130, 300]))
+        dt = np.float32 if trial % 3 == 2 else np.float64
+        ctr = np.array([A2, A1, A0]) / 2
+        cand = np.empty((K, 9))
+        cand[:, 0:3] = ctr + rng.normal(0, 1, (K, 3)) * 3 + np.array([0, 0, -3.0 * max(A0, A1, A2)])
+        cand[:, 3:6] = ctr + rng.normal(0, 1, (K, 3))
+        cand[:, 6] = rng.uniform(0.5, 3.0, K) * max(H, W)
+        cand[:, 7] = W / 2 + rng.normal(0, 3, K)
+        cand[:, 8] = H / 2 + rng.normal(0, 3, K)
+        cand = cand.astype(dt)
+        scorer = ce.CandidateScorer(grid, image, oracle.PART_COLORS, parts, dtype=dt)
+        scores, counts, best = scorer.score(cand)
+        pts, cols = oracle.get_voxel_points_by_parts(grid, oracle.PART_COLORS, parts)
+        seg = oracle.mask_parts_from_image(image, oracle.PART_COLORS, parts)
+        sel = {p: oracle.PART_COLORS[p] for p in parts}
+        ref_scores = []
+        for k in range(K):
+            cp, tg, f, cx, cy = row_to_args(cand[k], dt)
+            s, inter, uni = oracle.score_candidate(pts, cols, seg, sel, {"cam_pos": cp, "target": tg, "f": f, "cx": cx, "cy": cy}, H, W)
+            ref_scores.append(s)
+            assert np.array_equal(counts[k, :, 0], inter) and np.array_equal(counts[k, :, 1], uni), (trial, k)
+            assert scores[k] == s, (trial, k)
+        assert best == int(np.argmax(ref_scores))
