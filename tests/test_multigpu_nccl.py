@@ -1,0 +1,74 @@
+"""The sharded paths over real NCCL (needs >= 2 GPUs on the box; skipped otherwise): candidate sweep, deformation sweep
+and slab-sharded global_carve with all-gather, each against the single-GPU result of the same call."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ce, de, sw, vc, cfg = (pkg("utils.camera_estimation"), pkg("utils.deformation_estimation"), pkg("utils.sweep"),
+                           pkg("utils.voxel_carving_utils"), pkg("utils.config"))
+    ag = np.load(os.path.join(GOLDEN, "aligner_golden.npz"))
+    grid, image, base = ag["grid"], ag["image"], ag["free_saved"]
+    parts = ["front_minarets", "back_minarets"]
+    cand = ce.random_candidates(base, 37, np.random.default_rng(3))
+    cand[30] = cand[4]                                                       # equal scores in different shards
+    scorer = ce.CandidateScorer(grid, image, cfg.PART_COLORS, parts)
+    best_s, best_i, scores, span = sw.score_candidates_sharded(scorer, cand, gather_scores=True)
+    import contextlib, io
+    labels = {k: v for k, v in cfg.PART_COLORS.items() if k != "background"}
+    cam = ce.row_to_params(base)
+    with contextlib.redirect_stdout(io.StringIO()):
+        viewer = de.DeformViewer(grid, labels, image, cam, ["dome"])
+    rng = np.random.default_rng(8)
+    rows = np.column_stack([rng.uniform(0.8, 1.2, 21), rng.uniform(-20, 20, 21), rng.uniform(0.8, 1.2, 21), rng.uniform(-20, 20, 21)])
+    d_iou, d_i, d_local, d_span = sw.score_deformations_sharded(viewer, "dome", rows)
+    cg = np.load(os.path.join(GOLDEN, "carve_golden.npz"))
+    binm, ext = cg["syn_rect40x64_bin"], cg["syn_rect40x64_ext"]
+    full, _ = sw.carve_sharded(lambda a, b: vc.global_carve(binm, ext, 90, return_tensor=True, x_range=(a, b)), binm.shape[1], gather=True)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), best_s=best_s, best_i=best_i, scores=scores, d_iou=d_iou, d_i=d_i,
+             d_local=d_local, d_lo=d_span[0], carve=full.cpu().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_paths_over_nccl(tmp_path, carve_golden):
+    import contextlib, io
+    import torch.multiprocessing as mp
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    ce, de, cfg = pkg("utils.camera_estimation"), pkg("utils.deformation_estimation"), pkg("utils.config")
+    ag = np.load(os.path.join(GOLDEN, "aligner_golden.npz"))
+    grid, image, base = ag["grid"], ag["image"], ag["free_saved"]
+    cand = ce.random_candidates(base, 37, np.random.default_rng(3))
+    cand[30] = cand[4]
+    want_scores, _, want_best = ce.CandidateScorer(grid, image, cfg.PART_COLORS, ["front_minarets", "back_minarets"]).score(cand)
+    labels = {k: v for k, v in cfg.PART_COLORS.items() if k != "background"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        viewer = de.DeformViewer(grid, labels, image, ce.row_to_params(base), ["dome"])
+    rng = np.random.default_rng(8)
+    rows = np.column_stack([rng.uniform(0.8, 1.2, 21), rng.uniform(-20, 20, 21), rng.uniform(0.8, 1.2, 21), rng.uniform(-20, 20, 21)])
+    want_ious = viewer.score("dome", rows)[0]
+    got_ious = np.zeros(21)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(z["scores"], want_scores) and int(z["best_i"]) == int(want_best) == int(np.argmax(want_scores))
+        assert float(z["best_s"]) == want_scores[want_best]
+        got_ious[int(z["d_lo"]):int(z["d_lo"]) + len(z["d_local"])] = z["d_local"]
+        assert int(z["d_i"]) == int(np.argmax(want_ious)) and float(z["d_iou"]) == want_ious.max()
+        assert np.array_equal(z["carve"], carve_golden["syn_rect40x64_global"])
+    assert np.array_equal(got_ious, want_ious)
