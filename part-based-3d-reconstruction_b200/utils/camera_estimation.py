@@ -623,15 +623,18 @@ def optimize_camera_with_keypoints(voxel_keypoints_dict, image_keypoints_dict, i
     squared / absolute reprojection error; the look-at rotation of every evaluation comes from the device kernel the
     sweep uses (camera_geometry.project)."""
     from scipy.optimize import minimize
-    from .camera_geometry import project
+    from .camera_geometry import look_at_rotation
     H, W = np.asarray(image).shape[:2] if not isinstance(image, torch.Tensor) else image.shape[:2]
     keys = list(image_keypoints_dict.keys())
 
     def loss_fn(x):
         cam_pos, target = np.array([x[0], x[1], x[2]]), np.array([x[3], x[4], x[5]])
+        R = look_at_rotation(cam_pos, target)             # one device round trip per evaluation, shared by all key points
         total = 0
         for k in keys:
-            proj_pt = project(voxel_keypoints_dict[k], cam_pos, target, x[6], x[7], x[8])
+            X, Y, Z = (np.asarray(voxel_keypoints_dict[k]) - cam_pos) @ R.T      # camera_geometry.project :17-27
+            Z = max(Z, 1e-8)
+            proj_pt = np.array([(X / Z) * x[6] + x[7], -(Y / Z) * x[6] + x[8]])
             gt_pt = image_keypoints_dict[k]
             error = np.abs(proj_pt - gt_pt) if loss_type == "L1" else (proj_pt - gt_pt) ** 2
             total += error.sum()
