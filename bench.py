@@ -337,6 +337,43 @@ def carve_sharded_bench(N, dev, world, rank, dist):
                     "no collective on the data path"}
 
 
+def time_launches(launch, reps=20, rounds=5):
+    """Average device time of one `launch()` (a library call that only enqueues kernels on the current stream): `reps`
+    launches captured in a CUDA graph and replayed, so host-side launch cost (ctypes, GIL contention with the clock
+    sampler thread) cannot bound kernels that take tens of microseconds; best of `rounds` replays.  Falls back to a
+    plain launch loop if capture is refused."""
+    import torch
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(reps):
+                launch()
+        graph = g
+    except Exception:
+        graph = None
+        torch.cuda.synchronize()
+    best = None
+    for _ in range(rounds):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(reps):
+                launch()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        best = ms if best is None else min(best, ms)
+    return best, graph is not None
+
+
 def carve_bench(N, dev, peak):
     """Second metric of BASELINE.json: carving Gvoxel/s vs the HBM roofline.  global_carve of the synthetic monument's
     front silhouette at N^3 (3 B per output voxel), timed with CUDA events over the fused kernel; plus the
@@ -383,16 +420,7 @@ def carve_bench(N, dev, peak):
         def launch():
             nv.check(nv.lib.p3d_global_carve_fold_bits(N, N, N, 0, N, nv.ptr(bits[0]), bits[1], nv.ptr(mbits), wpr, nv.ptr(ext), 1,
                                                        nv.ptr(kout), nv.stream_ptr()))
-        for _ in range(3):
-            launch()
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(10):
-            launch()
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / 10
+        kms, graphed = time_launches(launch)
         assert torch.equal(kout, out)
     kgvox = N ** 3 / (kms * 1e-3) / 1e9 if kms else None
     res = {"global_carve_gvoxel_s": round(gvox, 2), "grid": N, "ms_per_call": round(ms, 4),
@@ -400,7 +428,8 @@ def carve_bench(N, dev, peak):
            "kernel_gvoxel_s": round(kgvox, 2) if kgvox else None, "kernel_ms": round(kms, 4) if kms else None,
            "roofline": {"bound": "hbm", "achieved": round(3 * kgvox, 1) if kgvox else None, "peak": peak, "unit": "GB/s",
                         "frac": round(3 * kgvox / peak, 4) if kgvox else None, "kernel": "global_fold_bits_kernel<RGB>",
-                        "note": "3 B per output voxel (RGB grid written once, SURVEY 8d), kernel-only; "
+                        "note": "3 B per output voxel (RGB grid written once, SURVEY 8d), kernel-only (20 launches replayed "
+                                "from a CUDA graph, best of 5); "
                                 "global_carve_gvoxel_s is the whole Python call (mask upload, table lookup, launch)"}}
     # part_carve (all six notebook groups at 90 degrees) on that grid: 6 B per voxel (read RGB + write RGB)
     jobs90 = [(["full_building"], 90), (["chhatris"], 90), (["plinth"], 90), (["front_minarets"], 90),
@@ -412,16 +441,7 @@ def carve_bench(N, dev, peak):
     pc_call_ms = (time.perf_counter() - t0) * 1e3
     launch_pc = vc._LAST_PART_CARVE_LAUNCH
     if launch_pc is not None:
-        for _ in range(2):
-            launch_pc()
-        torch.cuda.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for _ in range(10):
-            launch_pc()
-        p1.record()
-        torch.cuda.synchronize()
-        pms = p0.elapsed_time(p1) / 10
+        pms, _ = time_launches(launch_pc)
         res["part_carve"] = {"kernel_ms": round(pms, 4), "kernel_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2),
                              "call_ms": round(pc_call_ms, 3), "occupied": int(torch.count_nonzero(pc.view(-1, 3).any(dim=1)).item()),
                              "roofline": {"bound": "hbm", "achieved": round(6 * N ** 3 / (pms * 1e-3) / 1e9, 1), "peak": peak,

@@ -208,8 +208,10 @@ def test_part_carve_on_asymmetric_grids_vs_oracle(vc, oracle):
     rng = np.random.default_rng(77)
     names = ["full_building", "plinth", "dome", "front_minarets"]
     jobs = [([n], 90) for n in names]
+    # (256, 5): one full 256 x 256 bit tile per row (vector loads of the clear pass); (512, 3): 2 x 2 tiles;
+    # (288, 4): partial x and z tiles
     for (W, H), uniform in (((64, 40), False), ((64, 40), True), ((96, 33), True), ((32, 32), False), ((32, 32), True),
-                            ((48, 20), True)):
+                            ((48, 20), True), ((256, 5), True), ((512, 3), True), ((288, 4), False), ((288, 4), True)):
         sem = np.empty((H, W, 3), np.uint8)
         sem[:] = oracle.PART_COLORS["background"]
         lab = rng.integers(0, len(names) + 1, (H, W))
