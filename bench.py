@@ -337,7 +337,7 @@ def carve_sharded_bench(N, dev, world, rank, dist):
                     "no collective on the data path"}
 
 
-def time_launches(launch, reps=20, rounds=5):
+def time_launches(launch, reps=20, rounds=5, use_graph=True):
     """Average device time of one `launch()` (a library call that only enqueues kernels on the current stream): `reps`
     launches captured in a CUDA graph and replayed, so host-side launch cost (ctypes, GIL contention with the clock
     sampler thread) cannot bound kernels that take tens of microseconds; best of `rounds` replays.  Falls back to a
@@ -348,6 +348,8 @@ def time_launches(launch, reps=20, rounds=5):
     torch.cuda.synchronize()
     graph = None
     try:
+        if not use_graph:                     # launches that allocate or copy from the host cannot be captured
+            raise RuntimeError("plain loop requested")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         g = torch.cuda.CUDAGraph()
@@ -372,6 +374,39 @@ def time_launches(launch, reps=20, rounds=5):
         ms = e0.elapsed_time(e1) / reps
         best = ms if best is None else min(best, ms)
     return best, graph is not None
+
+
+def carve_kernels_at(N, dev, peak):
+    """Kernel-only carve timings at N^3 (BASELINE.json configs[4] carves 1024^3): global_carve's fused fold+colour kernel
+    (3 B/voxel) and the three part_carve kernels (6 B/voxel), graph-replayed like the 512^3 figures."""
+    import torch
+    syn = importlib.import_module(PKG + ".synthetic")
+    vc = importlib.import_module(PKG + ".utils.voxel_carving_utils")
+    cfg = importlib.import_module(PKG + ".utils.config")
+    lab = syn.monument_labels(N, dev)
+    front = torch.flip(lab.max(dim=0).values, dims=[0]).cpu().numpy()
+    del lab
+    lut = syn.label_lut()
+    lut[0] = cfg.PART_COLORS["background"]
+    ext = torch.from_numpy(lut[front]).to(dev)
+    binm = (front > 0).astype(np.uint8)
+    out = vc.global_carve(binm, ext, 90, return_tensor=True)
+    gms, _ = time_launches(lambda: vc.global_carve(binm, ext, 90, return_tensor=True), reps=5, rounds=3, use_graph=False)
+    jobs90 = [([n], 90) for n in ("full_building", "chhatris", "plinth", "front_minarets", "small_minarets", "dome")]
+    pc = vc.part_carve(out, ext, jobs90)
+    res = {"grid": N, "voxels": N ** 3, "global_carve_call_ms": round(gms, 4),
+           "global_carve_gvoxel_s": round(N ** 3 / (gms * 1e-3) / 1e9, 2),
+           "global_carve_frac_of_peak": round(3 * N ** 3 / (gms * 1e-3) / 1e9 / peak, 4)}
+    launch_pc = vc._LAST_PART_CARVE_LAUNCH
+    if launch_pc is not None:
+        pms, _ = time_launches(launch_pc, reps=10, rounds=3)
+        res.update({"part_carve_kernel_ms": round(pms, 4), "part_carve_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2),
+                    "part_carve_frac_of_peak": round(6 * N ** 3 / (pms * 1e-3) / 1e9 / peak, 4)})
+    res["note"] = ("global_carve: whole Python call on the device (mask upload, cached tables, one kernel), device tensor "
+                   "out, 3 B/voxel; part_carve: the three kernels, 6 B/voxel")
+    del out, pc
+    torch.cuda.empty_cache()
+    return res
 
 
 def carve_bench(N, dev, peak):
@@ -452,6 +487,12 @@ def carve_bench(N, dev, peak):
                                                   "(~0.25 B/voxel), pass B reads bits only and rewrites the runs whose "
                                                   "rotated source is empty (none for this 4-way-symmetric grid)"}}
     del out, kout, pc
+    torch.cuda.empty_cache()
+    if N != 1024:
+        try:
+            res["synthetic_1024"] = carve_kernels_at(1024, dev, peak)
+        except Exception as exc:
+            res["synthetic_1024"] = {"error": repr(exc)}
     data = os.path.join(ROOT, "tests", "golden", "data")
     try:
         sem, sem_ext, binary = mu.load_and_prepare_masks(data, "Bibi", "front", 256, cfg.PART_COLORS_NP, cfg.INTERIOR_PARTS)
@@ -468,10 +509,24 @@ def carve_bench(N, dev, peak):
                 final = vc.partwise_carve(g, sem_ext, sem, cfg.PART_COLORS_NP, jobs, sym, ext_d)
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
-        res["bibi256_pipeline"] = {"wall_ms": round(best * 1e3, 2), "voxels": int(g.shape[0] * g.shape[1] * g.shape[2]),
+        dbest = None                   # same chain with the grid kept on the device between the two calls
+        with contextlib.redirect_stdout(io.StringIO()):
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                gd = vc.global_carve(binary, sem_ext, 90, return_tensor=True)
+                fd = vc.partwise_carve(gd, sem_ext, sem, cfg.PART_COLORS_NP, jobs, sym, ext_d)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                dbest = dt if dbest is None else min(dbest, dt)
+        same = bool(torch.equal(fd, torch.from_numpy(final).to(fd.device))) if isinstance(fd, torch.Tensor) else None
+        res["bibi256_pipeline"] = {"wall_ms": round(best * 1e3, 2), "device_chain_wall_ms": round(dbest * 1e3, 2),
+                                   "device_chain_identical": same,
+                                   "voxels": int(g.shape[0] * g.shape[1] * g.shape[2]),
                                    "gvoxel_s": round(g.shape[0] * g.shape[1] * g.shape[2] / best / 1e9, 4),
                                    "note": "real Bibi front mask, load_and_prepare_masks(max_dim=256) -> global_carve -> "
-                                           "partwise_carve, NumPy in / NumPy out (host copies included), best of 3"}
+                                           "partwise_carve, NumPy in / NumPy out (host copies included), best of 3; device_chain_wall_ms: the "
+                                           "same two calls with device tensors in between (return_tensor=True)"}
     except Exception as exc:      # the real mask is a test asset; never fail the headline bench because of it
         res["bibi256_pipeline"] = {"error": repr(exc)}
     return res
