@@ -156,13 +156,15 @@ constexpr int kQueueCap = 64;        // per warp: at most 32 new entries on top 
 template <typename T>
 __global__ void __launch_bounds__(64) fast_cams_kernel(const T* __restrict__ cams, int K,
                                                         const float* __restrict__ bbox, int H, int W,
-                                                        float* __restrict__ fast) {
+                                                        float* __restrict__ fast, int4* __restrict__ rect) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   double cam[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) cam[i] = (double)cams[(size_t)k * 16 + i];       // float32 blocks widen exactly
-  make_fast_cam(cam, bbox, H, W, reinterpret_cast<FastCam*>(fast) + k, sizeof(T) == 4);
+  FastCam* fc = reinterpret_cast<FastCam*>(fast) + k;
+  make_fast_cam(cam, bbox, H, W, fc, sizeof(T) == 4);
+  if (rect) footprint_rect(cam, bbox, H, W, fc->thr_u >= 0.f && fc->thr_v >= 0.f, rect + k);
 }
 
 #ifndef P3D_SCALAR_FILTER
@@ -452,7 +454,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kScoreThreads)
 score_kernel(uint32_t* __restrict__ zbuf, const uint8_t* __restrict__ pt_label,
              const uint8_t* __restrict__ gt_label, const uint8_t* __restrict__ gt_any, int HW, int P,
-             unsigned long long* __restrict__ raw, int vec) {
+             unsigned long long* __restrict__ raw, int vec, int W, const int4* __restrict__ rect) {
   __shared__ unsigned int s_acc[kScoreThreads / 32][(kMaxParts + 1) * 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = (P + 1) * 2;
@@ -460,13 +462,27 @@ score_kernel(uint32_t* __restrict__ zbuf, const uint8_t* __restrict__ pt_label,
   __syncwarp();
   uint32_t* zb = zbuf + (size_t)blockIdx.y * HW;
   unsigned int* acc = s_acc[warp];
+  // footprint rectangle of this camera (footprint_rect): nothing outside it was written, so only it is read and cleared
+  int4 rc = make_int4(0, HW / W - 1, 0, W - 1);
+  if (rect) rc = rect[blockIdx.y];
+  if (rc.y < rc.x) return;                                   // nothing of this camera can be in the image
   if (vec) {
-    const int nq = HW >> 2;
+    // quads: with W % 4 == 0 a rectangle of whole quads, else the contiguous quad range covering rows rc.x .. rc.y
+    const bool rows4 = (W & 3) == 0;
+    const int wq_full = W >> 2;
+    const int q0 = rows4 ? rc.z >> 2 : 0, wq = rows4 ? (rc.w >> 2) - q0 + 1 : 0;
+    const int first = rows4 ? 0 : (int)(((int64_t)rc.x * W) >> 2);
+    const int nq = rows4 ? (rc.y - rc.x + 1) * wq : (int)((((int64_t)(rc.y + 1) * W + 3) >> 2) - first);
     const int stride = gridDim.x * kScoreThreads;
     const int iters = (nq + stride - 1) / stride;
     for (int it = 0; it < iters; ++it) {
-      const int qd = it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
-      const bool in = qd < nq;
+      const int idx = it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
+      const bool in = idx < nq;
+      int qd = first + idx;
+      if (rows4) {
+        const int r = idx / wq;
+        qd = (rc.x + r) * wq_full + q0 + (idx - r * wq);
+      }
       uint4 k4 = make_uint4(0, 0, 0, 0);
       if (in) k4 = __ldcg(reinterpret_cast<const uint4*>(zb) + qd);
       const bool touched = (k4.x | k4.y | k4.z | k4.w) != 0;
@@ -485,11 +501,12 @@ score_kernel(uint32_t* __restrict__ zbuf, const uint8_t* __restrict__ pt_label,
       }
     }
   } else {
+    const int first = rc.x * W, npx = (rc.y - rc.x + 1) * W;     // whole rows rc.x .. rc.y
     const int stride = gridDim.x * kScoreThreads;
-    const int iters = (HW + stride - 1) / stride;
+    const int iters = (npx + stride - 1) / stride;
     for (int it = 0; it < iters; ++it) {
-      const int pix = it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
-      const bool in = pix < HW;
+      const int pix = first + it * stride + blockIdx.x * kScoreThreads + threadIdx.x;
+      const bool in = pix < first + npx;
       const uint32_t key = in ? __ldcg(zb + pix) : 0u;
       if (!__any_sync(0xffffffffu, key != 0)) continue;
       if (key) zb[pix] = 0u;
@@ -817,11 +834,12 @@ int points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream) {
 }
 
 template <typename T>
-int fast_cameras(const T* cams, int K, const float* bbox, int H, int W, float* fast, p3d_stream_t stream) {
+int fast_cameras(const T* cams, int K, const float* bbox, int H, int W, float* fast, p3d_stream_t stream,
+                 int4* rect = nullptr) {
   P3D_REQUIRE(K >= 0 && H > 0 && W > 0, "fast_cameras: bad arguments");
   if (K == 0) return P3D_OK;
   P3D_REQUIRE(cams && bbox && fast, "fast_cameras: null pointer");
-  fast_cams_kernel<T><<<(K + 63) / 64, 64, 0, p3d::as_stream(stream)>>>(cams, K, bbox, H, W, fast);
+  fast_cams_kernel<T><<<(K + 63) / 64, 64, 0, p3d::as_stream(stream)>>>(cams, K, bbox, H, W, fast, rect);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -891,9 +909,16 @@ inline size_t default_zbuf_budget() {
 }
 
 struct SweepLayout {
-  size_t cams, raw, gt_area, bbox, fast, zbuf, total;
+  size_t cams, raw, gt_area, bbox, fast, rect, zbuf, total;
   int batch;
+  int zbufs;      // 2 = double-buffered: the score pass of one batch runs beside the splat of the next
 };
+
+// P3D_OVERLAP=0 keeps splat and score of every batch in sequence on the caller's stream (A/B runs)
+inline bool overlap_enabled() {
+  static const bool on = [] { const char* e = getenv("P3D_OVERLAP"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
 
 inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
   SweepLayout L;
@@ -904,10 +929,36 @@ inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
   L.gt_area = off; off = p3d_align_up(off + (size_t)(P + 1) * sizeof(unsigned long long), 256);
   L.bbox = off; off = p3d_align_up(off + 8 * sizeof(float), 256);
   L.fast = off; off = p3d_align_up(off + (size_t)K * sizeof(FastCam), 256);
-  L.zbuf = off; off = p3d_align_up(off + (size_t)L.batch * H * W * sizeof(uint32_t), 256);
+  L.rect = off; off = p3d_align_up(off + (size_t)K * sizeof(int4), 256);
+  L.zbufs = (overlap_enabled() && K > L.batch) ? 2 : 1;
+  L.zbuf = off; off = p3d_align_up(off + (size_t)L.zbufs * L.batch * H * W * sizeof(uint32_t), 256);
   L.total = off;
   return L;
 }
+
+// Helper stream + fork/join events of one sweep call (created per call: nothing is shared between concurrent callers;
+// destroying a stream or event with work in flight only defers the release).
+struct ScoreFork {
+  bool active = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t splatted[2] = {nullptr, nullptr}, scored[2] = {nullptr, nullptr};
+  int open() {
+    P3D_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      P3D_CUDA(cudaEventCreateWithFlags(&splatted[i], cudaEventDisableTiming));
+      P3D_CUDA(cudaEventCreateWithFlags(&scored[i], cudaEventDisableTiming));
+    }
+    active = true;
+    return P3D_OK;
+  }
+  ~ScoreFork() {
+    for (int i = 0; i < 2; ++i) {
+      if (splatted[i]) cudaEventDestroy(splatted[i]);
+      if (scored[i]) cudaEventDestroy(scored[i]);
+    }
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
 
 template <typename T>
 int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, int K, const uint8_t* gt_label,
@@ -937,8 +988,10 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
 
   float* bbox = reinterpret_cast<float*>(ws + L.bbox);
   float* fast = reinterpret_cast<float*>(ws + L.fast);
+  static const bool use_rect = [] { const char* e = getenv("P3D_SCORE_RECT"); return e == nullptr || atoi(e) != 0; }();
+  int4* rect = use_rect ? reinterpret_cast<int4*>(ws + L.rect) : nullptr;   // P3D_SCORE_RECT=0: score the whole image
   P3D_CUDA(cudaMemsetAsync(ws + L.raw, 0, L.bbox - L.raw, st));   // raw + gt_area
-  P3D_CUDA(cudaMemsetAsync(zbuf, 0, (size_t)L.batch * HW * sizeof(uint32_t), st));
+  P3D_CUDA(cudaMemsetAsync(zbuf, 0, (size_t)L.zbufs * L.batch * HW * sizeof(uint32_t), st));
   int rc = setup_cameras<T>(cand, K, cams, stream);
   if (rc) return rc;
   gt_area_kernel<<<grid_for(HW, 256, 4), 256, 0, st>>>(gt_label, mode == P3D_MODE_PER_PART ? gt_any : nullptr, HW, P,
@@ -948,22 +1001,45 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
   if (n > 0) {
     rc = points_bbox(pts, n, bbox, stream);
     if (rc) return rc;
-    rc = fast_cameras<T>(cams, K, bbox, H, W, fast, stream);
+    rc = fast_cameras<T>(cams, K, bbox, H, W, fast, stream, rect);
     if (rc) return rc;
     g_last_launches += 3;
   }
   // joint mode: carry the label in the key whenever it fits (P3D_NO_PACKED_KEYS=1 keeps the gather, for A/B runs)
   static const bool no_packed = getenv("P3D_NO_PACKED_KEYS") != nullptr;
   const int smode = (mode == P3D_MODE_JOINT && !no_packed && n < (1ll << (32 - kLabelBits)) - 1) ? kModeJointPacked : mode;
-  for (int k0 = 0; k0 < K; k0 += L.batch) {
+  // Double-buffered batches: splat(b) on the caller's stream, score(b) on a helper stream forked and joined with events,
+  // so the bandwidth-bound score/clear pass of one batch runs beside the issue-bound splat of the next.  Not used while
+  // the caller's stream is being captured into a graph, for single-batch sweeps, or with P3D_OVERLAP=0.
+  ScoreFork fork;
+  if (L.zbufs == 2 && n > 0) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+      rc = fork.open();
+      if (rc) return rc;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  int b = 0;
+  for (int k0 = 0; k0 < K; k0 += L.batch, ++b) {
     const int kb = K - k0 < L.batch ? K - k0 : L.batch;
     if (n > 0) {
+      const int buf = fork.active ? (b & 1) : 0;
+      uint32_t* zb = zbuf + (size_t)buf * L.batch * HW;
+      if (fork.active && b >= 2) P3D_CUDA(cudaStreamWaitEvent(st, fork.scored[buf], 0));   // score(b-2) has cleared zb
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
-      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, smode, zbuf,
+      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, smode, zb,
                     n > 0 ? fast + (size_t)k0 * 16 : nullptr, bbox, stream);
       if (rc) return rc;
       if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
+      cudaStream_t ss = st;
+      if (fork.active) {
+        P3D_CUDA(cudaEventRecord(fork.splatted[buf], st));
+        P3D_CUDA(cudaStreamWaitEvent(fork.stream, fork.splatted[buf], 0));
+        ss = fork.stream;
+      }
       const int vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(gt_label) & 3) == 0) &&
                       (gt_any == nullptr || (reinterpret_cast<uintptr_t>(gt_any) & 3) == 0);
       dim3 grid((unsigned)grid_for(vec ? HW / 4 : HW, kScoreThreads, 2), (unsigned)kb);
@@ -971,18 +1047,23 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
       static const int score_waves = [] { const char* e = getenv("P3D_SCORE_WAVES"); const int v = e ? atoi(e) : 32; return v > 0 ? v : 32; }();
       int per_cam = (p3d::sm_count() * score_waves + kb - 1) / kb;
       if ((int)grid.x > per_cam) grid.x = per_cam < 1 ? 1 : per_cam;
+      const int4* rk = rect ? rect + k0 : nullptr;
       if (smode == kModeJointPacked)
-        score_kernel<kModeJointPacked><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, nullptr, HW, P,
-                                                                       raw + (size_t)k0 * (P + 1) * 2, vec);
+        score_kernel<kModeJointPacked><<<grid, kScoreThreads, 0, ss>>>(zb, pt_label, gt_label, nullptr, HW, P,
+                                                                       raw + (size_t)k0 * (P + 1) * 2, vec, W, rk);
       else if (mode == P3D_MODE_JOINT)
-        score_kernel<P3D_MODE_JOINT><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, nullptr, HW, P,
-                                                                     raw + (size_t)k0 * (P + 1) * 2, vec);
+        score_kernel<P3D_MODE_JOINT><<<grid, kScoreThreads, 0, ss>>>(zb, pt_label, gt_label, nullptr, HW, P,
+                                                                     raw + (size_t)k0 * (P + 1) * 2, vec, W, rk);
       else
-        score_kernel<P3D_MODE_PER_PART><<<grid, kScoreThreads, 0, st>>>(zbuf, pt_label, gt_label, gt_any, HW, P,
-                                                                        raw + (size_t)k0 * (P + 1) * 2, vec);
+        score_kernel<P3D_MODE_PER_PART><<<grid, kScoreThreads, 0, ss>>>(zb, pt_label, gt_label, gt_any, HW, P,
+                                                                        raw + (size_t)k0 * (P + 1) * 2, vec, W, rk);
       P3D_LAUNCH_CHECK();
+      if (fork.active) P3D_CUDA(cudaEventRecord(fork.scored[buf], fork.stream));
       g_last_launches += 2;
     }
+  }
+  if (fork.active) {                                     // join: everything after this sees all score passes
+    for (int buf = 0; buf < (b < 2 ? b : 2); ++buf) P3D_CUDA(cudaStreamWaitEvent(st, fork.scored[buf], 0));
   }
   finalize_kernel<<<(K + 127) / 128, 128, 0, st>>>(raw, gt_area, K, P, rows, counts, scores);
   P3D_LAUNCH_CHECK();

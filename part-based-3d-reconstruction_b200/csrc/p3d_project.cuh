@@ -160,6 +160,40 @@ __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, co
   *out = fc;
 }
 
+// Image rectangle that contains every pixel a camera can touch: rect = (row0, row1, col0, col1), inclusive; row1 < row0
+// when nothing can land in the image.  For a camera that passed the filter's test (the whole bounding box lies in front
+// of the camera plane, Z >= zmin > 0, and |u32 - u_ref| <= 0.25) the perspective image of the box is the convex hull of
+// its 8 projected corners, so the reference's u, v of every point lie inside the corners' min/max; 2.5 px of margin
+// cover the reference's own rounding and the half-even pixel rounding.  Any other camera gets the full image.  The
+// score pass reads and clears only this rectangle of the camera's z-buffer (nothing outside it is ever written).
+__device__ __forceinline__ void footprint_rect(const double* __restrict__ cam, const float* __restrict__ bbox, int H, int W,
+                                               bool fast_ok, int4* out) {
+  int4 r = make_int4(0, H - 1, 0, W - 1);
+  if (fast_ok) {
+    double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
+    bool fin = true;
+    for (int corner = 0; corner < 8; ++corner) {
+      double d[3];
+      for (int k = 0; k < 3; ++k) d[k] = (double)bbox[((corner >> k) & 1) ? 3 + k : k] - cam[k];
+      const double X = d[0] * cam[3] + d[1] * cam[4] + d[2] * cam[5];
+      const double Y = d[0] * cam[6] + d[1] * cam[7] + d[2] * cam[8];
+      const double Z = d[0] * cam[9] + d[1] * cam[10] + d[2] * cam[11];
+      const double u = X / Z * cam[12] + cam[13], v = -(Y / Z) * cam[12] + cam[14];
+      fin = fin && Z > 0.0 && fabs(u) < 1e15 && fabs(v) < 1e15;                 // false for NaN
+      umin = fmin(umin, u); umax = fmax(umax, u);
+      vmin = fmin(vmin, v); vmax = fmax(vmax, v);
+    }
+    if (fin) {
+      const double m = 2.5;
+      const double r0 = fmax(0.0, floor(vmin - m)), r1 = fmin((double)(H - 1), ceil(vmax + m));
+      const double c0 = fmax(0.0, floor(umin - m)), c1 = fmin((double)(W - 1), ceil(umax + m));
+      if (r0 > r1 || c0 > c1) r = make_int4(0, -1, 0, -1);
+      else r = make_int4((int)r0, (int)r1, (int)c0, (int)c1);
+    }
+  }
+  *out = r;
+}
+
 // Packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2): one issue slot for two lanes' worth of IEEE-rn FP32 operations.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
