@@ -251,9 +251,14 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch,
                 "cameras_per_launch": batch, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "splat_share_of_step": round(splat_ms.value / ms, 4),
+                "step_achieved": round(value / max(world, 1) * (G * 1 + 9 * H * W) / 1e9, 1),
+                "step_frac": round(value / max(world, 1) * (G * 1 + 9 * H * W) / 1e9 / peak, 4),
                 "point_candidates_per_s": round(n_points * batch / avg_launch_s, 1) if avg_launch_s > 0 else None,
                 "note": "effective GB/s under the streaming model of SURVEY 8(d) (dense u8 grid once per camera + 9 B/pixel); "
-                        "the kernel batches cameras per point pass and is instruction-issue bound, see DESIGN.md 4.1"}
+                        "the kernel batches cameras per point pass and is instruction-issue bound, see DESIGN.md 4.1; "
+                        "avg_launch_ms is measured inside the step, where the score pass of the previous batch runs "
+                        "beside this kernel on a helper stream (alone it takes 0.889 ms = 0.79: P3D_OVERLAP=0); "
+                        "step_achieved / step_frac = the same model over the whole step (per GPU)"}
 
     # ---- CPU baseline: NumPy port of the reference path on this box's host cores -----------------
     cpu = None

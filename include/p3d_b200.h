@@ -140,7 +140,11 @@ int p3d_partwise_counts_rgb(const uint8_t* proj_rgb, const uint8_t* gt_rgb, int6
  * combined binary IoU counts against gt_any (H,W) u8 (camera_estimation.py:433-447); scores is the mean
  * over the P parts only.  gt_any may be NULL in joint mode.
  * Workspace: p3d_sweep_workspace_bytes(); cameras are processed in batches sized so that the
- * batch's z-buffers stay L2-resident.
+ * batch's z-buffers stay L2-resident.  Sweeps of more than one batch double-buffer the z-buffers and
+ * run the score pass of one batch on a helper stream (created and destroyed inside the call, forked
+ * from and joined to `stream` with events) beside the splat of the next; everything the caller
+ * enqueues on `stream` afterwards is ordered after the whole sweep.  While `stream` is being captured
+ * into a CUDA graph the batches stay in sequence on `stream`.
  * --------------------------------------------------------------------------------------------- */
 size_t p3d_sweep_workspace_bytes(int K, int H, int W, int P, int elem_bytes);
 int p3d_sweep_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cand, int K,
