@@ -291,6 +291,10 @@ global_fold_bits_kernel(int W, int H, int D, int x_begin, int x_count, const uin
                         const uint32_t* __restrict__ mask_bits, int wpr, const uint8_t* __restrict__ colour_hw,
                         uint8_t* __restrict__ out, unsigned long long magic_gpr, unsigned long long magic_h) {
   __shared__ uint4 stage[8][96];
+#ifdef P3D_GFB_TMA
+  __shared__ __align__(128) uint4 stage2[8][2][96];
+  int it = 0;
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t gpr = (uint32_t)D >> 4;                      // thread groups (16 voxels) per z-row
   const uint32_t groups = (uint32_t)x_count * (uint32_t)H * gpr;     // < 2^31 (the host splits larger slabs)
@@ -334,6 +338,37 @@ global_fold_bits_kernel(int W, int H, int D, int x_begin, int x_count, const uin
       uint32_t o[12];
 #pragma unroll
       for (int q = 0; q < 4; ++q) expand4((bits >> (4 * q)) & 0xfu, w0, w1, w2, o + 3 * q);
+#ifdef P3D_GFB_TMA
+      // experiment: the warp's 1536 bytes leave shared memory as ONE bulk async copy (TMA, 1-D) issued by lane 0;
+      // two staging buffers per warp, at most one copy still reading when the other buffer is rewritten
+      {
+        uint4* sbuf = stage2[warp][it & 1];
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        uint4* mine2 = &sbuf[lane * 3];
+        mine2[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        mine2[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        mine2[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        uint4* dst2 = reinterpret_cast<uint4*>(out) + (size_t)wg * 96;
+        ++it;
+        if ((wg + 1u) * 32u <= groups) {
+          if (lane == 0) {
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sbuf);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst2), "r"(sa), "r"(1536u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          const uint32_t left2 = (groups - wg * 32u) * 3u;
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+            if ((uint32_t)(p * 32 + lane) < left2) __stcs(dst2 + p * 32 + lane, sbuf[p * 32 + lane]);
+        }
+        __syncwarp();
+        continue;
+      }
+#endif
       uint4* mine = &stage[warp][lane * 3];
       mine[0] = make_uint4(o[0], o[1], o[2], o[3]);
       mine[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -361,6 +396,9 @@ global_fold_bits_kernel(int W, int H, int D, int x_begin, int x_count, const uin
       __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4(o[0], o[1], o[2], o[3]));
     }
   }
+#ifdef P3D_GFB_TMA
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
