@@ -257,7 +257,7 @@ def run_ours(args):
                 "note": "effective GB/s under the streaming model of SURVEY 8(d) (dense u8 grid once per camera + 9 B/pixel); "
                         "the kernel batches cameras per point pass and is instruction-issue bound, see DESIGN.md 4.1; "
                         "avg_launch_ms is measured inside the step, where the score pass of the previous batch runs "
-                        "beside this kernel on a helper stream (alone it takes 0.889 ms = 0.79: P3D_OVERLAP=0); "
+                        "beside this kernel on a helper stream; "
                         "step_achieved / step_frac = the same model over the whole step (per GPU)"}
 
     # ---- CPU baseline: NumPy port of the reference path on this box's host cores -----------------

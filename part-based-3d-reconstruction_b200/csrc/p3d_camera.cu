@@ -885,15 +885,14 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   return P3D_OK;
 }
 
-// cameras per batch: keep the batch's z-buffers within an L2-sized budget, but never fewer than 16 cameras per launch
-// while that stays under 1 GiB -- a launch streams the whole point list once, so few cameras per launch cost more than
-// an L2-overflowing z-buffer does (measured at 1024^3 / 2048^2: 8 cameras 3.5 k cand/s, 16 cameras 4.0 k, 32: 3.8 k).
-inline int batch_cameras(int K, int H, int W, size_t zbuf_budget) {
-  const size_t per = (size_t)H * W * sizeof(uint32_t);
-  int64_t c = (int64_t)(zbuf_budget / per);
-  int64_t floor16 = (int64_t)(((size_t)1 << 30) / per);
-  if (floor16 > 16) floor16 = 16;
-  if (c < floor16) c = floor16;
+// Cameras per splat launch.  Lower bound `batch_floor`: as many as fit a 128 MB z-buffer budget (P3D_ZBUF_BUDGET_MB), but
+// never fewer than 16 while that stays under 1 GiB -- a launch streams the whole point list once, so few cameras per
+// launch cost more than an L2-overflowing z-buffer does (1024^3 / 2048^2: 8 cameras 3.5 k cand/s, 16: 4.0 k, 32: 3.8 k).
+// Since the batches are double-buffered (the z-buffers alternate and are not L2-resident across launches any more)
+// longer launches win: the batch grows until a launch covers about 2.8e9 point-cameras (3-4 ms), up to a 512 MB
+// z-buffer set (P3D_ZBUF_CAP_MB).  Measured with this rule at 1024^2: 512^3 32 cameras 34.1 k cand/s, 64: 34.9 k,
+// 128: 35.2 k; 256^3 32: 154.9 k, 64: 163.1 k, 128: 172.3 k; at 1024^3 / 2048^2 the rule keeps 16 (32: -4 %, 64: -9 %).
+inline int clamp_batch(int64_t c, int K) {
   static const int max_batch = [] { const char* e = getenv("P3D_MAX_BATCH"); int v = e ? atoi(e) : 256; return v > 0 ? v : 256; }();
   if (c > max_batch) c = max_batch;
   if (c > K) c = K;
@@ -901,16 +900,45 @@ inline int batch_cameras(int K, int H, int W, size_t zbuf_budget) {
   return (int)c;
 }
 
-inline size_t default_zbuf_budget() {
-  const char* e = getenv("P3D_ZBUF_BUDGET_MB");
-  long mb = e ? atol(e) : 128;
-  if (mb < 1) mb = 128;
+inline size_t env_mb(const char* name, long dflt) {
+  const char* e = getenv(name);
+  long mb = e ? atol(e) : dflt;
+  if (mb < 1) mb = dflt;
   return (size_t)mb << 20;
+}
+
+inline int batch_floor(int K, int H, int W) {
+  static const size_t budget = env_mb("P3D_ZBUF_BUDGET_MB", 128);
+  const size_t per = (size_t)H * W * sizeof(uint32_t);
+  int64_t c = (int64_t)(budget / per);
+  int64_t floor16 = (int64_t)(((size_t)1 << 30) / per);
+  if (floor16 > 16) floor16 = 16;
+  if (c < floor16) c = floor16;
+  return clamp_batch(c, K);
+}
+
+// capacity of one z-buffer set in the workspace (independent of the point count, which the workspace query does not know)
+inline int batch_capacity(int K, int H, int W) {
+  static const size_t cap = env_mb("P3D_ZBUF_CAP_MB", 512);
+  const size_t per = (size_t)H * W * sizeof(uint32_t);
+  const int lo = batch_floor(K, H, W);
+  const int hi = clamp_batch((int64_t)(cap / per), K);
+  return hi > lo ? hi : lo;
+}
+
+// cameras per launch of one sweep over n points
+inline int batch_cameras(int K, int H, int W, int64_t n) {
+  const int lo = batch_floor(K, H, W), hi = batch_capacity(K, H, W);
+  const int64_t want = n > 0 ? (int64_t)((2.8e9 + (double)n - 1.0) / (double)n) : hi;
+  int64_t c = want < lo ? lo : want;
+  if (c > hi) c = hi;
+  return (int)c;
 }
 
 struct SweepLayout {
   size_t cams, raw, gt_area, bbox, fast, rect, zbuf, total;
-  int batch;
+  int batch;      // cameras one z-buffer set can hold
+  int floor;      // fewest cameras per launch the sweep will choose
   int zbufs;      // 2 = double-buffered: the score pass of one batch runs beside the splat of the next
 };
 
@@ -922,7 +950,8 @@ inline bool overlap_enabled() {
 
 inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
   SweepLayout L;
-  L.batch = batch_cameras(K, H, W, default_zbuf_budget());
+  L.batch = batch_capacity(K, H, W);                       // capacity of a set; the sweep may use fewer per launch
+  L.floor = batch_floor(K, H, W);
   size_t off = 0;
   L.cams = off; off = p3d_align_up(off + (size_t)K * 16 * elem_bytes, 256);
   L.raw = off; off = p3d_align_up(off + (size_t)K * (P + 1) * 2 * sizeof(unsigned long long), 256);
@@ -930,7 +959,7 @@ inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
   L.bbox = off; off = p3d_align_up(off + 8 * sizeof(float), 256);
   L.fast = off; off = p3d_align_up(off + (size_t)K * sizeof(FastCam), 256);
   L.rect = off; off = p3d_align_up(off + (size_t)K * sizeof(int4), 256);
-  L.zbufs = (overlap_enabled() && K > L.batch) ? 2 : 1;
+  L.zbufs = (overlap_enabled() && K > L.floor) ? 2 : 1;
   L.zbuf = off; off = p3d_align_up(off + (size_t)L.zbufs * L.batch * H * W * sizeof(uint32_t), 256);
   L.total = off;
   return L;
@@ -991,7 +1020,9 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
   static const bool use_rect = [] { const char* e = getenv("P3D_SCORE_RECT"); return e == nullptr || atoi(e) != 0; }();
   int4* rect = use_rect ? reinterpret_cast<int4*>(ws + L.rect) : nullptr;   // P3D_SCORE_RECT=0: score the whole image
   P3D_CUDA(cudaMemsetAsync(ws + L.raw, 0, L.bbox - L.raw, st));   // raw + gt_area
-  P3D_CUDA(cudaMemsetAsync(zbuf, 0, (size_t)L.zbufs * L.batch * HW * sizeof(uint32_t), st));
+  const int batch = batch_cameras(K, H, W, n);              // cameras per launch (<= L.batch)
+  for (int sidx = 0; sidx < (K > batch ? L.zbufs : 1); ++sidx)
+    P3D_CUDA(cudaMemsetAsync(zbuf + (size_t)sidx * L.batch * HW, 0, (size_t)batch * HW * sizeof(uint32_t), st));
   int rc = setup_cameras<T>(cand, K, cams, stream);
   if (rc) return rc;
   gt_area_kernel<<<grid_for(HW, 256, 4), 256, 0, st>>>(gt_label, mode == P3D_MODE_PER_PART ? gt_any : nullptr, HW, P,
@@ -1012,7 +1043,7 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
   // so the bandwidth-bound score/clear pass of one batch runs beside the issue-bound splat of the next.  Not used while
   // the caller's stream is being captured into a graph, for single-batch sweeps, or with P3D_OVERLAP=0.
   ScoreFork fork;
-  if (L.zbufs == 2 && n > 0) {
+  if (L.zbufs == 2 && K > batch && n > 0) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
       rc = fork.open();
@@ -1022,8 +1053,8 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
     }
   }
   int b = 0;
-  for (int k0 = 0; k0 < K; k0 += L.batch, ++b) {
-    const int kb = K - k0 < L.batch ? K - k0 : L.batch;
+  for (int k0 = 0; k0 < K; k0 += batch, ++b) {
+    const int kb = K - k0 < batch ? K - k0 : batch;
     if (n > 0) {
       const int buf = fork.active ? (b & 1) : 0;
       uint32_t* zb = zbuf + (size_t)buf * L.batch * HW;
