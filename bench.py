@@ -350,14 +350,27 @@ def carve_sharded_bench(N, dev, world, rank, dist):
             assert torch.equal(kout, slab)
     except Exception as exc:
         print("sharded carve kernel timing failed:", repr(exc), file=sys.stderr)
-    t = torch.tensor([e0.elapsed_time(e1) / reps, kms], dtype=torch.float64, device=dev)
+    # part_carve of the same grid by output x-slab from the replicated input (no exchange): the four slab kernels
+    pms = 0.0
+    try:
+        gfull = vc.global_carve(binm, ext, 90, return_tensor=True)
+        jobs90 = [([n], 90) for n in ("full_building", "chhatris", "plinth", "front_minarets", "small_minarets", "dome")]
+        pslab = vc.part_carve(gfull, ext, jobs90, x_range=span)
+        if vc._LAST_PART_CARVE_LAUNCH is not None:
+            pms, _ = time_launches(vc._LAST_PART_CARVE_LAUNCH, reps=10, rounds=3)
+        del gfull, pslab
+    except Exception as exc:
+        print("sharded part_carve timing failed:", repr(exc), file=sys.stderr)
+    t = torch.tensor([e0.elapsed_time(e1) / reps, kms, pms], dtype=torch.float64, device=dev)
     occ = torch.count_nonzero(slab.view(-1, 3).any(dim=1)).to(torch.float64).reshape(1)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(occ, op=dist.ReduceOp.SUM)
-    ms, kms = float(t[0].item()), float(t[1].item())
+    ms, kms, pms = float(t[0].item()), float(t[1].item()), float(t[2].item())
     return {"global_carve_sharded_gvoxel_s": round(N ** 3 / (ms * 1e-3) / 1e9, 2), "grid": N, "ms_per_call": round(ms, 4),
             "kernel_ms_max_over_ranks": round(kms, 4),
             "kernel_gvoxel_s": round(N ** 3 / (kms * 1e-3) / 1e9, 2) if kms > 0 else None,
+            "part_carve_slab_kernel_ms_max_over_ranks": round(pms, 4),
+            "part_carve_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2) if pms > 0 else None,
             "n_gpus": world, "scaling": "strong", "occupied": int(occ.item()), "slab_of_rank0": list(span),
             "note": "whole Python call per rank (mask upload, table lookup, slab kernel), x-slab per rank, max over ranks; "
                     "no collective on the data path"}

@@ -314,6 +314,14 @@ size_t p3d_part_carve_bits_workspace_bytes(int W, int H, int D, int n_groups);
 int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, const uint32_t* inside_bits, int c, int c2,
                              const uint32_t* group_mask_hw, int n_groups, uint8_t* out, void* workspace,
                              size_t workspace_bytes, p3d_stream_t stream);
+/* Output x slab [x_begin, x_begin + x_count) of the same carve (out_slab: (x_count,H,D,3)) from the whole, replicated
+ * input grid -- the unit of multi-GPU sharding of part_carve (voxel_carving_utils.py:139-160).  No exchange between
+ * ranks: besides its own rows the slab reads the z range [x_begin + c2, x_begin + x_count + c2) of every input row for
+ * the rotated source occupancy.  Same workspace size as the full call. */
+int p3d_part_carve_fold_bits_slab(const uint8_t* grid, int W, int H, int D, int x_begin, int x_count,
+                                  const uint32_t* inside_bits, int c, int c2, const uint32_t* group_mask_hw,
+                                  int n_groups, uint8_t* out_slab, void* workspace, size_t workspace_bytes,
+                                  p3d_stream_t stream);
 
 /* Building blocks of the general-angle part_carve and of left_right_guided_carve :163-210. */
 int p3d_crop_occupancy(const uint8_t* grid, int W, int H, int D, int x0, int y0, int z0, int w, int h, int d,

@@ -464,19 +464,38 @@ __device__ __forceinline__ void mask96(uint4 (&v)[6], uint32_t keep) {
   }
 }
 
+// Slab form (multi-GPU): the clear pass of an output x slab [x0, x1) needs occ[c - z, y, x + c2], i.e. the z range
+// [x0 + c2, x1 + c2) of EVERY row of the (replicated) input.  One thread per (row, word): 32 voxels = 96 contiguous bytes.
+__global__ void __launch_bounds__(256)
+occ_zrange_bits_kernel(const uint8_t* __restrict__ grid, int64_t rows, int D, int w_begin, int w_count,
+                       uint32_t* __restrict__ occz) {
+  const int words = D >> 5;
+  const int64_t n = rows * w_count;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / w_count;
+    const int w = w_begin + (int)(t - row * w_count);
+    const uint4* src = reinterpret_cast<const uint4*>(grid + (row * D + (int64_t)w * 32) * 3);
+    const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3), e = __ldg(src + 4), f = __ldg(src + 5);
+    occz[row * words + w] = rgb16_occupancy(a, b, c) | (rgb16_occupancy(d, e, f) << 16);
+  }
+}
+
 // pass A: thread = 16 voxels of one z-row (coalesced 48-byte loads and stores, like part_fold_bits_kernel); lane pairs
 // merge their 16 occupancy / alive bits into z-packed words occz / alive [x][y][z/32].
 __global__ void __launch_bounds__(256)
 part_copy_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const uint32_t* __restrict__ inside_bits,
                       int c, const uint32_t* __restrict__ gm_hw, const uint32_t* __restrict__ gbits, int xwp,
                       uint32_t* __restrict__ occz, uint32_t* __restrict__ alive, uint8_t* __restrict__ out,
-                      unsigned long long magic_gpr, unsigned long long magic_h) {
+                      unsigned long long magic_gpr, unsigned long long magic_h, uint32_t g_begin, uint32_t g_end) {
+  // groups [g_begin, g_end) of the full grid (an x slab, multiples of 32 groups since D % 32 == 0 ... H * D/16 even);
+  // `out` starts at the slab's first voxel; occz == nullptr: the caller already has the input's occupancy bits
   const uint32_t gpr = (uint32_t)D >> 4;                    // thread groups per z-row
-  const uint32_t groups = (uint32_t)W * (uint32_t)H * gpr;  // < 2^31 (checked by the host); even: D % 32 == 0
+  const uint32_t groups = g_end;                            // < 2^31 (checked by the host); even: D % 32 == 0
   const int words = D >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t wb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < groups; wb += stride) {
+  out -= (size_t)g_begin * 48;                              // 16 voxels x 3 bytes per group
+  for (uint32_t wb = g_begin + blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < groups; wb += stride) {
     const uint32_t g = wb + lane;
     const bool in = g < groups;
     uint32_t occ = 0, keep = 0;
@@ -512,7 +531,7 @@ part_copy_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, con
     }
     const uint32_t occ_hi = __shfl_xor_sync(0xffffffffu, occ, 1), keep_hi = __shfl_xor_sync(0xffffffffu, keep, 1);
     if (in && !(lane & 1)) {                                // even lane: z0 is a multiple of 32
-      occz[g >> 1] = occ | (occ_hi << 16);                  // (g * 16) / 32 == ((x * H + y) * D + z0) / 32
+      if (occz) occz[g >> 1] = occ | (occ_hi << 16);        // (g * 16) / 32 == ((x * H + y) * D + z0) / 32
       alive[g >> 1] = keep | (keep_hi << 16);
     }
   }
@@ -542,22 +561,26 @@ constexpr int kClearRowW = kClearZW + 1;   // staged words per source row (the c
 // alive voxels whose source is empty are rewritten.
 __global__ void __launch_bounds__(kClearX)
 part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict__ occz,
-                  const uint32_t* __restrict__ alive, uint8_t* __restrict__ out) {
+                  const uint32_t* __restrict__ alive, uint8_t* __restrict__ out, int x_begin, int x_count) {
+  // output x in [x_begin, x_begin + x_count); `out` starts at the slab's first voxel; bit arrays are indexed by the
+  // full grid
   __shared__ uint32_t s_occ[kClearX * kClearRowW];          // row stride 9 words: conflict-free both ways
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int words = D >> 5;
-  const int xb_n = (W + kClearX - 1) / kClearX, zb_n = (words + kClearZW - 1) / kClearZW;
+  const int xb_n = (x_count + kClearX - 1) / kClearX, zb_n = (words + kClearZW - 1) / kClearZW;
+  const int x_end = x_begin + x_count;
+  out -= (size_t)x_begin * H * D * 3;
   const int64_t tasks = (int64_t)H * zb_n * xb_n;
   const bool vec = (words % kClearZW) == 0;                  // rows of 8 words start on 32-byte boundaries
   for (int64_t t = blockIdx.x; t < tasks; t += gridDim.x) {
     const int xb = (int)(t % xb_n);
     const int64_t r = t / xb_n;
     const int zb = (int)(r % zb_n), y = (int)(r / zb_n);
-    const int x = xb * kClearX + (int)threadIdx.x, zw0 = zb * kClearZW;
+    const int x = x_begin + xb * kClearX + (int)threadIdx.x, zw0 = zb * kClearZW;
     uint32_t a[kClearZW];
 #pragma unroll
     for (int k = 0; k < kClearZW; ++k) a[k] = 0u;
-    if (x < W) {
+    if (x < x_end) {
       const uint32_t* row = alive + ((size_t)x * H + y) * words + zw0;
       if (vec) {
         const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row)), v1 = __ldg(reinterpret_cast<const uint4*>(row) + 1);
@@ -574,11 +597,11 @@ part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict
     if (!__syncthreads_or(any != 0u)) continue;              // also orders the previous task's s_occ reads before the writes below
     {
       const int sx = c - zw0 * 32 - (int)threadIdx.x;        // source row of z = z0 + threadIdx.x
-      const int wb = (xb * kClearX + c2) >> 5;                // arithmetic shift; bits outside [0, D) read 0
+      const int wb = (x_begin + xb * kClearX + c2) >> 5;      // arithmetic shift; bits outside [0, D) read 0
       const bool row_ok = sx >= 0 && sx < W;
       const uint32_t* row = occz + ((size_t)(row_ok ? sx : 0) * H + y) * words;
       uint32_t* so = s_occ + threadIdx.x * kClearRowW;
-      if (vec && ((xb * kClearX + c2) & (kClearX - 1)) == 0 && wb >= 0 && wb + kClearZW <= words) {
+      if (vec && ((x_begin + xb * kClearX + c2) & (kClearX - 1)) == 0 && wb >= 0 && wb + kClearZW <= words) {
         uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;      // aligned tile (c2 = 0, the usual fold): one sector per row
         if (row_ok) { v0 = __ldg(reinterpret_cast<const uint4*>(row + wb)); v1 = __ldg(reinterpret_cast<const uint4*>(row + wb) + 1); }
         so[0] = v0.x; so[1] = v0.y; so[2] = v0.z; so[3] = v0.w; so[4] = v1.x; so[5] = v1.y; so[6] = v1.z; so[7] = v1.w;
@@ -592,7 +615,7 @@ part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict
       }
     }
     __syncthreads();
-    const int sh = (xb * kClearX + c2) & 31;
+    const int sh = (x_begin + xb * kClearX + c2) & 31;
 #pragma unroll
     for (int k = 0; k < kClearZW; ++k) {
       if (!__any_sync(0xffffffffu, a[k] != 0u)) continue;
@@ -1372,9 +1395,57 @@ P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, c
   // 256: 0.135; capping the residency below 8 CTAs per SM costs 10 %
   static const int pcb_waves = [] { const char* e = getenv("P3D_PCB_WAVES"); const int v = e ? atoi(e) : 256; return v > 0 ? v : 256; }();
   part_copy_bits_kernel<<<grid_for(n16, 256, pcb_waves), 256, 0, st>>>(grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp,
-                                                              occz, alive, out, magic_gpr, magic_h);
+                                                              occz, alive, out, magic_gpr, magic_h, 0u, (uint32_t)n16);
   const int64_t tasks = (int64_t)H * ((D / 32 + kClearZW - 1) / kClearZW) * ((W + kClearX - 1) / kClearX);
-  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out);
+  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out, 0, W);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// Output x slab [x_begin, x_begin + x_count) of the same carve from the whole (replicated) input grid: the unit of
+// multi-GPU sharding.  No exchange: the slab reads its own rows (pass A) and the z range [x_begin + c2, ...) of every
+// row for the source occupancy (occ_zrange_bits_kernel), 2 x 3 bytes per slab voxel in all.
+P3D_API int p3d_part_carve_fold_bits_slab(const uint8_t* grid, int W, int H, int D, int x_begin, int x_count,
+                                          const uint32_t* inside_bits, int c, int c2, const uint32_t* group_mask_hw,
+                                          int n_groups, uint8_t* out_slab, void* workspace, size_t workspace_bytes,
+                                          p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0 && n_groups >= 1 && n_groups <= 32, "part_carve_fold_bits_slab: bad shape");
+  P3D_REQUIRE(x_begin >= 0 && x_count >= 0 && x_begin + x_count <= W, "part_carve_fold_bits_slab: bad x slab");
+  if (x_count == 0) return P3D_OK;
+  P3D_REQUIRE(grid && inside_bits && group_mask_hw && out_slab && workspace, "part_carve_fold_bits_slab: null pointer");
+  P3D_REQUIRE(((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out_slab)) & 15) == 0,
+              "part_carve_fold_bits_slab: grids must be 16-byte aligned");
+  if (workspace_bytes < p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups)) {
+    p3d::set_error("part_carve_fold_bits_slab: workspace too small");
+    return P3D_E_WORKSPACE;
+  }
+  const int xwp = (W + 31) / 32 + 2, words = D / 32;
+  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)words * 4, 256);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint32_t* occz = reinterpret_cast<uint32_t*>(ws);
+  uint32_t* alive = reinterpret_cast<uint32_t*>(ws + zbits);
+  uint32_t* gbits = reinterpret_cast<uint32_t*>(ws + 2 * zbits);
+  cudaStream_t st = p3d::as_stream(stream);
+  pack_group_bits_kernel<<<grid_for((int64_t)H * xwp, 8, 32), 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
+  // source occupancy: z range [x_begin + c2, x_begin + x_count + c2) clipped to the grid, whole words, every row
+  int z_lo = x_begin + c2, z_hi = x_begin + x_count + c2;
+  if (z_lo < 0) z_lo = 0;
+  if (z_hi > D) z_hi = D;
+  if (z_hi > z_lo) {
+    const int w_begin = z_lo >> 5, w_count = ((z_hi + 31) >> 5) - w_begin;
+    const int64_t rows = (int64_t)W * H;
+    occ_zrange_bits_kernel<<<grid_for(rows * w_count, 256, 64), 256, 0, st>>>(grid, rows, D, w_begin, w_count, occz);
+  }
+  const int64_t n16 = (int64_t)W * H * D / 16;
+  P3D_REQUIRE(n16 < (1ll << 31), "part_carve_fold_bits_slab: grid too large for 32-bit group indices");
+  const unsigned long long magic_gpr = magic_for((uint64_t)n16, (uint64_t)D / 16);
+  const unsigned long long magic_h = magic_for((uint64_t)W * H, (uint64_t)H);
+  const int64_t gps = (int64_t)H * (D / 16);                   // groups per x plane
+  const uint32_t g_begin = (uint32_t)(x_begin * gps), g_end = (uint32_t)((x_begin + x_count) * gps);
+  part_copy_bits_kernel<<<grid_for((int64_t)x_count * gps, 256, 256), 256, 0, st>>>(
+      grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp, nullptr, alive, out_slab, magic_gpr, magic_h, g_begin, g_end);
+  const int64_t tasks = (int64_t)H * ((words + kClearZW - 1) / kClearZW) * ((x_count + kClearX - 1) / kClearX);
+  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out_slab, x_begin, x_count);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

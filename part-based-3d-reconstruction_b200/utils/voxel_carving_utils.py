@@ -280,13 +280,22 @@ def apply_colored_mask_to_voxel_grid(carved_voxel_grid, colored_mask):
     return _ret(out, as_tensor)
 
 
-def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
+def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_range=None):
     """voxel_carving_utils.py:139-160: per part group, carve the group's voxels with the group's own mask under
-    the group's symmetry angle and merge the survivors."""
+    the group's symmetry angle and merge the survivors.
+
+    x_range=(x0, x1) (addition, multi-GPU): return only the output slab [x0, x1) along axis 0, computed from the whole
+    (replicated) input grid without any exchange -- `utils.sweep.carve_sharded(lambda a, b: part_carve(g, sem, jobs,
+    x_range=(a, b)), W)`.  Slabs of the all-90-degree bit path cost slab-sized traffic; any other job list computes the
+    full grid and slices it."""
     as_tensor = _is_tensor(colored_grid)
     dev = nv.require_cuda(colored_grid.device if as_tensor and colored_grid.is_cuda else None)
     grid = _to_dev_u8(colored_grid, dev, "colored_grid")
     W, H, D, _ = grid.shape
+    if x_range is not None:
+        x0, x1 = int(x_range[0]), int(x_range[1])
+        if not (0 <= x0 <= x1 <= W):
+            raise ValueError(f"x_range {x_range} outside [0, {W}]")
     jobs = []
     semantic_mask = semantic_mask if isinstance(semantic_mask, _PackedMask) else _PackedMask(semantic_mask)
     for names, angle in group_jobs:
@@ -308,8 +317,22 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
                 sel = (m2d & m2d.T) if W == H else m2d
                 gm |= sel.astype(np.uint32) << np.uint32(g)
             gm_hw = torch.from_numpy(gm.view(np.int32)).to(dev)
-            out = torch.empty_like(grid)
             bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
+            if x_range is not None and bits is not None and bits[2] is not None and x1 > x0:
+                ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                slab = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
+
+                def launch_slab(grid=grid, slab=slab, ws=ws, gm_hw=gm_hw, bits=bits, n=len(jobs)):
+                    check(lib.p3d_part_carve_fold_bits_slab(ptr(grid), W, H, D, x0, x1 - x0, ptr(bits[0]), bits[1], bits[2],
+                                                            ptr(gm_hw), n, ptr(slab), ptr(ws), ws_bytes, stream_ptr()),
+                          "p3d_part_carve_fold_bits_slab")
+                    _launched(4)
+                launch_slab()
+                global _LAST_PART_CARVE_LAUNCH
+                _LAST_PART_CARVE_LAUNCH = launch_slab
+                return _ret(slab, as_tensor)
+            out = torch.empty_like(grid)
             if bits is not None and bits[2] is not None:       # z-separable table: bit-packed occupancy / group masks
                 ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -319,7 +342,6 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
                                                        ptr(out), ptr(ws), ws_bytes, stream_ptr()), "p3d_part_carve_fold_bits")
                     _launched(3)
                 launch()
-                global _LAST_PART_CARVE_LAUNCH
                 _LAST_PART_CARVE_LAUNCH = launch              # bench.py re-issues it to time the kernels alone
             else:
                 check(lib.p3d_part_carve_fold(ptr(grid), W, H, D, ptr(table), ptr(gm_hw), ptr(out), stream_ptr()),
@@ -338,6 +360,8 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False):
             check(lib.p3d_accumulate_part(ptr(grid), ptr(carved), W, H, D, ptr(sel), ptr(out), stream_ptr()),
                   "p3d_accumulate_part")
             _launched(2)
+    if x_range is not None:
+        out = out[x0:x1].contiguous()
     return _ret(out, as_tensor)
 
 

@@ -228,3 +228,34 @@ def test_part_carve_on_asymmetric_grids_vs_oracle(vc, oracle):
         want = oracle.part_carve(grid, sem, jobs)
         assert np.array_equal(got, want), (W, H)
         assert 0 < np.count_nonzero(want.any(-1)) < np.count_nonzero(grid.any(-1))   # the carve removed something
+
+
+def test_part_carve_x_slabs_tile_the_full_grid(vc, oracle):
+    """part_carve(..., x_range=(a, b)) -- the multi-GPU unit: every slab is computed from the whole input without
+    exchange and the slabs concatenate to the full result.  Random asymmetric grids (the clear pass has work), slab
+    borders inside and on 256-voxel tiles, a width whose bit rows are vector-aligned (512) and one that is not (288),
+    and a job list with a general angle (full computation + slice)."""
+    rng = np.random.default_rng(5)
+    names = ["full_building", "plinth", "dome", "front_minarets"]
+    for (W, H), cuts, jobs in (((512, 3), (0, 100, 256, 300, 512), [([n], 90) for n in names]),
+                               ((288, 4), (0, 1, 33, 287, 288), [([n], 90) for n in names]),
+                               ((64, 9), (0, 20, 64), [([n], 90) for n in names]),
+                               ((32, 6), (0, 7, 32), [(["dome"], 45), (["plinth"], 90)])):
+        sem = np.empty((H, W, 3), np.uint8)
+        sem[:] = oracle.PART_COLORS["background"]
+        lab = np.full((H, W), 2)
+        lab[:, :3] = 0
+        lab[H // 2:, W // 2:] = 3
+        lab[0, ::5] = 1
+        for k, n in enumerate(names):
+            sem[lab == k + 1] = oracle.PART_COLORS[n]
+        grid = np.zeros((W, H, W, 3), np.uint8)
+        occ = rng.random((W, H, W)) < 0.6
+        grid[occ] = sem.transpose(1, 0, 2)[:, :, None, :].repeat(W, axis=2)[occ]
+        full = vc.part_carve(grid, sem, jobs)
+        assert np.array_equal(full, oracle.part_carve(grid, sem, jobs)), (W, H)
+        slabs = [vc.part_carve(grid, sem, jobs, x_range=(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert [s.shape[0] for s in slabs] == [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+        assert np.array_equal(np.concatenate(slabs, axis=0), full), (W, H)
+    with pytest.raises(ValueError):
+        vc.part_carve(grid, sem, jobs, x_range=(3, 99))

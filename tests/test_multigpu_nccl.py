@@ -1,5 +1,5 @@
 """The sharded paths over real NCCL (needs >= 2 GPUs on the box; skipped otherwise): candidate sweep, deformation sweep
-and slab-sharded global_carve with all-gather, each against the single-GPU result of the same call."""
+and slab-sharded global_carve / part_carve with all-gather, each against the single-GPU result of the same call."""
 import os
 import socket
 
@@ -37,8 +37,11 @@ def _worker(rank, world, port, out_dir):
     cg = np.load(os.path.join(GOLDEN, "carve_golden.npz"))
     binm, ext = cg["syn_rect40x64_bin"], cg["syn_rect40x64_ext"]
     full, _ = sw.carve_sharded(lambda a, b: vc.global_carve(binm, ext, 90, return_tensor=True, x_range=(a, b)), binm.shape[1], gather=True)
+    from helpers import GROUP_JOBS
+    # part_carve by output x-slab from the replicated global_carve grid (live-reference golden vector), no exchange
+    pc, _ = sw.carve_sharded(lambda a, b: vc.part_carve(full, ext, GROUP_JOBS, x_range=(a, b)), binm.shape[1], gather=True)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), best_s=best_s, best_i=best_i, scores=scores, d_iou=d_iou, d_i=d_i,
-             d_local=d_local, d_lo=d_span[0], carve=full.cpu().numpy())
+             d_local=d_local, d_lo=d_span[0], carve=full.cpu().numpy(), partcarve=pc.cpu().numpy())
     dist.destroy_process_group()
 
 
@@ -71,4 +74,5 @@ def test_sharded_paths_over_nccl(tmp_path, carve_golden):
         got_ious[int(z["d_lo"]):int(z["d_lo"]) + len(z["d_local"])] = z["d_local"]
         assert int(z["d_i"]) == int(np.argmax(want_ious)) and float(z["d_iou"]) == want_ious.max()
         assert np.array_equal(z["carve"], carve_golden["syn_rect40x64_global"])
+        assert np.array_equal(z["partcarve"], carve_golden["syn_rect40x64_partcarve"])
     assert np.array_equal(got_ious, want_ious)
