@@ -322,6 +322,15 @@ int p3d_part_carve_fold_bits_slab(const uint8_t* grid, int W, int H, int D, int 
                                   const uint32_t* inside_bits, int c, int c2, const uint32_t* group_mask_hw,
                                   int n_groups, uint8_t* out_slab, void* workspace, size_t workspace_bytes,
                                   p3d_stream_t stream);
+/* The same slab carve with a SHARDED input (every rank holds only its x slab): pass A writes out_slab and the slab's
+ * rows of the z-packed occupancy bits -- the first W*H*(D/32) uint32 of the workspace, [x][y][word], slab rows
+ * contiguous -- the ranks all-gather those rows (1/24 of the grid bytes; NCCL in utils/sweep.py), pass B clears the runs
+ * whose rotated source is empty.  pass_a + pass_b over [0, W) equal p3d_part_carve_fold_bits. */
+int p3d_part_carve_slab_pass_a(const uint8_t* grid_slab, int W, int H, int D, int x_begin, int x_count,
+                               const uint32_t* inside_bits, int c, const uint32_t* group_mask_hw, int n_groups,
+                               uint8_t* out_slab, void* workspace, size_t workspace_bytes, p3d_stream_t stream);
+int p3d_part_carve_slab_pass_b(int W, int H, int D, int x_begin, int x_count, int c, int c2, uint8_t* out_slab,
+                               void* workspace, size_t workspace_bytes, p3d_stream_t stream);
 
 /* Building blocks of the general-angle part_carve and of left_right_guided_carve :163-210. */
 int p3d_crop_occupancy(const uint8_t* grid, int W, int H, int D, int x0, int y0, int z0, int w, int h, int d,

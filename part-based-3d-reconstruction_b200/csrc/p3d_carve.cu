@@ -486,7 +486,8 @@ __global__ void __launch_bounds__(256)
 part_copy_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const uint32_t* __restrict__ inside_bits,
                       int c, const uint32_t* __restrict__ gm_hw, const uint32_t* __restrict__ gbits, int xwp,
                       uint32_t* __restrict__ occz, uint32_t* __restrict__ alive, uint8_t* __restrict__ out,
-                      unsigned long long magic_gpr, unsigned long long magic_h, uint32_t g_begin, uint32_t g_end) {
+                      unsigned long long magic_gpr, unsigned long long magic_h, uint32_t g_begin, uint32_t g_end,
+                      uint32_t grid_g0 /* first group held by `grid`: 0 = whole grid, g_begin = the slab only */) {
   // groups [g_begin, g_end) of the full grid (an x slab, multiples of 32 groups since D % 32 == 0 ... H * D/16 even);
   // `out` starts at the slab's first voxel; occz == nullptr: the caller already has the input's occupancy bits
   const uint32_t gpr = (uint32_t)D >> 4;                    // thread groups per z-row
@@ -495,6 +496,7 @@ part_copy_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, con
   const int lane = threadIdx.x & 31;
   const uint32_t stride = gridDim.x * blockDim.x;
   out -= (size_t)g_begin * 48;                              // 16 voxels x 3 bytes per group
+  grid -= (size_t)grid_g0 * 48;
   for (uint32_t wb = g_begin + blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wb < groups; wb += stride) {
     const uint32_t g = wb + lane;
     const bool in = g < groups;
@@ -1395,7 +1397,7 @@ P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, c
   // 256: 0.135; capping the residency below 8 CTAs per SM costs 10 %
   static const int pcb_waves = [] { const char* e = getenv("P3D_PCB_WAVES"); const int v = e ? atoi(e) : 256; return v > 0 ? v : 256; }();
   part_copy_bits_kernel<<<grid_for(n16, 256, pcb_waves), 256, 0, st>>>(grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp,
-                                                              occz, alive, out, magic_gpr, magic_h, 0u, (uint32_t)n16);
+                                                              occz, alive, out, magic_gpr, magic_h, 0u, (uint32_t)n16, 0u);
   const int64_t tasks = (int64_t)H * ((D / 32 + kClearZW - 1) / kClearZW) * ((W + kClearX - 1) / kClearX);
   part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out, 0, W);
   P3D_LAUNCH_CHECK();
@@ -1443,9 +1445,70 @@ P3D_API int p3d_part_carve_fold_bits_slab(const uint8_t* grid, int W, int H, int
   const int64_t gps = (int64_t)H * (D / 16);                   // groups per x plane
   const uint32_t g_begin = (uint32_t)(x_begin * gps), g_end = (uint32_t)((x_begin + x_count) * gps);
   part_copy_bits_kernel<<<grid_for((int64_t)x_count * gps, 256, 256), 256, 0, st>>>(
-      grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp, nullptr, alive, out_slab, magic_gpr, magic_h, g_begin, g_end);
+      grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp, nullptr, alive, out_slab, magic_gpr, magic_h, g_begin, g_end, 0u);
   const int64_t tasks = (int64_t)H * ((words + kClearZW - 1) / kClearZW) * ((x_count + kClearX - 1) / kClearX);
   part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out_slab, x_begin, x_count);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// The same slab carve with a SHARDED input: every rank holds only its x slab of the grid.  Pass A writes the slab's
+// output and its rows of the z-packed occupancy / alive bits; the ranks then exchange the occupancy rows (the first
+// W*H*(D/32) uint32 of the workspace, [x][y][word], slab rows contiguous: one all-gather, 1/24 of the grid bytes) and pass
+// B clears the runs whose rotated source is empty.
+P3D_API int p3d_part_carve_slab_pass_a(const uint8_t* grid_slab, int W, int H, int D, int x_begin, int x_count,
+                                       const uint32_t* inside_bits, int c, const uint32_t* group_mask_hw, int n_groups,
+                                       uint8_t* out_slab, void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0 && n_groups >= 1 && n_groups <= 32, "part_carve_slab_pass_a: bad shape");
+  P3D_REQUIRE(x_begin >= 0 && x_count >= 0 && x_begin + x_count <= W, "part_carve_slab_pass_a: bad x slab");
+  if (x_count == 0) return P3D_OK;
+  P3D_REQUIRE(grid_slab && inside_bits && group_mask_hw && out_slab && workspace && grid_slab != out_slab,
+              "part_carve_slab_pass_a: null/aliased");
+  P3D_REQUIRE(((reinterpret_cast<uintptr_t>(grid_slab) | reinterpret_cast<uintptr_t>(out_slab)) & 15) == 0,
+              "part_carve_slab_pass_a: grids must be 16-byte aligned");
+  if (workspace_bytes < p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups)) {
+    p3d::set_error("part_carve_slab_pass_a: workspace too small");
+    return P3D_E_WORKSPACE;
+  }
+  const int xwp = (W + 31) / 32 + 2;
+  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)(D / 32) * 4, 256);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint32_t* occz = reinterpret_cast<uint32_t*>(ws);
+  uint32_t* alive = reinterpret_cast<uint32_t*>(ws + zbits);
+  uint32_t* gbits = reinterpret_cast<uint32_t*>(ws + 2 * zbits);
+  cudaStream_t st = p3d::as_stream(stream);
+  pack_group_bits_kernel<<<grid_for((int64_t)H * xwp, 8, 32), 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
+  const int64_t n16 = (int64_t)W * H * D / 16;
+  P3D_REQUIRE(n16 < (1ll << 31), "part_carve_slab_pass_a: grid too large for 32-bit group indices");
+  const unsigned long long magic_gpr = magic_for((uint64_t)n16, (uint64_t)D / 16);
+  const unsigned long long magic_h = magic_for((uint64_t)W * H, (uint64_t)H);
+  const int64_t gps = (int64_t)H * (D / 16);
+  const uint32_t g_begin = (uint32_t)(x_begin * gps), g_end = (uint32_t)((x_begin + x_count) * gps);
+  part_copy_bits_kernel<<<grid_for((int64_t)x_count * gps, 256, 256), 256, 0, st>>>(
+      grid_slab, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp, occz, alive, out_slab, magic_gpr, magic_h, g_begin, g_end,
+      g_begin);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_part_carve_slab_pass_b(int W, int H, int D, int x_begin, int x_count, int c, int c2, uint8_t* out_slab,
+                                       void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0, "part_carve_slab_pass_b: bad shape");
+  P3D_REQUIRE(x_begin >= 0 && x_count >= 0 && x_begin + x_count <= W, "part_carve_slab_pass_b: bad x slab");
+  if (x_count == 0) return P3D_OK;
+  P3D_REQUIRE(out_slab && workspace, "part_carve_slab_pass_b: null pointer");
+  const int words = D / 32;
+  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)words * 4, 256);
+  if (workspace_bytes < 2 * zbits) {
+    p3d::set_error("part_carve_slab_pass_b: workspace too small");
+    return P3D_E_WORKSPACE;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const uint32_t* occz = reinterpret_cast<const uint32_t*>(ws);
+  const uint32_t* alive = reinterpret_cast<const uint32_t*>(ws + zbits);
+  const int64_t tasks = (int64_t)H * ((words + kClearZW - 1) / kClearZW) * ((x_count + kClearX - 1) / kClearX);
+  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, p3d::as_stream(stream)>>>(W, H, D, c, c2, occz, alive, out_slab,
+                                                                                  x_begin, x_count);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

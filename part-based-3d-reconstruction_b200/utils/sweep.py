@@ -155,3 +155,22 @@ def carve_sharded(carve_slab, W: int, group=None, gather: bool = False):
     dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
     full = torch.cat([out[r * width:r * width + (b - a)] for r, (a, b) in enumerate(spans)], dim=0)
     return full, (0, W)
+
+
+def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None):
+    """part_carve of a grid whose x rows are sharded over the ranks (rank r holds rows shard_range(W, world, r); W must
+    divide evenly): pass A per slab, ONE all-gather of the slabs' occupancy bits (W*H*D/8 bytes in total, 1/24 of the RGB
+    grid; NCCL on GPUs), pass B per slab.  Returns (output slab, (x0, x1)).  The exchange is real: the fold of
+    voxel_carving_utils.py:139-160 reads occ[W - z, y, x], the x<->z transposed source."""
+    from . import voxel_carving_utils as vc
+    inited = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if inited else 1
+    rank = dist.get_rank(group) if inited else 0
+    if W % world:
+        raise ValueError(f"part_carve_sharded: width {W} does not divide over {world} ranks")
+    x0, x1 = shard_range(W, world, rank)
+    job = vc.PartCarveSlab(grid_slab, semantic_mask, group_jobs, W, (x0, x1)).begin()
+    if world > 1:
+        mine = job.occ[x0:x1].clone()
+        dist.all_gather_into_tensor(job.occ.view(-1), mine.view(-1), group=group)
+    return job.finish(), (x0, x1)

@@ -365,6 +365,73 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_ra
     return _ret(out, as_tensor)
 
 
+class PartCarveSlab:
+    """part_carve of ONE x slab of a grid whose rows are sharded over ranks (addition; the reference is single process,
+    voxel_carving_utils.py:139-160).  begin(): pass A on this rank's rows (output from the voxel-local terms + the rows'
+    occupancy bits); `occ` is the occupancy-bit array of the WHOLE grid, (W, H, D/32) int32, of which only rows
+    [x0, x1) are filled -- the caller fills the other rows from the other ranks (utils.sweep.part_carve_sharded: one NCCL
+    all-gather, 1/24 of the grid bytes); finish(): pass B clears the runs whose rotated source is empty and returns the
+    (x1-x0, H, D, 3) output slab.  Only the all-90-degree bit path can be sharded this way (ValueError otherwise: carve
+    a replicated grid with part_carve(..., x_range=...) instead)."""
+
+    def __init__(self, grid_slab, semantic_mask, group_jobs, W, x_range):
+        self.as_tensor = _is_tensor(grid_slab)
+        dev = nv.require_cuda(grid_slab.device if self.as_tensor and grid_slab.is_cuda else None)
+        self.grid = _to_dev_u8(grid_slab, dev, "grid_slab")
+        self.x0, self.x1 = int(x_range[0]), int(x_range[1])
+        n, H, D, _ = self.grid.shape
+        self.W, self.H, self.D = int(W), int(H), int(D)
+        if not (0 <= self.x0 <= self.x1 <= self.W) or n != self.x1 - self.x0:
+            raise ValueError(f"slab of {n} rows does not match x_range {x_range} of width {W}")
+        semantic_mask = semantic_mask if isinstance(semantic_mask, _PackedMask) else _PackedMask(semantic_mask)
+        jobs = []
+        for names, angle in group_jobs:
+            m2d = _mask2d_bool(semantic_mask, [PART_COLORS[nm] for nm in names])
+            if m2d.any():
+                jobs.append((m2d, angle))
+        ok = bool(jobs) and all(a == 90 for _, a in jobs) and len(jobs) <= 32 and D == W and D % 32 == 0
+        bits = None
+        if ok:
+            M, off = _pass_transform((W, H, D), 90)
+            table, foldable = _fold_table(W, D, M, off, dev)
+            M0, off0 = _pass_transform((W, H, D), 0)
+            ok = foldable and np.array_equal(M0, np.eye(3)) and not off0.any()
+            if ok:
+                bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev)))
+                ok = bits is not None and bits[2] is not None
+        if not ok:
+            raise ValueError("sharded-input part_carve needs the all-90-degree bit path (cubic grid, D % 32 == 0, at "
+                             "least one non-empty group); carve a replicated grid with part_carve(..., x_range=...)")
+        gm = np.zeros((H, W), np.uint32)
+        for g, (m2d, _) in enumerate(jobs):
+            sel = (m2d & m2d.T) if W == H else m2d
+            gm |= sel.astype(np.uint32) << np.uint32(g)
+        self.gm_hw = torch.from_numpy(gm.view(np.int32)).to(dev)
+        self.bits, self.n_groups = bits, len(jobs)
+        self.ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        words = D // 32
+        self.occ = self.ws[:W * H * words * 4].view(torch.int32).view(W, H, words)
+        self.out = torch.empty_like(self.grid)
+
+    def begin(self):
+        if self.x1 > self.x0:
+            check(lib.p3d_part_carve_slab_pass_a(ptr(self.grid), self.W, self.H, self.D, self.x0, self.x1 - self.x0,
+                                                 ptr(self.bits[0]), self.bits[1], ptr(self.gm_hw), self.n_groups,
+                                                 ptr(self.out), ptr(self.ws), self.ws_bytes, stream_ptr()),
+                  "p3d_part_carve_slab_pass_a")
+            _launched(2)
+        return self
+
+    def finish(self):
+        if self.x1 > self.x0:
+            check(lib.p3d_part_carve_slab_pass_b(self.W, self.H, self.D, self.x0, self.x1 - self.x0, self.bits[1],
+                                                 self.bits[2], ptr(self.out), ptr(self.ws), self.ws_bytes, stream_ptr()),
+                  "p3d_part_carve_slab_pass_b")
+            _launched()
+        return _ret(self.out, self.as_tensor)
+
+
 def _label_components(mask_u8):
     """scipy.ndimage.label (6-connectivity) on device: (labels int32, n, bbox (n,6) ndarray, sums (n,4) ndarray)."""
     n0, n1, n2 = mask_u8.shape

@@ -259,3 +259,30 @@ def test_part_carve_x_slabs_tile_the_full_grid(vc, oracle):
         assert np.array_equal(np.concatenate(slabs, axis=0), full), (W, H)
     with pytest.raises(ValueError):
         vc.part_carve(grid, sem, jobs, x_range=(3, 99))
+
+
+def test_part_carve_sharded_input_two_slabs_emulated(vc, oracle):
+    """PartCarveSlab: each 'rank' sees only its rows of the grid; the occupancy rows are exchanged by hand here (the
+    all-gather of utils.sweep.part_carve_sharded) and the two output slabs concatenate to the oracle's part_carve."""
+    rng = np.random.default_rng(9)
+    names = ["full_building", "plinth", "dome", "front_minarets"]
+    jobs = [([n], 90) for n in names]
+    for (W, H), cut in (((64, 7), 32), ((512, 2), 256), ((96, 5), 40)):
+        sem = np.empty((H, W, 3), np.uint8)
+        sem[:] = oracle.PART_COLORS["background"]
+        lab = np.full((H, W), 2)
+        lab[:, :3] = 0
+        lab[H // 2:, W // 2:] = 3
+        for k, n in enumerate(names):
+            sem[lab == k + 1] = oracle.PART_COLORS[n]
+        grid = np.zeros((W, H, W, 3), np.uint8)
+        occ = rng.random((W, H, W)) < 0.6
+        grid[occ] = sem.transpose(1, 0, 2)[:, :, None, :].repeat(W, axis=2)[occ]
+        a = vc.PartCarveSlab(np.ascontiguousarray(grid[:cut]), sem, jobs, W, (0, cut)).begin()
+        b = vc.PartCarveSlab(np.ascontiguousarray(grid[cut:]), sem, jobs, W, (cut, W)).begin()
+        a.occ[cut:] = b.occ[cut:]
+        b.occ[:cut] = a.occ[:cut]
+        got = np.concatenate([a.finish(), b.finish()], axis=0)
+        assert np.array_equal(got, oracle.part_carve(grid, sem, jobs)), (W, H)
+    with pytest.raises(ValueError):
+        vc.PartCarveSlab(np.ascontiguousarray(grid[:cut]), sem, [(["dome"], 45)], W, (0, cut))

@@ -40,8 +40,12 @@ def _worker(rank, world, port, out_dir):
     from helpers import GROUP_JOBS
     # part_carve by output x-slab from the replicated global_carve grid (live-reference golden vector), no exchange
     pc, _ = sw.carve_sharded(lambda a, b: vc.part_carve(full, ext, GROUP_JOBS, x_range=(a, b)), binm.shape[1], gather=True)
+    # ... and with the INPUT sharded as well: each rank passes only its rows, one all-gather of occupancy bits
+    a, b = sw.shard_range(binm.shape[1], world, rank)
+    ps, _ = sw.part_carve_sharded(full[a:b].contiguous(), ext, GROUP_JOBS, binm.shape[1])
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), best_s=best_s, best_i=best_i, scores=scores, d_iou=d_iou, d_i=d_i,
-             d_local=d_local, d_lo=d_span[0], carve=full.cpu().numpy(), partcarve=pc.cpu().numpy())
+             d_local=d_local, d_lo=d_span[0], carve=full.cpu().numpy(), partcarve=pc.cpu().numpy(),
+             partcarve_slab=ps.cpu().numpy(), slab=np.array([a, b]))
     dist.destroy_process_group()
 
 
@@ -75,4 +79,6 @@ def test_sharded_paths_over_nccl(tmp_path, carve_golden):
         assert int(z["d_i"]) == int(np.argmax(want_ious)) and float(z["d_iou"]) == want_ious.max()
         assert np.array_equal(z["carve"], carve_golden["syn_rect40x64_global"])
         assert np.array_equal(z["partcarve"], carve_golden["syn_rect40x64_partcarve"])
+        a, b = (int(v) for v in z["slab"])
+        assert np.array_equal(z["partcarve_slab"], carve_golden["syn_rect40x64_partcarve"][a:b])
     assert np.array_equal(got_ious, want_ious)
