@@ -392,7 +392,7 @@ def time_launches(launch, reps=20, rounds=5, use_graph=True):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) stay free
             for _ in range(reps):
                 launch()
         graph = g
