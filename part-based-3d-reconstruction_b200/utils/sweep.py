@@ -157,19 +157,22 @@ def carve_sharded(carve_slab, W: int, group=None, gather: bool = False):
     return full, (0, W)
 
 
-def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None):
+def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None, slab_cls=None):
     """part_carve of a grid whose x rows are sharded over the ranks (rank r holds rows shard_range(W, world, r); W must
     divide evenly): pass A per slab, ONE all-gather of the slabs' occupancy bits (W*H*D/8 bytes in total, 1/24 of the RGB
     grid; NCCL on GPUs), pass B per slab.  Returns (output slab, (x0, x1)).  The exchange is real: the fold of
-    voxel_carving_utils.py:139-160 reads occ[W - z, y, x], the x<->z transposed source."""
-    from . import voxel_carving_utils as vc
+    voxel_carving_utils.py:139-160 reads occ[W - z, y, x], the x<->z transposed source.  `slab_cls` replaces
+    voxel_carving_utils.PartCarveSlab (same begin / occ / finish interface) in the CPU tests of this plumbing."""
+    if slab_cls is None:
+        from . import voxel_carving_utils as vc
+        slab_cls = vc.PartCarveSlab
     inited = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if inited else 1
     rank = dist.get_rank(group) if inited else 0
     if W % world:
         raise ValueError(f"part_carve_sharded: width {W} does not divide over {world} ranks")
     x0, x1 = shard_range(W, world, rank)
-    job = vc.PartCarveSlab(grid_slab, semantic_mask, group_jobs, W, (x0, x1)).begin()
+    job = slab_cls(grid_slab, semantic_mask, group_jobs, W, (x0, x1)).begin()
     if world > 1:
         mine = job.occ[x0:x1].clone()
         dist.all_gather_into_tensor(job.occ.view(-1), mine.view(-1), group=group)

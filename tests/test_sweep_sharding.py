@@ -170,3 +170,61 @@ def test_sharded_deformation_sweep_gloo(tmp_path, world, D):
     for r in range(world):
         z = np.load(tmp_path / f"d{r}.npz")
         assert int(z["best_i"]) == want and float(z["best_iou"]) == full[want]
+
+
+class OraclePartCarveSlab:
+    """Stand-in for voxel_carving_utils.PartCarveSlab on CPU: begin() packs the occupancy bits of this rank's rows,
+    finish() rebuilds a full grid from the gathered bits (other ranks' rows only need their occupancy: the reference
+    selects a group's voxels with the 2-D mask, voxel_carving_utils.py:143-152) and slices the oracle's part_carve."""
+
+    def __init__(self, grid_slab, semantic_mask, group_jobs, W, x_range):
+        import torch
+        self.rows, self.sem, self.jobs, self.W = np.asarray(grid_slab), semantic_mask, group_jobs, W
+        self.x0, self.x1 = x_range
+        _, self.H, self.D, _ = self.rows.shape
+        self.occ = torch.zeros((W, self.H, self.D // 32), dtype=torch.int32)
+
+    def begin(self):
+        import torch
+        bits = np.packbits(self.rows.any(-1), axis=-1, bitorder="little")                  # (rows, H, D/8) uint8
+        self.occ[self.x0:self.x1] = torch.from_numpy(bits.view(np.int32).reshape(self.x1 - self.x0, self.H, self.D // 32).copy())
+        return self
+
+    def finish(self):
+        from oracle import oracle as orc
+        occ = np.unpackbits(self.occ.numpy().view(np.uint8).reshape(self.W, self.H, self.D // 8), axis=-1, bitorder="little")
+        full = np.zeros((self.W, self.H, self.D, 3), np.uint8)
+        full[occ.astype(bool)] = 1
+        full[self.x0:self.x1] = self.rows
+        return orc.part_carve(full, self.sem, self.jobs)[self.x0:self.x1]
+
+
+def _part_carve_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helpers import GROUP_JOBS
+    sw = pkg("utils.sweep")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "carve_golden.npz"))
+    grid, ext = g["syn_rect40x64_global"], g["syn_rect40x64_ext"]
+    a, b = sw.shard_range(grid.shape[0], world, rank)
+    slab, span = sw.part_carve_sharded(np.ascontiguousarray(grid[a:b]), ext, GROUP_JOBS, grid.shape[0], slab_cls=OraclePartCarveSlab)
+    assert span == (a, b)
+    np.savez(os.path.join(out_dir, f"p{rank}.npz"), slab=slab, a=a, b=b)
+    if world == 2:
+        with pytest.raises(ValueError):
+            sw.part_carve_sharded(np.ascontiguousarray(grid[:31]), ext, GROUP_JOBS, 63, slab_cls=OraclePartCarveSlab)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_part_carve_sharded_gloo(tmp_path, world, carve_golden):
+    """Host logic of the sharded-input part_carve (slab ranges, ONE all-gather of occupancy bits into the full bit array,
+    the divisibility rule) over gloo with an oracle-backed slab; the CUDA slab passes are covered by the GPU tests."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_part_carve_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    want = carve_golden["syn_rect40x64_partcarve"]
+    for r in range(world):
+        z = np.load(tmp_path / f"p{r}.npz")
+        assert np.array_equal(z["slab"], want[int(z["a"]):int(z["b"])])
