@@ -53,6 +53,12 @@ def test_product_fails_loudly_without_cuda():
     with pytest.raises(nv.P3DError):
         pu.project_colored_voxels(np.zeros((1, 3), np.float32), np.zeros((1, 3), np.uint8), np.zeros(3), np.ones(3),
                                   1.0, 0.0, 0.0, 4, 4)
+    vc = pkg("utils.voxel_carving_utils")
+    sem = np.zeros((4, 32, 3), np.uint8)
+    with pytest.raises(nv.P3DError):
+        vc.part_carve(np.zeros((32, 4, 32, 3), np.uint8), sem, [(["dome"], 90)], x_range=(0, 16))
+    with pytest.raises(nv.P3DError):
+        vc.PartCarveSlab(np.zeros((16, 4, 32, 3), np.uint8), sem, [(["dome"], 90)], 32, (0, 16))
 
 
 def test_product_never_imports_the_oracle():
