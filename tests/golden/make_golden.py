@@ -597,8 +597,35 @@ def depth_golden():
     np.savez_compressed(os.path.join(HERE, "depth_golden.npz"), **out)
 
 
+def partcarve_asym_golden():
+    """part_carve (voxel_carving_utils.py:139-160) of grids that are NOT 4-way symmetric: the inputs on which the rotated
+    source occupancy decides (global_carve's output never is).  Random sparse grids coloured column-wise from a blocky
+    semantic image, every notebook group at 90 degrees, through the live reference."""
+    out = {}
+    rng = np.random.default_rng(SEED + 17)
+    cases = [("w32h8", 32, 8, 0.55), ("w64h7", 64, 7, 0.6), ("w32h32", 32, 32, 0.5), ("w96h6", 96, 6, 0.65)]
+    for tag, W, H, p in cases:
+        sem = blocky_semantic(rng, H, W, False)
+        ext = sem.copy()
+        for q in C.INTERIOR_PARTS:
+            ext[np.all(sem == C.PART_COLORS_NP[q], axis=-1)] = C.PART_COLORS_NP["full_building"]
+        occ = rng.random((W, H, W)) < p
+        grid = np.zeros((W, H, W, 3), np.uint8)
+        grid[occ] = ext.transpose(1, 0, 2)[:, :, None, :].repeat(W, axis=2)[occ]
+        bg = np.all(grid == C.PART_COLORS_NP["background"], axis=-1)
+        grid[bg] = 0                                                   # background columns carry no voxels
+        pc = ref.vc.part_carve(grid, ext, GROUP_JOBS)
+        key = "asym_" + tag
+        out[key + "_ext"], out[key + "_grid"], out[key + "_partcarve"] = ext, grid, pc
+        n_in, n_out = np.count_nonzero(grid.any(-1)), np.count_nonzero(pc.any(-1))
+        assert 0 < n_out < n_in
+        print(key, grid.shape, n_in, n_out)
+    out["asym_cases"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(HERE, "partcarve_asym_golden.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth", "deform", "init", "handoff", "tables"]
+    which = sys.argv[1:] or ["assets", "camera", "carve", "aligner", "depth", "deform", "init", "handoff", "tables", "partcarve_asym"]
     if "assets" in which:
         copy_assets()
     if "camera" in which:
@@ -617,6 +644,8 @@ if __name__ == "__main__":
         handoff_golden()
     if "tables" in which:
         tables_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz", "handoff_golden.npz", "tables_golden.npz"):
+    if "partcarve_asym" in which:
+        partcarve_asym_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz", "handoff_golden.npz", "tables_golden.npz", "partcarve_asym_golden.npz"):
         if os.path.exists(os.path.join(HERE, f)):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

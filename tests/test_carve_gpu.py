@@ -286,3 +286,25 @@ def test_part_carve_sharded_input_two_slabs_emulated(vc, oracle):
         assert np.array_equal(got, oracle.part_carve(grid, sem, jobs)), (W, H)
     with pytest.raises(ValueError):
         vc.PartCarveSlab(np.ascontiguousarray(grid[:cut]), sem, [(["dome"], 45)], W, (0, cut))
+
+
+def test_part_carve_asymmetric_golden_full_and_slabs(vc):
+    """The live reference's part_carve of asymmetric grids (tests/golden/partcarve_asym_golden.npz): the full call, the
+    replicated-input slabs and the sharded-input slab pair all reproduce it byte for byte."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "partcarve_asym_golden.npz"))
+    for tag in g["asym_cases"]:
+        key = f"asym_{tag}"
+        grid, ext, want = g[key + "_grid"], g[key + "_ext"], g[key + "_partcarve"]
+        W = grid.shape[0]
+        assert np.array_equal(vc.part_carve(grid, ext, GROUP_JOBS), want), tag
+        cut = W // 2 + 3
+        slabs = [vc.part_carve(grid, ext, GROUP_JOBS, x_range=r) for r in ((0, cut), (cut, W))]
+        assert np.array_equal(np.concatenate(slabs, axis=0), want), tag
+        if W % 32 == 0:
+            a = vc.PartCarveSlab(np.ascontiguousarray(grid[:cut]), ext, GROUP_JOBS, W, (0, cut)).begin()
+            b = vc.PartCarveSlab(np.ascontiguousarray(grid[cut:]), ext, GROUP_JOBS, W, (cut, W)).begin()
+            a.occ[cut:] = b.occ[cut:]
+            b.occ[:cut] = a.occ[:cut]
+            assert np.array_equal(np.concatenate([a.finish(), b.finish()], axis=0), want), tag

@@ -153,3 +153,15 @@ def test_per_part_scoring_core(oracle, camera_golden, taj):
     cg = np.any(img != np.array(oracle.PART_COLORS["background"], np.uint8), axis=-1)
     rows.append(((cg & comb).sum(), (cg | comb).sum()))
     assert np.array_equal(np.array(rows, np.int64), g["taj_front_perpart_counts"])
+
+
+def test_part_carve_on_asymmetric_grids_matches_live_reference(oracle):
+    """tests/golden/partcarve_asym_golden.npz (make_golden.py partcarve_asym): the live reference's part_carve of grids
+    that are not 4-way symmetric -- the inputs on which the rotated source occupancy decides a voxel's fate.  Pins the
+    oracle on the branch the GPU clear pass / slab passes are tested against."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "partcarve_asym_golden.npz"))
+    for tag in g["asym_cases"]:
+        key = f"asym_{tag}"
+        assert np.array_equal(oracle.part_carve(g[key + "_grid"], g[key + "_ext"], GROUP_JOBS), g[key + "_partcarve"]), tag
