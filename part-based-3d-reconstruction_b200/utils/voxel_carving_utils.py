@@ -280,6 +280,18 @@ def apply_colored_mask_to_voxel_grid(carved_voxel_grid, colored_mask):
     return _ret(out, as_tensor)
 
 
+def _group_image(jobs, H, W):
+    """(H,W) uint32: bit g where the pixel is in group g's mask m AND in _mask_to_wh(m) -- m itself for W != H, m.T for a
+    square image (the reference's quirk), i.e. m & m.T there; bit g of (gm & gm.T) is exactly that, so the square case
+    costs one transpose for all groups."""
+    gm = np.zeros((H, W), np.uint32)
+    for g, (m2d, _) in enumerate(jobs):
+        gm |= m2d.view(np.uint8).astype(np.uint32) << np.uint32(g)
+    if W == H:
+        gm &= np.ascontiguousarray(gm.T)
+    return gm
+
+
 def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_range=None):
     """voxel_carving_utils.py:139-160: per part group, carve the group's voxels with the group's own mask under
     the group's symmetry angle and merge the survivors.
@@ -312,11 +324,7 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_ra
         if foldable and identity0:
             # group image in (H,W): bit g where pixel is in m AND in _mask_to_wh(m) -- m itself for W != H, m.T for a
             # square image (the quirk), i.e. m2d & m2d.T there
-            gm = np.zeros((H, W), np.uint32)
-            for g, (m2d, _) in enumerate(jobs):
-                sel = (m2d & m2d.T) if W == H else m2d
-                gm |= sel.astype(np.uint32) << np.uint32(g)
-            gm_hw = torch.from_numpy(gm.view(np.int32)).to(dev)
+            gm_hw = torch.from_numpy(_group_image(jobs, H, W).view(np.int32)).to(dev)
             bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
             if x_range is not None and bits is not None and bits[2] is not None and x1 > x0:
                 ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
@@ -402,11 +410,7 @@ class PartCarveSlab:
         if not ok:
             raise ValueError("sharded-input part_carve needs the all-90-degree bit path (cubic grid, D % 32 == 0, at "
                              "least one non-empty group); carve a replicated grid with part_carve(..., x_range=...)")
-        gm = np.zeros((H, W), np.uint32)
-        for g, (m2d, _) in enumerate(jobs):
-            sel = (m2d & m2d.T) if W == H else m2d
-            gm |= sel.astype(np.uint32) << np.uint32(g)
-        self.gm_hw = torch.from_numpy(gm.view(np.int32)).to(dev)
+        self.gm_hw = torch.from_numpy(_group_image(jobs, H, W).view(np.int32)).to(dev)
         self.bits, self.n_groups = bits, len(jobs)
         self.ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
