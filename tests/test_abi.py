@@ -70,3 +70,17 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "p3d_oracle" in src:
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_group_image_matches_the_per_group_formula():
+    """Host logic of part_carve: bit g of the group image = m_g & _mask_to_wh(m_g) (m_g.T for a square image, the
+    reference's quirk at voxel_carving_utils.py:19-28), built with one transpose for all groups."""
+    import numpy as np
+    vc = pkg("utils.voxel_carving_utils")
+    rng = np.random.default_rng(0)
+    for H, W in ((17, 17), (64, 64), (40, 64), (33, 48), (1, 1)):
+        jobs = [(rng.random((H, W)) < 0.4, 90) for _ in range(7)]
+        want = np.zeros((H, W), np.uint32)
+        for g, (m, _) in enumerate(jobs):
+            want |= ((m & m.T) if W == H else m).astype(np.uint32) << np.uint32(g)
+        assert np.array_equal(vc._group_image(jobs, H, W), want)
