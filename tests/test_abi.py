@@ -84,3 +84,19 @@ def test_group_image_matches_the_per_group_formula():
         for g, (m, _) in enumerate(jobs):
             want |= ((m & m.T) if W == H else m).astype(np.uint32) << np.uint32(g)
         assert np.array_equal(vc._group_image(jobs, H, W), want)
+
+
+def test_sweep_workspace_follows_the_batch_rule():
+    """p3d_sweep_workspace_bytes (host arithmetic only): one z-buffer set while all cameras fit the 128 MB floor, two
+    sets (double-buffered batches) of at most 512 MB each beyond it, never fewer than 16 cameras per set at 2048^2."""
+    nv = pkg("utils._native")
+    ws = lambda K, H, W: int(nv.lib.p3d_sweep_workspace_bytes(K, H, W, 9, 8))
+    mb = 1 << 20
+    per = 1024 * 1024 * 4
+    small = ws(32, 1024, 1024)                       # 32 cameras = the floor at 1024^2: one set of 32
+    assert 32 * per <= small < 32 * per + 2 * mb
+    big = ws(65536, 1024, 1024)                      # two sets of 128 cameras (512 MB each) + per-camera blocks
+    assert 2 * 128 * per <= big < 2 * 128 * per + 64 * mb
+    assert ws(33, 1024, 1024) >= 2 * 33 * per        # just above the floor: two sets, capacity limited by K
+    huge = ws(4096, 2048, 2048)                      # 2048^2: 16 cameras per set (268 MB, the floor rule), two sets
+    assert 2 * 16 * 4 * per <= huge < 2 * 32 * 4 * per + 8 * mb
