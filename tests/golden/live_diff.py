@@ -1,0 +1,143 @@
+"""Randomised differential run of the oracle against the LIVE reference (build container only; a tool, not a test --
+the test-suite stays hermetic and reads the committed fixtures).  Many more trials than the fixtures hold: every
+mismatch is printed and counted, the summary goes to stdout.
+
+    python tests/golden/live_diff.py [seed] [trials]  >  tests/golden/live_diff_r1.log
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import _live_reference                                   # noqa: E402
+ref = _live_reference.load()
+from oracle import oracle as orc                         # noqa: E402
+
+orc.build()
+seed = int(sys.argv[1]) if len(sys.argv) > 1 else 20240607
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+rng = np.random.default_rng(seed)
+C = ref.cfg
+names = [k for k in C.PART_COLORS if k != "background"]
+results = {}
+
+
+def tally(name, ok):
+    r = results.setdefault(name, [0, 0])
+    r[0] += 1
+    r[1] += 0 if ok else 1
+    if not ok:
+        print(f"MISMATCH {name} (trial {r[0]})")
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ---- camera path -----------------------------------------------------------------------------------------------
+for t in range(T * 4):
+    dt = np.float32 if t % 3 == 2 else np.float64
+    eye = (rng.normal(0, 50, 3)).astype(dt)
+    tgt = (rng.normal(0, 50, 3)).astype(dt)
+    if t % 11 == 0:
+        tgt = eye + np.array([0, rng.choice([-1, 1]) * rng.uniform(1, 80), 0], dtype=dt)      # |z.up| ~ 1 branch
+    tally("look_at_rotation", np.array_equal(orc.look_at_rotation(eye, tgt), ref.cg.look_at_rotation(eye, tgt)))
+for t in range(T):
+    dt = np.float32 if t % 3 == 2 else np.float64
+    n = int(rng.integers(1, 4000))
+    H, W = (int(v) for v in rng.integers(8, 160, 2))
+    size = rng.uniform(8, 200)
+    pts = rng.integers(0, int(size) + 1, (n, 3)).astype(np.float32)
+    cols = rng.integers(0, 256, (n, 3)).astype(np.uint8)
+    ctr = pts.mean(0)
+    eye = (ctr + rng.normal(0, 1, 3) * size * rng.choice([0.2, 1.5, 4.0])).astype(dt)
+    tgt = (ctr + rng.normal(0, 1, 3) * size * 0.2).astype(dt)
+    f, cx, cy = dt(rng.uniform(0.3, 4) * max(H, W)), dt(W / 2 + rng.normal(0, W / 3)), dt(H / 2 + rng.normal(0, H / 3))
+    a = orc.project_colored_voxels(pts, cols, eye, tgt, f, cx, cy, H, W)
+    b = ref.pu.project_colored_voxels(pts, cols, eye, tgt, f, cx, cy, H, W)
+    tally(f"project_colored_voxels[{np.dtype(dt).name}]", np.array_equal(a, b))
+    parts = list(rng.choice(names, size=int(rng.integers(1, 6)), replace=False))
+    pc = {p: C.PART_COLORS[p] for p in parts}
+    img_a = np.zeros((H, W, 3), np.uint8)
+    img_b = np.zeros((H, W, 3), np.uint8)
+    for im in (img_a, img_b):
+        lab = rng.integers(0, len(parts) + 2, (H, W))
+        for k, p in enumerate(parts):
+            im[lab == k + 1] = C.PART_COLORS[p]
+    da, ma = orc.compute_partwise_iou(img_a, img_b, pc)
+    db, mb = ref.ce.compute_partwise_iou(img_a, img_b, pc)
+    tally("compute_partwise_iou", da == db and ma == mb)
+    tally("mask_parts_from_image", np.array_equal(orc.mask_parts_from_image(img_a, C.PART_COLORS, parts),
+                                                  ref.mu.mask_parts_from_image(img_a, C.PART_COLORS, parts)))
+    g = np.zeros((int(rng.integers(2, 14)), int(rng.integers(2, 14)), int(rng.integers(2, 14)), 3), np.uint8)
+    lab = rng.integers(0, len(parts) + 2, g.shape[:3])
+    for k, p in enumerate(parts):
+        g[lab == k + 1] = C.PART_COLORS[p]
+    pa, ca = orc.get_voxel_points_by_parts(g, C.PART_COLORS, parts)
+    pb, cb = ref.vu.get_voxel_points_by_parts(g, C.PART_COLORS, parts)
+    tally("get_voxel_points_by_parts", np.array_equal(pa, pb) and np.array_equal(ca, cb) and pa.dtype == pb.dtype)
+
+# ---- carving path ----------------------------------------------------------------------------------------------
+for t in range(T):
+    W, H = int(rng.integers(3, 40)), int(rng.integers(2, 30))
+    D = W if t % 2 == 0 else int(rng.integers(3, 40))
+    vol = (rng.random((W, H, D)) < rng.uniform(0.2, 0.9)).astype(np.uint8)
+    mask = (rng.random((H, W)) < 0.7).astype(np.uint8)
+    interval = int(rng.choice([90, 45, 30, 60, 5, 13]))
+    with quiet():
+        b = ref.vc.process_voxel_grid(vol, mask, interval)
+    tally(f"process_voxel_grid[{interval}]", np.array_equal(orc.process_voxel_grid(vol, mask, interval), b))
+for t in range(T // 2):
+    H, W = int(rng.integers(8, 48)), int(rng.integers(8, 48))
+    if t % 4 == 0:
+        H = W
+    sem = np.empty((H, W, 3), np.uint8)
+    sem[:] = C.PART_COLORS["background"]
+    for _ in range(6):
+        p = rng.choice(names)
+        y0, x0 = int(rng.integers(0, H - 3)), int(rng.integers(0, W - 3))
+        sem[y0:y0 + int(rng.integers(2, H)), x0:x0 + int(rng.integers(2, W))] = C.PART_COLORS[p]
+    ext = sem.copy()
+    for q in C.INTERIOR_PARTS:
+        ext[np.all(sem == C.PART_COLORS_NP[q], axis=-1)] = C.PART_COLORS_NP["full_building"]
+    binm = (~np.all(ext == C.PART_COLORS_NP["background"], axis=-1)).astype(np.uint8)
+    ga = orc.global_carve(binm, ext, 90)
+    gb = ref.vc.global_carve(binm, ext, 90)
+    tally("global_carve", np.array_equal(ga, gb))
+    jobs = [([n], int(rng.choice([90, 90, 90, 45]))) for n in rng.choice(names, size=4, replace=False)]
+    # part_carve on a perturbed (no longer symmetric) grid
+    gp = gb.copy()
+    gp[rng.random(gp.shape[:3]) < 0.3] = 0
+    tally("part_carve", np.array_equal(orc.part_carve(gp, ext, jobs), ref.vc.part_carve(gp, ext, jobs)))
+    present = [n for n in names if np.all(gp == np.asarray(C.PART_COLORS[n], np.uint8), axis=-1).any()] or names
+    col = C.PART_COLORS[str(rng.choice(present))]
+    ang = int(rng.choice([5, 45, 60]))
+    buf_b, log_a = io.StringIO(), []
+    with contextlib.redirect_stdout(buf_b):
+        lb = ref.vc.left_right_guided_carve(gp, ext, col, angle=ang)
+    la = orc.left_right_guided_carve(gp, ext, col, angle=ang, log=log_a)
+    tally(f"left_right_guided_carve[{ang}]", np.array_equal(la, lb))
+    axis, direction = int(rng.choice([0, 2])), str(rng.choice(["+", "-"]))
+    Wg, Hg, Dg = gp.shape[:3]
+    m2 = rng.random((Hg, Wg)) < 0.3 if axis == 2 else rng.random((Hg, Dg)) < 0.3
+    depth = int(rng.integers(1, 9))
+    fill = None if t % 5 == 0 else (9, 8, 7)
+    tally("extrude_from_surface", np.array_equal(orc.extrude_from_surface(gp, m2, axis, direction, depth=depth, fill_color=fill),
+                                                 ref.vc.extrude_from_surface(gp, m2, axis, direction, depth=depth, fill_color=fill)))
+    k, sa = int(rng.integers(1, 4)), int(rng.choice([0, 2]))
+    tally("recolor_backward_components", np.array_equal(orc.recolor_backward_components(gp, col, (1, 2, 3), k=k, sort_axis=sa),
+                                                        ref.vc.recolor_backward_components(gp, col, (1, 2, 3), k=k, sort_axis=sa)))
+
+print("\nfunction                                   trials  mismatches")
+bad = 0
+for k in sorted(results):
+    n, m = results[k]
+    bad += m
+    print(f"{k:42s} {n:6d}  {m:6d}")
+print(f"\nseed {seed}; numpy {np.__version__}; total mismatches: {bad}")
+sys.exit(1 if bad else 0)
