@@ -133,6 +133,35 @@ for t in range(T // 2):
     tally("recolor_backward_components", np.array_equal(orc.recolor_backward_components(gp, col, (1, 2, 3), k=k, sort_axis=sa),
                                                         ref.vc.recolor_backward_components(gp, col, (1, 2, 3), k=k, sort_axis=sa)))
 
+# ---- next rows: depth-buffer visibility evaluator (eval_helpers_intra.py:134-190), hand-off points ----------------
+import importlib                                          # noqa: E402
+eh = importlib.import_module("utils.eval_helpers_intra")
+for t in range(max(4, T // 4)):
+    dt = np.float32 if t % 2 == 0 else np.float64
+    A0, A1, A2 = (int(v) for v in rng.integers(4, 14, 3))
+    parts = list(rng.choice(names, size=3, replace=False))
+    g = np.zeros((A0, A1, A2, 3), np.uint8)
+    lab = rng.integers(0, 6, (A0, A1, A2))
+    for k, p in enumerate(parts):
+        g[lab == k + 1] = C.PART_COLORS[p]
+    H, W = (int(v) for v in rng.integers(12, 48, 2))
+    ctr = np.array([A2, A1, A0]) / 2
+    cam = {"cam_pos": (ctr + rng.normal(0, 1, 3) * 4 + np.array([0, 0, -3.0 * max(A0, A1, A2)])).astype(dt),
+           "target": (ctr + rng.normal(0, 1, 3)).astype(dt), "f": float(rng.uniform(0.8, 2.5) * max(H, W)),
+           "cx": W / 2 + float(rng.normal(0, 3)), "cy": H / 2 + float(rng.normal(0, 3))}
+    zb = eh.compute_global_depth_buffer(g, cam, H, W)
+    za = orc.compute_global_depth_buffer(g, cam, H, W)
+    tally(f"compute_global_depth_buffer[{np.dtype(dt).name}]", np.array_equal(za, zb) and za.dtype == zb.dtype)
+    pts, _ = ref.vu.get_voxel_points_by_parts(g, C.PART_COLORS, parts[:1])
+    if len(pts):
+        eps = float(rng.choice([1e-3, 0.75]))
+        tally(f"project_part_visible[{np.dtype(dt).name}]", np.array_equal(orc.project_part_visible(pts, cam, zb, H, W, eps=eps),
+                                                                            eh.project_part_visible(pts, cam, zb, H, W, eps=eps)))
+    stride = int(rng.choice([1, 2, 3]))
+    pa, ca = orc.voxel_grid_to_points(g, stride=stride)[:2]
+    pb, cb = ref.vu.voxel_grid_to_points(g, stride=stride)[:2]
+    tally("voxel_grid_to_points", np.array_equal(pa, pb) and np.array_equal(ca, cb))
+
 print("\nfunction                                   trials  mismatches")
 bad = 0
 for k in sorted(results):
