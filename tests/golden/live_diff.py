@@ -133,6 +133,36 @@ for t in range(T // 2):
     tally("recolor_backward_components", np.array_equal(orc.recolor_backward_components(gp, col, (1, 2, 3), k=k, sort_axis=sa),
                                                         ref.vc.recolor_backward_components(gp, col, (1, 2, 3), k=k, sort_axis=sa)))
 
+# ---- the whole notebook-1 chain on random blocky masks (notebook jobs / symmetries / extrusion depths) ---------------
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import EXTRUSION_DEPTHS, GROUP_JOBS, PART_SYMMETRY     # noqa: E402
+for t in range(max(3, T // 6)):
+    H, W = int(rng.integers(24, 56)), int(rng.integers(24, 56))
+    if t % 3 == 0:
+        H = W
+    sem = np.empty((H, W, 3), np.uint8)
+    sem[:] = C.PART_COLORS["background"]
+    sem[H // 3:, W // 6: W - W // 6] = C.PART_COLORS["full_building"]
+    for _ in range(8):
+        p = rng.choice(names)
+        y0, x0 = int(rng.integers(0, H - 3)), int(rng.integers(0, W - 3))
+        sem[y0:y0 + int(rng.integers(2, H // 2)), x0:x0 + int(rng.integers(2, W // 2))] = C.PART_COLORS[p]
+    ext = sem.copy()
+    for q in C.INTERIOR_PARTS:
+        ext[np.all(sem == C.PART_COLORS_NP[q], axis=-1)] = C.PART_COLORS_NP["full_building"]
+    binm = (~np.all(ext == C.PART_COLORS_NP["background"], axis=-1)).astype(np.uint8)
+    gb = ref.vc.global_carve(binm, ext, 90)
+    recolor = bool(t % 2 == 0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        pb = ref.vc.partwise_carve(gb, ext, sem, C.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS,
+                                   recolor_back_minarets=recolor)
+    log_a = []
+    pa = orc.partwise_carve(gb, ext, sem, C.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS,
+                            recolor_back_minarets=recolor, log=log_a)
+    tally("partwise_carve", np.array_equal(pa, pb))
+    tally("partwise_carve printed log", "\n".join(log_a) == buf.getvalue().strip("\n"))
+
 # ---- next rows: depth-buffer visibility evaluator (eval_helpers_intra.py:134-190), hand-off points ----------------
 import importlib                                          # noqa: E402
 eh = importlib.import_module("utils.eval_helpers_intra")
