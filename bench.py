@@ -175,7 +175,7 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = nv.launch_count
-    nv.lib.p3d_sweep_timing_enable(1)
+    scorer.workspace.timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
     e0.record()
@@ -188,9 +188,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     wall1 = time.time()
     ms = e0.elapsed_time(e1)
-    splat_ms, splat_launches = ctypes.c_double(), ctypes.c_int()
-    nv.lib.p3d_sweep_timing_read(ctypes.byref(splat_ms), ctypes.byref(splat_launches))
-    nv.lib.p3d_sweep_timing_enable(0)
+    splat_ms_v, splat_launches_v = scorer.workspace.timing_read()
+    scorer.workspace.timing(False)
     launches = nv.launch_count - launches0 + args.steps * reducer.launches_per_reduce
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -235,9 +234,9 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (splat) --------------------------------------------------
     peak, peak_src = peaks()
     G = N ** 3
-    batch = -(-B * args.steps // max(1, splat_launches.value))       # cameras per splat launch, from the launch count
+    batch = -(-B * args.steps // max(1, splat_launches_v))       # cameras per splat launch, from the launch count
     alg_per_launch = batch * (G * 1 + 9 * H * W)
-    avg_launch_s = (splat_ms.value / max(1, splat_launches.value)) * 1e-3
+    avg_launch_s = (splat_ms_v / max(1, splat_launches_v)) * 1e-3
     achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
     traffic = None
     try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same batch size only)
@@ -250,7 +249,7 @@ def run_ours(args):
                 "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "splat_filtered_kernel<joint> (FP32 filter + exact FP64 queue)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch,
                 "cameras_per_launch": batch, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
-                "splat_share_of_step": round(splat_ms.value / ms, 4),
+                "splat_share_of_step": round(splat_ms_v / ms, 4),
                 "step_achieved": round(value / max(world, 1) * (G * 1 + 9 * H * W) / 1e9, 1),
                 "step_frac": round(value / max(world, 1) * (G * 1 + 9 * H * W) / 1e9 / peak, 4),
                 "point_candidates_per_s": round(n_points * batch / avg_launch_s, 1) if avg_launch_s > 0 else None,

@@ -18,7 +18,8 @@
  *     NULL = the legacy default stream); the caller synchronises;
  *   - return value 0 = success, <0 = error (P3D_E_*); p3d_last_error() returns a
  *     thread-local message for the last failing call on this thread;
- *   - no global mutable state; re-entrant per stream;
+ *   - no global mutable state (host-side state such as helper streams lives in caller-owned
+ *     context objects); re-entrant per stream;
  *   - arrays are C-order; grids are (A0,A1,A2) with flat index (a0*A1 + a1)*A2 + a2;
  *     RGB arrays carry a trailing channel axis of 3 uint8.
  */
@@ -139,24 +140,57 @@ int p3d_partwise_counts_rgb(const uint8_t* proj_rgb, const uint8_t* gt_rgb, int6
  * In P3D_MODE_PER_PART one extra row is appended per camera: counts is (K,P+1,2) and row P holds the
  * combined binary IoU counts against gt_any (H,W) u8 (camera_estimation.py:433-447); scores is the mean
  * over the P parts only.  gt_any may be NULL in joint mode.
- * Workspace: p3d_sweep_workspace_bytes(); cameras are processed in batches sized so that the
- * batch's z-buffers stay L2-resident.  Sweeps of more than one batch double-buffer the z-buffers and
- * run the score pass of one batch on a helper stream (created and destroyed inside the call, forked
- * from and joined to `stream` with events) beside the splat of the next; everything the caller
- * enqueues on `stream` afterwards is ordered after the whole sweep.  While `stream` is being captured
- * into a CUDA graph the batches stay in sequence on `stream`.
+ * Workspace: p3d_sweep_workspace_bytes(); cameras are processed in batches of z-buffers.
+ *
+ * segs / n_seg (optional, NULL / 0 = none): the x-run segments of `pts` from p3d_segments_fill().  With them the
+ * sweep launches the segment splat (one thread per run of <= p3d_segment_length() consecutive voxels of a row, see
+ * csrc/p3d_camera.cu); without them, for images above 2^22 pixels, or with P3D_SPLAT_POINTS=1, the per-point splat.
+ * Both give identical counts.
+ *
+ * ctx (optional, NULL = none): caller-owned host state created by p3d_sweep_ctx_create() -- the helper stream and
+ * events of the double-buffered batches, the launch counter and the optional splat timing.  With a context, sweeps of
+ * more than one batch double-buffer the z-buffers and run the score pass of one batch on the context's helper stream
+ * (forked from and joined to `stream` with events) beside the splat of the next; everything the caller enqueues on
+ * `stream` afterwards is ordered after the whole sweep, also when the call fails midway.  Without a context, or while
+ * `stream` is being captured into a CUDA graph, the batches stay in sequence on `stream`.  A context must not be used
+ * by two calls at the same time; the library itself keeps no global mutable state.
  * --------------------------------------------------------------------------------------------- */
+typedef struct p3d_sweep_ctx p3d_sweep_ctx;
+p3d_sweep_ctx* p3d_sweep_ctx_create(void);              /* NULL on allocation failure */
+void p3d_sweep_ctx_destroy(p3d_sweep_ctx* ctx);
+/* kernel launches issued by the last p3d_sweep_* call that used ctx (bench accounting) */
+int p3d_sweep_ctx_launches(const p3d_sweep_ctx* ctx);
+/* Measurement: while enabled, p3d_sweep_* records a CUDA-event pair on the launch stream around every splat launch;
+ * p3d_sweep_ctx_timing_read() waits for them, returns the summed splat duration (ms) and the number of launches
+ * (host out-pointers), and resets the counters. */
+int p3d_sweep_ctx_timing(p3d_sweep_ctx* ctx, int on);
+int p3d_sweep_ctx_timing_read(p3d_sweep_ctx* ctx, double* splat_ms, int* n_launches);
+
 size_t p3d_sweep_workspace_bytes(int K, int H, int W, int P, int elem_bytes);
-int p3d_sweep_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cand, int K,
-                  const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
-                  int64_t* counts, double* scores, int64_t* best, void* workspace,
-                  size_t workspace_bytes, p3d_stream_t stream);
-int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cand, int K,
-                  const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
-                  int64_t* counts, double* scores, int64_t* best, void* workspace,
-                  size_t workspace_bytes, p3d_stream_t stream);
-/* Number of kernel launches the last p3d_sweep_* call on this thread issued (for bench accounting). */
-int p3d_sweep_last_launches(void);
+int p3d_sweep_f64(const float* pts, const uint8_t* pt_label, int64_t n, const uint32_t* segs, int64_t n_seg,
+                  const double* cand, int K, const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P,
+                  int mode, int64_t* counts, double* scores, int64_t* best, void* workspace,
+                  size_t workspace_bytes, p3d_sweep_ctx* ctx, p3d_stream_t stream);
+int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, const uint32_t* segs, int64_t n_seg,
+                  const float* cand, int K, const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P,
+                  int mode, int64_t* counts, double* scores, int64_t* best, void* workspace,
+                  size_t workspace_bytes, p3d_sweep_ctx* ctx, p3d_stream_t stream);
+
+/* x-run segments of a point list in get_voxel_points_by_parts order (utils/voxel_utils.py:17-19: ascending flat
+ * index, so the voxels of one (z, y) row are consecutive in the list and in x).  A segment = up to L = seg_len
+ * list-consecutive points with equal label, equal (y, z), x increasing by exactly 1, not crossing a multiple of L in
+ * x; record = 4 uint32 { x0 | y << 16, z | (len-1) << 16 | label << 24, index of the first point, 0 }.
+ *   p3d_segments_count : n_out (2) int64 device = [number of segments, number of points the segment form cannot
+ *                        represent (non-integer or outside 0..65535, label outside 1..32)]; if n_out[1] != 0 the
+ *                        caller must not pass segments to p3d_sweep_*.  workspace: p3d_segments_workspace_bytes(n).
+ *   p3d_segments_fill  : writes the records (16-byte aligned, capacity >= n_out[0]) from the same workspace.
+ * seg_len must equal p3d_segment_length() for segments handed to p3d_sweep_*. */
+int p3d_segment_length(void);
+size_t p3d_segments_workspace_bytes(int64_t n_points);
+int p3d_segments_count(const float* pts, const uint8_t* pt_label, int64_t n, int seg_len, int64_t* n_out,
+                       void* workspace, size_t workspace_bytes, p3d_stream_t stream);
+int p3d_segments_fill(const float* pts, const uint8_t* pt_label, int64_t n, int seg_len, const void* workspace,
+                      uint32_t* segs, int64_t capacity, p3d_stream_t stream);
 /* Best-candidate reduction across GPUs (camera_estimation.py:646: the first candidate with the greatest
  * score wins).  p3d_best_pack writes pair = [bits of scores[best[0]], best[0] + offset] (index -1 if the
  * block was empty); the caller all-gathers the 16-byte pairs (NCCL); p3d_best_select picks the greatest
@@ -219,12 +253,6 @@ int p3d_deform_sweep_f32(const float* pts, int64_t n, int64_t stride, const doub
 int p3d_deform_scatter(const float* pts, int64_t n, int64_t stride, const double* centres, const double* deform,
                        const double* pix2vox, int A0, int A1, int A2, int r, int g, int b, uint8_t* grid_rgb,
                        int64_t* nvalid, p3d_stream_t stream);
-
-/* Measurement hook: while enabled on the calling thread, p3d_sweep_* records a CUDA-event pair on the launch
- * stream around every splat launch; p3d_sweep_timing_read() waits for them, returns the summed splat
- * duration (ms) and the number of launches (host out-pointers), and resets the counters. */
-int p3d_sweep_timing_enable(int on);
-int p3d_sweep_timing_read(double* splat_ms, int* n_launches);
 
 /* voxel_grid_to_points for RGB grids      utils/voxel_utils.py:35-51   (inspection without a CPU round trip)
  *   p3d_strided_occupancy  : mask (ceil(A0/s), ceil(A1/s), ceil(A2/s)) u8 = any(grid[::s, ::s, ::s], axis=-1)

@@ -715,3 +715,33 @@ def voxel_grid_to_points(grid, stride=2):
     a0, a1, a2 = np.nonzero(ds.any(axis=-1))
     pts = np.stack([a2, a1, a0], axis=1).astype(np.float32) * stride
     return pts, ds[a0, a1, a2], (g.shape[1], g.shape[0], g.shape[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# x-run segments of a point list (checker of p3d_segments_*; not a reference function: the segment
+# splat is an implementation detail of the CUDA sweep, the reference's point order is
+# utils/voxel_utils.py:17-19)
+# ------------------------------------------------------------------------------------------------
+def point_segments(pts, labels, L):
+    """(S,4) uint32 records {x0 | y << 16, z | (len-1) << 16 | label << 24, first point index, 0} of the runs of
+    <= L list-consecutive points with equal label, equal (y, z), x increasing by exactly 1, not crossing a multiple
+    of L in x; plus the number of points the form cannot represent."""
+    pts = np.asarray(pts, dtype=np.float32).reshape(-1, 3)
+    labels = np.asarray(labels, dtype=np.uint8).reshape(-1)
+    n = len(pts)
+    if n == 0:
+        return np.zeros((0, 4), np.uint32), 0
+    with np.errstate(invalid="ignore"):
+        ok = (labels >= 1) & (labels <= 32) & np.all((pts >= 0) & (pts <= 65535) & (pts == np.trunc(pts)), axis=1)
+        xi = np.nan_to_num(pts[:, 0], nan=0.0, posinf=0.0, neginf=0.0).astype(np.int64)
+    start = np.ones(n, bool)
+    start[1:] = ((labels[1:] != labels[:-1]) | (pts[1:, 1] != pts[:-1, 1]) | (pts[1:, 2] != pts[:-1, 2]) |
+                 (pts[1:, 0] != pts[:-1, 0] + np.float32(1)) | (xi[1:] % L == 0))
+    first = np.flatnonzero(start)
+    length = np.diff(np.append(first, n))
+    p = np.nan_to_num(pts[first], nan=0.0, posinf=0.0, neginf=0.0).astype(np.int64) & 0xffff
+    rec = np.zeros((len(first), 4), np.uint32)
+    rec[:, 0] = p[:, 0] | (p[:, 1] << 16)
+    rec[:, 1] = p[:, 2] | ((length - 1) << 16) | (labels[first].astype(np.int64) << 24)
+    rec[:, 2] = first
+    return rec, int((~ok).sum())

@@ -16,6 +16,7 @@
 // end so that this filter hits for most points.
 #include <stdlib.h>
 
+#include <new>
 #include <vector>
 
 #include "p3d_common.cuh"
@@ -156,7 +157,8 @@ constexpr int kQueueCap = 64;        // per warp: at most 32 new entries on top 
 template <typename T>
 __global__ void __launch_bounds__(64) fast_cams_kernel(const T* __restrict__ cams, int K,
                                                         const float* __restrict__ bbox, int H, int W,
-                                                        float* __restrict__ fast, int4* __restrict__ rect) {
+                                                        float* __restrict__ fast, int4* __restrict__ rect,
+                                                        uint32_t* __restrict__ flags) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   double cam[16];
@@ -164,7 +166,10 @@ __global__ void __launch_bounds__(64) fast_cams_kernel(const T* __restrict__ cam
   for (int i = 0; i < 16; ++i) cam[i] = (double)cams[(size_t)k * 16 + i];       // float32 blocks widen exactly
   FastCam* fc = reinterpret_cast<FastCam*>(fast) + k;
   make_fast_cam(cam, bbox, H, W, fc, sizeof(T) == 4);
-  if (rect) footprint_rect(cam, bbox, H, W, fc->thr_u >= 0.f && fc->thr_v >= 0.f, rect + k);
+  if (rect || flags) {
+    const bool inside = footprint_rect(cam, bbox, H, W, fc->thr_u >= 0.f && fc->thr_v >= 0.f, rect ? rect + k : nullptr);
+    if (flags) flags[k] = inside ? 1u : 0u;
+  }
 }
 
 #ifndef P3D_SCALAR_FILTER
@@ -350,6 +355,231 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
       }
     }
     if ((c & (kFlushEvery - 1)) == kFlushEvery - 1) {
+      flush(parked, c);
+      parked = 0ull;
+    }
+  }
+  flush(parked, nc - 1);
+  while (qn > 0) drain32();
+}
+
+// ------------------------------------------------------------------------------------------
+// Segment splat: the same filter, one thread per x-run segment (p3d_segments_*, p3d_core.cu) instead of kPptF unrelated
+// points.  What the run structure buys per (point, camera):
+//   * the (y, z) part of the three fma chains is evaluated once per segment:  Xrow = fma(qz,A2, fma(qy,A1, TA)) (X and Y
+//     rows share packed instructions), then X_j = fma(qx_j, A0, Xrow) for the points of the run -- the same three
+//     roundings per coordinate as the per-point chain in another association order, and the error model above bounds
+//     every partial sum by f S + |T_A| regardless of order, so the thresholds of make_fast_cam() hold unchanged;
+//     qx_j = fl((x0 + j) - c_x) is the very value the per-point kernel computes (x0 + j is an exact integer);
+//   * a thread carries 3 coordinates + one key for kSegLen points (key_j = key0 + j * step), so kSegLen = 8 points per
+//     thread fit the register budget and the per-camera loop overhead (camera block loads, parked-mask upkeep) is
+//     shared by twice as many points;
+//   * the pixel index comes out of the FP pipe: lin = fma(rint(v), W, u + magic) holds row * W + col in its mantissa
+//     (exact while H W <= 2^22), one shift-add turns it into a 32-bit byte offset into the batch's z-buffer set;
+//   * cameras whose footprint rectangle (footprint_rect, unclamped, 2.5 px margin) lies inside the image need no bounds
+//     test at all: a decided point of such a camera is in range by construction (kCamInView).
+// Points beyond a segment's length carry NaN coordinates: never decided, never parked (`live`).
+// Bit-identical to splat_kernel<T> like the per-point filter (tests/test_camera_gpu.py, tests/test_segments_gpu.py).
+// ------------------------------------------------------------------------------------------
+#ifndef P3D_SEG_LEN
+#define P3D_SEG_LEN 8
+#endif
+#ifndef P3D_SEG_GROUP
+#define P3D_SEG_GROUP 4
+#endif
+#ifndef P3D_SEG_MINBLOCKS
+#define P3D_SEG_MINBLOCKS 8
+#endif
+constexpr int kSegLen = P3D_SEG_LEN;          // points per segment (p3d_segment_length())
+constexpr int kSegGroup = P3D_SEG_GROUP;      // points whose early-out loads are in flight together
+constexpr int kSegThreads = 128;
+constexpr int kSegFlushEvery = 64 / kSegLen;  // cameras between queue flushes: kSegLen bits per camera in a 64-bit mask
+constexpr uint32_t kCamInView = 1u;           // cam_flags bit: every decided point of this camera is inside the image
+static_assert(kSegLen % kSegGroup == 0 && kSegGroup % 2 == 0 && 64 % kSegLen == 0, "segment shape");
+
+template <int MODE>
+__device__ __forceinline__ uint32_t seg_key0(uint32_t idx0, uint32_t lab) {
+  if (MODE == P3D_MODE_JOINT) return idx0 + 1u;
+  if (MODE == kModeJointPacked) return ((idx0 + 1u) << kLabelBits) | (lab - 1u);
+  return 1u << (lab - 1u);
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t seg_key(uint32_t key0, int j) {
+  if (MODE == P3D_MODE_JOINT) return key0 + (uint32_t)j;
+  if (MODE == kModeJointPacked) return key0 + ((uint32_t)j << kLabelBits);
+  return key0;
+}
+
+// One camera for one segment: returns the mask of undecided points (bit j).  zb = this camera's z-buffer minus
+// bits(magic) elements, so that the raw bits of `lin` index it.
+template <bool INVIEW, int MODE>
+__device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 2], float qy, float qz, uint32_t key0,
+                                                    const float4* __restrict__ fc4, uint32_t* __restrict__ zb,
+                                                    uint32_t W, uint32_t H, float Wf) {
+  const float kMagic = 12582912.f;                          // 1.5 * 2^23
+  const uint32_t kMagicBits = 0x4B400000u;
+  const float4 c0 = fc4[0];                                 // A0 B0 C0 thr_u
+  const float4 c1 = fc4[1];                                 // A1 B1 A2 B2
+  const float4 c2 = fc4[2];                                 // TA TB C1 C2
+  const float4 c3 = fc4[3];                                 // TC cx cy thr_v
+  const f32x2 XYr = fma2(pack2(qz, qz), pack2(c1.z, c1.w), fma2(pack2(qy, qy), pack2(c1.x, c1.y), pack2(c2.x, c2.y)));
+  float xr, yr;
+  unpack2(XYr, xr, yr);
+  const float zr = __fmaf_rn(qz, c2.w, __fmaf_rn(qy, c2.z, c3.x));
+  const f32x2 A0 = pack2(c0.x, c0.x), B0 = pack2(c0.y, c0.y), C0 = pack2(c0.z, c0.z);
+  const f32x2 XR = pack2(xr, xr), YR = pack2(yr, yr), ZR = pack2(zr, zr);
+  const f32x2 CX = pack2(c3.y, c3.y), CY = pack2(c3.z, c3.z), WF = pack2(Wf, Wf);
+  const f32x2 kM2 = pack2(kMagic, kMagic), kNegM2 = pack2(-kMagic, -kMagic), kNeg1 = pack2(-1.f, -1.f);
+  const float thr_u = c0.w, thr_v = c3.w;
+  uint32_t und = 0;
+#pragma unroll
+  for (int g = 0; g < kSegLen / kSegGroup; ++g) {
+    uint32_t* addr[kSegGroup];
+    bool hit[kSegGroup];
+#pragma unroll
+    for (int mp = 0; mp < kSegGroup / 2; ++mp) {
+      const int m = g * (kSegGroup / 2) + mp;
+      const f32x2 X = fma2(QX[m], A0, XR), Y = fma2(QX[m], B0, YR), Z = fma2(QX[m], C0, ZR);
+      float z0, z1, r0, r1;
+      unpack2(Z, z0, z1);
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(z0));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(z1));
+      const f32x2 R = pack2(r0, r1);
+      const f32x2 U = fma2(X, R, CX), V = fma2(Y, R, CY);
+      const f32x2 SU = add2(U, kM2), SV = add2(V, kM2);
+      const f32x2 RV = add2(SV, kNegM2);
+      const f32x2 DU = fma2(add2(SU, kNegM2), kNeg1, U), DV = fma2(RV, kNeg1, V);          // u - rint(u)
+      const f32x2 LIN = fma2(RV, WF, SU);                                                   // row * W + col + magic
+      float du[2], dv[2], su[2], sv[2], lin[2];
+      unpack2(DU, du[0], du[1]); unpack2(DV, dv[0], dv[1]); unpack2(LIN, lin[0], lin[1]);
+      unpack2(SU, su[0], su[1]); unpack2(SV, sv[0], sv[1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int jj = 2 * mp + h;
+        const bool decided = fabsf(du[h]) < thr_u && fabsf(dv[h]) < thr_v;                  // false for NaN
+        if (INVIEW) {
+          hit[jj] = decided;
+        } else {
+          const uint32_t iu = (uint32_t)__float_as_int(su[h]) - kMagicBits, iv = (uint32_t)__float_as_int(sv[h]) - kMagicBits;
+          hit[jj] = decided && iu < W && iv < H;
+        }
+        addr[jj] = zb + (uint32_t)__float_as_int(lin[h]);                                   // only dereferenced when hit
+        if (!decided) und |= 1u << (g * kSegGroup + jj);
+      }
+    }
+    uint32_t cur[kSegGroup];                                 // only meaningful (and only read) where hit
+#pragma unroll
+    for (int jj = 0; jj < kSegGroup; ++jj)
+      if (hit[jj]) cur[jj] = __ldcg(addr[jj]);
+#pragma unroll
+    for (int jj = 0; jj < kSegGroup; ++jj) {
+      const uint32_t key = seg_key<MODE>(key0, g * kSegGroup + jj);
+      if (MODE != P3D_MODE_PER_PART) {
+        if (hit[jj] && cur[jj] < key) atomicMax(addr[jj], key);
+      } else {
+        if (hit[jj] && (cur[jj] & key) != key) atomicOr(addr[jj], key);
+      }
+    }
+  }
+  return und;
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kSegThreads, P3D_SEG_MINBLOCKS)
+splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __restrict__ pts,
+                 const uint8_t* __restrict__ pt_label, const T* __restrict__ cams, int K, int cams_per_block, int H,
+                 int W, uint32_t* __restrict__ zbuf, const float* __restrict__ fast, const float* __restrict__ bbox,
+                 const uint32_t* __restrict__ cam_flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s_cam = reinterpret_cast<T*>(smem_raw);                                             // nc x 16 camera scalars
+  float* s_fast = reinterpret_cast<float*>(s_cam + (size_t)cams_per_block * 16);          // nc x 16, permuted FastCam
+  uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_fast + (size_t)cams_per_block * 16);   // nc
+  uint2* s_queue = reinterpret_cast<uint2*>(s_flag + ((cams_per_block + 3) & ~3));        // warps x kQueueCap
+
+  const int c0 = blockIdx.y * cams_per_block;
+  const int nc = min(cams_per_block, K - c0);
+  // FastCam = A[3],TA, B[3],TB, C[3],TC, cx, cy, thr_u, thr_v  ->  A0 B0 C0 thr_u | A1 B1 A2 B2 | TA TB C1 C2 | TC cx cy thr_v
+  const unsigned long long kPerm = 0xFDCBA9736251E840ull;   // nibble i = source slot of destination slot i
+  for (int i = threadIdx.x; i < nc * 16; i += kSegThreads) {
+    s_cam[i] = cams[(size_t)c0 * 16 + i];
+    s_fast[i] = fast[(size_t)c0 * 16 + (i & ~15) + (int)((kPerm >> (4 * (i & 15))) & 15ull)];
+  }
+  for (int i = threadIdx.x; i < nc; i += kSegThreads) s_flag[i] = cam_flags ? cam_flags[c0 + i] : 0u;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint2* q = s_queue + warp * kQueueCap;
+  int qn = 0;                                              // entries pending in the warp's queue (warp-uniform)
+  const float ctr0 = bbox_centre(bbox, 0), ctr1 = bbox_centre(bbox, 1), ctr2 = bbox_centre(bbox, 2);
+
+  // walk the segment list from its high-index end: later points own the pixels
+  const int64_t tile = (int64_t)gridDim.x - 1 - blockIdx.x;
+  const int64_t si = tile * kSegThreads + threadIdx.x;
+  uint4 sg = make_uint4(0, 0, 0, 0);
+  int len = 0;
+  if (si < n_seg) {
+    sg = __ldg(segs + si);
+    len = (int)((sg.y >> 16) & 0xffu) + 1;
+  }
+  const uint32_t idx0 = sg.z;
+  const uint32_t key0 = seg_key0<MODE>(idx0, len ? (sg.y >> 24) : 1u);
+  const float qy = __fsub_rn((float)(sg.x >> 16), ctr1), qz = __fsub_rn((float)(sg.y & 0xffffu), ctr2);
+  const float nan = __int_as_float(0x7fc00000);
+  f32x2 QX[kSegLen / 2];
+#pragma unroll
+  for (int m = 0; m < kSegLen / 2; ++m) {
+    const float xa = __fsub_rn((float)((sg.x & 0xffffu) + 2 * m), ctr0), xb = __fsub_rn((float)((sg.x & 0xffffu) + 2 * m + 1), ctr0);
+    QX[m] = pack2(2 * m < len ? xa : nan, 2 * m + 1 < len ? xb : nan);
+  }
+  unsigned long long live = len >= 64 ? ~0ull : ((1ull << len) - 1ull);   // parked-mask bits of the points that exist
+#pragma unroll
+  for (int g = kSegLen; g < 64; g <<= 1) live |= live << g;
+  const T dW = (T)W, dH = (T)H;
+  const uint32_t HW = (uint32_t)H * (uint32_t)W;
+  const float Wf = (float)W;
+
+  auto drain32 = [&]() {
+    const int take = qn < 32 ? qn : 32;
+    if (lane < take) {
+      const uint2 e = q[qn - take + lane];                  // (point index, camera)
+      const float* pp = pts + 3 * (size_t)e.x;
+      const uint32_t k = make_key<MODE>((int64_t)e.x, pt_label);
+      exact_splat<T, MODE>((T)__ldg(pp), (T)__ldg(pp + 1), (T)__ldg(pp + 2), k, s_cam + e.y * 16,
+                           zbuf + (size_t)(c0 + e.y) * HW, W, dW, dH);
+    }
+    qn -= take;
+    __syncwarp();
+  };
+  // group g of kSegLen bits (from the low end) belongs to camera clast - g, bit j of the group to point idx0 + j
+  auto flush = [&](unsigned long long mask, int clast) {
+    mask &= live;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (;;) {
+      const bool has = mask != 0ull;
+      const uint32_t m = __ballot_sync(0xffffffffu, has);
+      if (m == 0u) break;
+      if (has) {
+        const uint32_t b = (uint32_t)(__ffsll((long long)mask) - 1);
+        mask &= mask - 1ull;
+        q[qn + __popc(m & lt)] = make_uint2(idx0 + (b % (uint32_t)kSegLen), (uint32_t)clast - b / (uint32_t)kSegLen);
+      }
+      qn += __popc(m);
+      __syncwarp();
+      if (qn >= 32) drain32();
+    }
+  };
+
+  unsigned long long parked = 0ull;
+  uint32_t* zb = zbuf + (size_t)c0 * HW - 0x4B400000ll;    // biased by bits(magic): indexed by the raw bits of `lin`
+  for (int c = 0; c < nc; ++c, zb += HW) {
+    const float4* fc4 = reinterpret_cast<const float4*>(s_fast + c * 16);
+    uint32_t und;
+    if (s_flag[c] & kCamInView)
+      und = seg_camera_pass<true, MODE>(QX, qy, qz, key0, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
+    else
+      und = seg_camera_pass<false, MODE>(QX, qy, qz, key0, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
+    parked = (parked << kSegLen) | (unsigned long long)und;
+    if ((c & (kSegFlushEvery - 1)) == kSegFlushEvery - 1) {
       flush(parked, c);
       parked = 0ull;
     }
@@ -773,30 +1003,53 @@ inline int grid_for(int64_t items, int threads, int waves) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
-thread_local int g_last_launches = 0;
-
-// P3D_SPLAT_EXACT=1 forces the unfiltered FP64 kernel (A/B testing of the FP32 filter).
+// P3D_SPLAT_EXACT=1 forces the unfiltered FP64 kernel (A/B testing of the FP32 filter); P3D_SPLAT_POINTS=1 keeps the
+// per-point filtered kernel even when segments are supplied (A/B testing of the segment splat).
 inline bool splat_exact_only() {
   const char* e = getenv("P3D_SPLAT_EXACT");
   return e && e[0] == '1';
 }
+inline bool splat_points_only() {
+  static const bool on = [] { const char* e = getenv("P3D_SPLAT_POINTS"); return e && e[0] == '1'; }();
+  return on;
+}
 
-// Optional per-launch timing of the splat kernel (bench.py's roofline leg): CUDA events recorded on the
-// launch stream around every splat launch of p3d_sweep_* while enabled on this thread.
-struct SplatTiming {
-  bool enabled = false;
-  std::vector<cudaEvent_t> pool;     // start/stop pairs
+}  // namespace
+
+// Caller-owned host-side state of p3d_sweep_* (p3d_sweep_ctx_create): the helper stream and fork/join events of the
+// double-buffered batches, the launch counter and the optional per-launch timing events.  One context per concurrent
+// caller; the library keeps no global mutable state.
+struct p3d_sweep_ctx {
+  cudaStream_t helper = nullptr;
+  cudaEvent_t splatted[2] = {nullptr, nullptr}, scored[2] = {nullptr, nullptr};
+  bool scored_pending[2] = {false, false};
+  int device = -1;
+  int last_launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> pool;     // start/stop pairs around splat launches
   size_t used = 0;
 };
-thread_local SplatTiming g_timing;
 
-inline cudaEvent_t timing_event() {
-  if (g_timing.used == g_timing.pool.size()) {
+namespace {
+
+inline cudaEvent_t timing_event(p3d_sweep_ctx* ctx) {
+  if (ctx->used == ctx->pool.size()) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-    g_timing.pool.push_back(e);
+    ctx->pool.push_back(e);
   }
-  return g_timing.pool[g_timing.used++];
+  return ctx->pool[ctx->used++];
+}
+
+inline int ctx_open_fork(p3d_sweep_ctx* ctx) {
+  if (ctx->helper) return P3D_OK;
+  P3D_CUDA(cudaGetDevice(&ctx->device));
+  P3D_CUDA(cudaStreamCreateWithFlags(&ctx->helper, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    P3D_CUDA(cudaEventCreateWithFlags(&ctx->splatted[i], cudaEventDisableTiming));
+    P3D_CUDA(cudaEventCreateWithFlags(&ctx->scored[i], cudaEventDisableTiming));
+  }
+  return P3D_OK;
 }
 
 template <typename T>
@@ -835,18 +1088,26 @@ int points_bbox(const float* pts, int64_t n, float* bbox, p3d_stream_t stream) {
 
 template <typename T>
 int fast_cameras(const T* cams, int K, const float* bbox, int H, int W, float* fast, p3d_stream_t stream,
-                 int4* rect = nullptr) {
+                 int4* rect = nullptr, uint32_t* flags = nullptr) {
   P3D_REQUIRE(K >= 0 && H > 0 && W > 0, "fast_cameras: bad arguments");
   if (K == 0) return P3D_OK;
   P3D_REQUIRE(cams && bbox && fast, "fast_cameras: null pointer");
-  fast_cams_kernel<T><<<(K + 63) / 64, 64, 0, p3d::as_stream(stream)>>>(cams, K, bbox, H, W, fast, rect);
+  fast_cams_kernel<T><<<(K + 63) / 64, 64, 0, p3d::as_stream(stream)>>>(cams, K, bbox, H, W, fast, rect, flags);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
 
+// the segment splat applies when segments are supplied, the FP32 filter is on, the pixel index fits the FP32 mantissa
+// trick (H W <= 2^22) and the launch's z-buffer set stays below 4 GiB (32-bit byte offsets)
+inline bool use_segments(const void* segs, int64_t n_seg, bool filtered, int K, int H, int W) {
+  return segs != nullptr && n_seg > 0 && filtered && !splat_points_only() && (int64_t)H * W <= (1ll << 22) &&
+         (int64_t)K * H * W * 4 < (1ll << 32);
+}
+
 template <typename T>
 int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, int K, int H, int W, int mode,
-          uint32_t* zbuf, const float* fast, const float* bbox, p3d_stream_t stream) {
+          uint32_t* zbuf, const float* fast, const float* bbox, p3d_stream_t stream, const uint4* segs = nullptr,
+          int64_t n_seg = 0, const uint32_t* cam_flags = nullptr) {
   P3D_REQUIRE(n >= 0 && K >= 0 && H > 0 && W > 0, "splat: n=%lld K=%d H=%d W=%d", (long long)n, K, H, W);
   P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART || mode == kModeJointPacked, "splat: mode=%d", mode);
   P3D_REQUIRE(n < 0xffffffffll, "splat: n=%lld does not fit 32-bit keys", (long long)n);
@@ -856,12 +1117,29 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   P3D_REQUIRE(pts && cams && zbuf, "splat: null pointer");
   P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: this mode needs pt_label");
   const bool filtered = fast != nullptr && bbox != nullptr && !splat_exact_only();
+  cudaStream_t st = p3d::as_stream(stream);
+  if (use_segments(segs, n_seg, filtered, K, H, W)) {
+    P3D_REQUIRE(pt_label, "splat: the segment path needs pt_label");
+    const int64_t tiles = (n_seg + kSegThreads - 1) / kSegThreads;
+    P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
+    const int cpb = pick_cams_per_block(tiles, K);
+    dim3 grid((unsigned)tiles, (unsigned)((K + cpb - 1) / cpb));
+    const size_t smem = (size_t)cpb * (16 * sizeof(T) + 16 * sizeof(float)) + (size_t)((cpb + 3) & ~3) * sizeof(uint32_t) +
+                        (size_t)(kSegThreads / 32) * (kQueueCap * sizeof(uint2));
+    if (mode == P3D_MODE_JOINT)
+      splat_seg_kernel<T, P3D_MODE_JOINT><<<grid, kSegThreads, smem, st>>>(segs, n_seg, pts, pt_label, cams, K, cpb, H, W, zbuf, fast, bbox, cam_flags);
+    else if (mode == kModeJointPacked)
+      splat_seg_kernel<T, kModeJointPacked><<<grid, kSegThreads, smem, st>>>(segs, n_seg, pts, pt_label, cams, K, cpb, H, W, zbuf, fast, bbox, cam_flags);
+    else
+      splat_seg_kernel<T, P3D_MODE_PER_PART><<<grid, kSegThreads, smem, st>>>(segs, n_seg, pts, pt_label, cams, K, cpb, H, W, zbuf, fast, bbox, cam_flags);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+  }
   const int ppt = filtered ? kPptF : kPpt;
   const int64_t tiles = (n + kSplatThreads * ppt - 1) / (kSplatThreads * ppt);
   P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
   const int cpb = pick_cams_per_block(tiles, K);
   dim3 grid((unsigned)tiles, (unsigned)((K + cpb - 1) / cpb));
-  cudaStream_t st = p3d::as_stream(stream);
   if (filtered) {
     const size_t smem = (size_t)cpb * (16 * sizeof(T) + kPackCamFloats * sizeof(float)) +
                         (size_t)(kSplatThreads / 32) * (kQueueCap * sizeof(uint2));
@@ -936,7 +1214,7 @@ inline int batch_cameras(int K, int H, int W, int64_t n) {
 }
 
 struct SweepLayout {
-  size_t cams, raw, gt_area, bbox, fast, rect, zbuf, total;
+  size_t cams, raw, gt_area, bbox, fast, rect, flags, zbuf, total;
   int batch;      // cameras one z-buffer set can hold
   int floor;      // fewest cameras per launch the sweep will choose
   int zbufs;      // 2 = double-buffered: the score pass of one batch runs beside the splat of the next
@@ -959,47 +1237,26 @@ inline SweepLayout sweep_layout(int K, int H, int W, int P, int elem_bytes) {
   L.bbox = off; off = p3d_align_up(off + 8 * sizeof(float), 256);
   L.fast = off; off = p3d_align_up(off + (size_t)K * sizeof(FastCam), 256);
   L.rect = off; off = p3d_align_up(off + (size_t)K * sizeof(int4), 256);
+  L.flags = off; off = p3d_align_up(off + (size_t)K * sizeof(uint32_t), 256);
   L.zbufs = (overlap_enabled() && K > L.floor) ? 2 : 1;
   L.zbuf = off; off = p3d_align_up(off + (size_t)L.zbufs * L.batch * H * W * sizeof(uint32_t), 256);
   L.total = off;
   return L;
 }
 
-// Helper stream + fork/join events of one sweep call (created per call: nothing is shared between concurrent callers;
-// destroying a stream or event with work in flight only defers the release).
-struct ScoreFork {
-  bool active = false;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t splatted[2] = {nullptr, nullptr}, scored[2] = {nullptr, nullptr};
-  int open() {
-    P3D_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      P3D_CUDA(cudaEventCreateWithFlags(&splatted[i], cudaEventDisableTiming));
-      P3D_CUDA(cudaEventCreateWithFlags(&scored[i], cudaEventDisableTiming));
-    }
-    active = true;
-    return P3D_OK;
-  }
-  ~ScoreFork() {
-    for (int i = 0; i < 2; ++i) {
-      if (splatted[i]) cudaEventDestroy(splatted[i]);
-      if (scored[i]) cudaEventDestroy(scored[i]);
-    }
-    if (stream) cudaStreamDestroy(stream);
-  }
-};
-
 template <typename T>
-int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, int K, const uint8_t* gt_label,
-          const uint8_t* gt_any, int H, int W, int P, int mode, int64_t* counts, double* scores, int64_t* best,
-          void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
-  g_last_launches = 0;
+int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const uint4* segs, int64_t n_seg, const T* cand, int K,
+          const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode, int64_t* counts, double* scores,
+          int64_t* best, void* workspace, size_t workspace_bytes, p3d_sweep_ctx* ctx, p3d_stream_t stream) {
+  int launches = 0;
+  if (ctx) ctx->last_launches = 0;
   P3D_REQUIRE(K > 0 && H > 0 && W > 0 && n >= 0, "sweep: K=%d H=%d W=%d n=%lld", K, H, W, (long long)n);
   P3D_REQUIRE(P >= 1 && P <= kMaxParts, "sweep: P=%d (1..%d)", P, kMaxParts);
   P3D_REQUIRE(mode == P3D_MODE_JOINT || mode == P3D_MODE_PER_PART, "sweep: mode=%d", mode);
   P3D_REQUIRE((int64_t)H * W < (1ll << 31), "sweep: image too large");
   P3D_REQUIRE(cand && gt_label && counts && scores && workspace, "sweep: null pointer");
   P3D_REQUIRE(n == 0 || (pts && pt_label), "sweep: null points");
+  P3D_REQUIRE(n_seg >= 0 && (segs == nullptr || (reinterpret_cast<uintptr_t>(segs) & 15) == 0), "sweep: bad segments");
   P3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sweep: workspace must be 256-byte aligned");
   const SweepLayout L = sweep_layout(K, H, W, P, (int)sizeof(T));
   if (workspace_bytes < L.total) {
@@ -1017,6 +1274,7 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
 
   float* bbox = reinterpret_cast<float*>(ws + L.bbox);
   float* fast = reinterpret_cast<float*>(ws + L.fast);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(ws + L.flags);
   static const bool use_rect = [] { const char* e = getenv("P3D_SCORE_RECT"); return e == nullptr || atoi(e) != 0; }();
   int4* rect = use_rect ? reinterpret_cast<int4*>(ws + L.rect) : nullptr;   // P3D_SCORE_RECT=0: score the whole image
   P3D_CUDA(cudaMemsetAsync(ws + L.raw, 0, L.bbox - L.raw, st));   // raw + gt_area
@@ -1028,48 +1286,70 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
   gt_area_kernel<<<grid_for(HW, 256, 4), 256, 0, st>>>(gt_label, mode == P3D_MODE_PER_PART ? gt_any : nullptr, HW, P,
                                                       gt_area);
   P3D_LAUNCH_CHECK();
-  g_last_launches += 2;
+  launches += 2;
   if (n > 0) {
     rc = points_bbox(pts, n, bbox, stream);
     if (rc) return rc;
-    rc = fast_cameras<T>(cams, K, bbox, H, W, fast, stream, rect);
+    rc = fast_cameras<T>(cams, K, bbox, H, W, fast, stream, rect, flags);
     if (rc) return rc;
-    g_last_launches += 3;
+    launches += 3;
   }
   // joint mode: carry the label in the key whenever it fits (P3D_NO_PACKED_KEYS=1 keeps the gather, for A/B runs)
   static const bool no_packed = getenv("P3D_NO_PACKED_KEYS") != nullptr;
   const int smode = (mode == P3D_MODE_JOINT && !no_packed && n < (1ll << (32 - kLabelBits)) - 1) ? kModeJointPacked : mode;
-  // Double-buffered batches: splat(b) on the caller's stream, score(b) on a helper stream forked and joined with events,
-  // so the bandwidth-bound score/clear pass of one batch runs beside the issue-bound splat of the next.  Not used while
-  // the caller's stream is being captured into a graph, for single-batch sweeps, or with P3D_OVERLAP=0.
-  ScoreFork fork;
-  if (L.zbufs == 2 && K > batch && n > 0) {
+  // Double-buffered batches: splat(b) on the caller's stream, score(b) on the context's helper stream forked and joined
+  // with events, so the bandwidth-bound score/clear pass of one batch runs beside the issue-bound splat of the next.
+  // Needs a context (the helper stream is caller-owned state); not used while the caller's stream is being captured
+  // into a graph, for single-batch sweeps, or with P3D_OVERLAP=0.
+  bool forked = false;
+  if (ctx && L.zbufs == 2 && K > batch && n > 0) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
-      rc = fork.open();
+      rc = ctx_open_fork(ctx);
       if (rc) return rc;
+      forked = true;
     } else {
       (void)cudaGetLastError();
     }
   }
+  bool pending[2] = {false, false};                         // score pass of that buffer not yet joined into `st`
+  // error path: the helper stream may still be reading the caller-owned workspace; order it before anything the
+  // caller enqueues next (or frees) by joining it into `st`
+  auto fail = [&](int code) {
+    if (forked)
+      for (int i = 0; i < 2; ++i)
+        if (pending[i]) (void)cudaStreamWaitEvent(st, ctx->scored[i], 0);
+    return code;
+  };
+#define P3D_SWEEP_CUDA(expr)                                                                                        \
+  do {                                                                                                              \
+    cudaError_t _e = (expr);                                                                                        \
+    if (_e != cudaSuccess) {                                                                                        \
+      p3d::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+      return fail(P3D_E_CUDA);                                                                                      \
+    }                                                                                                               \
+  } while (0)
   int b = 0;
   for (int k0 = 0; k0 < K; k0 += batch, ++b) {
     const int kb = K - k0 < batch ? K - k0 : batch;
     if (n > 0) {
-      const int buf = fork.active ? (b & 1) : 0;
+      const int buf = forked ? (b & 1) : 0;
       uint32_t* zb = zbuf + (size_t)buf * L.batch * HW;
-      if (fork.active && b >= 2) P3D_CUDA(cudaStreamWaitEvent(st, fork.scored[buf], 0));   // score(b-2) has cleared zb
+      if (forked && b >= 2) {                              // score(b-2) has cleared zb
+        P3D_SWEEP_CUDA(cudaStreamWaitEvent(st, ctx->scored[buf], 0));
+        pending[buf] = false;
+      }
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-      if (g_timing.enabled && (ev0 = timing_event()) && (ev1 = timing_event())) P3D_CUDA(cudaEventRecord(ev0, st));
-      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, smode, zb,
-                    n > 0 ? fast + (size_t)k0 * 16 : nullptr, bbox, stream);
-      if (rc) return rc;
-      if (ev1) P3D_CUDA(cudaEventRecord(ev1, st));
+      if (ctx && ctx->timing && (ev0 = timing_event(ctx)) && (ev1 = timing_event(ctx))) P3D_SWEEP_CUDA(cudaEventRecord(ev0, st));
+      rc = splat<T>(pts, pt_label, n, cams + (size_t)k0 * 16, kb, H, W, smode, zb, fast + (size_t)k0 * 16, bbox, stream,
+                    segs, n_seg, flags + k0);
+      if (rc) return fail(rc);
+      if (ev1) P3D_SWEEP_CUDA(cudaEventRecord(ev1, st));
       cudaStream_t ss = st;
-      if (fork.active) {
-        P3D_CUDA(cudaEventRecord(fork.splatted[buf], st));
-        P3D_CUDA(cudaStreamWaitEvent(fork.stream, fork.splatted[buf], 0));
-        ss = fork.stream;
+      if (forked) {
+        P3D_SWEEP_CUDA(cudaEventRecord(ctx->splatted[buf], st));
+        P3D_SWEEP_CUDA(cudaStreamWaitEvent(ctx->helper, ctx->splatted[buf], 0));
+        ss = ctx->helper;
       }
       const int vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(gt_label) & 3) == 0) &&
                       (gt_any == nullptr || (reinterpret_cast<uintptr_t>(gt_any) & 3) == 0);
@@ -1088,22 +1368,31 @@ int sweep(const float* pts, const uint8_t* pt_label, int64_t n, const T* cand, i
       else
         score_kernel<P3D_MODE_PER_PART><<<grid, kScoreThreads, 0, ss>>>(zb, pt_label, gt_label, gt_any, HW, P,
                                                                         raw + (size_t)k0 * (P + 1) * 2, vec, W, rk);
-      P3D_LAUNCH_CHECK();
-      if (fork.active) P3D_CUDA(cudaEventRecord(fork.scored[buf], fork.stream));
-      g_last_launches += 2;
+      P3D_SWEEP_CUDA(cudaGetLastError());
+      if (forked) {
+        P3D_SWEEP_CUDA(cudaEventRecord(ctx->scored[buf], ctx->helper));
+        pending[buf] = true;
+      }
+      launches += 2;
     }
   }
-  if (fork.active) {                                     // join: everything after this sees all score passes
-    for (int buf = 0; buf < (b < 2 ? b : 2); ++buf) P3D_CUDA(cudaStreamWaitEvent(st, fork.scored[buf], 0));
+  if (forked) {                                          // join: everything after this sees all score passes
+    for (int buf = 0; buf < 2; ++buf)
+      if (pending[buf]) {
+        P3D_SWEEP_CUDA(cudaStreamWaitEvent(st, ctx->scored[buf], 0));
+        pending[buf] = false;
+      }
   }
+#undef P3D_SWEEP_CUDA
   finalize_kernel<<<(K + 127) / 128, 128, 0, st>>>(raw, gt_area, K, P, rows, counts, scores);
   P3D_LAUNCH_CHECK();
-  ++g_last_launches;
+  ++launches;
   if (best) {
     argmax_kernel<<<1, 1024, 0, st>>>(scores, K, best);
     P3D_LAUNCH_CHECK();
-    ++g_last_launches;
+    ++launches;
   }
+  if (ctx) ctx->last_launches = launches;
   return P3D_OK;
 }
 
@@ -1172,22 +1461,61 @@ P3D_API size_t p3d_sweep_workspace_bytes(int K, int H, int W, int P, int elem_by
   return sweep_layout(K, H, W, P, elem_bytes).total;
 }
 
-P3D_API int p3d_sweep_f64(const float* pts, const uint8_t* pt_label, int64_t n, const double* cand, int K,
-                          const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
-                          int64_t* counts, double* scores, int64_t* best, void* workspace, size_t workspace_bytes,
-                          p3d_stream_t stream) {
-  return sweep<double>(pts, pt_label, n, cand, K, gt_label, gt_any, H, W, P, mode, counts, scores, best, workspace,
-                       workspace_bytes, stream);
+P3D_API int p3d_sweep_f64(const float* pts, const uint8_t* pt_label, int64_t n, const uint32_t* segs, int64_t n_seg,
+                          const double* cand, int K, const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P,
+                          int mode, int64_t* counts, double* scores, int64_t* best, void* workspace,
+                          size_t workspace_bytes, p3d_sweep_ctx* ctx, p3d_stream_t stream) {
+  return sweep<double>(pts, pt_label, n, reinterpret_cast<const uint4*>(segs), n_seg, cand, K, gt_label, gt_any, H, W, P,
+                       mode, counts, scores, best, workspace, workspace_bytes, ctx, stream);
 }
-P3D_API int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, const float* cand, int K,
-                          const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P, int mode,
-                          int64_t* counts, double* scores, int64_t* best, void* workspace, size_t workspace_bytes,
-                          p3d_stream_t stream) {
-  return sweep<float>(pts, pt_label, n, cand, K, gt_label, gt_any, H, W, P, mode, counts, scores, best, workspace,
-                      workspace_bytes, stream);
+P3D_API int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, const uint32_t* segs, int64_t n_seg,
+                          const float* cand, int K, const uint8_t* gt_label, const uint8_t* gt_any, int H, int W, int P,
+                          int mode, int64_t* counts, double* scores, int64_t* best, void* workspace,
+                          size_t workspace_bytes, p3d_sweep_ctx* ctx, p3d_stream_t stream) {
+  return sweep<float>(pts, pt_label, n, reinterpret_cast<const uint4*>(segs), n_seg, cand, K, gt_label, gt_any, H, W, P,
+                      mode, counts, scores, best, workspace, workspace_bytes, ctx, stream);
 }
 
-P3D_API int p3d_sweep_last_launches(void) { return g_last_launches; }
+P3D_API int p3d_segment_length(void) { return kSegLen; }
+
+P3D_API p3d_sweep_ctx* p3d_sweep_ctx_create(void) { return new (std::nothrow) p3d_sweep_ctx(); }
+
+P3D_API void p3d_sweep_ctx_destroy(p3d_sweep_ctx* ctx) {
+  if (!ctx) return;
+  for (cudaEvent_t e : ctx->pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->splatted[i]) cudaEventDestroy(ctx->splatted[i]);
+    if (ctx->scored[i]) cudaEventDestroy(ctx->scored[i]);
+  }
+  if (ctx->helper) cudaStreamDestroy(ctx->helper);
+  delete ctx;
+}
+
+P3D_API int p3d_sweep_ctx_launches(const p3d_sweep_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+P3D_API int p3d_sweep_ctx_timing(p3d_sweep_ctx* ctx, int on) {
+  P3D_REQUIRE(ctx, "sweep_ctx_timing: null context");
+  ctx->timing = on != 0;
+  ctx->used = 0;
+  return P3D_OK;
+}
+
+P3D_API int p3d_sweep_ctx_timing_read(p3d_sweep_ctx* ctx, double* splat_ms, int* n_launches) {
+  P3D_REQUIRE(ctx, "sweep_ctx_timing_read: null context");
+  double total = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < ctx->used; i += 2) {
+    P3D_CUDA(cudaEventSynchronize(ctx->pool[i + 1]));
+    float ms = 0.f;
+    P3D_CUDA(cudaEventElapsedTime(&ms, ctx->pool[i], ctx->pool[i + 1]));
+    total += ms;
+    ++n;
+  }
+  ctx->used = 0;
+  if (splat_ms) *splat_ms = total;
+  if (n_launches) *n_launches = n;
+  return P3D_OK;
+}
 
 P3D_API size_t p3d_depth_workspace_bytes(int H, int W, int elem_bytes) {
   if (H <= 0 || W <= 0) return 0;
@@ -1257,27 +1585,5 @@ P3D_API int p3d_best_select(const int64_t* pairs, int n, int64_t* out, p3d_strea
   P3D_REQUIRE(pairs && out && n >= 1, "best_select: bad arguments");
   best_select_kernel<<<1, 32, 0, p3d::as_stream(stream)>>>(pairs, n, out);
   P3D_LAUNCH_CHECK();
-  return P3D_OK;
-}
-
-P3D_API int p3d_sweep_timing_enable(int on) {
-  g_timing.enabled = on != 0;
-  g_timing.used = 0;
-  return P3D_OK;
-}
-
-P3D_API int p3d_sweep_timing_read(double* splat_ms, int* n_launches) {
-  double total = 0.0;
-  int n = 0;
-  for (size_t i = 0; i + 1 < g_timing.used; i += 2) {
-    P3D_CUDA(cudaEventSynchronize(g_timing.pool[i + 1]));
-    float ms = 0.f;
-    P3D_CUDA(cudaEventElapsedTime(&ms, g_timing.pool[i], g_timing.pool[i + 1]));
-    total += ms;
-    ++n;
-  }
-  g_timing.used = 0;
-  if (splat_ms) *splat_ms = total;
-  if (n_launches) *n_launches = n;
   return P3D_OK;
 }

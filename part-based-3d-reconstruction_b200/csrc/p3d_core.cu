@@ -338,6 +338,132 @@ P3D_API int p3d_points_fill(const uint8_t* labels, int A0, int A1, int A2, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// x-run segments of a point list (input of the segment splat, p3d_camera.cu).  get_voxel_points_by_parts
+// (utils/voxel_utils.py:17-19) emits points in ascending flat index, so the voxels of one (z, y) row are consecutive in
+// the list and in x.  A segment is a run of <= L list-consecutive points with the same label, the same (y, z),
+// x increasing by exactly 1, that does not cross a multiple of L in x.  Point i starts a segment iff any of these breaks
+// against point i-1 (a purely local test on the list, so any point list works; a list without such runs degenerates to
+// one segment per point).  Record = uint4 { x0 | y << 16, z | (len-1) << 16 | label << 24, idx0, 0 }.
+// Points that are not integer-valued in [0, 65535]^3 or whose label is outside 1..32 are counted in n_out[1]; the
+// caller must then not use the segment path.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kSegTile = 1024;
+
+__device__ __forceinline__ bool seg_point_ok(const float* __restrict__ p, uint32_t lab) {
+  bool ok = lab >= 1u && lab <= 32u;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float v = p[k];
+    ok = ok && v >= 0.f && v <= 65535.f && v == truncf(v);
+  }
+  return ok;
+}
+
+__device__ __forceinline__ bool seg_is_start(const float* __restrict__ pts, const uint8_t* __restrict__ lab, int64_t i,
+                                             int L) {
+  if (i == 0) return true;
+  const float* a = pts + 3 * (i - 1);
+  const float* b = pts + 3 * i;
+  const float bx = __ldg(b);
+  return __ldg(lab + i) != __ldg(lab + i - 1) || __ldg(b + 1) != __ldg(a + 1) || __ldg(b + 2) != __ldg(a + 2) ||
+         bx != __ldg(a) + 1.f || ((int)bx % L) == 0;
+}
+
+__global__ void __launch_bounds__(kSegTile) segments_count_kernel(const float* __restrict__ pts,
+                                                                  const uint8_t* __restrict__ lab, int64_t n, int L,
+                                                                  int64_t* __restrict__ tile_counts,
+                                                                  unsigned long long* __restrict__ bad) {
+  __shared__ int s_count, s_bad;
+  if (threadIdx.x == 0) { s_count = 0; s_bad = 0; }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kSegTile + threadIdx.x;
+  bool start = false, isbad = false;
+  if (i < n) {
+    start = seg_is_start(pts, lab, i, L);
+    isbad = !seg_point_ok(pts + 3 * i, lab[i]);
+  }
+  const uint32_t ms = __ballot_sync(0xffffffffu, start), mb = __ballot_sync(0xffffffffu, isbad);
+  if ((threadIdx.x & 31) == 0) {
+    if (ms) atomicAdd(&s_count, __popc(ms));
+    if (mb) atomicAdd(&s_bad, __popc(mb));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tile_counts[blockIdx.x] = s_count;
+    if (s_bad) atomicAdd(bad, (unsigned long long)s_bad);
+  }
+}
+
+__global__ void __launch_bounds__(kSegTile) segments_fill_kernel(const float* __restrict__ pts,
+                                                                 const uint8_t* __restrict__ lab, int64_t n, int L,
+                                                                 const int64_t* __restrict__ tile_offsets,
+                                                                 uint4* __restrict__ segs, int64_t capacity) {
+  __shared__ int warp_sums[kSegTile / 32];
+  const int64_t i = (int64_t)blockIdx.x * kSegTile + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool start = i < n && seg_is_start(pts, lab, i, L);
+  const uint32_t ms = __ballot_sync(0xffffffffu, start);
+  if (lane == 0) warp_sums[warp] = __popc(ms);
+  __syncthreads();
+  if (!start) return;
+  int before = __popc(ms & ((1u << lane) - 1u));
+  for (int w = 0; w < warp; ++w) before += warp_sums[w];
+  const int64_t out = tile_offsets[blockIdx.x] + before;
+  if (out >= capacity) return;
+  int len = 1;
+  while (len < L && i + len < n && !seg_is_start(pts, lab, i + len, L)) ++len;
+  const float* p = pts + 3 * i;
+  const uint32_t x0 = (uint32_t)(int)p[0] & 0xffffu, y = (uint32_t)(int)p[1] & 0xffffu, z = (uint32_t)(int)p[2] & 0xffffu;
+  segs[out] = make_uint4(x0 | (y << 16), z | ((uint32_t)(len - 1) << 16) | ((uint32_t)lab[i] << 24), (uint32_t)i, 0u);
+}
+
+}  // namespace
+
+P3D_API size_t p3d_segments_workspace_bytes(int64_t n_points) {
+  if (n_points < 0) return 0;
+  const int64_t tiles = (n_points + kSegTile - 1) / kSegTile;
+  return (size_t)(tiles + 1) * sizeof(int64_t);
+}
+
+P3D_API int p3d_segments_count(const float* pts, const uint8_t* pt_label, int64_t n, int seg_len, int64_t* n_out,
+                               void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && n < 0xffffffffll && n_out && workspace, "segments_count: bad arguments");
+  P3D_REQUIRE(seg_len >= 1 && seg_len <= 32, "segments_count: seg_len=%d", seg_len);
+  P3D_REQUIRE((pts && pt_label) || n == 0, "segments_count: null points");
+  if (workspace_bytes < p3d_segments_workspace_bytes(n)) {
+    p3d::set_error("segments_count: workspace %zu < %zu", workspace_bytes, p3d_segments_workspace_bytes(n));
+    return P3D_E_WORKSPACE;
+  }
+  const int64_t tiles = (n + kSegTile - 1) / kSegTile;
+  int64_t* tc = static_cast<int64_t*>(workspace);
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(n_out, 0, 2 * sizeof(int64_t), st));
+  if (tiles > 0) {
+    segments_count_kernel<<<(unsigned)tiles, kSegTile, 0, st>>>(pts, pt_label, n, seg_len, tc,
+                                                                reinterpret_cast<unsigned long long*>(n_out + 1));
+    P3D_LAUNCH_CHECK();
+  }
+  points_scan_kernel<<<1, 1024, 0, st>>>(tc, tiles, n_out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_segments_fill(const float* pts, const uint8_t* pt_label, int64_t n, int seg_len, const void* workspace,
+                              uint32_t* segs, int64_t capacity, p3d_stream_t stream) {
+  P3D_REQUIRE(n >= 0 && capacity >= 0 && workspace && seg_len >= 1 && seg_len <= 32, "segments_fill: bad arguments");
+  if (n == 0 || capacity == 0) return P3D_OK;
+  P3D_REQUIRE(pts && pt_label && segs, "segments_fill: null pointer");
+  P3D_REQUIRE((reinterpret_cast<uintptr_t>(segs) & 15) == 0, "segments_fill: segs must be 16-byte aligned");
+  const int64_t tiles = (n + kSegTile - 1) / kSegTile;
+  segments_fill_kernel<<<(unsigned)tiles, kSegTile, 0, p3d::as_stream(stream)>>>(
+      pts, pt_label, n, seg_len, static_cast<const int64_t*>(workspace), reinterpret_cast<uint4*>(segs), capacity);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // voxel_grid_to_points (utils/voxel_utils.py:35-51): strided occupancy of an RGB grid and the colours of the kept
 // voxels.  mask[(a,b,c)] = any(grid[a*s, b*s, c*s, :]) on the sub-sampled lattice; colours are gathered at the
 // compacted points afterwards.

@@ -166,9 +166,12 @@ __device__ __forceinline__ void make_fast_cam(const double* __restrict__ cam, co
 // its 8 projected corners, so the reference's u, v of every point lie inside the corners' min/max; 2.5 px of margin
 // cover the reference's own rounding and the half-even pixel rounding.  Any other camera gets the full image.  The
 // score pass reads and clears only this rectangle of the camera's z-buffer (nothing outside it is ever written).
-__device__ __forceinline__ void footprint_rect(const double* __restrict__ cam, const float* __restrict__ bbox, int H, int W,
+// Returns true when the unclamped rectangle lies inside the image: then every decided point of the camera is in range
+// and the segment splat skips the bounds test (kCamInView).
+__device__ __forceinline__ bool footprint_rect(const double* __restrict__ cam, const float* __restrict__ bbox, int H, int W,
                                                bool fast_ok, int4* out) {
   int4 r = make_int4(0, H - 1, 0, W - 1);
+  bool inside = false;
   if (fast_ok) {
     double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
     bool fin = true;
@@ -189,9 +192,12 @@ __device__ __forceinline__ void footprint_rect(const double* __restrict__ cam, c
       const double c0 = fmax(0.0, floor(umin - m)), c1 = fmin((double)(W - 1), ceil(umax + m));
       if (r0 > r1 || c0 > c1) r = make_int4(0, -1, 0, -1);
       else r = make_int4((int)r0, (int)r1, (int)c0, (int)c1);
+      inside = floor(vmin - m) >= 0.0 && ceil(vmax + m) <= (double)(H - 1) && floor(umin - m) >= 0.0 &&
+               ceil(umax + m) <= (double)(W - 1);
     }
   }
-  *out = r;
+  if (out) *out = r;
+  return inside;
 }
 
 // Packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2): one issue slot for two lanes' worth of IEEE-rn FP32 operations.

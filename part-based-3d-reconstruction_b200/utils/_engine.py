@@ -137,22 +137,79 @@ def partwise_counts_rgb(proj: torch.Tensor, gt: torch.Tensor, part_rgb: torch.Te
 
 
 class SweepWorkspace:
-    """Caller-owned scratch for p3d_sweep_* (z-buffer batch, camera blocks, raw counters)."""
+    """Caller-owned state of p3d_sweep_*: the device scratch (z-buffer batches, camera blocks, raw counters) and the
+    host-side context (p3d_sweep_ctx: helper stream + events of the double-buffered batches, launch counter, optional
+    splat timing).  One per concurrent caller."""
 
     def __init__(self, device):
         self.device = device
         self.buf = None
+        self._ctx = None
 
     def get(self, nbytes: int) -> torch.Tensor:
         if self.buf is None or self.buf.numel() < nbytes:
             self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self.buf
 
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = lib.p3d_sweep_ctx_create()
+            if not self._ctx:
+                raise MemoryError("p3d_sweep_ctx_create failed")
+        return self._ctx
+
+    def timing(self, on: bool) -> None:
+        check(lib.p3d_sweep_ctx_timing(self.ctx, 1 if on else 0), "p3d_sweep_ctx_timing")
+
+    def timing_read(self):
+        """(summed splat-launch duration in ms, number of splat launches) since timing(True); synchronises."""
+        import ctypes
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        check(lib.p3d_sweep_ctx_timing_read(self.ctx, ctypes.byref(ms), ctypes.byref(n)), "p3d_sweep_ctx_timing_read")
+        return ms.value, n.value
+
+    def __del__(self):
+        ctx, self._ctx = self._ctx, None
+        if ctx:
+            try:
+                lib.p3d_sweep_ctx_destroy(ctx)
+            except Exception:
+                pass
+
+
+def build_segments(pts: torch.Tensor, pt_label: torch.Tensor):
+    """x-run segments of a point list for the segment splat (p3d_segments_*): (S,4) int32 tensor, or None when the list
+    cannot be represented (non-integer coordinates, coordinates outside 0..65535, labels outside 1..32) -- the sweep
+    then runs the per-point splat."""
+    assert pts.is_cuda and pts.dtype == torch.float32 and pts.is_contiguous()
+    assert pt_label.dtype == torch.uint8 and pt_label.is_contiguous()
+    n = int(pts.shape[0])
+    if n == 0:
+        return None
+    dev = pts.device
+    L = int(lib.p3d_segment_length())
+    ws_bytes = int(lib.p3d_segments_workspace_bytes(n))
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    n_out = torch.zeros(2, dtype=torch.int64, device=dev)
+    check(lib.p3d_segments_count(ptr(pts), ptr(pt_label), n, L, ptr(n_out), ptr(ws), ws_bytes, stream_ptr()),
+          "p3d_segments_count")
+    _launched(2)
+    n_seg, bad = (int(v) for v in n_out.cpu().numpy())      # one 16-byte read-back: sizes the output
+    if bad or n_seg == 0:
+        return None
+    segs = torch.empty((n_seg, 4), dtype=torch.int32, device=dev)
+    check(lib.p3d_segments_fill(ptr(pts), ptr(pt_label), n, L, ptr(ws), ptr(segs), n_seg, stream_ptr()),
+          "p3d_segments_fill")
+    _launched(1)
+    return segs
+
 
 def sweep(pts: torch.Tensor, pt_label: torch.Tensor, cand: torch.Tensor, gt_label: torch.Tensor, H: int, W: int,
           P: int, mode: int = nv.MODE_JOINT, gt_any=None, workspace: SweepWorkspace | None = None,
-          want_best: bool = True):
-    """Score K candidate cameras.  Returns (counts (K,rows,2) i64, scores (K) f64, best (2) i64 | None)."""
+          want_best: bool = True, segs=None):
+    """Score K candidate cameras.  Returns (counts (K,rows,2) i64, scores (K) f64, best (2) i64 | None).
+    `segs` = build_segments(pts, pt_label) selects the segment splat."""
     assert pts.is_cuda and pts.dtype == torch.float32 and pts.is_contiguous()
     assert pt_label.dtype == torch.uint8 and pt_label.is_contiguous()
     assert gt_label.dtype == torch.uint8 and gt_label.is_contiguous() and gt_label.numel() == H * W
@@ -167,9 +224,11 @@ def sweep(pts: torch.Tensor, pt_label: torch.Tensor, cand: torch.Tensor, gt_labe
         return counts, scores, best
     elem = _elem(cand.dtype)
     nbytes = int(lib.p3d_sweep_workspace_bytes(K, H, W, P, 8 if elem == "f64" else 4))
-    ws = (workspace or SweepWorkspace(dev)).get(nbytes)
+    workspace = workspace or SweepWorkspace(dev)
+    ws = workspace.get(nbytes)
     fn = getattr(lib, f"p3d_sweep_{elem}")
-    check(fn(ptr(pts), ptr(pt_label), pts.shape[0], ptr(cand), K, ptr(gt_label), ptr(gt_any), H, W, P, mode,
-             ptr(counts), ptr(scores), ptr(best), ptr(ws), ws.numel(), stream_ptr()), "p3d_sweep")
-    _launched(int(lib.p3d_sweep_last_launches()))
+    n_seg = int(segs.shape[0]) if segs is not None else 0
+    check(fn(ptr(pts), ptr(pt_label), pts.shape[0], ptr(segs), n_seg, ptr(cand), K, ptr(gt_label), ptr(gt_any), H, W, P,
+             mode, ptr(counts), ptr(scores), ptr(best), ptr(ws), ws.numel(), workspace.ctx, stream_ptr()), "p3d_sweep")
+    _launched(int(lib.p3d_sweep_ctx_launches(workspace.ctx)))
     return counts, scores, best

@@ -58,9 +58,19 @@ _SIGNATURES = {
     "p3d_resolve_rgb": ([_vp, _vp, _i64, _vp, _vp], _i32),
     "p3d_partwise_counts_rgb": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp], _i32),
     "p3d_sweep_workspace_bytes": ([_i32, _i32, _i32, _i32, _i32], _sz),
-    "p3d_sweep_f64": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp], _i32),
-    "p3d_sweep_f32": ([_vp, _vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp], _i32),
-    "p3d_sweep_last_launches": ([], _i32),
+    "p3d_sweep_f64": ([_vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp,
+                       _vp], _i32),
+    "p3d_sweep_f32": ([_vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp,
+                       _vp], _i32),
+    "p3d_sweep_ctx_create": ([], _vp),
+    "p3d_sweep_ctx_destroy": ([_vp], None),
+    "p3d_sweep_ctx_launches": ([_vp], _i32),
+    "p3d_sweep_ctx_timing": ([_vp, _i32], _i32),
+    "p3d_sweep_ctx_timing_read": ([_vp, _vp, _vp], _i32),
+    "p3d_segment_length": ([], _i32),
+    "p3d_segments_workspace_bytes": ([_i64], _sz),
+    "p3d_segments_count": ([_vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp], _i32),
+    "p3d_segments_fill": ([_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp], _i32),
     "p3d_best_pack": ([_vp, _vp, _i64, _vp, _vp], _i32),
     "p3d_best_select": ([_vp, _i32, _vp, _vp], _i32),
     "p3d_depth_workspace_bytes": ([_i32, _i32, _i32], _sz),
@@ -76,8 +86,6 @@ _SIGNATURES = {
     "p3d_deform_sweep_f32": ([_vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
                               _vp, _vp, _vp], _i32),
     "p3d_deform_scatter": ([_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
-    "p3d_sweep_timing_enable": ([_i32], _i32),
-    "p3d_sweep_timing_read": ([_vp, _vp], _i32),
     "p3d_resample_carve": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "p3d_resample_carve_passes": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp], _i32),
     "p3d_fold_table": ([_i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),

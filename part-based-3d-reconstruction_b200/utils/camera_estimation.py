@@ -94,7 +94,7 @@ class CandidateScorer:
     """
 
     def __init__(self, voxel_grid, image, part_colors, parts, *, mode="joint", device=None,
-                 dtype=np.float64, background=None):
+                 dtype=np.float64, background=None, use_segments=True):
         self.device = nv.require_cuda(device)
         self.mode = {"joint": nv.MODE_JOINT, "per_part": nv.MODE_PER_PART}[mode]
         self.parts = list(parts)
@@ -117,6 +117,9 @@ class CandidateScorer:
                 self.gt_any = (image_labels(img, [tuple(int(v) for v in bg)], self.device) == 0).to(torch.uint8)
             self.pal = nv.palette_tensor(self.colours, self.device)
             self.workspace = eng.SweepWorkspace(self.device)
+            # x-run segments of the point list (ascending flat index => rows are consecutive in x): the sweep's
+            # segment splat evaluates the (y, z) part of the projection once per run
+            self.segs = eng.build_segments(self.pts, self.pt_label) if use_segments else None
         self.P = len(self.colours)
         self._cols = [self.label_of[p] - 1 for p in self.parts]
         self._dedup = len(self.colours) != len(self.parts)
@@ -130,7 +133,7 @@ class CandidateScorer:
         best (2)) with rows indexed by DISTINCT colour label (see `label_of`)."""
         with torch.cuda.device(self.device):
             return eng.sweep(self.pts, self.pt_label, cand, self.gt_label, self.H, self.W, self.P, self.mode,
-                             gt_any=self.gt_any, workspace=self.workspace, want_best=want_best)
+                             gt_any=self.gt_any, workspace=self.workspace, want_best=want_best, segs=self.segs)
 
     def score(self, candidates):
         """candidates: (K,9) array-like [cam_pos, target, f, cx, cy].

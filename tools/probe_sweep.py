@@ -24,9 +24,16 @@ t0 = time.time(); scorer = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, parts); 
 cand = torch.from_numpy(syn.candidates(base, K)).to(dev)
 for it in range(3):
     torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True)
-    nv.lib.p3d_sweep_timing_enable(1)
+    scorer.workspace.timing(True)
     e0.record(); counts, scores, best = scorer.score_device(cand); e1.record(); torch.cuda.synchronize()
-    import ctypes
-    ms = ctypes.c_double(); nl = ctypes.c_int(); nv.lib.p3d_sweep_timing_read(ctypes.byref(ms), ctypes.byref(nl)); nv.lib.p3d_sweep_timing_enable(0)
+    ms, nl = scorer.workspace.timing_read(); scorer.workspace.timing(False)
     t = e0.elapsed_time(e1)
-    print(f"sweep K={K} {t:.1f} ms -> {K / t * 1e3:.1f} cand/s ; splat {ms.value:.1f} ms in {nl.value} launches; point-cands/s {scorer.n_points * K / t * 1e3:.3e}; best {int(best[0])} score {float(scores[int(best[0])]):.5f}")
+    print(f"sweep K={K} {t:.1f} ms -> {K / t * 1e3:.1f} cand/s ; splat {ms:.1f} ms in {nl} launches; point-cands/s {scorer.n_points * K / t * 1e3:.3e}; best {int(best[0])} score {float(scores[int(best[0])]):.5f}; segs {None if scorer.segs is None else int(scorer.segs.shape[0])}")
+if os.environ.get("PROBE_COMPARE"):          # same candidates through the per-point splat: counts must be identical
+    ref = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, parts, use_segments=False)
+    c2, s2, b2 = ref.score_device(cand)
+    torch.cuda.synchronize()
+    for it in range(2):
+        e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True); e0.record(); c2, s2, b2 = ref.score_device(cand); e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1)
+    print(f"per-point splat: {t:.1f} ms -> {K / t * 1e3:.1f} cand/s; counts identical: {bool(torch.equal(c2, counts))} scores identical: {bool(torch.equal(s2, scores))}")
