@@ -143,7 +143,7 @@ int p3d_partwise_counts_rgb(const uint8_t* proj_rgb, const uint8_t* gt_rgb, int6
  * Workspace: p3d_sweep_workspace_bytes(); cameras are processed in batches of z-buffers.
  *
  * segs / n_seg (optional, NULL / 0 = none): the x-run segments of `pts` from p3d_segments_fill().  With them the
- * sweep launches the segment splat (one thread per run of <= p3d_segment_length() consecutive voxels of a row, see
+ * sweep launches the segment splat (one thread per <= p3d_segment_length() voxels of a row at a constant x step, see
  * csrc/p3d_camera.cu); without them, for images above 2^22 pixels, or with P3D_SPLAT_POINTS=1, the per-point splat.
  * Both give identical counts.
  *
@@ -177,9 +177,11 @@ int p3d_sweep_f32(const float* pts, const uint8_t* pt_label, int64_t n, const ui
                   size_t workspace_bytes, p3d_sweep_ctx* ctx, p3d_stream_t stream);
 
 /* x-run segments of a point list in get_voxel_points_by_parts order (utils/voxel_utils.py:17-19: ascending flat
- * index, so the voxels of one (z, y) row are consecutive in the list and in x).  A segment = up to L = seg_len
- * list-consecutive points with equal label, equal (y, z), x increasing by exactly 1, not crossing a multiple of L in
- * x; record = 4 uint32 { x0 | y << 16, z | (len-1) << 16 | label << 24, index of the first point, 0 }.
+ * index, so the voxels of one (z, y) row are consecutive in the list and in x).  A chunk = up to 32 L (L = seg_len)
+ * list-consecutive points with equal label, equal (y, z), x increasing by exactly 1, not crossing a multiple of 32 L
+ * in x.  A chunk of n points becomes T = ceil(n / L) segments; segment r owns the points r, r + T, r + 2T, ... of the
+ * chunk (at most L).  Record = 4 uint32 { x_first | y << 16, z | (count-1) << 16 | (T-1) << 20 | label << 26,
+ * list index of the first point, 0 }.
  *   p3d_segments_count : n_out (2) int64 device = [number of segments, number of points the segment form cannot
  *                        represent (non-integer or outside 0..65535, label outside 1..32)]; if n_out[1] != 0 the
  *                        caller must not pass segments to p3d_sweep_*.  workspace: p3d_segments_workspace_bytes(n).

@@ -723,25 +723,32 @@ def voxel_grid_to_points(grid, stride=2):
 # utils/voxel_utils.py:17-19)
 # ------------------------------------------------------------------------------------------------
 def point_segments(pts, labels, L):
-    """(S,4) uint32 records {x0 | y << 16, z | (len-1) << 16 | label << 24, first point index, 0} of the runs of
-    <= L list-consecutive points with equal label, equal (y, z), x increasing by exactly 1, not crossing a multiple
-    of L in x; plus the number of points the form cannot represent."""
+    """(S,4) uint32 segment records and the number of points the form cannot represent.  Chunks = runs of <= 32 L
+    list-consecutive points with equal label, equal (y, z), x increasing by exactly 1, not crossing a multiple of 32 L
+    in x; a chunk of n points is dealt out column-wise to T = ceil(n / L) segments, segment r owning the points
+    r, r + T, ... of the chunk.  Record = {x_first | y << 16, z | (count-1) << 16 | (T-1) << 20 | label << 26,
+    list index of the first point, 0}."""
     pts = np.asarray(pts, dtype=np.float32).reshape(-1, 3)
     labels = np.asarray(labels, dtype=np.uint8).reshape(-1)
     n = len(pts)
     if n == 0:
         return np.zeros((0, 4), np.uint32), 0
+    C = 32 * L
     with np.errstate(invalid="ignore"):
         ok = (labels >= 1) & (labels <= 32) & np.all((pts >= 0) & (pts <= 65535) & (pts == np.trunc(pts)), axis=1)
         xi = np.nan_to_num(pts[:, 0], nan=0.0, posinf=0.0, neginf=0.0).astype(np.int64)
     start = np.ones(n, bool)
     start[1:] = ((labels[1:] != labels[:-1]) | (pts[1:, 1] != pts[:-1, 1]) | (pts[1:, 2] != pts[:-1, 2]) |
-                 (pts[1:, 0] != pts[:-1, 0] + np.float32(1)) | (xi[1:] % L == 0))
+                 (pts[1:, 0] != pts[:-1, 0] + np.float32(1)) | (xi[1:] % C == 0))
     first = np.flatnonzero(start)
     length = np.diff(np.append(first, n))
-    p = np.nan_to_num(pts[first], nan=0.0, posinf=0.0, neginf=0.0).astype(np.int64) & 0xffff
-    rec = np.zeros((len(first), 4), np.uint32)
-    rec[:, 0] = p[:, 0] | (p[:, 1] << 16)
-    rec[:, 1] = p[:, 2] | ((length - 1) << 16) | (labels[first].astype(np.int64) << 24)
-    rec[:, 2] = first
+    T = (length + L - 1) // L
+    chunk = np.repeat(np.arange(len(first)), T)                       # chunk of every segment
+    r = np.arange(T.sum()) - np.repeat(np.cumsum(T) - T, T)           # column of every segment
+    cnt = (length[chunk] - r + T[chunk] - 1) // T[chunk]
+    p = np.nan_to_num(pts[first], nan=0.0, posinf=0.0, neginf=0.0).astype(np.int64)
+    rec = np.zeros((len(chunk), 4), np.uint32)
+    rec[:, 0] = ((p[chunk, 0] + r) & 0xffff) | ((p[chunk, 1] & 0xffff) << 16)
+    rec[:, 1] = (p[chunk, 2] & 0xffff) | ((cnt - 1) << 16) | ((T[chunk] - 1) << 20) | (labels[first][chunk].astype(np.int64) << 26)
+    rec[:, 2] = first[chunk] + r
     return rec, int((~ok).sum())

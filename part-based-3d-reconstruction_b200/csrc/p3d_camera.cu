@@ -364,21 +364,26 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// Segment splat: the same filter, one thread per x-run segment (p3d_segments_*, p3d_core.cu) instead of kPptF unrelated
-// points.  What the run structure buys per (point, camera):
+// Segment splat: the same filter, one thread per segment of an x-run (p3d_segments_*, p3d_core.cu) instead of kPptF
+// unrelated points.  A chunk of n <= 32 L consecutive voxels of one (y, z) row is dealt out column-wise to T = ceil(n/L)
+// neighbouring threads: thread r owns x0 + r + T j, j < L.  What the run structure buys per (point, camera):
 //   * the (y, z) part of the three fma chains is evaluated once per segment:  Xrow = fma(qz,A2, fma(qy,A1, TA)) (X and Y
-//     rows share packed instructions), then X_j = fma(qx_j, A0, Xrow) for the points of the run -- the same three
+//     rows share packed instructions), then X_j = fma(qx_j, A0, Xrow) for the points of the segment -- the same three
 //     roundings per coordinate as the per-point chain in another association order, and the error model above bounds
 //     every partial sum by f S + |T_A| regardless of order, so the thresholds of make_fast_cam() hold unchanged;
-//     qx_j = fl((x0 + j) - c_x) is the very value the per-point kernel computes (x0 + j is an exact integer);
-//   * a thread carries 3 coordinates + one key for kSegLen points (key_j = key0 + j * step), so kSegLen = 8 points per
-//     thread fit the register budget and the per-camera loop overhead (camera block loads, parked-mask upkeep) is
-//     shared by twice as many points;
+//     qx_j = fl((x_first + T j) - c_x) is the very value the per-point kernel computes (x_first + T j is an exact
+//     integer);
+//   * a thread carries 3 coordinates + key and key step for kSegLen points (key_j = key0 + j * step), so kSegLen = 8
+//     points per thread fit the register budget and the per-camera loop overhead (camera block loads, parked-mask
+//     upkeep) is shared by twice as many points;
 //   * the pixel index comes out of the FP pipe: lin = fma(rint(v), W, u + magic) holds row * W + col in its mantissa
-//     (exact while H W <= 2^22), one shift-add turns it into a 32-bit byte offset into the batch's z-buffer set;
+//     (exact while H W <= 2^22) and indexes the camera's z-buffer directly (base biased by bits(magic));
 //   * cameras whose footprint rectangle (footprint_rect, unclamped, 2.5 px margin) lies inside the image need no bounds
-//     test at all: a decided point of such a camera is in range by construction (kCamInView).
-// Points beyond a segment's length carry NaN coordinates: never decided, never parked (`live`).
+//     test at all: a decided point of such a camera is in range by construction (kCamInView);
+//   * neighbouring threads still hold neighbouring voxels, so a warp's early-out loads touch about as many 32-byte
+//     sectors as the per-point kernel's (a thread owning 8 ADJACENT voxels measured 23 k cand/s against 35 k: every
+//     lane its own sector, L2-sector bound).
+// Points beyond a segment's count carry NaN coordinates: never decided, never parked (`live`).
 // Bit-identical to splat_kernel<T> like the per-point filter (tests/test_camera_gpu.py, tests/test_segments_gpu.py).
 // ------------------------------------------------------------------------------------------
 #ifndef P3D_SEG_LEN
@@ -403,19 +408,20 @@ __device__ __forceinline__ uint32_t seg_key0(uint32_t idx0, uint32_t lab) {
   if (MODE == kModeJointPacked) return ((idx0 + 1u) << kLabelBits) | (lab - 1u);
   return 1u << (lab - 1u);
 }
+// key step between two points of a segment whose list indices are T apart
 template <int MODE>
-__device__ __forceinline__ uint32_t seg_key(uint32_t key0, int j) {
-  if (MODE == P3D_MODE_JOINT) return key0 + (uint32_t)j;
-  if (MODE == kModeJointPacked) return key0 + ((uint32_t)j << kLabelBits);
-  return key0;
+__device__ __forceinline__ uint32_t seg_key_step(uint32_t T) {
+  if (MODE == P3D_MODE_JOINT) return T;
+  if (MODE == kModeJointPacked) return T << kLabelBits;
+  return 0u;
 }
 
 // One camera for one segment: returns the mask of undecided points (bit j).  zb = this camera's z-buffer minus
 // bits(magic) elements, so that the raw bits of `lin` index it.
 template <bool INVIEW, int MODE>
 __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 2], float qy, float qz, uint32_t key0,
-                                                    const float4* __restrict__ fc4, uint32_t* __restrict__ zb,
-                                                    uint32_t W, uint32_t H, float Wf) {
+                                                    uint32_t kstep, const float4* __restrict__ fc4,
+                                                    uint32_t* __restrict__ zb, uint32_t W, uint32_t H, float Wf) {
   const float kMagic = 12582912.f;                          // 1.5 * 2^23
   const uint32_t kMagicBits = 0x4B400000u;
   const float4 c0 = fc4[0];                                 // A0 B0 C0 thr_u
@@ -473,7 +479,7 @@ __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 
       if (hit[jj]) cur[jj] = __ldcg(addr[jj]);
 #pragma unroll
     for (int jj = 0; jj < kSegGroup; ++jj) {
-      const uint32_t key = seg_key<MODE>(key0, g * kSegGroup + jj);
+      const uint32_t key = key0 + (uint32_t)(g * kSegGroup + jj) * kstep;
       if (MODE != P3D_MODE_PER_PART) {
         if (hit[jj] && cur[jj] < key) atomicMax(addr[jj], key);
       } else {
@@ -516,19 +522,20 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
   const int64_t tile = (int64_t)gridDim.x - 1 - blockIdx.x;
   const int64_t si = tile * kSegThreads + threadIdx.x;
   uint4 sg = make_uint4(0, 0, 0, 0);
-  int len = 0;
+  int len = 0;                                             // points of this segment: x_first + nT j, j < len
   if (si < n_seg) {
     sg = __ldg(segs + si);
-    len = (int)((sg.y >> 16) & 0xffu) + 1;
+    len = (int)((sg.y >> 16) & 0xfu) + 1;
   }
-  const uint32_t idx0 = sg.z;
-  const uint32_t key0 = seg_key0<MODE>(idx0, len ? (sg.y >> 24) : 1u);
+  const uint32_t idx0 = sg.z, nT = ((sg.y >> 20) & 0x3fu) + 1u;   // nT = segments of this chunk = x step
+  const uint32_t key0 = seg_key0<MODE>(idx0, len ? (sg.y >> 26) : 1u), kstep = seg_key_step<MODE>(nT);
   const float qy = __fsub_rn((float)(sg.x >> 16), ctr1), qz = __fsub_rn((float)(sg.y & 0xffffu), ctr2);
   const float nan = __int_as_float(0x7fc00000);
   f32x2 QX[kSegLen / 2];
 #pragma unroll
   for (int m = 0; m < kSegLen / 2; ++m) {
-    const float xa = __fsub_rn((float)((sg.x & 0xffffu) + 2 * m), ctr0), xb = __fsub_rn((float)((sg.x & 0xffffu) + 2 * m + 1), ctr0);
+    const float xa = __fsub_rn((float)((sg.x & 0xffffu) + nT * (2 * m)), ctr0);
+    const float xb = __fsub_rn((float)((sg.x & 0xffffu) + nT * (2 * m + 1)), ctr0);
     QX[m] = pack2(2 * m < len ? xa : nan, 2 * m + 1 < len ? xb : nan);
   }
   unsigned long long live = len >= 64 ? ~0ull : ((1ull << len) - 1ull);   // parked-mask bits of the points that exist
@@ -550,7 +557,7 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
     qn -= take;
     __syncwarp();
   };
-  // group g of kSegLen bits (from the low end) belongs to camera clast - g, bit j of the group to point idx0 + j
+  // group g of kSegLen bits (from the low end) belongs to camera clast - g, bit j of the group to point idx0 + T j
   auto flush = [&](unsigned long long mask, int clast) {
     mask &= live;
     const uint32_t lt = (1u << lane) - 1u;
@@ -561,7 +568,7 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
       if (has) {
         const uint32_t b = (uint32_t)(__ffsll((long long)mask) - 1);
         mask &= mask - 1ull;
-        q[qn + __popc(m & lt)] = make_uint2(idx0 + (b % (uint32_t)kSegLen), (uint32_t)clast - b / (uint32_t)kSegLen);
+        q[qn + __popc(m & lt)] = make_uint2(idx0 + nT * (b % (uint32_t)kSegLen), (uint32_t)clast - b / (uint32_t)kSegLen);
       }
       qn += __popc(m);
       __syncwarp();
@@ -575,9 +582,9 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
     const float4* fc4 = reinterpret_cast<const float4*>(s_fast + c * 16);
     uint32_t und;
     if (s_flag[c] & kCamInView)
-      und = seg_camera_pass<true, MODE>(QX, qy, qz, key0, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
+      und = seg_camera_pass<true, MODE>(QX, qy, qz, key0, kstep, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
     else
-      und = seg_camera_pass<false, MODE>(QX, qy, qz, key0, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
+      und = seg_camera_pass<false, MODE>(QX, qy, qz, key0, kstep, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
     parked = (parked << kSegLen) | (unsigned long long)und;
     if ((c & (kSegFlushEvery - 1)) == kSegFlushEvery - 1) {
       flush(parked, c);

@@ -340,10 +340,13 @@ P3D_API int p3d_points_fill(const uint8_t* labels, int A0, int A1, int A2, const
 // ---------------------------------------------------------------------------------------------
 // x-run segments of a point list (input of the segment splat, p3d_camera.cu).  get_voxel_points_by_parts
 // (utils/voxel_utils.py:17-19) emits points in ascending flat index, so the voxels of one (z, y) row are consecutive in
-// the list and in x.  A segment is a run of <= L list-consecutive points with the same label, the same (y, z),
-// x increasing by exactly 1, that does not cross a multiple of L in x.  Point i starts a segment iff any of these breaks
+// the list and in x.  A chunk is a run of <= 32 L list-consecutive points with the same label, the same (y, z),
+// x increasing by exactly 1, that does not cross a multiple of 32 L in x; point i starts a chunk iff any of these breaks
 // against point i-1 (a purely local test on the list, so any point list works; a list without such runs degenerates to
-// one segment per point).  Record = uint4 { x0 | y << 16, z | (len-1) << 16 | label << 24, idx0, 0 }.
+// one segment per point).  A chunk of n points is dealt out column-wise to T = ceil(n / L) segments (threads of the
+// splat): segment r = 0..T-1 owns the points r, r + T, r + 2T, ... (<= L of them), so that neighbouring threads hold
+// neighbouring voxels (their z-buffer accesses coalesce) while every thread still walks an arithmetic progression in x.
+// Record = uint4 { x_first | y << 16, z | (count-1) << 16 | (T-1) << 20 | label << 26, index of the first point, 0 }.
 // Points that are not integer-valued in [0, 65535]^3 or whose label is outside 1..32 are counted in n_out[1]; the
 // caller must then not use the segment path.
 // ---------------------------------------------------------------------------------------------
@@ -362,36 +365,64 @@ __device__ __forceinline__ bool seg_point_ok(const float* __restrict__ p, uint32
 }
 
 __device__ __forceinline__ bool seg_is_start(const float* __restrict__ pts, const uint8_t* __restrict__ lab, int64_t i,
-                                             int L) {
+                                             int chunk) {
   if (i == 0) return true;
   const float* a = pts + 3 * (i - 1);
   const float* b = pts + 3 * i;
   const float bx = __ldg(b);
   return __ldg(lab + i) != __ldg(lab + i - 1) || __ldg(b + 1) != __ldg(a + 1) || __ldg(b + 2) != __ldg(a + 2) ||
-         bx != __ldg(a) + 1.f || ((int)bx % L) == 0;
+         bx != __ldg(a) + 1.f || ((int)bx % chunk) == 0;
+}
+
+// points in the chunk that starts at i
+__device__ __forceinline__ int seg_chunk_points(const float* __restrict__ pts, const uint8_t* __restrict__ lab, int64_t i,
+                                                int64_t n, int chunk) {
+  int len = 1;
+  while (len < chunk && i + len < n && !seg_is_start(pts, lab, i + len, chunk)) ++len;
+  return len;
+}
+
+__device__ __forceinline__ int seg_block_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int base = 0, all = 0;
+  for (int w = 0; w < kSegTile / 32; ++w) {
+    const int sv = warp_sums[w];
+    if (w < warp) base += sv;
+    all += sv;
+  }
+  *total = all;
+  return base + incl - v;
 }
 
 __global__ void __launch_bounds__(kSegTile) segments_count_kernel(const float* __restrict__ pts,
                                                                   const uint8_t* __restrict__ lab, int64_t n, int L,
                                                                   int64_t* __restrict__ tile_counts,
                                                                   unsigned long long* __restrict__ bad) {
-  __shared__ int s_count, s_bad;
-  if (threadIdx.x == 0) { s_count = 0; s_bad = 0; }
-  __syncthreads();
+  __shared__ int warp_sums[kSegTile / 32];
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
   const int64_t i = (int64_t)blockIdx.x * kSegTile + threadIdx.x;
-  bool start = false, isbad = false;
+  int mine = 0;
+  bool isbad = false;
   if (i < n) {
-    start = seg_is_start(pts, lab, i, L);
+    if (seg_is_start(pts, lab, i, 32 * L)) mine = (seg_chunk_points(pts, lab, i, n, 32 * L) + L - 1) / L;
     isbad = !seg_point_ok(pts + 3 * i, lab[i]);
   }
-  const uint32_t ms = __ballot_sync(0xffffffffu, start), mb = __ballot_sync(0xffffffffu, isbad);
-  if ((threadIdx.x & 31) == 0) {
-    if (ms) atomicAdd(&s_count, __popc(ms));
-    if (mb) atomicAdd(&s_bad, __popc(mb));
-  }
+  int total;
+  seg_block_scan(mine, warp_sums, &total);                   // contains the barrier that publishes s_bad = 0
+  const uint32_t mb = __ballot_sync(0xffffffffu, isbad);
+  if ((threadIdx.x & 31) == 0 && mb) atomicAdd(&s_bad, __popc(mb));
   __syncthreads();
   if (threadIdx.x == 0) {
-    tile_counts[blockIdx.x] = s_count;
+    tile_counts[blockIdx.x] = total;
     if (s_bad) atomicAdd(bad, (unsigned long long)s_bad);
   }
 }
@@ -402,21 +433,25 @@ __global__ void __launch_bounds__(kSegTile) segments_fill_kernel(const float* __
                                                                  uint4* __restrict__ segs, int64_t capacity) {
   __shared__ int warp_sums[kSegTile / 32];
   const int64_t i = (int64_t)blockIdx.x * kSegTile + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool start = i < n && seg_is_start(pts, lab, i, L);
-  const uint32_t ms = __ballot_sync(0xffffffffu, start);
-  if (lane == 0) warp_sums[warp] = __popc(ms);
-  __syncthreads();
-  if (!start) return;
-  int before = __popc(ms & ((1u << lane) - 1u));
-  for (int w = 0; w < warp; ++w) before += warp_sums[w];
+  int len = 0, T = 0;
+  if (i < n && seg_is_start(pts, lab, i, 32 * L)) {
+    len = seg_chunk_points(pts, lab, i, n, 32 * L);
+    T = (len + L - 1) / L;
+  }
+  int total;
+  const int before = seg_block_scan(T, warp_sums, &total);
+  if (T == 0) return;
   const int64_t out = tile_offsets[blockIdx.x] + before;
-  if (out >= capacity) return;
-  int len = 1;
-  while (len < L && i + len < n && !seg_is_start(pts, lab, i + len, L)) ++len;
   const float* p = pts + 3 * i;
-  const uint32_t x0 = (uint32_t)(int)p[0] & 0xffffu, y = (uint32_t)(int)p[1] & 0xffffu, z = (uint32_t)(int)p[2] & 0xffffu;
-  segs[out] = make_uint4(x0 | (y << 16), z | ((uint32_t)(len - 1) << 16) | ((uint32_t)lab[i] << 24), (uint32_t)i, 0u);
+  const uint32_t x0 = (uint32_t)(int)p[0], y = (uint32_t)(int)p[1] & 0xffffu, z = (uint32_t)(int)p[2] & 0xffffu;
+  const uint32_t label = lab[i];
+  for (int r = 0; r < T; ++r) {
+    if (out + r >= capacity) break;
+    const int cnt = (len - r + T - 1) / T;                   // points r, r + T, ... < len
+    segs[out + r] = make_uint4(((x0 + (uint32_t)r) & 0xffffu) | (y << 16),
+                               z | ((uint32_t)(cnt - 1) << 16) | ((uint32_t)(T - 1) << 20) | (label << 26),
+                               (uint32_t)(i + r), 0u);
+  }
 }
 
 }  // namespace
@@ -430,7 +465,7 @@ P3D_API size_t p3d_segments_workspace_bytes(int64_t n_points) {
 P3D_API int p3d_segments_count(const float* pts, const uint8_t* pt_label, int64_t n, int seg_len, int64_t* n_out,
                                void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
   P3D_REQUIRE(n >= 0 && n < 0xffffffffll && n_out && workspace, "segments_count: bad arguments");
-  P3D_REQUIRE(seg_len >= 1 && seg_len <= 32, "segments_count: seg_len=%d", seg_len);
+  P3D_REQUIRE(seg_len >= 1 && seg_len <= 16, "segments_count: seg_len=%d", seg_len);
   P3D_REQUIRE((pts && pt_label) || n == 0, "segments_count: null points");
   if (workspace_bytes < p3d_segments_workspace_bytes(n)) {
     p3d::set_error("segments_count: workspace %zu < %zu", workspace_bytes, p3d_segments_workspace_bytes(n));
@@ -452,7 +487,7 @@ P3D_API int p3d_segments_count(const float* pts, const uint8_t* pt_label, int64_
 
 P3D_API int p3d_segments_fill(const float* pts, const uint8_t* pt_label, int64_t n, int seg_len, const void* workspace,
                               uint32_t* segs, int64_t capacity, p3d_stream_t stream) {
-  P3D_REQUIRE(n >= 0 && capacity >= 0 && workspace && seg_len >= 1 && seg_len <= 32, "segments_fill: bad arguments");
+  P3D_REQUIRE(n >= 0 && capacity >= 0 && workspace && seg_len >= 1 && seg_len <= 16, "segments_fill: bad arguments");
   if (n == 0 || capacity == 0) return P3D_OK;
   P3D_REQUIRE(pts && pt_label && segs, "segments_fill: null pointer");
   P3D_REQUIRE((reinterpret_cast<uintptr_t>(segs) & 15) == 0, "segments_fill: segs must be 16-byte aligned");

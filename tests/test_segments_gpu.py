@@ -44,7 +44,7 @@ def test_segment_records_match_the_numpy_restatement(oracle):
     rng = np.random.default_rng(5)
     L = int(nv.lib.p3d_segment_length())
     names = [k for k in oracle.PART_COLORS if k != "background"]
-    for shape in ((9, 7, 40), (5, 6, 129), (3, 3, 8), (2, 2, 1)):
+    for shape in ((9, 7, 40), (5, 6, 129), (3, 4, 600), (3, 3, 8), (2, 2, 1)):
         parts = names[:5]
         for grid in (blocky_grid(rng, shape, parts, oracle.PART_COLORS) if min(shape) > 2 else np.zeros(shape + (3,), np.uint8),
                      np.where(rng.random(shape + (1,)) < 0.6, np.array(oracle.PART_COLORS[parts[0]], np.uint8), 0).astype(np.uint8)):
@@ -58,8 +58,12 @@ def test_segment_records_match_the_numpy_restatement(oracle):
                 assert got is None
                 continue
             assert np.array_equal(got.cpu().numpy().view(np.uint32), want)
-            lens = ((want[:, 1] >> 16) & 0xff) + 1
+            lens = ((want[:, 1] >> 16) & 0xf) + 1
             assert lens.sum() == len(pts) and lens.max() <= L
+            # every point is owned by exactly one (segment, j)
+            Ts = ((want[:, 1] >> 20) & 0x3f) + 1
+            owned = np.concatenate([f + t * np.arange(c) for f, t, c in zip(want[:, 2].astype(np.int64), Ts, lens)])
+            assert np.array_equal(np.sort(owned), np.arange(len(pts)))
     # lists the segment form cannot represent are refused (the sweep then runs the per-point splat)
     pts = torch.tensor([[0.5, 1, 1], [1.5, 1, 1]], dtype=torch.float32).cuda()
     assert eng.build_segments(pts, torch.ones(2, dtype=torch.uint8).cuda()) is None
