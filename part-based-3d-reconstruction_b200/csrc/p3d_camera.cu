@@ -416,18 +416,27 @@ __device__ __forceinline__ uint32_t seg_key_step(uint32_t T) {
   return 0u;
 }
 
+// 16-byte shared-memory load from a 32-bit shared address (kept in a register and stepped per camera: the compiler's own
+// address arithmetic re-derived the CTA's shared window every iteration)
+__device__ __forceinline__ float4 lds128(uint32_t saddr, int byte_off) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr + byte_off));
+  return v;
+}
+
 // One camera for one segment: returns the mask of undecided points (bit j).  zb = this camera's z-buffer minus
-// bits(magic) elements, so that the raw bits of `lin` index it.
+// bits(magic) elements, so that the raw bits of `lin` index it.  c0..c3 = the camera's 16 floats (layout below).
+// kmax = the greatest key of the segment: `cur >= kmax` proves that no point of the segment can win the pixel; a
+// pixel that fails this coarser test gets the reduction with the point's exact key (atomicMax is idempotent), which
+// only costs extra reductions for pixels currently owned by another voxel of the same chunk.
 template <bool INVIEW, int MODE>
 __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 2], float qy, float qz, uint32_t key0,
-                                                    uint32_t kstep, const float4* __restrict__ fc4,
-                                                    uint32_t* __restrict__ zb, uint32_t W, uint32_t H, float Wf) {
+                                                    uint32_t kstep, uint32_t kmax, const float4 c0, const float4 c1,
+                                                    const float4 c2, const float4 c3, uint32_t* __restrict__ zb,
+                                                    uint32_t W, uint32_t H, float Wf) {
   const float kMagic = 12582912.f;                          // 1.5 * 2^23
   const uint32_t kMagicBits = 0x4B400000u;
-  const float4 c0 = fc4[0];                                 // A0 B0 C0 thr_u
-  const float4 c1 = fc4[1];                                 // A1 B1 A2 B2
-  const float4 c2 = fc4[2];                                 // TA TB C1 C2
-  const float4 c3 = fc4[3];                                 // TC cx cy thr_v
+  // c0 = A0 B0 C0 thr | c1 = A1 B1 A2 B2 | c2 = TA TB C1 C2 | c3 = TC cx cy flags
   const f32x2 XYr = fma2(pack2(qz, qz), pack2(c1.z, c1.w), fma2(pack2(qy, qy), pack2(c1.x, c1.y), pack2(c2.x, c2.y)));
   float xr, yr;
   unpack2(XYr, xr, yr);
@@ -436,7 +445,7 @@ __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 
   const f32x2 XR = pack2(xr, xr), YR = pack2(yr, yr), ZR = pack2(zr, zr);
   const f32x2 CX = pack2(c3.y, c3.y), CY = pack2(c3.z, c3.z), WF = pack2(Wf, Wf);
   const f32x2 kM2 = pack2(kMagic, kMagic), kNegM2 = pack2(-kMagic, -kMagic), kNeg1 = pack2(-1.f, -1.f);
-  const float thr_u = c0.w, thr_v = c3.w;
+  const float thr = c0.w;                                   // min(thr_u, thr_v)
   uint32_t und = 0;
 #pragma unroll
   for (int g = 0; g < kSegLen / kSegGroup; ++g) {
@@ -462,7 +471,7 @@ __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int jj = 2 * mp + h;
-        const bool decided = fabsf(du[h]) < thr_u && fabsf(dv[h]) < thr_v;                  // false for NaN
+        const bool decided = fabsf(du[h]) < thr && fabsf(dv[h]) < thr;                      // false for NaN
         if (INVIEW) {
           hit[jj] = decided;
         } else {
@@ -479,16 +488,20 @@ __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 
       if (hit[jj]) cur[jj] = __ldcg(addr[jj]);
 #pragma unroll
     for (int jj = 0; jj < kSegGroup; ++jj) {
-      const uint32_t key = key0 + (uint32_t)(g * kSegGroup + jj) * kstep;
       if (MODE != P3D_MODE_PER_PART) {
-        if (hit[jj] && cur[jj] < key) atomicMax(addr[jj], key);
+        if (hit[jj] && cur[jj] < kmax) atomicMax(addr[jj], key0 + (uint32_t)(g * kSegGroup + jj) * kstep);
       } else {
-        if (hit[jj] && (cur[jj] & key) != key) atomicOr(addr[jj], key);
+        if (hit[jj] && (cur[jj] & key0) != key0) atomicOr(addr[jj], key0);
       }
     }
   }
   return und;
 }
+
+#ifndef P3D_SEG_QUEUE
+#define P3D_SEG_QUEUE 96
+#endif
+constexpr int kSegQueueCap = P3D_SEG_QUEUE;   // per warp: < 32 pending + one bulk push of <= kSegQueueCap - 32 entries
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kSegThreads, P3D_SEG_MINBLOCKS)
@@ -497,24 +510,29 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
                  int W, uint32_t* __restrict__ zbuf, const float* __restrict__ fast, const float* __restrict__ bbox,
                  const uint32_t* __restrict__ cam_flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* s_cam = reinterpret_cast<T*>(smem_raw);                                             // nc x 16 camera scalars
+  T* s_cam = reinterpret_cast<T*>(smem_raw);                                             // nc x 16 camera scalars (exact path)
   float* s_fast = reinterpret_cast<float*>(s_cam + (size_t)cams_per_block * 16);          // nc x 16, permuted FastCam
-  uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_fast + (size_t)cams_per_block * 16);   // nc
-  uint2* s_queue = reinterpret_cast<uint2*>(s_flag + ((cams_per_block + 3) & ~3));        // warps x kQueueCap
+  uint2* s_queue = reinterpret_cast<uint2*>(s_fast + (size_t)cams_per_block * 16);        // warps x kSegQueueCap
+  // (reading the exact path's camera blocks from global memory instead measured 15 % slower: 32 scattered 120-byte
+  // reads per drain)
 
   const int c0 = blockIdx.y * cams_per_block;
   const int nc = min(cams_per_block, K - c0);
-  // FastCam = A[3],TA, B[3],TB, C[3],TC, cx, cy, thr_u, thr_v  ->  A0 B0 C0 thr_u | A1 B1 A2 B2 | TA TB C1 C2 | TC cx cy thr_v
+  // FastCam = A[3],TA, B[3],TB, C[3],TC, cx, cy, thr_u, thr_v  ->  A0 B0 C0 thr | A1 B1 A2 B2 | TA TB C1 C2 | TC cx cy flags
+  // with thr = min(thr_u, thr_v) (one threshold for both coordinates) and flags = the camera's cam_flags word
   const unsigned long long kPerm = 0xFDCBA9736251E840ull;   // nibble i = source slot of destination slot i
   for (int i = threadIdx.x; i < nc * 16; i += kSegThreads) {
     s_cam[i] = cams[(size_t)c0 * 16 + i];
-    s_fast[i] = fast[(size_t)c0 * 16 + (i & ~15) + (int)((kPerm >> (4 * (i & 15))) & 15ull)];
+    const float* f = fast + (size_t)(c0 + (i >> 4)) * 16;
+    float v = f[(int)((kPerm >> (4 * (i & 15))) & 15ull)];
+    if ((i & 15) == 3) v = fminf(f[14], f[15]);
+    if ((i & 15) == 15) v = __uint_as_float(cam_flags ? cam_flags[c0 + (i >> 4)] : 0u);
+    s_fast[i] = v;
   }
-  for (int i = threadIdx.x; i < nc; i += kSegThreads) s_flag[i] = cam_flags ? cam_flags[c0 + i] : 0u;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint2* q = s_queue + warp * kQueueCap;
+  uint2* q = s_queue + warp * kSegQueueCap;
   int qn = 0;                                              // entries pending in the warp's queue (warp-uniform)
   const float ctr0 = bbox_centre(bbox, 0), ctr1 = bbox_centre(bbox, 1), ctr2 = bbox_centre(bbox, 2);
 
@@ -529,6 +547,7 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
   }
   const uint32_t idx0 = sg.z, nT = ((sg.y >> 20) & 0x3fu) + 1u;   // nT = segments of this chunk = x step
   const uint32_t key0 = seg_key0<MODE>(idx0, len ? (sg.y >> 26) : 1u), kstep = seg_key_step<MODE>(nT);
+  const uint32_t kmax = key0 + (uint32_t)(kSegLen - 1) * kstep;   // >= every key of the segment (n < 2^27: no wrap)
   const float qy = __fsub_rn((float)(sg.x >> 16), ctr1), qz = __fsub_rn((float)(sg.y & 0xffffu), ctr2);
   const float nan = __int_as_float(0x7fc00000);
   f32x2 QX[kSegLen / 2];
@@ -557,9 +576,33 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
     qn -= take;
     __syncwarp();
   };
-  // group g of kSegLen bits (from the low end) belongs to camera clast - g, bit j of the group to point idx0 + T j
+  // Push the undecided (point, camera) pairs of `mask`: group g of kSegLen bits (from the low end) belongs to camera
+  // clast - g, bit j of the group to point idx0 + nT j.  Usual case: the warp's entries fit the queue, every lane writes
+  // its own at an offset from a warp scan of the counts.  Otherwise (cameras without a valid filter: everything is
+  // undecided) rounds of at most one entry per lane, draining as the queue fills.
   auto flush = [&](unsigned long long mask, int clast) {
     mask &= live;
+    const int cnt = __popcll(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    if (qn + total <= kSegQueueCap) {
+      uint2* w = q + qn + incl - cnt;
+      while (mask) {
+        const uint32_t b = (uint32_t)(__ffsll((long long)mask) - 1);
+        mask &= mask - 1ull;
+        *w++ = make_uint2(idx0 + nT * (b % (uint32_t)kSegLen), (uint32_t)clast - b / (uint32_t)kSegLen);
+      }
+      qn += total;
+      __syncwarp();
+      while (qn >= 32) drain32();
+      return;
+    }
     const uint32_t lt = (1u << lane) - 1u;
     for (;;) {
       const bool has = mask != 0ull;
@@ -578,13 +621,14 @@ splat_seg_kernel(const uint4* __restrict__ segs, int64_t n_seg, const float* __r
 
   unsigned long long parked = 0ull;
   uint32_t* zb = zbuf + (size_t)c0 * HW - 0x4B400000ll;    // biased by bits(magic): indexed by the raw bits of `lin`
-  for (int c = 0; c < nc; ++c, zb += HW) {
-    const float4* fc4 = reinterpret_cast<const float4*>(s_fast + c * 16);
+  uint32_t sf = (uint32_t)__cvta_generic_to_shared(s_fast);
+  for (int c = 0; c < nc; ++c, zb += HW, sf += 64) {
+    const float4 k0 = lds128(sf, 0), k1 = lds128(sf, 16), k2 = lds128(sf, 32), k3 = lds128(sf, 48);
     uint32_t und;
-    if (s_flag[c] & kCamInView)
-      und = seg_camera_pass<true, MODE>(QX, qy, qz, key0, kstep, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
+    if (__float_as_uint(k3.w) & kCamInView)
+      und = seg_camera_pass<true, MODE>(QX, qy, qz, key0, kstep, kmax, k0, k1, k2, k3, zb, (uint32_t)W, (uint32_t)H, Wf);
     else
-      und = seg_camera_pass<false, MODE>(QX, qy, qz, key0, kstep, fc4, zb, (uint32_t)W, (uint32_t)H, Wf);
+      und = seg_camera_pass<false, MODE>(QX, qy, qz, key0, kstep, kmax, k0, k1, k2, k3, zb, (uint32_t)W, (uint32_t)H, Wf);
     parked = (parked << kSegLen) | (unsigned long long)und;
     if ((c & (kSegFlushEvery - 1)) == kSegFlushEvery - 1) {
       flush(parked, c);
@@ -1070,14 +1114,18 @@ int setup_cameras(const T* cand, int K, T* cams, p3d_stream_t stream) {
 }
 
 // cameras handled by one CTA: enough CTAs for ~8 waves when the point list is short
-inline int pick_cams_per_block(int64_t tiles, int K) {
+#ifndef P3D_SEG_MAXCAMS
+#define P3D_SEG_MAXCAMS 64
+#endif
+constexpr int kSegMaxCams = P3D_SEG_MAXCAMS;   // cameras per CTA of the segment splat (192 B of shared memory each; 128 measured slower)
+inline int pick_cams_per_block(int64_t tiles, int K, int max_cams = 64) {
   const int64_t want = (int64_t)p3d::sm_count() * 24;
   int groups = (int)((want + tiles - 1) / (tiles > 0 ? tiles : 1));
   if (groups < 1) groups = 1;
   if (groups > K) groups = K;
   int cpb = (K + groups - 1) / groups;
   if (cpb < 4) cpb = K < 4 ? K : 4;
-  if (cpb > 64) cpb = 64;                                  // 192 B of shared memory per camera: keep 8 CTAs per SM
+  if (cpb > max_cams) cpb = max_cams;                      // 192 B of shared memory per camera: keep 8 CTAs per SM
   return cpb;
 }
 
@@ -1129,10 +1177,9 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
     P3D_REQUIRE(pt_label, "splat: the segment path needs pt_label");
     const int64_t tiles = (n_seg + kSegThreads - 1) / kSegThreads;
     P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
-    const int cpb = pick_cams_per_block(tiles, K);
+    const int cpb = pick_cams_per_block(tiles, K, kSegMaxCams);
     dim3 grid((unsigned)tiles, (unsigned)((K + cpb - 1) / cpb));
-    const size_t smem = (size_t)cpb * (16 * sizeof(T) + 16 * sizeof(float)) + (size_t)((cpb + 3) & ~3) * sizeof(uint32_t) +
-                        (size_t)(kSegThreads / 32) * (kQueueCap * sizeof(uint2));
+    const size_t smem = (size_t)cpb * 16 * (sizeof(T) + sizeof(float)) + (size_t)(kSegThreads / 32) * (kSegQueueCap * sizeof(uint2));
     if (mode == P3D_MODE_JOINT)
       splat_seg_kernel<T, P3D_MODE_JOINT><<<grid, kSegThreads, smem, st>>>(segs, n_seg, pts, pt_label, cams, K, cpb, H, W, zbuf, fast, bbox, cam_flags);
     else if (mode == kModeJointPacked)

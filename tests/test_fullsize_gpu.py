@@ -139,3 +139,62 @@ def test_filtered_splat_equals_exact_over_many_cameras():
                 got = eng.splat(pts, pt_label, cams, H, W, bbox=bbox)
                 assert torch.equal(ref, got), (H, W, view, k0, dt)
                 del ref, got
+
+
+def test_bench_configuration_identical_under_every_sweep_mode(tmp_path):
+    """The very configuration bench.py times -- 512^3, all parts, 1024^2, batches of 128 cameras, double-buffered
+    z-buffers with the score pass on the helper stream, footprint rectangles, segment splat -- against the same 384
+    candidates scored with every one of those mechanisms switched off (batches in sequence on one stream, whole-image
+    score passes, per-point splat), each in its own process: counts, scores and the winner must be identical bit for
+    bit, on the first sweep and on the second one that re-uses the cleared z-buffers."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    runs = {}
+    for tag, env in (("default", {}),
+                     ("plain", {"P3D_OVERLAP": "0", "P3D_SCORE_RECT": "0", "P3D_SPLAT_POINTS": "1"}),
+                     ("small_batches", {"P3D_MAX_BATCH": "48"})):
+        e = dict(os.environ)
+        e.update(env)
+        out = str(tmp_path / f"{tag}.npz")
+        r = subprocess.run([sys.executable, os.path.join(here, "sweep_fullsize_dump.py"), out], env=e, capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[tag] = np.load(out)
+    assert int(runs["default"]["segs"]) > 0
+    ref = runs["plain"]
+    assert ref["counts0"].shape == (384, 9, 2) and int(ref["counts0"][:, :, 1].sum()) > 0
+    for tag in ("default", "small_batches"):
+        for rep in (0, 1):
+            assert np.array_equal(runs[tag][f"counts{rep}"], ref["counts0"]), (tag, rep)
+            assert np.array_equal(runs[tag][f"scores{rep}"], ref["scores0"]), (tag, rep)
+            assert int(runs[tag][f"best{rep}"]) == int(ref["best0"])
+    assert np.array_equal(ref["counts1"], ref["counts0"])
+
+
+@pytest.mark.parametrize("mode", ["joint", "per_part"])
+def test_segment_splat_equals_point_splat_full_size(mode):
+    """The segment splat under the stress mix of test_filtered_splat_equals_exact_over_many_cameras (front and aerial
+    views, odd image sizes, principal points far outside the image, float64 and float32 cameras) at full 512^3 size:
+    counts identical to the per-point splat, which that test pins to the exact FP64 kernel."""
+    syn, cfg, ce = pkg("synthetic"), pkg("utils.config"), pkg("utils.camera_estimation")
+    N = 512
+    dev = torch.device("cuda")
+    rgb = torch.from_numpy(syn.label_lut()).to(dev)[syn.monument_labels(N, dev).long()]
+    rng = np.random.default_rng(321)
+    for (H, W), view, K in (((1024, 1024), "front", 96), ((777, 1023), "aerial", 64), ((2048, 2048), "front", 24)):
+        gt = torch.from_numpy(rng.integers(0, 10, (H // 8 + 1, W // 8 + 1)).repeat(8, 0).repeat(8, 1)[:H, :W].astype(np.uint8))
+        img = torch.from_numpy(syn.label_lut())[gt.long()].to(dev)
+        cand = syn.candidates(syn.base_camera(N, H, W, view), K, seed=int(rng.integers(1 << 30)))
+        cand[K // 2:, 7] += rng.uniform(-1.5 * W, 1.5 * W, K - K // 2)
+        cand[K // 2:, 8] += rng.uniform(-1.0 * H, 1.0 * H, K - K // 2)
+        for dt in (np.float64, np.float32):
+            a = ce.CandidateScorer(rgb, img, cfg.PART_COLORS, syn.PART_NAMES, dtype=dt, mode=mode)
+            b = ce.CandidateScorer(rgb, img, cfg.PART_COLORS, syn.PART_NAMES, dtype=dt, mode=mode, use_segments=False)
+            assert a.segs is not None
+            sa, ca, ba = a.score(cand.astype(dt))
+            sb, cb, bb = b.score(cand.astype(dt))
+            assert np.array_equal(ca, cb) and np.array_equal(sa, sb) and ba == bb, (H, W, view, dt)
+            assert int(ca[:, :, 0].sum()) > 0
+            del a, b
