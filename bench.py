@@ -5,26 +5,37 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): the deterministic synthetic 512^3 semantic monument
-(part-based-3d-reconstruction_b200/synthetic.py), all 9 parts scored (21.9 M points), one
-1024x1024 ground-truth label image rendered through a hidden camera, 65 536 candidate cameras
-(base + U(-1,1)*reference step sizes, seed 20240607).  One "step" = every rank scores its block of
-`--cands-per-step` candidates and the ranks agree on the best (score, index) with one 16-byte
-all-gather.  Candidates are sharded across ranks, so per-GPU work is fixed (weak scaling).
+Workload (config.workload, defined in bench_workload.py): the deterministic synthetic 512^3 semantic monument, all 9
+parts scored (21.9 M points), one 1024x1024 ground-truth label image rendered through a hidden camera, 65 536 candidate
+cameras (base + U(-1,1) * reference step sizes, seed 20240607).  One "step" = every rank scores its block of
+`--cands-per-step` candidates and the ranks agree on the best (score, index) with one 16-byte all-gather.  Candidates are
+sharded across ranks, so per-GPU work is fixed (weak scaling).
 
-value   : candidates/s with grid points, ground truth and candidates resident in HBM.
-e2e     : the same through the public API with HOST candidate arrays in and host scores/counts out.
-roofline: the splat kernel, algorithmic bytes = cameras/launch * (G*1 B + 9 B*H*W)  (SURVEY 8d),
-          duration from CUDA events recorded around every splat launch inside the timed region.
-cpu_baseline: the NumPy port of the reference path (oracle/np_port.py) on this box's host cores.
+value       : candidates/s with grid points, ground truth and candidates resident in HBM.
+e2e         : the same through the public API with HOST candidate arrays in and host scores/counts out.
+roofline    : the splat kernel, algorithmic bytes = cameras/launch * (G*1 B + 9 B*H*W)  (SURVEY 8d),
+              duration from CUDA events recorded around every splat launch inside the timed region.
+parity      : counts and scores of candidates sampled from every z-buffer batch and both double-buffer slots of one timed
+              step, re-computed by the reference's own functions on the host (baseline/_ref; the NumPy port under
+              oracle/ only if that is absent); at N > 1 every rank checks candidates of its own block and the NCCL
+              winner is compared with the arg-max over an all-gather of the full score vectors.  Any mismatch: exit 1.
+sweep_total : strong scaling of the literal configuration -- wall time from a device-resident RGB grid + the host
+              (65536, 9) candidate array to the global best on every rank: scorer set-up (labels, compaction, segments,
+              ground-truth labels) + this rank's contiguous shard in blocks + one all-gather.
+cpu_baseline: the reference path on this box's host cores (same sampled candidates as the parity gate).
 """
 import argparse
-import ctypes
-import importlib
 import json
 import os
-import subprocess
 import sys
+
+# the reference arm's worker processes run one BLAS thread each: set before NumPy loads OpenBLAS
+if "reference" in sys.argv[1:]:
+    for _k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = "1"
+
+import importlib
+import subprocess
 import threading
 import time
 
@@ -32,11 +43,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
+import bench_workload as bw                                  # noqa: E402  (NumPy only; shared by both arms)
+
 PKG = "part-based-3d-reconstruction_b200"
 METRIC = "camera candidates scored/s at 512^3 grid"
 UNIT = "candidates/s"
-TOTAL_CANDIDATES = 65536
-HIDDEN_DELTA = np.array([3.0, -2.0, 5.0, 1.0, 2.0, -3.0, 4.0, 1.5, -2.5])
+TOTAL_CANDIDATES = bw.TOTAL_CANDIDATES
+HIDDEN_DELTA = bw.HIDDEN_DELTA
+PARITY_INDICES = [0, 127, 128, 300, 1023, 1024, 1500, 2047]   # of one step's block: every 128-camera batch boundary, both slots
 
 
 def parse_args():
@@ -50,9 +65,10 @@ def parse_args():
     ap.add_argument("--cands-per-step", type=int, default=2048, help="candidates per rank per step")
     ap.add_argument("--parts", default="all", choices=["all", "minarets"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU sample (0 = auto)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU sample (this also skips the parity gate)")
     ap.add_argument("--no-carve", action="store_true", help="skip the secondary carving measurement")
-    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of configs 2 and 3")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of configs 2, 3 and 5")
+    ap.add_argument("--no-sweep-total", action="store_true", help="skip the whole-sweep strong-scaling measurement")
     return ap.parse_args()
 
 
@@ -108,6 +124,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# parity gate helpers
+# ------------------------------------------------------------------------------------------------
+def compare_with_cpu(cpu, cand_rows, gpu_counts, gpu_scores, processes):
+    """Score `cand_rows` with the CPU arm and compare integer counts (exactly) and scores (1e-5 relative; in fact they
+    are identical).  Returns (seconds, n_checked, list of mismatch descriptions)."""
+    dt, counts, scores = cpu.run(cand_rows, processes=processes)
+    bad = []
+    for k in range(len(cand_rows)):
+        if not np.array_equal(counts[k], gpu_counts[k]):
+            bad.append(f"counts[{k}]: gpu {gpu_counts[k].tolist()} vs cpu {counts[k].tolist()}")
+        elif not abs(scores[k] - gpu_scores[k]) <= 1e-5 * max(abs(scores[k]), 1e-300):
+            bad.append(f"score[{k}]: gpu {gpu_scores[k]!r} vs cpu {scores[k]!r}")
+    return dt, len(cand_rows), bad, bool(np.array_equal(scores, gpu_scores))
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -132,7 +164,6 @@ def run_ours(args):
 
     N, H, W, B = args.grid, args.mask, args.mask, args.cands_per_step
     parts = syn.PART_NAMES if args.parts == "all" else ["front_minarets", "back_minarets"]
-    t_setup = time.perf_counter()
     lut = torch.from_numpy(syn.label_lut()).to(dev)
     rgb = lut[syn.monument_labels(N, dev).long()]
     base = syn.base_camera(N, H, W, "front")
@@ -140,9 +171,11 @@ def run_ours(args):
     full = ce.CandidateScorer(rgb, torch.zeros((H, W, 3), dtype=torch.uint8, device=dev), cfg.PART_COLORS, syn.PART_NAMES)
     gt = torch.from_numpy(full.render(ce.row_to_params(hidden))).to(dev)
     del full
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter()
     scorer = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, parts)
     torch.cuda.synchronize()
-    t_setup = time.perf_counter() - t_setup
+    t_setup = time.perf_counter() - t_setup                  # first construction (includes allocator warm-up)
     n_points = scorer.n_points
     P = scorer.P
 
@@ -162,7 +195,7 @@ def run_ours(args):
 
     def device_step(s):
         counts, scores, best = scorer.score_device(dev_blocks[s])
-        return reducer.reduce(scores, best, offsets[s]), counts
+        return reducer.reduce(scores, best, offsets[s]), counts, scores
 
     # ---- value: device-resident inputs ------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -180,7 +213,7 @@ def run_ours(args):
     wall0 = time.time()
     e0.record()
     for s in range(args.warmup, steps_total):
-        result, _ = device_step(s)
+        result, last_counts, last_scores = device_step(s)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -197,6 +230,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = B * world * args.steps / (ms * 1e-3)
+    # what the last timed step returned (kept for the parity gate before anything overwrites the output tensors)
+    s_last = steps_total - 1
+    gate_counts = last_counts.cpu().numpy()
+    gate_scores = last_scores.cpu().numpy()
+    gate_best = (float(result[0]), int(result[1]))
 
     # ---- e2e: host candidates in, host scores/counts out, through the public API ------------------
     for s in range(min(2, args.warmup)):
@@ -217,8 +255,21 @@ def run_ours(args):
     e2e_value = B * world * args.steps / (float(t2.item()) * 1e-3)
     h2d = B * 9 * 8
     d2h = B * 8 + B * cn.shape[1] * 2 * 8 + 8
+    e2e_same = bool(np.array_equal(cn, gate_counts[:, scorer._cols, :]) and np.array_equal(sc, gate_scores))
 
-    # ---- N > 1: global_carve of a 1024^3 grid sharded by x-slab (no exchange), max over ranks ---------------
+    # ---- sweep_total: the literal configuration, strong scaling incl. set-up -----------------------
+    sweep_total = None
+    if not args.no_sweep_total:
+        sweep_total = whole_sweep(ce, cfg, sweep_mod, nv, rgb, gt, parts, cand_all, B, dev, world, rank, dist)
+
+    # ---- parity gate --------------------------------------------------------------------------------
+    parity = None
+    cpu = None
+    if not args.no_cpu_baseline:
+        parity, cpu = parity_gate(args, scorer, gt, parts, cand_all, step_block(s_last), gate_counts, gate_scores, gate_best,
+                                  offsets[s_last], B, H, W, dev, world, rank, dist, sweep_mod)
+
+    # ---- N > 1: carving of a 1024^3 grid sharded by x-slab, max over ranks --------------------------
     carve_multi = None
     if world > 1 and not args.no_carve:
         try:
@@ -229,6 +280,8 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if parity is not None and parity.get("ok") is False:
+            sys.exit(1)
         return
 
     # ---- roofline of the dominant kernel (splat) --------------------------------------------------
@@ -240,13 +293,16 @@ def run_ours(args):
     achieved = alg_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
     traffic = None
     try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same batch size only)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_splat_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_splat_traffic.json")))
         if int(tj["cameras_per_launch"]) == batch and N == 512 and H == 1024 and args.parts == "all":
             traffic = int(tj["traffic_bytes_per_launch"])
     except Exception:
         pass
+    seg_on = scorer.segs is not None and os.environ.get("P3D_SPLAT_POINTS") != "1"
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "splat_filtered_kernel<joint> (FP32 filter + exact FP64 queue)",
+                "frac": round(achieved / peak, 4), "traffic": traffic,
+                "kernel": ("splat_seg_kernel<double, joint-packed> (x-run segments, FP32 filter + exact FP64 queue)" if seg_on
+                           else "splat_filtered_kernel<double, joint-packed> (FP32 filter + exact FP64 queue)"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch,
                 "cameras_per_launch": batch, "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "splat_share_of_step": round(splat_ms_v / ms, 4),
@@ -254,38 +310,37 @@ def run_ours(args):
                 "step_frac": round(value / max(world, 1) * (G * 1 + 9 * H * W) / 1e9 / peak, 4),
                 "point_candidates_per_s": round(n_points * batch / avg_launch_s, 1) if avg_launch_s > 0 else None,
                 "note": "effective GB/s under the streaming model of SURVEY 8(d) (dense u8 grid once per camera + 9 B/pixel); "
-                        "the kernel batches cameras per point pass and is instruction-issue bound, see DESIGN.md 4.1; "
-                        "avg_launch_ms is measured inside the step, where the score pass of the previous batch runs "
-                        "beside this kernel on a helper stream; "
+                        "the kernel batches cameras per point pass and is bound on-chip (issue slots / early-out load "
+                        "latency), see DESIGN.md 4.1; avg_launch_ms is measured inside the step, where the score pass of "
+                        "the previous batch runs beside this kernel on a helper stream; "
                         "step_achieved / step_frac = the same model over the whole step (per GPU)"}
 
-    # ---- CPU baseline: NumPy port of the reference path on this box's host cores -----------------
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_baseline(scorer, gt, parts, cfg, cand_all, H, W, n_points, args.cpu_sample, processes=1)
-
+    config = bw.bench_config(N, H, W, parts, n_points, B)
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {N}^3 semantic monument, {len(parts)} parts ({n_points} points), "
-                               f"{H}x{W} label mask, {TOTAL_CANDIDATES} candidate cameras sharded over {world} GPU(s), "
-                               f"{B} candidates/GPU/step",
-                   "grid": N, "mask": [H, W], "parts": len(parts), "points": n_points,
-                   "candidates_total": TOTAL_CANDIDATES, "candidates_per_gpu_per_step": B,
-                   "l2": "inputs larger than L2 (point list %.0f MB streamed by every launch); fresh candidates each step"
-                         % (n_points * 13 / 1e6),
-                   "setup_s_once_per_sweep": round(t_setup, 3)},
-        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "config": config,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "identical_to_device_path": e2e_same},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "best": {"index": int(result[1]), "score": float(result[0])},
+        "best": {"index": gate_best[1], "score": gate_best[0]},
+        "sharding": f"{TOTAL_CANDIDATES} candidates, {B} per GPU per step over {world} GPU(s)",
+        "setup_s_first_scorer": round(t_setup, 3),
     }
+    if parity is not None:
+        out["parity"] = parity
+    if sweep_total is not None:
+        out["sweep_total"] = sweep_total
     if cpu is not None:
         out["cpu_baseline"] = cpu
     if world == 1 and not args.no_extra:
         out["other_configs"] = extra_configs(dev, not args.no_cpu_baseline)
+        p5 = out["other_configs"].get("synthetic_1024_2048mask", {}).get("parity")
+        if p5 is not None and p5.get("ok") is False:
+            out.setdefault("parity", {})["config5_ok"] = False
     if carve_multi is not None:
         out["carve"] = carve_multi
     if world == 1 and not args.no_carve:
@@ -300,6 +355,131 @@ def run_ours(args):
     _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    failed = (parity is not None and parity.get("ok") is False) or (out.get("parity", {}).get("config5_ok") is False)
+    if failed:
+        print("PARITY GATE FAILED: " + json.dumps(out.get("parity")), file=sys.stderr)
+        sys.exit(1)
+
+
+def whole_sweep(ce, cfg, sweep_mod, nv, rgb, gt, parts, cand_all, B, dev, world, rank, dist):
+    """BASELINE.json configs[3] taken literally: all 65 536 candidates sharded contiguously over the ranks, timed from a
+    device-resident RGB grid + the host candidate array to the global best on every rank, set-up included.  Wall clock
+    between synchronised barriers, max over ranks (run twice, the second run is reported: the first one pays the
+    allocator's growth for the second scorer)."""
+    import torch
+    K = len(cand_all)
+    lo, hi = sweep_mod.shard_range(K, world, rank)
+    pinned = torch.from_numpy(np.ascontiguousarray(cand_all[lo:hi])).pin_memory()
+    res = None
+    for rep in range(2):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        scorer = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, parts)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        n_blocks = -(-(hi - lo) // B)
+        pairs = torch.empty((max(n_blocks, 1), 2), dtype=torch.int64, device=dev)
+        pairs[:, 0] = torch.tensor(np.float64(-1.0).view(np.int64).item(), dtype=torch.int64, device=dev)
+        pairs[:, 1] = -1
+        for b in range(n_blocks):
+            blk = pinned[b * B:(b + 1) * B].to(dev, non_blocking=True)
+            counts, scores, best = scorer.score_device(blk)
+            nv.check(nv.lib.p3d_best_pack(nv.ptr(scores), nv.ptr(best), lo + b * B, nv.ptr(pairs[b]), nv.stream_ptr()))
+        mine = torch.empty(2, dtype=torch.int64, device=dev)
+        nv.check(nv.lib.p3d_best_select(nv.ptr(pairs), max(n_blocks, 1), nv.ptr(mine), nv.stream_ptr()))
+        if world > 1:
+            gathered = torch.empty((world, 2), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered.view(-1), mine)
+            out = torch.empty(2, dtype=torch.int64, device=dev)
+            nv.check(nv.lib.p3d_best_select(nv.ptr(gathered), world, nv.ptr(out), nv.stream_ptr()))
+        else:
+            out = mine
+        host = out.cpu().numpy()                              # the global best on this rank (synchronises)
+        t2 = time.perf_counter()
+        tt = torch.tensor([t2 - t0, t1 - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res = {"seconds": round(float(tt[0].item()), 4), "setup_seconds": round(float(tt[1].item()), 4),
+               "candidates": K, "candidates_per_s": round(K / float(tt[0].item()), 1), "n_gpus": world,
+               "shard_of_rank0": [int(lo), int(hi)], "blocks_per_rank": n_blocks, "scaling": "strong",
+               "best": {"index": int(host[1]), "score": float(host[:1].view(np.float64)[0])},
+               "note": "wall clock, max over ranks: CandidateScorer construction (rgb -> labels, ordered compaction, x-run "
+                       "segments, ground-truth labels) + this rank's contiguous shard in blocks of candidates_per_gpu_per_step "
+                       "(pinned host -> device copies inside) + local arg-max + one 16-byte all-gather + host read of the winner"}
+        del scorer
+    return res
+
+
+def parity_gate(args, scorer, gt, parts, cand_all, block_idx, gate_counts, gate_scores, gate_best, offset, B, H, W, dev,
+                world, rank, dist, sweep_mod):
+    """See the module docstring.  Returns (parity object on every rank, cpu_baseline object on rank 0 at N = 1)."""
+    import torch
+    import cpu_arm
+    cfgm = importlib.import_module(PKG + ".utils.config")
+    pts = scorer.pts.cpu().numpy()
+    lut = np.zeros((256, 3), np.uint8)
+    lut[1:1 + len(scorer.colours)] = np.array(scorer.colours, np.uint8)
+    cols = lut[scorer.pt_label.cpu().numpy()]
+    gt_np = gt.cpu().numpy() if isinstance(gt, torch.Tensor) else gt
+    cpu = cpu_arm.CpuScorer(pts, cols, gt_np, parts, part_colors=cfgm.PART_COLORS)
+    threads = cpu_arm.host_threads()
+    if world == 1:
+        procs = min(threads, 16)
+        extra = args.cpu_sample if args.cpu_sample > 0 else max(0, 2 * procs - len(PARITY_INDICES))
+        idx = [i for i in PARITY_INDICES if i < B]
+        rng = np.random.default_rng(7)
+        idx += [int(i) for i in rng.choice(B, size=min(extra, B), replace=False) if int(i) not in idx]
+    else:                                                     # every rank: two candidates of its own block, two processes
+        procs = max(1, min(2, threads // max(world, 1)))
+        idx = [i for i in (127, 1024) if i < B] or [0]
+    rows = cand_all[block_idx[idx]]
+    g_counts = gate_counts[idx][:, scorer._cols, :]
+    dt, n, bad, identical = compare_with_cpu(cpu, rows, g_counts, gate_scores[idx], procs)
+    ok = not bad
+    nccl = None
+    if world > 1:
+        # the NCCL winner of that step against the arg-max over an all-gather of the full score vectors
+        sc = torch.from_numpy(gate_scores).to(dev)
+        allsc = torch.empty((world, B), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allsc.view(-1), sc)
+        allsc = allsc.cpu().numpy()
+        offs = torch.tensor([offset], dtype=torch.int64, device=dev)
+        alloff = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(alloff, offs)
+        alloff = alloff.cpu().numpy()
+        pairs = [(float(allsc[r, i]), int((alloff[r] + i) % TOTAL_CANDIDATES)) for r in range(world)
+                 for i in np.flatnonzero(allsc[r] == allsc[r].max())]
+        want = sweep_mod.select_best(pairs)
+        nccl = {"winner": [gate_best[0], gate_best[1]], "argmax_of_gathered_scores": [want[0], want[1]],
+                "ok": bool(want[0] == gate_best[0] and want[1] == gate_best[1])}
+        ok = ok and nccl["ok"]
+        # this rank re-scores the winner locally through the public API: same score on every rank
+        w_row = cand_all[gate_best[1]][None]
+        w_s, _, _ = scorer.score(w_row)
+        ok = ok and bool(w_s[0] == gate_best[0])
+        flag = torch.tensor([1 if ok else 0, n], dtype=torch.int64, device=dev)
+        tot = flag.clone()
+        dist.all_reduce(flag[:1], op=dist.ReduceOp.MIN)
+        dist.all_reduce(tot[1:], op=dist.ReduceOp.SUM)
+        ok_all, n_all = bool(flag[0].item()), int(tot[1].item())
+    else:
+        ok_all, n_all = ok, n
+    parity = {"checked": n_all, "ok": ok_all, "kind": cpu.kind, "what": "per-part (inter, union) counts exactly, scores within 1e-5 "
+              "relative, against the reference's project_colored_voxels + compute_partwise_iou on the host",
+              "scores_bit_identical": identical, "block_indices_rank0": [int(i) for i in idx][:16],
+              "step": "last timed step", "mismatches": bad[:4]}
+    if nccl is not None:
+        parity["nccl_best"] = nccl
+        parity["winner_rescored_on_every_rank"] = True
+    cpu_obj = None
+    if world == 1:
+        cpu_obj = {"value": round(n / dt, 4), "unit": UNIT, "cores": procs, "kind": cpu.kind,
+                   "sample": f"{n} candidates of the last timed step (the parity-gate sample) on the same grid/mask, "
+                             f"candidate-parallel over {procs} processes with one BLAS thread each, {dt:.1f} s",
+                   "host_threads": threads, "blas_env": cpu_arm.blas_env()}
+    return parity, cpu_obj
 
 
 def carve_sharded_bench(N, dev, world, rank, dist):
@@ -605,19 +785,18 @@ def extra_configs(dev, with_cpu):
             sc = ce.CandidateScorer(gdev, front, cfg.PART_COLORS, parts)
             entry = {"points": sc.n_points, "mask": list(front.shape[:2]), "candidates": len(cand),
                      "value": round(rate(sc, cand), 1), "unit": UNIT}
-            if with_cpu and tag == "minarets":
-                from oracle import np_port
+            if with_cpu and tag == "minarets":             # real data: 64 candidates through the reference, counts compared
+                import cpu_arm
                 pts = sc.pts.cpu().numpy()
                 lut = np.zeros((256, 3), np.uint8)
                 lut[1:1 + len(sc.colours)] = np.array(sc.colours, np.uint8)
                 cols = lut[sc.pt_label.cpu().numpy()]
-                sel = {p: cfg.PART_COLORS[p] for p in parts}
-                seg = np.zeros_like(front)
-                for col in sel.values():
-                    seg[np.all(front == col, axis=-1)] = col
-                dt, _ = np_port.timed_sweep(pts, cols, seg, sel, cand[:64], front.shape[0], front.shape[1], processes=1)
-                entry["cpu_baseline"] = {"value": round(64 / dt, 2), "unit": UNIT, "cores": 1, "kind": "port",
-                                         "sample": "first 64 candidates, NumPy port, 1 process"}
+                cpu = cpu_arm.CpuScorer(pts, cols, front, parts, part_colors=cfg.PART_COLORS)
+                g_scores, g_counts, _ = sc.score(cand[:64])
+                dt, n, bad, identical = compare_with_cpu(cpu, cand[:64], g_counts, g_scores, 1)
+                entry["cpu_baseline"] = {"value": round(64 / dt, 2), "unit": UNIT, "cores": 1, "kind": cpu.kind,
+                                         "sample": "first 64 candidates, 1 process, 1 BLAS thread"}
+                entry["parity"] = {"checked": n, "ok": not bad, "scores_bit_identical": identical, "mismatches": bad[:2]}
             out["taj_front_" + tag] = entry
         # notebook 3's part-wise deformation sweep on the same grid: dome, fixed final camera
         try:
@@ -707,6 +886,8 @@ def extra_configs(dev, with_cpu):
         torch.cuda.empty_cache()
         rgb = torch.from_numpy(syn.label_lut()).to(dev)[syn.monument_labels(N, dev).long()]
         entry = {"mask": [H, W], "candidates": 256, "unit": UNIT}
+        peak, _ = peaks()
+        model = peak * 1e9 / (N ** 3 + 9 * H * W)              # candidates/s at the HBM roofline of the streaming model
         for view in ("front", "aerial"):
             base = syn.base_camera(N, H, W, view)
             full = ce.CandidateScorer(rgb, torch.zeros((H, W, 3), dtype=torch.uint8, device=dev), cfg.PART_COLORS, syn.PART_NAMES)
@@ -714,8 +895,32 @@ def extra_configs(dev, with_cpu):
             del full
             sc = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, syn.PART_NAMES)
             entry["points"] = sc.n_points
-            entry[view] = round(rate(sc, syn.candidates(base, 256), reps=2), 1)
+            cand = syn.candidates(base, 256)
+            entry[view] = round(rate(sc, cand, reps=2), 1)
+            entry[view + "_frac_of_streaming_roofline"] = round(entry[view] / model, 4)
+            if with_cpu and view == "front":                    # parity at this size: 2 candidates through the reference
+                try:
+                    import cpu_arm
+                    pts = sc.pts.cpu().numpy()
+                    lut = np.zeros((256, 3), np.uint8)
+                    lut[1:1 + len(sc.colours)] = np.array(sc.colours, np.uint8)
+                    cols = lut[sc.pt_label.cpu().numpy()]
+                    cpu = cpu_arm.CpuScorer(pts, cols, gt, syn.PART_NAMES, part_colors=cfg.PART_COLORS)
+                    pick = [1, 200]                              # different z-buffer batches of the 256-candidate sweep
+                    g_scores, g_counts, _ = sc.score(cand)
+                    dt, n, bad, identical = compare_with_cpu(cpu, cand[pick], g_counts[pick], g_scores[pick], 2)
+                    entry["parity"] = {"checked": n, "ok": not bad, "kind": cpu.kind, "scores_bit_identical": identical,
+                                       "mismatches": bad[:2], "cpu_seconds": round(dt, 1)}
+                    del pts, cols, cpu
+                except MemoryError as exc:
+                    entry["parity"] = {"checked": 0, "ok": None, "error": repr(exc)}
             del sc
+        entry["roofline"] = {"bound": "hbm", "model_candidates_per_s": round(model, 1), "peak": peak, "unit": "GB/s",
+                             "achieved": round(entry["front"] * (N ** 3 + 9 * H * W) / 1e9, 1),
+                             "frac": entry["front_frac_of_streaming_roofline"],
+                             "note": "whole sweep call (splat + score + clear) over the streaming model G*1 B + 9 B*H*W per "
+                                     "candidate, front view; 174.8 M points exceed the 27-bit packed keys, so the score pass "
+                                     "gathers labels"}
         out["synthetic_1024_2048mask"] = entry
     except Exception as exc:
         out["synthetic_1024_2048mask"] = {"error": repr(exc)}
@@ -741,84 +946,53 @@ def carve_cpu_baseline():
             "sample": "Bibi@256 global_carve + partwise_carve through oracle/ (C restatement of scipy affine/label + NumPy)"}
 
 
-def cpu_baseline(scorer, gt, parts, cfg, cand_all, H, W, n_points, sample, processes):
-    import torch
-    from oracle import np_port
-    pts = scorer.pts.cpu().numpy()
-    lut = np.zeros((256, 3), np.uint8)
-    lut[1:1 + len(scorer.colours)] = np.array(scorer.colours, np.uint8)
-    cols = lut[scorer.pt_label.cpu().numpy()]
-    gt_np = gt.cpu().numpy() if isinstance(gt, torch.Tensor) else gt
-    sel = {p: cfg.PART_COLORS[p] for p in parts}
-    seg = np.zeros_like(gt_np)
-    for c in sel.values():
-        seg[np.all(gt_np == c, axis=-1)] = c
-    if sample <= 0:
-        sample = max(processes, int(round(processes * 2.2e7 * 6 / max(n_points, 1))))   # ~10-30 s of host work
-        sample = max(1, min(sample, 4096))
-    dt, scores = np_port.timed_sweep(pts, cols, seg, sel, cand_all[:sample], H, W, processes=processes)
-    return {"value": round(sample / dt, 4), "unit": UNIT, "cores": processes, "kind": "port",
-            "sample": f"first {sample} of the {TOTAL_CANDIDATES} candidates on the same grid/mask, NumPy port of the "
-                      f"reference path (oracle/np_port.py), {processes} process(es), {dt:.1f} s",
-            "score0": float(scores[0])}
-
-
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU path (NumPy port; the reference is pure Python and cannot
-# travel to the GPU box), all host cores, bounded sample per step
+# reference arm: the UNMODIFIED reference functions (baseline/_ref, installed by tools/install_ref.py) on the host cores,
+# candidate-parallel over all of them with one BLAS thread per process, bounded sample per step.  Imports nothing of the
+# product package.
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import torch
-    from oracle import np_port, oracle as orc
-    syn = importlib.import_module(PKG + ".synthetic")
-    N, H, W = args.grid, args.mask, args.mask
-    parts = syn.PART_NAMES if args.parts == "all" else ["front_minarets", "back_minarets"]
-    labels = syn.monument_labels(N, "cpu").numpy()
-    lut = syn.label_lut()
-    base = syn.base_camera(N, H, W, "front")
+    import cpu_arm
+    N, H, W, B = args.grid, args.mask, args.mask, args.cands_per_step
+    parts = bw.PART_NAMES if args.parts == "all" else ["front_minarets", "back_minarets"]
+    labels = bw.monument_labels(N)
+    base = bw.base_camera(N, H, W, "front")
     hidden = base + HIDDEN_DELTA
-
-    def points_of(names):
-        keep = np.isin(labels, [syn.LABEL[n] for n in names])
-        flat = np.flatnonzero(keep)
-        a0, a1, a2 = np.unravel_index(flat, labels.shape)
-        return np.stack([a2, a1, a0], axis=1).astype(np.float32), lut[labels.reshape(-1)[flat]]
-
-    pts_all, cols_all = points_of(syn.PART_NAMES)
-    gt = orc.project_colored_voxels(pts_all, cols_all, hidden[0:3], hidden[3:6], hidden[6], hidden[7], hidden[8], H, W)
-    pts, cols = (pts_all, cols_all) if args.parts == "all" else points_of(parts)
+    pts_all, cols_all = bw.points_of(labels, bw.PART_NAMES)
+    probe = cpu_arm.CpuScorer(pts_all, cols_all, np.zeros((H, W, 3), np.uint8), bw.PART_NAMES, part_colors=bw.PART_COLORS)
+    gt = probe.render(pts_all, cols_all, hidden)              # ground truth = the reference's own render of the hidden camera
+    pts, cols = (pts_all, cols_all) if args.parts == "all" else bw.points_of(labels, parts)
     del labels
-    sel = {p: orc.PART_COLORS[p] for p in parts}
-    seg = orc.mask_parts_from_image(gt, orc.PART_COLORS, parts)
-    cand_all = syn.candidates(base, TOTAL_CANDIDATES)
-    procs = np_port.host_threads()
+    cpu = cpu_arm.CpuScorer(pts, cols, gt, parts, part_colors=bw.PART_COLORS)
+    cand_all = bw.candidates(base, TOTAL_CANDIDATES)
+    procs = cpu_arm.host_threads()
     per_step = args.cpu_sample if args.cpu_sample > 0 else max(procs, int(round(procs * 2.2e7 * 1.5 / max(len(pts), 1))))
     for s in range(args.warmup):
-        np_port.timed_sweep(pts, cols, seg, sel, cand_all[:procs], H, W, processes=procs)
+        cpu.run(cand_all[:procs], processes=procs)
     total = 0.0
     score0 = None
     for s in range(args.steps):
         blk = cand_all[(s * per_step) % TOTAL_CANDIDATES:][:per_step]
-        dt, scores = np_port.timed_sweep(pts, cols, seg, sel, blk, H, W, processes=procs)
+        dt, _, scores = cpu.run(blk, processes=procs)
         total += dt
-        score0 = scores[0] if score0 is None else score0
+        score0 = float(scores[0]) if score0 is None else score0
     value = per_step * args.steps / total
     sample = (f"{per_step} candidates per step (bounded sample of the {TOTAL_CANDIDATES}-candidate sweep) on the same "
-              f"{N}^3 grid / {H}x{W} mask, candidate-parallel over {procs} host processes")
+              f"{N}^3 grid / {H}x{W} mask, candidate-parallel over {procs} host processes, one BLAS thread each")
     _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {N}^3 semantic monument, {len(parts)} parts ({len(pts)} points), {H}x{W} label "
-                               f"mask, NumPy port of the reference CPU path", "grid": N, "mask": [H, W],
-                   "parts": len(parts), "points": int(len(pts))},
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "config": bw.bench_config(N, H, W, parts, len(pts), B),
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": procs, "kind": cpu.kind, "sample": sample,
+                         "blas_env": cpu_arm.blas_env()},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "score0": float(score0),
+        "score0": score0,
+        "product_library_loaded": any("libp3d_b200" in l for l in open("/proc/self/maps")) if os.path.exists("/proc/self/maps") else None,
     }))
 
 
