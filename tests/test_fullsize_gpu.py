@@ -190,7 +190,7 @@ def test_segment_splat_equals_point_splat_full_size(mode):
         cand[K // 2:, 7] += rng.uniform(-1.5 * W, 1.5 * W, K - K // 2)
         cand[K // 2:, 8] += rng.uniform(-1.0 * H, 1.0 * H, K - K // 2)
         for dt in (np.float64, np.float32):
-            a = ce.CandidateScorer(rgb, img, cfg.PART_COLORS, syn.PART_NAMES, dtype=dt, mode=mode)
+            a = ce.CandidateScorer(rgb, img, cfg.PART_COLORS, syn.PART_NAMES, dtype=dt, mode=mode, use_segments=True)
             b = ce.CandidateScorer(rgb, img, cfg.PART_COLORS, syn.PART_NAMES, dtype=dt, mode=mode, use_segments=False)
             assert a.segs is not None
             sa, ca, ba = a.score(cand.astype(dt))

@@ -87,7 +87,7 @@ def test_segment_splat_equals_point_splat_and_oracle(oracle, mode, dt):
             image[ilab == k + 1] = oracle.PART_COLORS[n]
         K = 48
         cand = cameras(rng, shape, H, W, K, dt)
-        seg_scorer = ce.CandidateScorer(grid, image, oracle.PART_COLORS, parts, dtype=dt, mode=mode)
+        seg_scorer = ce.CandidateScorer(grid, image, oracle.PART_COLORS, parts, dtype=dt, mode=mode, use_segments=True)
         pt_scorer = ce.CandidateScorer(grid, image, oracle.PART_COLORS, parts, dtype=dt, mode=mode, use_segments=False)
         assert seg_scorer.segs is not None and pt_scorer.segs is None
         s1, c1, b1 = seg_scorer.score(cand)
