@@ -19,17 +19,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int sm_count() {
-  static thread_local int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      return 148;
+int sm_count() {                       // SMs of the CURRENT device (cached per device, read-mostly)
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cached[dev];
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached[dev] = n;                   // benign race: every thread writes the same value
   }
-  return cached;
+  return n;
 }
 
 }  // namespace p3d

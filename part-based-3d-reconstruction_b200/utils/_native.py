@@ -153,6 +153,38 @@ def require_cuda(device=None) -> torch.device:
     return dev
 
 
+def on_device(fn):
+    """Decorator for public entry points: run `fn` with the CUDA device of its `device=` argument -- or, without one, of
+    its first CUDA tensor argument -- made current.  The C ABI launches on the current device's stream
+    (`stream_ptr()`), so a call that names another GPU than the current one must switch to it for its duration;
+    otherwise kernels would run on one GPU against memory of another."""
+    import functools
+    import inspect
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        try:
+            bound = sig.bind_partial(*args, **kwargs).arguments
+        except TypeError:
+            bound = {}
+        d = bound.get("device")
+        if d is not None:
+            dev = torch.device(d)
+        else:
+            for v in bound.values():
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    dev = v.device
+                    break
+        if dev is None or dev.type != "cuda" or dev.index is None or not torch.cuda.is_available() \
+                or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def ptr(t) -> ctypes.c_void_p:
     if t is None:
         return ctypes.c_void_p(0)

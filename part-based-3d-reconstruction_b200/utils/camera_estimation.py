@@ -33,6 +33,7 @@ def iou_from_counts(inter, union):
     return inter / union if union > 0 else 0.0
 
 
+@nv.on_device
 def compute_partwise_iou(proj_mask, gt_mask, part_colors, device=None):
     """camera_estimation.py:770-787 -> (dict part -> IoU, mean IoU over all parts).
 

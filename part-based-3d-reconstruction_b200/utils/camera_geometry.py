@@ -31,6 +31,7 @@ def candidate_row(cam_pos, target, f, cx, cy, dtype) -> np.ndarray:
     return row
 
 
+@nv.on_device
 def look_at_rotation(eye, target, up=_DEFAULT_UP, device=None):
     """camera_geometry.py:3-14, evaluated on the GPU with the reference's operation order.
     Returns a (3,3) ndarray with rows [x; y; z] in the promoted dtype of (eye, target)."""

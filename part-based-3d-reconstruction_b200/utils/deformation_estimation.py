@@ -62,6 +62,7 @@ def _as_points(coords, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
+@nv.on_device
 def deform_coords(coords, image_shape, voxel_shape, deform, device=None):
     """The `deform_coords` closure (deformation_estimation.py:70-103): seven jittered copies of the coordinates, each
     scaled/shifted about its own mean and rounded half-even; unique rows in lexicographic (x, y, z) order, int64.

@@ -33,6 +33,7 @@ def _camera_block(cam, dtype, dev):
     return block
 
 
+@nv.on_device
 def compute_global_depth_buffer(voxel_grid, cam, H, W, device=None, return_tensor=False):
     """eval_helpers_intra.py:134-161: float32 (H,W) buffer of the smallest camera-space Z among ALL occupied voxels
     projecting into each pixel (Z > 1e-6), +inf where nothing lands.  Arithmetic dtype follows the camera arrays
@@ -57,6 +58,7 @@ def compute_global_depth_buffer(voxel_grid, cam, H, W, device=None, return_tenso
     return zbuf if return_tensor else zbuf.cpu().numpy()
 
 
+@nv.on_device
 def project_part_visible(pts3d, cam, zbuf, H, W, eps=1e-3, device=None, return_tensor=False):
     """eval_helpers_intra.py:168-190: boolean (H,W) mask of the pixels where one of `pts3d` lies within `eps` of the
     global depth buffer."""
@@ -131,6 +133,7 @@ def project_keypoints(voxel_kps, cam):
     return {k: project(pt, cam["cam_pos"], cam["target"], cam["f"], cam["cx"], cam["cy"]) for k, pt in voxel_kps.items()}
 
 
+@nv.on_device
 def compute_binary_gt(mask_img, voxel_grid, device=None):
     """:274-285: pixels of the mask whose colour is one of the non-black colours present in the voxel grid."""
     dev = nv.require_cuda(device)

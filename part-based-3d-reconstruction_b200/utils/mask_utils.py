@@ -81,6 +81,7 @@ def load_and_prepare_masks(root_path, monument_name, view_name, max_dim, part_co
     return semantic_r, exterior_r, binary
 
 
+@nv.on_device
 def image_labels(image, colours, device) -> torch.Tensor:
     """(H,W,3) uint8 image -> (H,W) u8 labels: 1 + index into `colours`, 0 elsewhere (device tensor)."""
     img = nv.to_device(image, torch.uint8, device)
@@ -90,6 +91,7 @@ def image_labels(image, colours, device) -> torch.Tensor:
     return eng.rgb_to_labels(img, pal)
 
 
+@nv.on_device
 def mask_parts_from_image(image, part_colors, selected_parts, device=None):
     """mask_utils.py:89-97: keep the pixels whose colour is one of the selected part colours, zero
     everything else."""

@@ -29,6 +29,7 @@ def _points_f32(pts3d, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a.reshape(-1, 3))).to(device)
 
 
+@nv.on_device
 def project_colored_voxels(pts3d, colors, cam_pos, target, f, cx, cy, H, W, device=None, return_tensor=False):
     """projection_utils.py:5-23.  Projects the coloured points through one look-at camera and
     returns the (H, W, 3) uint8 image in which, per pixel, the LAST point in array order wins

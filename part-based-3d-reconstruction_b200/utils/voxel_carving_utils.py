@@ -227,6 +227,7 @@ def _colour_args(colour):
 # =========================================================
 # Public API (reference names and signatures)
 # =========================================================
+@nv.on_device
 def carve_voxel_grid_with_masks(voxel_grid, combined_mask):
     """voxel_carving_utils.py:76-97: np.where(mask, voxel_grid, 0) with the mask broadcast along depth."""
     as_tensor = _is_tensor(voxel_grid)
@@ -248,6 +249,7 @@ def carve_voxel_grid_with_masks(voxel_grid, combined_mask):
     return _ret(out, as_tensor)
 
 
+@nv.on_device
 def process_voxel_grid(voxel_grid, combined_mask, angle_interval=90):
     """voxel_carving_utils.py:104-126: for angle in range(0, 91, angle_interval): rotate the (already rotated)
     grid by `angle` about shape/2 with trilinear interpolation, then carve with the mask."""
@@ -265,6 +267,7 @@ def process_voxel_grid(voxel_grid, combined_mask, angle_interval=90):
     return _ret(_process_device(vol, m, angle_interval), as_tensor)
 
 
+@nv.on_device
 def apply_colored_mask_to_voxel_grid(carved_voxel_grid, colored_mask):
     """voxel_carving_utils.py:128-136: out[x,y,z,:] = colored_mask[y,x,:] where carved == 1, else 0."""
     as_tensor = _is_tensor(carved_voxel_grid)
@@ -292,6 +295,7 @@ def _group_image(jobs, H, W):
     return gm
 
 
+@nv.on_device
 def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_range=None):
     """voxel_carving_utils.py:139-160: per part group, carve the group's voxels with the group's own mask under
     the group's symmetry angle and merge the survivors.
@@ -464,6 +468,7 @@ def _colour_mask(grid, colour):
     return mask
 
 
+@nv.on_device
 def left_right_guided_carve(colored_grid, semantic_mask, target_color, angle=60, visualize=False, stride=2):
     """voxel_carving_utils.py:163-210: for every 6-connected 3-D component of `target_color`, carve the
     component's bounding-box crop with the matching crop of the part's 2-D mask under `angle` symmetry."""
@@ -520,6 +525,7 @@ def _extrude_inplace(out, mask_2d, axis, direction, depth, fill_color):
     _launched()
 
 
+@nv.on_device
 def extrude_from_surface(grid, mask_2d, axis, direction="+", depth=5, fill_color=None):
     """voxel_carving_utils.py:213-248: from the first occupied voxel of each masked column (index 0 / last when
     the column is empty), paint `depth` voxels along `axis` in `direction`."""
@@ -530,6 +536,7 @@ def extrude_from_surface(grid, mask_2d, axis, direction="+", depth=5, fill_color
     return _ret(out, as_tensor)
 
 
+@nv.on_device
 def recolor_backward_components(voxel_grid, color, new_color, k=4, sort_axis=2):
     """voxel_carving_utils.py:252-266: keep the k components of `color` with the smallest mean coordinate on
     `sort_axis` (stable: ties keep the lower scipy id), recolour the others to `new_color`."""
@@ -555,6 +562,7 @@ def recolor_backward_components(voxel_grid, color, new_color, k=4, sort_axis=2):
     return _ret(grid, as_tensor)
 
 
+@nv.on_device
 def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=4, visualize=False,
                  device=None, return_tensor=False, x_range=None):
     """voxel_carving_utils.py:269-298: start from a full (w,h,w) grid, carve it with the binary front mask under
@@ -617,6 +625,7 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
     return _ret(out, as_tensor)
 
 
+@nv.on_device
 def partwise_carve(colored_voxel_grid, semantic_mask_exterior, semantic_mask_full, part_colors_np, group_jobs,
                    part_symmetry, extrusion_depths, recolor_back_minarets=True, visualize=False, stride=4):
     """voxel_carving_utils.py:302-400: part_carve -> left_right_guided_carve per symmetric part -> interior

@@ -30,6 +30,7 @@ def grid_to_device(grid, device) -> torch.Tensor:
     return t.to(device).contiguous()
 
 
+@nv.on_device
 def device_points_by_parts(grid, part_colors, part_names, device=None):
     """Device-resident form of get_voxel_points_by_parts: (pts (N,3) f32, pt_label (N) u8,
     colours list, label_of dict).  `grid` may be a NumPy array or a CUDA tensor."""
@@ -42,6 +43,7 @@ def device_points_by_parts(grid, part_colors, part_names, device=None):
     return pts, pt_label, colours, label_of
 
 
+@nv.on_device
 def get_voxel_points_by_parts(grid, part_colors, part_names, device=None):
     """voxel_utils.py:7-21.  Returns (pts float32 (N,3) as [x=a2, y=a1, z=a0], colors uint8 (N,3)) of
     the voxels whose colour equals one of the selected part colours, in ascending flat index."""
@@ -53,6 +55,7 @@ def get_voxel_points_by_parts(grid, part_colors, part_names, device=None):
     return pts.cpu().numpy(), cols.cpu().numpy()
 
 
+@nv.on_device
 def voxel_grid_to_points(grid, axis="z", colormap="viridis", stride=2, device=None):
     """voxel_utils.py:35-51 for RGB grids: every `stride`-th voxel along each axis that is not black, as
     (pts float32 (N,3) = [a2, a1, a0] * stride, colors uint8 (N,3), (H, W, D)) with the reference's shape tuple
