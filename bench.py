@@ -535,9 +535,11 @@ def carve_sharded_bench(N, dev, world, rank, dist):
         gfull = vc.global_carve(binm, ext, 90, return_tensor=True)
         jobs90 = [([n], 90) for n in ("full_building", "chhatris", "plinth", "front_minarets", "small_minarets", "dome")]
         pslab = vc.part_carve(gfull, ext, jobs90, x_range=span)
-        if vc._LAST_PART_CARVE_LAUNCH is not None:
-            pms, _ = time_launches(vc._LAST_PART_CARVE_LAUNCH, reps=10, rounds=3)
-        del gfull, pslab
+        launch_pc, kslab = part_carve_launcher(gfull, ext, jobs90, dev, x_range=span)
+        if launch_pc is not None:
+            pms, _ = time_launches(launch_pc, reps=10, rounds=3)
+            assert torch.equal(kslab, pslab)
+        del gfull, pslab, kslab
     except Exception as exc:
         print("sharded part_carve timing failed:", repr(exc), file=sys.stderr)
     t = torch.tensor([e0.elapsed_time(e1) / reps, kms, pms], dtype=torch.float64, device=dev)
@@ -553,6 +555,40 @@ def carve_sharded_bench(N, dev, world, rank, dist):
             "n_gpus": world, "scaling": "strong", "occupied": int(occ.item()), "slab_of_rank0": list(span),
             "note": "whole Python call per rank (mask upload, table lookup, slab kernel), x-slab per rank, max over ranks; "
                     "no collective on the data path"}
+
+
+def part_carve_launcher(grid, ext, jobs, dev, x_range=None):
+    """The kernels of part_carve's all-90-degree bit path as a re-issuable closure (bench scaffolding: inputs prepared
+    with the package's own helpers, launches through the C ABI), for graph-replayed kernel-only timing.  Returns
+    (launch, output tensor) or (None, None) when the grid does not take that path."""
+    import torch
+    vc = importlib.import_module(PKG + ".utils.voxel_carving_utils")
+    nv = importlib.import_module(PKG + ".utils._native")
+    W, H, D, _ = grid.shape
+    if D != W or D % 32:
+        return None, None
+    M, off = vc._pass_transform((W, H, D), 90)
+    table, foldable = vc._fold_table(W, D, M, off, dev)
+    bits = vc._fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if foldable else None
+    if bits is None or bits[2] is None:
+        return None, None
+    gm = vc._group_image_device(vc._PackedMask(ext), [[vc.PART_COLORS[n] for n in names] for names, _ in jobs], dev)
+    ws_bytes = int(nv.lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if x_range is None:
+        out = torch.empty_like(grid)
+
+        def launch():
+            nv.check(nv.lib.p3d_part_carve_fold_bits(nv.ptr(grid), W, H, D, nv.ptr(bits[0]), bits[1], bits[2], nv.ptr(gm), len(jobs),
+                                                     nv.ptr(out), nv.ptr(ws), ws_bytes, nv.stream_ptr()))
+    else:
+        x0, x1 = x_range
+        out = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
+
+        def launch():
+            nv.check(nv.lib.p3d_part_carve_fold_bits_slab(nv.ptr(grid), W, H, D, x0, x1 - x0, nv.ptr(bits[0]), bits[1], bits[2],
+                                                          nv.ptr(gm), len(jobs), nv.ptr(out), nv.ptr(ws), ws_bytes, nv.stream_ptr()))
+    return launch, out
 
 
 def time_launches(launch, reps=20, rounds=5, use_graph=True):
@@ -615,9 +651,10 @@ def carve_kernels_at(N, dev, peak):
     res = {"grid": N, "voxels": N ** 3, "global_carve_call_ms": round(gms, 4),
            "global_carve_gvoxel_s": round(N ** 3 / (gms * 1e-3) / 1e9, 2),
            "global_carve_frac_of_peak": round(3 * N ** 3 / (gms * 1e-3) / 1e9 / peak, 4)}
-    launch_pc = vc._LAST_PART_CARVE_LAUNCH
+    launch_pc, kout = part_carve_launcher(out, ext, jobs90, dev)
     if launch_pc is not None:
         pms, _ = time_launches(launch_pc, reps=10, rounds=3)
+        assert torch.equal(kout, pc)
         res.update({"part_carve_kernel_ms": round(pms, 4), "part_carve_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2),
                     "part_carve_frac_of_peak": round(6 * N ** 3 / (pms * 1e-3) / 1e9 / peak, 4)})
     res["note"] = ("global_carve: whole Python call on the device (mask upload, cached tables, one kernel), device tensor "
@@ -687,14 +724,17 @@ def carve_bench(N, dev, peak):
     # part_carve (all six notebook groups at 90 degrees) on that grid: 6 B per voxel (read RGB + write RGB)
     jobs90 = [(["full_building"], 90), (["chhatris"], 90), (["plinth"], 90), (["front_minarets"], 90),
               (["small_minarets"], 90), (["dome"], 90)]
+    pc = vc.part_carve(out, ext, jobs90)                      # first call: allocator growth, cached tables
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pc = vc.part_carve(out, ext, jobs90)
+    for _ in range(5):
+        pc = vc.part_carve(out, ext, jobs90)
     torch.cuda.synchronize()
-    pc_call_ms = (time.perf_counter() - t0) * 1e3
-    launch_pc = vc._LAST_PART_CARVE_LAUNCH
+    pc_call_ms = (time.perf_counter() - t0) * 1e3 / 5
+    launch_pc, kpc = part_carve_launcher(out, ext, jobs90, dev)
     if launch_pc is not None:
         pms, _ = time_launches(launch_pc)
+        assert torch.equal(kpc, pc)
         res["part_carve"] = {"kernel_ms": round(pms, 4), "kernel_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2),
                              "call_ms": round(pc_call_ms, 3), "occupied": int(torch.count_nonzero(pc.view(-1, 3).any(dim=1)).item()),
                              "roofline": {"bound": "hbm", "achieved": round(6 * N ** 3 / (pms * 1e-3) / 1e9, 1), "peak": peak,
@@ -703,7 +743,30 @@ def carve_bench(N, dev, peak):
                                           "note": "6 B per voxel (SURVEY 8d: read RGB + write RGB); copy-then-clear: pass A "
                                                   "writes the output from voxel-local terms and packs occupancy/alive bits "
                                                   "(~0.25 B/voxel), pass B reads bits only and rewrites the runs whose "
-                                                  "rotated source is empty (none for this 4-way-symmetric grid)"}}
+                                                  "rotated source is empty (none for this 4-way-symmetric grid); call_ms = "
+                                                  "the whole Python call (device tensors in and out), mean of 5 after a warm-up"}}
+        # the hard input: the same grid with 2 % of its occupied voxels knocked out at random -- no longer 4-way symmetric,
+        # so the clear pass has real work
+        try:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(3)
+            hole = torch.rand(out.shape[:3], device=dev, generator=gen) < 0.02
+            asym = out.clone()
+            asym[hole] = 0
+            del hole
+            want = vc.part_carve(asym, ext, jobs90)
+            launch_as, kas = part_carve_launcher(asym, ext, jobs90, dev)
+            ams, _ = time_launches(launch_as)
+            assert torch.equal(kas, want)
+            res["part_carve"]["asymmetric_input"] = {
+                "kernel_ms": round(ams, 4), "frac": round(6 * N ** 3 / (ams * 1e-3) / 1e9 / peak, 4),
+                "cleared_voxels": int((torch.count_nonzero(asym.view(-1, 3).any(dim=1)) - torch.count_nonzero(want.view(-1, 3).any(dim=1))).item()),
+                "note": "global_carve output with 2 % of the occupied voxels removed at random: every removed voxel empties up "
+                        "to three rotated partners, the clear pass rewrites those runs"}
+            del asym, want, kas
+        except Exception as exc:
+            res["part_carve"]["asymmetric_input"] = {"error": repr(exc)}
+        del kpc
     del out, kout, pc
     torch.cuda.empty_cache()
     if N != 1024:

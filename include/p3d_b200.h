@@ -370,6 +370,29 @@ int p3d_accumulate_part(const uint8_t* grid, const uint8_t* carved, int W, int H
 int p3d_paste_component(const uint8_t* src, const int32_t* labels, int comp, const uint8_t* kept, int W, int H,
                         int D, int x0, int y0, int z0, int w, int h, int d, uint8_t* out, p3d_stream_t stream);
 
+/* left_right_guided_carve          utils/voxel_carving_utils.py:163-210, all components of one colour in one call:
+ * crop every component's bounding box (occupancy of ANY colour, :191-193), run the n_pass rotate-and-carve passes of
+ * process_voxel_grid (:104-126) on every crop at once (one launch per pass), paste (:199-201) and count the kept voxels
+ * of each crop (the "carved voxels" log line, :196).
+ *   labels (W,H,D) int32 from p3d_label6 of the colour's 3-D mask; mask_hw (H,W) u8 = the colour's 2-D mask (the crop
+ *   mask is read in place: the reference's _mask_to_wh of an (h,w) crop is always its transpose);
+ *   comps (n_comp,8) int32 device = { x0,y0,z0, w,h,d, scratch offset low, high } per component (1-based id = row + 1);
+ *   Ms (n_pass,9), offs (n_comp,n_pass,3) doubles DEVICE: the host-computed inverse rotation of each pass and the
+ *   offset for each crop shape (:116-123);  buf_a / buf_b: scratch of sum(w h d) bytes each;
+ *   out: the result grid, a copy of `grid` on entry;  counts (n_comp) int64.
+ *   sequential_paste != 0: one paste launch per component in id order (needed when bounding boxes overlap: the
+ *   reference's loop order decides which component's write survives). */
+int p3d_lr_carve_components(const uint8_t* grid, const int32_t* labels, int W, int H, int D, const uint8_t* mask_hw,
+                            const int32_t* comps, int n_comp, int64_t max_crop_voxels, const double* Ms,
+                            const double* offs, int n_pass, uint8_t* buf_a, uint8_t* buf_b, int sequential_paste,
+                            uint8_t* out, int64_t* counts, p3d_stream_t stream);
+/* part_carve's per-pixel group bits (:143-146 for every group at once): gm (H,W) uint32, bit g set where the pixel's
+ * colour is one of group g's colours -- for a square image AND at the transposed pixel as well (the reference's
+ * _mask_to_wh always transposes a square mask, so a group's effective mask is m & m.T).  keys[k] = r | g << 8 | b << 16,
+ * group_of[k] = group of colour k (device arrays, n_keys <= 128). */
+int p3d_group_image(const uint8_t* mask_rgb, int H, int W, const uint32_t* keys, const int32_t* group_of, int n_keys,
+                    uint32_t* gm, p3d_stream_t stream);
+
 /* np.all(grid == colour, axis=-1) :175,253 -> uint8 mask; a colour outside 0..255 matches nothing. */
 int p3d_colour_mask(const uint8_t* grid_rgb, int64_t n, int r, int g, int b, uint8_t* mask, p3d_stream_t stream);
 

@@ -38,6 +38,8 @@ inline int grid_for(int64_t items, int threads, int waves) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
+__device__ __forceinline__ bool rgb_nonzero(const uint8_t* p) { return (p[0] | p[1] | p[2]) != 0; }
+
 // ------------------------------------------------------------------------------------------
 // General trilinear resample + mask carve (one thread per output voxel).
 // ------------------------------------------------------------------------------------------
@@ -47,6 +49,162 @@ __device__ __forceinline__ double coord(const Affine& A, int h, int o0, int o1, 
   c = __dadd_rn(c, __dmul_rn(A.M[3 * h + 1], (double)o1));
   c = __dadd_rn(c, __dmul_rn(A.M[3 * h + 2], (double)o2));
   return c;
+}
+
+// scipy.ndimage.affine_transform(order=1, mode="constant", cval=0) at output voxel (o0, o1, o2) of an (n0, n1, n2) uint8
+// volume: FP64 coordinates accumulated in scipy's order, bounds rule, 8 corners, round half up.
+__device__ __forceinline__ uint8_t resample_voxel(const uint8_t* __restrict__ vin, int n0, int n1, int n2, const Affine& A,
+                                                  int o0, int o1, int o2) {
+  uint8_t res = 0;
+  const int dim[3] = {n0, n1, n2};
+  double cc[3];
+  bool inside = true;
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    cc[h] = coord(A, h, o0, o1, o2);
+    if (cc[h] < 0.0 || cc[h] > (double)(dim[h] - 1)) inside = false;
+  }
+  if (inside) {
+    int i0[3], i1[3];
+    double t[3];
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      const double fl = floor(cc[h]);
+      t[h] = __dsub_rn(cc[h], fl);
+      i0[h] = (int)fl;
+      i1[h] = i0[h] + 1 < dim[h] ? i0[h] + 1 : dim[h] - 1;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int ix = a ? i1[0] : i0[0], iy = b ? i1[1] : i0[1], iz = c ? i1[2] : i0[2];
+          double w = (double)vin[((size_t)ix * n1 + iy) * n2 + iz];
+          w = __dmul_rn(w, a ? t[0] : __dsub_rn(1.0, t[0]));
+          w = __dmul_rn(w, b ? t[1] : __dsub_rn(1.0, t[1]));
+          w = __dmul_rn(w, c ? t[2] : __dsub_rn(1.0, t[2]));
+          acc = __dadd_rn(acc, w);
+        }
+    if (acc > 0.0) {
+      const double rr = __dadd_rn(acc, 0.5);
+      res = rr >= 255.0 ? 255 : (uint8_t)rr;
+    }
+  }
+  return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// left_right_guided_carve (:163-210) for ALL components of one colour in a fixed number of launches: blockIdx.y = the
+// component.  comps[c] = { x0, y0, z0, w, h, d, scratch offset low, high } (bounding-box crop and where it lives in the
+// two scratch buffers); the crop's 2-D mask is read in place, m[x][y] = mask_hw[y0 + y][x0 + x] (the reference's
+// _mask_to_wh of the (h, w) crop is always its transpose).  One pass = one launch over every crop: Ms[pass] is the
+// pass's inverse rotation, offs[c][pass] the offset for crop c's shape.
+// ------------------------------------------------------------------------------------------
+struct CompBox { int x0, y0, z0, w, h, d; long long off; };
+__device__ __forceinline__ CompBox load_comp(const int32_t* __restrict__ comps, int c) {
+  const int32_t* p = comps + (size_t)c * 8;
+  CompBox b;
+  b.x0 = p[0]; b.y0 = p[1]; b.z0 = p[2]; b.w = p[3]; b.h = p[4]; b.d = p[5];
+  b.off = (long long)(uint32_t)p[6] | ((long long)p[7] << 32);
+  return b;
+}
+
+__global__ void __launch_bounds__(256)
+lr_crop_kernel(const uint8_t* __restrict__ grid, int H, int D, const int32_t* __restrict__ comps, uint8_t* __restrict__ buf) {
+  const CompBox b = load_comp(comps, blockIdx.y);
+  const int64_t n = (int64_t)b.w * b.h * b.d;
+  uint8_t* occ = buf + b.off;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % b.d);
+    const int64_t q = i / b.d;
+    const int y = (int)(q % b.h), x = (int)(q / b.h);
+    occ[i] = rgb_nonzero(grid + 3 * ((((size_t)(b.x0 + x)) * H + (b.y0 + y)) * D + (b.z0 + z))) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lr_resample_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int32_t* __restrict__ comps,
+                   const double* __restrict__ M, const double* __restrict__ offs, int pass, int n_pass,
+                   const uint8_t* __restrict__ mask_hw, int Wfull) {
+  const CompBox b = load_comp(comps, blockIdx.y);
+  Affine A;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) A.M[k] = M[(size_t)pass * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) A.off[k] = offs[((size_t)blockIdx.y * n_pass + pass) * 3 + k];
+  const int64_t n = (int64_t)b.w * b.h * b.d;
+  const uint8_t* vin = src + b.off;
+  uint8_t* vout = dst + b.off;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o2 = (int)(i % b.d);
+    const int64_t q = i / b.d;
+    const int o1 = (int)(q % b.h), o0 = (int)(q / b.h);
+    uint8_t res = 0;
+    if (mask_hw[(size_t)(b.y0 + o1) * Wfull + (b.x0 + o0)]) res = resample_voxel(vin, b.w, b.h, b.d, A, o0, o1, o2);
+    vout[i] = res;
+  }
+}
+
+// paste of :199-201 over each crop (src = the call's INPUT grid) + the component's "carved voxels" count.  With
+// comp_first >= 0 only that component is pasted (sequential launches when bounding boxes overlap: the reference's
+// loop order decides there).
+__global__ void __launch_bounds__(256)
+lr_paste_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ labels, const uint8_t* __restrict__ buf,
+                const int32_t* __restrict__ comps, int comp_first, int H, int D, uint8_t* __restrict__ out,
+                unsigned long long* __restrict__ counts) {
+  const int c = comp_first >= 0 ? comp_first : (int)blockIdx.y;
+  const CompBox b = load_comp(comps, c);
+  const int64_t n = (int64_t)b.w * b.h * b.d;
+  const uint8_t* kept = buf + b.off;
+  unsigned int mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % b.d);
+    const int64_t q = i / b.d;
+    const int y = (int)(q % b.h), x = (int)(q / b.h);
+    const size_t v = (((size_t)(b.x0 + x)) * H + (b.y0 + y)) * D + (b.z0 + z);
+    const uint8_t* p = src + 3 * v;
+    const bool k = kept[i] != 0;
+    mine += k;
+    if (k && rgb_nonzero(p)) {
+      out[3 * v] = p[0]; out[3 * v + 1] = p[1]; out[3 * v + 2] = p[2];
+    } else if (labels[v] == c + 1) {
+      out[3 * v] = 0; out[3 * v + 1] = 0; out[3 * v + 2] = 0;
+    }
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(counts + c, (unsigned long long)mine);
+}
+
+// part_carve's group image on the device: gm[y][x] bit g = pixel colour is one of group g's colours -- and, for a
+// square image, also at the transposed pixel (the reference's _mask_to_wh quirk: m & m.T).  keys[k] = r | g << 8 |
+// b << 16, group_of[k] = its group.
+__global__ void __launch_bounds__(256)
+group_image_kernel(const uint8_t* __restrict__ mask_rgb, int H, int W, const uint32_t* __restrict__ keys,
+                   const int32_t* __restrict__ group_of, int n_keys, uint32_t* __restrict__ gm) {
+  __shared__ uint32_t s_key[128];
+  __shared__ int32_t s_grp[128];
+  for (int k = threadIdx.x; k < n_keys; k += blockDim.x) { s_key[k] = keys[k]; s_grp[k] = group_of[k]; }
+  __syncthreads();
+  const int n = H * W;
+  auto bits_at = [&](int pix) {
+    const uint8_t* p = mask_rgb + 3 * (size_t)pix;
+    const uint32_t c = p[0] | (p[1] << 8) | (p[2] << 16);
+    uint32_t bits = 0;
+    for (int k = 0; k < n_keys; ++k)
+      if (s_key[k] == c) bits |= 1u << s_grp[k];
+    return bits;
+  };
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t bits = bits_at(i);
+    if (W == H && bits) {
+      const int y = i / W, x = i - y * W;
+      bits &= bits_at(x * W + y);
+    }
+    gm[i] = bits;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -59,45 +217,7 @@ resample_carve_kernel(const uint8_t* __restrict__ vin, int n0, int n1, int n2, A
     const int o1 = (int)(r % n1);
     const int o0 = (int)(r / n1);
     uint8_t res = 0;
-    if (mask_wh == nullptr || mask_wh[(size_t)o0 * n1 + o1]) {
-      const int dim[3] = {n0, n1, n2};
-      double cc[3];
-      bool inside = true;
-#pragma unroll
-      for (int h = 0; h < 3; ++h) {
-        cc[h] = coord(A, h, o0, o1, o2);
-        if (cc[h] < 0.0 || cc[h] > (double)(dim[h] - 1)) inside = false;
-      }
-      if (inside) {
-        int i0[3], i1[3];
-        double t[3];
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-          const double fl = floor(cc[h]);
-          t[h] = __dsub_rn(cc[h], fl);
-          i0[h] = (int)fl;
-          i1[h] = i0[h] + 1 < dim[h] ? i0[h] + 1 : dim[h] - 1;
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int ix = a ? i1[0] : i0[0], iy = b ? i1[1] : i0[1], iz = c ? i1[2] : i0[2];
-              double w = (double)vin[((size_t)ix * n1 + iy) * n2 + iz];
-              w = __dmul_rn(w, a ? t[0] : __dsub_rn(1.0, t[0]));
-              w = __dmul_rn(w, b ? t[1] : __dsub_rn(1.0, t[1]));
-              w = __dmul_rn(w, c ? t[2] : __dsub_rn(1.0, t[2]));
-              acc = __dadd_rn(acc, w);
-            }
-        if (acc > 0.0) {
-          const double rr = __dadd_rn(acc, 0.5);
-          res = rr >= 255.0 ? 255 : (uint8_t)rr;
-        }
-      }
-    }
+    if (mask_wh == nullptr || mask_wh[(size_t)o0 * n1 + o1]) res = resample_voxel(vin, n0, n1, n2, A, o0, o1, o2);
     vout[i] = res;
   }
 }
@@ -686,7 +806,6 @@ colourise_kernel(const uint8_t* __restrict__ carved, int W, int H, int D, const 
 // G  = bit g set when pixel (x,y) belongs to group g's 2-D mask; MM = the same masks after the reference's
 // _mask_to_wh (transposed when W == H).  Both are (H,W) uint32 images.  Output = grid where keep else 0.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool rgb_nonzero(const uint8_t* p) { return (p[0] | p[1] | p[2]) != 0; }
 
 __global__ void __launch_bounds__(256)
 part_fold_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const int32_t* __restrict__ table,
@@ -943,12 +1062,13 @@ ccl_relabel_kernel(const int32_t* parent, const int32_t* __restrict__ rank_of, i
 
 // per component: bbox (min0,min1,min2,max0,max1,max2), voxel count and coordinate sums along each axis
 __global__ void __launch_bounds__(256)
-component_stats_kernel(const int32_t* __restrict__ labels, int n0, int n1, int n2, int32_t* __restrict__ bbox,
+component_stats_kernel(const int32_t* __restrict__ labels, int n0, int n1, int n2, int capacity,
+                       int32_t* __restrict__ bbox,
                        unsigned long long* __restrict__ sums /* [comp][4] = count, sum0, sum1, sum2 */) {
   const int64_t n = (int64_t)n0 * n1 * n2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t l = labels[i];
-    if (l <= 0) continue;
+    if (l <= 0 || l > capacity) continue;
     const int c = (int)(i % n2);
     const int64_t r = i / n2;
     const int b = (int)(r % n1);
@@ -1547,6 +1667,50 @@ P3D_API int p3d_paste_component(const uint8_t* src, const int32_t* labels, int c
   return P3D_OK;
 }
 
+P3D_API int p3d_lr_carve_components(const uint8_t* grid, const int32_t* labels, int W, int H, int D,
+                                    const uint8_t* mask_hw, const int32_t* comps, int n_comp, int64_t max_crop_voxels,
+                                    const double* Ms, const double* offs, int n_pass, uint8_t* buf_a, uint8_t* buf_b,
+                                    int sequential_paste, uint8_t* out, int64_t* counts, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && n_comp >= 0 && n_pass >= 0 && max_crop_voxels >= 0, "lr_carve_components: bad arguments");
+  if (n_comp == 0) return P3D_OK;
+  P3D_REQUIRE(grid && labels && mask_hw && comps && buf_a && buf_b && buf_a != buf_b && out && counts &&
+              (n_pass == 0 || (Ms && offs)), "lr_carve_components: null or aliased pointer");
+  P3D_REQUIRE(n_comp <= 65535, "lr_carve_components: %d components exceed one launch", n_comp);
+  cudaStream_t st = p3d::as_stream(stream);
+  P3D_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_comp * sizeof(int64_t), st));
+  int per = grid_for(max_crop_voxels, 256, 16);
+  const int cap = (p3d::sm_count() * 16 + n_comp - 1) / n_comp;         // about 16 CTAs per SM over all components
+  if (per > cap) per = cap < 1 ? 1 : cap;
+  dim3 g((unsigned)per, (unsigned)n_comp);
+  lr_crop_kernel<<<g, 256, 0, st>>>(grid, H, D, comps, buf_a);
+  uint8_t* src = buf_a;
+  uint8_t* dst = buf_b;
+  for (int p = 0; p < n_pass; ++p) {
+    lr_resample_kernel<<<g, 256, 0, st>>>(src, dst, comps, Ms, offs, p, n_pass, mask_hw, W);
+    uint8_t* t = src; src = dst; dst = t;
+  }
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts);
+  if (sequential_paste) {
+    for (int c = 0; c < n_comp; ++c) lr_paste_kernel<<<dim3((unsigned)per, 1), 256, 0, st>>>(grid, labels, src, comps, c, H, D, out, cnt);
+  } else {
+    lr_paste_kernel<<<g, 256, 0, st>>>(grid, labels, src, comps, -1, H, D, out, cnt);
+  }
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_group_image(const uint8_t* mask_rgb, int H, int W, const uint32_t* keys, const int32_t* group_of, int n_keys,
+                            uint32_t* gm, p3d_stream_t stream) {
+  P3D_REQUIRE(H >= 0 && W >= 0 && n_keys >= 0 && n_keys <= 128, "group_image: bad arguments (at most 128 colours)");
+  if ((int64_t)H * W == 0) return P3D_OK;
+  P3D_REQUIRE((int64_t)H * W < (1ll << 31), "group_image: image too large");
+  P3D_REQUIRE(mask_rgb && gm && (n_keys == 0 || (keys && group_of)), "group_image: null pointer");
+  group_image_kernel<<<grid_for((int64_t)H * W, 256, 8), 256, 0, p3d::as_stream(stream)>>>(mask_rgb, H, W, keys, group_of,
+                                                                                          n_keys, gm);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
 P3D_API int p3d_colour_mask(const uint8_t* grid_rgb, int64_t n, int r, int g, int b, uint8_t* mask, p3d_stream_t stream) {
   P3D_REQUIRE(n >= 0, "colour_mask: n < 0");
   if (n == 0) return P3D_OK;
@@ -1615,7 +1779,7 @@ P3D_API int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, i
   cudaStream_t st = p3d::as_stream(stream);
   bbox_init_kernel<<<(n_components * 6 + 255) / 256, 256, 0, st>>>(bbox, n_components);
   P3D_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_components * 4 * sizeof(int64_t), st));
-  component_stats_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(labels, n0, n1, n2, bbox,
+  component_stats_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(labels, n0, n1, n2, n_components, bbox,
                                                              reinterpret_cast<unsigned long long*>(sums));
   P3D_LAUNCH_CHECK();
   return P3D_OK;

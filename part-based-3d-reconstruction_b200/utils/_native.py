@@ -105,6 +105,9 @@ _SIGNATURES = {
     "p3d_crop_occupancy": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "p3d_accumulate_part": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "p3d_paste_component": ([_vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "p3d_lr_carve_components": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp,
+                                 _vp], _i32),
+    "p3d_group_image": ([_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp], _i32),
     "p3d_colour_mask": ([_vp, _i64, _i32, _i32, _i32, _vp, _vp], _i32),
     "p3d_label6_workspace_bytes": ([_i64], _sz),
     "p3d_label6": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp], _i32),

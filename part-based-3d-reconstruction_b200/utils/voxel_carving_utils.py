@@ -46,7 +46,10 @@ def _to_dev_u8(a, dev, what="array"):
         arr = np.asarray(a)
         if arr.dtype == np.bool_:
             arr = arr.astype(np.uint8)
-        t = torch.from_numpy(np.ascontiguousarray(arr))
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype == np.uint8:
+            return _upload_u8(arr, dev)
+        t = torch.from_numpy(arr)
     if t.dtype == torch.bool:
         t = t.to(torch.uint8)
     if t.dtype != torch.uint8:
@@ -54,8 +57,41 @@ def _to_dev_u8(a, dev, what="array"):
     return t.to(dev).contiguous()
 
 
+_PINNED = {}              # staging buffers for the NumPy boundary (one per direction), grown on demand
+_PIN_MIN_BYTES = 1 << 20  # below this a pageable copy is as fast as staging
+
+
+def _pinned(kind, nbytes):
+    buf = _PINNED.get(kind)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        _PINNED[kind] = buf
+    return buf[:nbytes]
+
+
+def _upload_u8(arr, dev):
+    """Contiguous uint8 NumPy array -> device tensor; large arrays go through a pinned staging buffer (one host memcpy
+    + a DMA at full PCIe rate instead of the driver's pageable path)."""
+    if arr.nbytes < _PIN_MIN_BYTES:
+        return torch.from_numpy(arr).to(dev)
+    stage = _pinned("h2d", arr.nbytes)
+    stage.numpy()[:] = arr.reshape(-1)
+    out = torch.empty(arr.shape, dtype=torch.uint8, device=dev)
+    out.view(-1).copy_(stage, non_blocking=True)
+    torch.cuda.current_stream().synchronize()              # the staging buffer is reused by the next call
+    return out
+
+
 def _ret(t, as_tensor):
-    return t if as_tensor else t.cpu().numpy()
+    """Device tensor -> what the caller asked for: the tensor itself, or a FRESH NumPy array the caller owns."""
+    if as_tensor:
+        return t
+    if t.numel() * t.element_size() < _PIN_MIN_BYTES or t.dtype != torch.uint8:
+        return t.cpu().numpy()
+    stage = _pinned("d2h", t.numel())
+    stage.copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return stage.numpy().reshape(tuple(t.shape)).copy()
 
 
 def _mask_to_wh(mask, W, H):
@@ -128,7 +164,6 @@ def _fold_table(n0, n2, M, off, dev):
 
 
 _FOLD_BITS_CACHE = {}
-_LAST_PART_CARVE_LAUNCH = None
 
 
 def _fold_bits(table, W, D, cache_key):
@@ -194,12 +229,38 @@ class _PackedMask:
 
     def __init__(self, semantic_mask):
         sem = semantic_mask.cpu().numpy() if _is_tensor(semantic_mask) else np.asarray(semantic_mask)
+        self._src = semantic_mask
+        self._dev = {}
         self.sem = sem
         self.shape = sem.shape
         self.packed = None
         if sem.dtype == np.uint8 and sem.ndim == 3 and sem.shape[2] == 3:
             self.packed = (sem[..., 0].astype(np.uint32) | (sem[..., 1].astype(np.uint32) << 8)
                            | (sem[..., 2].astype(np.uint32) << 16))
+
+    def device_rgb(self, dev):
+        """The mask as a contiguous (H,W,3) uint8 device tensor (uploaded once), or None when it is not an RGB u8 image."""
+        if self.packed is None:
+            return None
+        t = self._dev.get(str(dev))
+        if t is None:
+            t = self._src if (_is_tensor(self._src) and self._src.device == dev and self._src.dtype == torch.uint8) \
+                else torch.from_numpy(np.ascontiguousarray(self.sem)).to(dev)
+            t = self._dev[str(dev)] = t.contiguous()
+        return t
+
+    def device_match(self, colour, dev):
+        """(H,W) uint8 device mask of all(mask == colour, axis=-1) (cached per colour)."""
+        key = (str(dev), tuple(int(v) for v in np.asarray(colour).reshape(3)))
+        m = self._dev.get(key)
+        if m is None:
+            rgb = self.device_rgb(dev)
+            if rgb is None:
+                m = torch.from_numpy(self.match([colour]).astype(np.uint8)).to(dev)
+            else:
+                m = _colour_mask(rgb.view(1, *rgb.shape), colour).view(rgb.shape[0], rgb.shape[1])
+            self._dev[key] = m
+        return m
 
     def match(self, colours):
         """any over colours of all(mask == colour, axis=-1)  (voxel_carving_utils.py:143-146, :170)."""
@@ -295,6 +356,37 @@ def _group_image(jobs, H, W):
     return gm
 
 
+_GROUP_KEYS = {}          # (device, colours per group) -> (keys u32, group_of i32) device tensors
+
+
+def _group_image_device(semantic_mask, group_colours, dev):
+    """(H,W) int32 device image of group bits (p3d_group_image): bit g where the pixel's colour belongs to group g, for a
+    square image also at the transposed pixel (the reference's _mask_to_wh quirk).  Colours outside 0..255 match
+    nothing, as in the reference's comparison with a uint8 image."""
+    flat = tuple(tuple(tuple(int(v) for v in np.asarray(c).reshape(3)) for c in cols) for cols in group_colours)
+    hit = _GROUP_KEYS.get((str(dev), flat))
+    if hit is None:
+        keys, grp = [], []
+        for g, cols in enumerate(flat):
+            for r, gg, b in cols:
+                if 0 <= r < 256 and 0 <= gg < 256 and 0 <= b < 256:
+                    keys.append(r | (gg << 8) | (b << 16))
+                    grp.append(g)
+        if len(keys) > 128:
+            raise ValueError("part_carve: more than 128 part colours")
+        hit = (torch.tensor(keys or [0], dtype=torch.int32, device=dev), torch.tensor(grp or [0], dtype=torch.int32, device=dev),
+               len(keys))
+        if len(_GROUP_KEYS) >= 16:
+            _GROUP_KEYS.pop(next(iter(_GROUP_KEYS)))
+        _GROUP_KEYS[(str(dev), flat)] = hit
+    rgb = semantic_mask.device_rgb(dev)
+    H, W = int(rgb.shape[0]), int(rgb.shape[1])
+    gm = torch.empty((H, W), dtype=torch.int32, device=dev)
+    check(lib.p3d_group_image(ptr(rgb), H, W, ptr(hit[0]), ptr(hit[1]), hit[2], ptr(gm), stream_ptr()), "p3d_group_image")
+    _launched()
+    return gm
+
+
 @nv.on_device
 def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_range=None):
     """voxel_carving_utils.py:139-160: per part group, carve the group's voxels with the group's own mask under
@@ -312,53 +404,48 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_ra
         x0, x1 = int(x_range[0]), int(x_range[1])
         if not (0 <= x0 <= x1 <= W):
             raise ValueError(f"x_range {x_range} outside [0, {W}]")
-    jobs = []
     semantic_mask = semantic_mask if isinstance(semantic_mask, _PackedMask) else _PackedMask(semantic_mask)
-    for names, angle in group_jobs:
-        m2d = _mask2d_bool(semantic_mask, [PART_COLORS[n] for n in names])          # (H,W)
-        if not m2d.any():
-            continue
-        jobs.append((m2d, angle))                                                   # (H,W) bool; m = m2d.T is the reference's (W,H)
+    group_jobs = list(group_jobs)
     out = None
-    if jobs and all(a == 90 for _, a in jobs) and len(jobs) <= 32 and D == W:
+    # All groups at 90 degrees on a cubic grid: every group in ONE fused pass, the per-pixel group bits built on the
+    # device (an empty group simply contributes no bits; the reference skips it, :148-149).
+    if (group_jobs and all(a == 90 for _, a in group_jobs) and len(group_jobs) <= 32 and D == W
+            and semantic_mask.packed is not None and tuple(semantic_mask.shape[:2]) == (H, W)):
         M, off = _pass_transform((W, H, D), 90)
         table, foldable = _fold_table(W, D, M, off, dev)
         M0, off0 = _pass_transform((W, H, D), 0)
         identity0 = np.array_equal(M0, np.eye(3)) and not off0.any()
         if foldable and identity0:
-            # group image in (H,W): bit g where pixel is in m AND in _mask_to_wh(m) -- m itself for W != H, m.T for a
-            # square image (the quirk), i.e. m2d & m2d.T there
-            gm_hw = torch.from_numpy(_group_image(jobs, H, W).view(np.int32)).to(dev)
+            n_groups = len(group_jobs)
+            gm_hw = _group_image_device(semantic_mask, [[PART_COLORS[n] for n in names] for names, _ in group_jobs], dev)
             bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
             if x_range is not None and bits is not None and bits[2] is not None and x1 > x0:
-                ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
+                ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 slab = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
-
-                def launch_slab(grid=grid, slab=slab, ws=ws, gm_hw=gm_hw, bits=bits, n=len(jobs)):
-                    check(lib.p3d_part_carve_fold_bits_slab(ptr(grid), W, H, D, x0, x1 - x0, ptr(bits[0]), bits[1], bits[2],
-                                                            ptr(gm_hw), n, ptr(slab), ptr(ws), ws_bytes, stream_ptr()),
-                          "p3d_part_carve_fold_bits_slab")
-                    _launched(4)
-                launch_slab()
-                global _LAST_PART_CARVE_LAUNCH
-                _LAST_PART_CARVE_LAUNCH = launch_slab
+                check(lib.p3d_part_carve_fold_bits_slab(ptr(grid), W, H, D, x0, x1 - x0, ptr(bits[0]), bits[1], bits[2],
+                                                        ptr(gm_hw), n_groups, ptr(slab), ptr(ws), ws_bytes, stream_ptr()),
+                      "p3d_part_carve_fold_bits_slab")
+                _launched(4)
                 return _ret(slab, as_tensor)
             out = torch.empty_like(grid)
             if bits is not None and bits[2] is not None:       # z-separable table: bit-packed occupancy / group masks
-                ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
+                ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-
-                def launch(grid=grid, out=out, ws=ws, gm_hw=gm_hw, bits=bits, n=len(jobs)):
-                    check(lib.p3d_part_carve_fold_bits(ptr(grid), W, H, D, ptr(bits[0]), bits[1], bits[2], ptr(gm_hw), n,
-                                                       ptr(out), ptr(ws), ws_bytes, stream_ptr()), "p3d_part_carve_fold_bits")
-                    _launched(3)
-                launch()
-                _LAST_PART_CARVE_LAUNCH = launch              # bench.py re-issues it to time the kernels alone
+                check(lib.p3d_part_carve_fold_bits(ptr(grid), W, H, D, ptr(bits[0]), bits[1], bits[2], ptr(gm_hw), n_groups,
+                                                   ptr(out), ptr(ws), ws_bytes, stream_ptr()), "p3d_part_carve_fold_bits")
+                _launched(3)
             else:
                 check(lib.p3d_part_carve_fold(ptr(grid), W, H, D, ptr(table), ptr(gm_hw), ptr(out), stream_ptr()),
                       "p3d_part_carve_fold")
                 _launched()
+    jobs = []
+    if out is None:
+        for names, angle in group_jobs:
+            m2d = _mask2d_bool(semantic_mask, [PART_COLORS[n] for n in names])          # (H,W)
+            if not m2d.any():
+                continue
+            jobs.append((m2d, angle))                                                   # (H,W) bool; m = m2d.T is the reference's (W,H)
     if out is None:
         out = torch.zeros_like(grid)
         for m2d, angle in jobs:
@@ -440,8 +527,14 @@ class PartCarveSlab:
         return _ret(self.out, self.as_tensor)
 
 
-def _label_components(mask_u8):
-    """scipy.ndimage.label (6-connectivity) on device: (labels int32, n, bbox (n,6) ndarray, sums (n,4) ndarray)."""
+_STATS_CAP = 1024         # components whose statistics are gathered before the one host read-back
+
+
+def _label_components(mask_u8, extra=None):
+    """scipy.ndimage.label (6-connectivity) on device: (labels int32, n, bbox (n,6) ndarray, sums (n,4) ndarray).
+    Labelling and the per-component statistics of up to _STATS_CAP components are enqueued back to back and read with
+    ONE synchronisation (more components: a second statistics pass).  `extra`: a small device tensor whose host copy is
+    wanted from the same synchronisation (returned as a fifth value)."""
     n0, n1, n2 = mask_u8.shape
     dev = mask_u8.device
     nvox = mask_u8.numel()
@@ -451,12 +544,20 @@ def _label_components(mask_u8):
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
     check(lib.p3d_label6(ptr(mask_u8), n0, n1, n2, ptr(labels), ptr(ncomp), ptr(ws), ws_bytes, stream_ptr()), "p3d_label6")
     _launched(7)
-    n = int(ncomp.item())
-    bbox = torch.empty((max(n, 1), 6), dtype=torch.int32, device=dev)
-    sums = torch.empty((max(n, 1), 4), dtype=torch.int64, device=dev)
-    check(lib.p3d_component_stats(ptr(labels), n0, n1, n2, n, ptr(bbox), ptr(sums), stream_ptr()), "p3d_component_stats")
-    _launched(2 if n else 0)
-    return labels, n, bbox.cpu().numpy()[:n], sums.cpu().numpy()[:n]
+
+    def stats(cap):
+        bbox = torch.empty((cap, 6), dtype=torch.int32, device=dev)
+        sums = torch.empty((cap, 4), dtype=torch.int64, device=dev)
+        check(lib.p3d_component_stats(ptr(labels), n0, n1, n2, cap, ptr(bbox), ptr(sums), stream_ptr()), "p3d_component_stats")
+        _launched(2)
+        return bbox, sums
+
+    bbox, sums = stats(_STATS_CAP)
+    n = int(ncomp.cpu().item())                               # the one synchronisation
+    if n > _STATS_CAP:
+        bbox, sums = stats(n)
+    res = (labels, n, bbox[:n].cpu().numpy(), sums[:n].cpu().numpy())
+    return res + (extra.cpu().numpy(),) if extra is not None else res
 
 
 def _colour_mask(grid, colour):
@@ -468,40 +569,74 @@ def _colour_mask(grid, colour):
     return mask
 
 
+def _lr_tables(boxes, angle):
+    """Host tables of one left_right_guided_carve call: per pass the inverse rotation handed to scipy at :116-123, per
+    (component, pass) the offset for that crop's shape -- the very NumPy expressions the per-component path evaluates."""
+    angles = list(range(0, 91, angle))
+    Ms = np.stack([_pass_transform((1, 1, 1), a)[0] for a in angles])
+    offs = np.stack([np.stack([_pass_transform((w, h, d), a)[1] for a in angles]) for (_, _, _, w, h, d) in boxes])
+    return np.ascontiguousarray(Ms, dtype=np.float64), np.ascontiguousarray(offs, dtype=np.float64)
+
+
+def _boxes_overlap(boxes):
+    """True when two bounding boxes intersect (then the paste order of the reference's loop matters)."""
+    n = len(boxes)
+    if n < 2:
+        return False
+    b = np.asarray(boxes, dtype=np.int64)
+    lo, hi = b[:, 0:3], b[:, 0:3] + b[:, 3:6]
+    for i in range(n - 1):
+        if np.any(np.all((lo[i + 1:] < hi[i]) & (lo[i] < hi[i + 1:]), axis=1)):
+            return True
+    return False
+
+
 @nv.on_device
 def left_right_guided_carve(colored_grid, semantic_mask, target_color, angle=60, visualize=False, stride=2):
     """voxel_carving_utils.py:163-210: for every 6-connected 3-D component of `target_color`, carve the
-    component's bounding-box crop with the matching crop of the part's 2-D mask under `angle` symmetry."""
+    component's bounding-box crop with the matching crop of the part's 2-D mask under `angle` symmetry.
+
+    Device schedule: colour masks -> 3-D labelling + component boxes -> ONE host read (boxes; sizes the scratch) ->
+    one crop launch, one launch per rotate-and-carve pass and one paste launch for ALL components (blockIdx.y = the
+    component) -> one host read of the per-component counts for the log."""
     as_tensor = _is_tensor(colored_grid)
     dev = nv.require_cuda(colored_grid.device if as_tensor and colored_grid.is_cuda else None)
     grid = _to_dev_u8(colored_grid, dev, "colored_grid")
     W, H, D, _ = grid.shape
     carved = grid.clone()
-    mask2d = _mask2d_bool(semantic_mask, [target_color])
-    if not np.any(mask2d):
+    pm = semantic_mask if isinstance(semantic_mask, _PackedMask) else _PackedMask(semantic_mask)
+    mask2d = pm.device_match(target_color, dev)                                  # (H,W) u8 on the device
+    if tuple(mask2d.shape) != (H, W):
+        raise ValueError(f"semantic_mask {tuple(pm.shape)} does not match the grid's (H,W)=({H},{W})")
+    any2d = mask2d.max().reshape(1)
+    labels, n, bbox, _, any_host = _label_components(_colour_mask(grid, target_color), extra=any2d)
+    if not int(any_host[0]):
         print(f"[SKIP] No mask for color {target_color}")
         return _ret(carved, as_tensor)
-    labels, n, bbox, _ = _label_components(_colour_mask(grid, target_color))
     print(f"[{target_color}] 3D components: {n}")
-    log = []                                   # (bbox line, device count) per component: printed after ONE sync
-    for i in range(1, n + 1):
-        x0, y0, z0 = (int(v) for v in bbox[i - 1, 0:3])
-        x1, y1, z1 = (int(v) + 1 for v in bbox[i - 1, 3:6])
-        w, h, d = x1 - x0, y1 - y0, z1 - z0
-        crop2d = mask2d[y0:y1, x0:x1]
-        m_wh = _to_dev_u8(np.ascontiguousarray(_mask_to_wh(crop2d, w, h)), dev)
-        occ = torch.empty((w, h, d), dtype=torch.uint8, device=dev)
-        check(lib.p3d_crop_occupancy(ptr(grid), W, H, D, x0, y0, z0, w, h, d, None, ptr(occ), stream_ptr()),
-              "p3d_crop_occupancy")
-        kept = _process_device(occ, m_wh, angle)
-        log.append((f"  - Component {i}: bbox ({x0},{y0},{z0}) → ({x1},{y1},{z1})", torch.count_nonzero(kept)))
-        check(lib.p3d_paste_component(ptr(grid), ptr(labels), i, ptr(kept), W, H, D, x0, y0, z0, w, h, d, ptr(carved),
-                                      stream_ptr()), "p3d_paste_component")
-        _launched(2)
-    if log:
-        counts = torch.stack([c for _, c in log]).cpu().tolist()
-        for (line, _), c in zip(log, counts):
-            print(line)
+    if n:
+        boxes = [(int(b[0]), int(b[1]), int(b[2]), int(b[3]) + 1 - int(b[0]), int(b[4]) + 1 - int(b[1]), int(b[5]) + 1 - int(b[2]))
+                 for b in bbox]
+        vols = np.array([w * h * d for (_, _, _, w, h, d) in boxes], dtype=np.int64)
+        offsets = np.concatenate([[0], np.cumsum(vols)[:-1]])
+        comps = np.zeros((n, 8), np.int32)
+        comps[:, 0:6] = np.asarray(boxes, dtype=np.int32)
+        comps[:, 6] = (offsets & 0xffffffff).astype(np.uint32).view(np.int32)
+        comps[:, 7] = (offsets >> 32).astype(np.int32)
+        Ms, offs = _lr_tables(boxes, angle)
+        total = int(vols.sum())
+        comps_d = torch.from_numpy(comps).to(dev)
+        tab = torch.from_numpy(np.concatenate([Ms.reshape(-1), offs.reshape(-1)])).to(dev)
+        Ms_d, offs_d = tab[:Ms.size], tab[Ms.size:]
+        buf = torch.empty((2, max(total, 1)), dtype=torch.uint8, device=dev)
+        counts = torch.empty(n, dtype=torch.int64, device=dev)
+        check(lib.p3d_lr_carve_components(ptr(grid), ptr(labels), W, H, D, ptr(mask2d), ptr(comps_d), n, int(vols.max()),
+                                          ptr(Ms_d), ptr(offs_d), Ms.shape[0], ptr(buf[0]), ptr(buf[1]),
+                                          1 if _boxes_overlap(boxes) else 0, ptr(carved), ptr(counts), stream_ptr()),
+              "p3d_lr_carve_components")
+        _launched(2 + Ms.shape[0])
+        for i, ((x0, y0, z0, w, h, d), c) in enumerate(zip(boxes, counts.cpu().tolist()), start=1):
+            print(f"  - Component {i}: bbox ({x0},{y0},{z0}) → ({x0 + w},{y0 + h},{z0 + d})")
             print(f"    carved voxels: {int(c)}")
     if visualize:
         warnings.warn("visualize=True is ignored: plotting is outside this package's scope")
@@ -512,15 +647,17 @@ def _extrude_inplace(out, mask_2d, axis, direction, depth, fill_color):
     W, H, D, _ = out.shape
     if axis not in (0, 2):
         return
-    m = mask_2d.cpu().numpy() if _is_tensor(mask_2d) else np.asarray(mask_2d)
-    m = np.ascontiguousarray(m != 0).astype(np.uint8)
+    if _is_tensor(mask_2d) and mask_2d.is_cuda and mask_2d.dtype == torch.uint8:
+        md = mask_2d.contiguous()                             # device mask (any non-zero byte selects the column)
+    else:
+        m = mask_2d.cpu().numpy() if _is_tensor(mask_2d) else np.asarray(mask_2d)
+        md = torch.from_numpy(np.ascontiguousarray(m != 0).astype(np.uint8)).to(out.device)
     want = (H, W) if axis == 2 else (H, D)
-    if m.shape != want:
-        raise ValueError(f"operands could not be broadcast together: mask {m.shape} vs {want}")
+    if tuple(md.shape) != want:
+        raise ValueError(f"operands could not be broadcast together: mask {tuple(md.shape)} vs {want}")
     colour = (0, 0, 0) if fill_color is None else _colour_args(fill_color)
     sign = 1 if direction == "+" else -1
-    md = torch.from_numpy(m).to(out.device)
-    check(lib.p3d_extrude(ptr(out), W, H, D, ptr(md), m.shape[0], m.shape[1], axis, sign, int(depth), colour[0],
+    check(lib.p3d_extrude(ptr(out), W, H, D, ptr(md), int(md.shape[0]), int(md.shape[1]), axis, sign, int(depth), colour[0],
                           colour[1], colour[2], stream_ptr()), "p3d_extrude")
     _launched()
 
@@ -642,7 +779,7 @@ def partwise_carve(colored_voxel_grid, semantic_mask_exterior, semantic_mask_ful
         grid = left_right_guided_carve(colored_grid=grid, semantic_mask=semantic_mask_exterior,
                                        target_color=part_colors_np[part], angle=angle, visualize=False, stride=stride)
     for part, depth in extrusion_depths.items():
-        mask = _mask2d_bool(semantic_mask_full, [part_colors_np[part]])
+        mask = semantic_mask_full.device_match(part_colors_np[part], dev)    # one device mask for the four directions
         for axis, direction in ((2, "+"), (2, "-"), (0, "+"), (0, "-")):     # extrude_4dirs :356-361
             _extrude_inplace(grid, mask, axis, direction, depth, part_colors_np[part])
     if recolor_back_minarets:
