@@ -111,7 +111,7 @@ def _rotation_matrix_inv(angle):
     return np.linalg.inv(R)
 
 
-@functools.lru_cache(maxsize=64)
+@functools.lru_cache(maxsize=8192)       # (crop shape, angle): a guided carve asks for 19 angles per component shape
 def _pass_transform_cached(shape, angle):
     M, off = _pass_transform_uncached(shape, angle)
     M.setflags(write=False)
@@ -224,23 +224,36 @@ def _process_device(vol, mask_wh, angle_interval):
 
 
 class _PackedMask:
-    """A (H,W,3) uint8 semantic mask with its channels packed into one 32-bit key per pixel, so that every colour
-    test is a single integer compare (host side, O(H*W) per colour)."""
+    """A (H,W,3) uint8 semantic mask.  Device side: the RGB image as a tensor (uploaded once) and per-colour (H,W) masks
+    from the colour-compare kernel.  Host side (built lazily, only for the general-angle paths): the channels packed
+    into one 32-bit key per pixel, so that every colour test is a single integer compare."""
 
     def __init__(self, semantic_mask):
-        sem = semantic_mask.cpu().numpy() if _is_tensor(semantic_mask) else np.asarray(semantic_mask)
         self._src = semantic_mask
         self._dev = {}
-        self.sem = sem
-        self.shape = sem.shape
-        self.packed = None
-        if sem.dtype == np.uint8 and sem.ndim == 3 and sem.shape[2] == 3:
-            self.packed = (sem[..., 0].astype(np.uint32) | (sem[..., 1].astype(np.uint32) << 8)
-                           | (sem[..., 2].astype(np.uint32) << 16))
+        self._sem = None
+        self._packed = None
+        self.shape = tuple(semantic_mask.shape)
+        dt = semantic_mask.dtype
+        self.is_rgb_u8 = len(self.shape) == 3 and self.shape[2] == 3 and dt in (torch.uint8, np.uint8, np.dtype(np.uint8))
+
+    @property
+    def sem(self):
+        if self._sem is None:
+            self._sem = self._src.cpu().numpy() if _is_tensor(self._src) else np.asarray(self._src)
+        return self._sem
+
+    @property
+    def packed(self):
+        if self._packed is None and self.is_rgb_u8:
+            sem = self.sem
+            self._packed = (sem[..., 0].astype(np.uint32) | (sem[..., 1].astype(np.uint32) << 8)
+                            | (sem[..., 2].astype(np.uint32) << 16))
+        return self._packed
 
     def device_rgb(self, dev):
         """The mask as a contiguous (H,W,3) uint8 device tensor (uploaded once), or None when it is not an RGB u8 image."""
-        if self.packed is None:
+        if not self.is_rgb_u8:
             return None
         t = self._dev.get(str(dev))
         if t is None:
@@ -410,7 +423,7 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_ra
     # All groups at 90 degrees on a cubic grid: every group in ONE fused pass, the per-pixel group bits built on the
     # device (an empty group simply contributes no bits; the reference skips it, :148-149).
     if (group_jobs and all(a == 90 for _, a in group_jobs) and len(group_jobs) <= 32 and D == W
-            and semantic_mask.packed is not None and tuple(semantic_mask.shape[:2]) == (H, W)):
+            and semantic_mask.is_rgb_u8 and tuple(semantic_mask.shape[:2]) == (H, W)):
         M, off = _pass_transform((W, H, D), 90)
         table, foldable = _fold_table(W, D, M, off, dev)
         M0, off0 = _pass_transform((W, H, D), 0)
@@ -556,7 +569,8 @@ def _label_components(mask_u8, extra=None):
     n = int(ncomp.cpu().item())                               # the one synchronisation
     if n > _STATS_CAP:
         bbox, sums = stats(n)
-    res = (labels, n, bbox[:n].cpu().numpy(), sums[:n].cpu().numpy())
+    res = (labels, n, bbox[:n].cpu().numpy() if n else np.zeros((0, 6), np.int32),
+           sums[:n].cpu().numpy() if n else np.zeros((0, 4), np.int64))
     return res + (extra.cpu().numpy(),) if extra is not None else res
 
 

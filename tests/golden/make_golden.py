@@ -597,6 +597,34 @@ def depth_golden():
     np.savez_compressed(os.path.join(HERE, "depth_golden.npz"), **out)
 
 
+def real5_golden():
+    """The two monuments carve_golden.npz does not hold (SURVEY 4 asks for all five): Charminar -- a PORTRAIT mask (width
+    177 at max_dim 256, 88 at 128: no multiple of 32, the branch of mask_utils.py:65-71) -- and Itimad, through the live
+    global_carve + partwise_carve with notebook 1's jobs.  Masks, hashes, occupied counts and the printed component log;
+    full arrays only at max_dim 128."""
+    out = {}
+    cases = [("Charminar", 128), ("Charminar", 256), ("Itimad", 256)]
+    for name, md in cases:
+        sem, ext, binm = ref.mu.load_and_prepare_masks(os.path.join(ref.root, "data"), name, "front", md,
+                                                       C.PART_COLORS_NP, C.INTERIOR_PARTS)
+        g = ref.vc.global_carve(binm, ext, 90)
+        pc = ref.vc.part_carve(g, ext, GROUP_JOBS)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            p = ref.vc.partwise_carve(g, ext, sem, C.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS)
+        key = f"real_{name}_{md}"
+        out[key + "_sem"], out[key + "_ext"], out[key + "_bin"] = sem, ext, binm
+        out[key + "_global_sha"], out[key + "_partcarve_sha"], out[key + "_partwise_sha"] = np.array(sha(g)), np.array(sha(pc)), np.array(sha(p))
+        out[key + "_global_occ"] = np.array(np.count_nonzero(g.any(-1)))
+        out[key + "_partwise_occ"] = np.array(np.count_nonzero(p.any(-1)))
+        out[key + "_log"] = np.array(buf.getvalue())
+        if md <= 128:
+            out[key + "_global"], out[key + "_partwise"] = g, p
+        print(key, sem.shape, g.shape, out[key + "_partwise_sha"], out[key + "_partwise_occ"])
+    out["real_cases"] = np.array([f"{n}_{m}" for n, m in cases])
+    np.savez_compressed(os.path.join(HERE, "real5_golden.npz"), **out)
+
+
 def partcarve_asym_golden():
     """part_carve (voxel_carving_utils.py:139-160) of grids that are NOT 4-way symmetric: the inputs on which the rotated
     source occupancy decides (global_carve's output never is).  Random sparse grids coloured column-wise from a blocky
@@ -646,6 +674,8 @@ if __name__ == "__main__":
         tables_golden()
     if "partcarve_asym" in which:
         partcarve_asym_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz", "handoff_golden.npz", "tables_golden.npz", "partcarve_asym_golden.npz"):
+    if "real5" in which:
+        real5_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz", "handoff_golden.npz", "tables_golden.npz", "partcarve_asym_golden.npz", "real5_golden.npz"):
         if os.path.exists(os.path.join(HERE, f)):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

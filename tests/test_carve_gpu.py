@@ -95,6 +95,33 @@ def test_real_mask_carving_matches_reference(vc, carve_golden, case, capsys):
         assert np.array_equal(out, g[key + "_partwise"])
 
 
+@pytest.mark.parametrize("case", ["Charminar_128", "Charminar_256", "Itimad_256"])
+def test_remaining_monuments_match_reference(vc, case, capsys):
+    """The two monuments beside Bibi / Taj / Akbar (tests/golden/real5_golden.npz, live reference): Charminar is a PORTRAIT
+    mask (grid width 88 / 177: neither a multiple of 32 nor of 4 -- every vectorised or bit-packed kernel sees its ragged
+    tail), Itimad a landscape one; global_carve, part_carve and the whole partwise_carve chain with the printed log."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "real5_golden.npz"))
+    key = "real_" + case
+    sem, ext, binm = g[key + "_sem"], g[key + "_ext"], g[key + "_bin"]
+    cfg = pkg("utils.config")
+    grid = vc.global_carve(binm, ext, 90)
+    assert grid.shape == (binm.shape[1], binm.shape[0], binm.shape[1], 3)
+    assert sha(grid) == str(g[key + "_global_sha"]) and np.count_nonzero(grid.any(-1)) == int(g[key + "_global_occ"])
+    assert sha(vc.part_carve(grid, ext, GROUP_JOBS)) == str(g[key + "_partcarve_sha"])
+    for x_range in ((0, 5), (grid.shape[0] // 2 - 3, grid.shape[0] - 1)):            # x-slabs tile the same bytes
+        slab = vc.global_carve(binm, ext, 90, x_range=x_range)
+        assert np.array_equal(slab, grid[x_range[0]:x_range[1]])
+    capsys.readouterr()
+    out = vc.partwise_carve(grid, ext, sem, cfg.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS)
+    log = capsys.readouterr().out
+    assert sha(out) == str(g[key + "_partwise_sha"]) and np.count_nonzero(out.any(-1)) == int(g[key + "_partwise_occ"])
+    assert log.strip("\n") == str(g[key + "_log"]).strip("\n")
+    if key + "_partwise" in g.files:
+        assert np.array_equal(out, g[key + "_partwise"]) and np.array_equal(grid, g[key + "_global"])
+
+
 def test_synthetic_quirk_cases_match_reference(vc, carve_golden):
     """Square image (_mask_to_wh transposes), foreground in the last column, widths with the odd FP offsets."""
     g = carve_golden

@@ -165,3 +165,20 @@ def test_part_carve_on_asymmetric_grids_matches_live_reference(oracle):
     for tag in g["asym_cases"]:
         key = f"asym_{tag}"
         assert np.array_equal(oracle.part_carve(g[key + "_grid"], g[key + "_ext"], GROUP_JOBS), g[key + "_partcarve"]), tag
+
+
+def test_portrait_monument_carving(oracle):
+    """Charminar@128 (portrait mask, grid width 88) of tests/golden/real5_golden.npz: the oracle against the live
+    reference's arrays and printed log (the larger cases of that file are GPU-side checks only: minutes in the oracle)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "real5_golden.npz"))
+    key = "real_Charminar_128"
+    sem, ext, binm = g[key + "_sem"], g[key + "_ext"], g[key + "_bin"]
+    grid = oracle.global_carve(binm, ext, 90)
+    assert np.array_equal(grid, g[key + "_global"])
+    assert sha(oracle.part_carve(grid, ext, GROUP_JOBS)) == str(g[key + "_partcarve_sha"])
+    log = []
+    out = oracle.partwise_carve(grid, ext, sem, oracle.PART_COLORS_NP, GROUP_JOBS, PART_SYMMETRY, EXTRUSION_DEPTHS, log=log)
+    assert np.array_equal(out, g[key + "_partwise"])
+    assert "\n".join(log) == str(g[key + "_log"]).strip("\n")
