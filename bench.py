@@ -542,60 +542,56 @@ def carve_sharded_bench(N, dev, world, rank, dist):
         del gfull, pslab, kslab
     except Exception as exc:
         print("sharded part_carve timing failed:", repr(exc), file=sys.stderr)
-    # part_carve with the INPUT sharded as well (rank r holds only its x rows): pass A -> one all-gather of the occupancy
-    # bits (W*H*D/8 bytes in total) -> pass B; 6 B per slab voxel + the exchange.  CUDA events over the three steps.
-    sms, xms = 0.0, 0.0
+    # part_carve with the INPUT sharded as well (rank r holds only its x rows): pass A -> exchange of occupancy bits ->
+    # pass B; 6 B per slab voxel + the exchange.  Three exchange forms (utils.sweep.part_carve_sharded), whole calls
+    # through the public function, CUDA events, max over ranks.
+    sharded_ms = {}
     try:
         gfull = vc.global_carve(binm, ext, 90, return_tensor=True)
         x0, x1 = span
-        job = vc.PartCarveSlab(gfull[x0:x1].contiguous(), ext, jobs90, N, span)
+        slab_in = gfull[x0:x1].contiguous()
         want = vc.part_carve(gfull, ext, jobs90, x_range=span)
         del gfull
-
-        def sharded_once():
-            job.begin()
-            mine = job.occ[x0:x1].clone()
-            dist.all_gather_into_tensor(job.occ.view(-1), mine.view(-1))
-            return job.finish()
-        got = sharded_once()
-        assert torch.equal(got, want)
-        del want
-        for _ in range(2):
-            sharded_once()
-        torch.cuda.synchronize()
-        dist.barrier()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        for _ in range(5):
-            sharded_once()
-        eb.record()
-        torch.cuda.synchronize()
-        sms = ea.elapsed_time(eb) / 5
-        mine = job.occ[x0:x1].clone()
-        dist.barrier()
-        ea.record()
-        for _ in range(5):
-            dist.all_gather_into_tensor(job.occ.view(-1), mine.view(-1))
-        eb.record()
-        torch.cuda.synchronize()
-        xms = ea.elapsed_time(eb) / 5
-        del job, got, mine
+        for mode in ("alltoall", "peer", "allgather"):
+            try:
+                got, _ = sw.part_carve_sharded(slab_in, ext, jobs90, N, exchange=mode)
+                assert torch.equal(got, want), mode
+                for _ in range(2):
+                    sw.part_carve_sharded(slab_in, ext, jobs90, N, exchange=mode)
+                torch.cuda.synchronize()
+                dist.barrier()
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                for _ in range(5):
+                    sw.part_carve_sharded(slab_in, ext, jobs90, N, exchange=mode)
+                eb.record()
+                torch.cuda.synchronize()
+                sharded_ms[mode] = ea.elapsed_time(eb) / 5
+            except Exception as exc:
+                print(f"sharded-input part_carve ({mode}) failed:", repr(exc), file=sys.stderr)
+                sharded_ms[mode] = 0.0
+        del want, slab_in
     except Exception as exc:
         print("sharded-input part_carve timing failed:", repr(exc), file=sys.stderr)
-    t = torch.tensor([e0.elapsed_time(e1) / reps, kms, pms, sms, xms], dtype=torch.float64, device=dev)
+    sms, xms = sharded_ms.get("alltoall", 0.0), sharded_ms.get("peer", 0.0)
+    gms_ag = sharded_ms.get("allgather", 0.0)
+    t = torch.tensor([e0.elapsed_time(e1) / reps, kms, pms, sms, xms, gms_ag], dtype=torch.float64, device=dev)
     occ = torch.count_nonzero(slab.view(-1, 3).any(dim=1)).to(torch.float64).reshape(1)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(occ, op=dist.ReduceOp.SUM)
-    ms, kms, pms, sms, xms = (float(v) for v in t.tolist())
+    ms, kms, pms, sms, xms, gms_ag = (float(v) for v in t.tolist())
     return {"global_carve_sharded_gvoxel_s": round(N ** 3 / (ms * 1e-3) / 1e9, 2), "grid": N, "ms_per_call": round(ms, 4),
             "kernel_ms_max_over_ranks": round(kms, 4),
             "kernel_gvoxel_s": round(N ** 3 / (kms * 1e-3) / 1e9, 2) if kms > 0 else None,
             "part_carve_slab_kernel_ms_max_over_ranks": round(pms, 4),
             "part_carve_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2) if pms > 0 else None,
-            "part_carve_sharded_input_ms_max_over_ranks": round(sms, 4),
-            "part_carve_sharded_input_gvoxel_s": round(N ** 3 / (sms * 1e-3) / 1e9, 2) if sms > 0 else None,
-            "part_carve_sharded_input_exchange_ms": round(xms, 4),
-            "part_carve_sharded_input_exchange_bytes": N * N * (N // 32) * 4,
+            "part_carve_sharded_input": {
+                "alltoall_ms": round(sms, 4), "peer_ms": round(xms, 4), "allgather_ms": round(gms_ag, 4),
+                "best_gvoxel_s": round(N ** 3 / (min(v for v in (sms, xms, gms_ag) if v > 0) * 1e-3) / 1e9, 2) if max(sms, xms, gms_ag) > 0 else None,
+                "note": "whole part_carve_sharded call per rank (PartCarveSlab set-up, pass A, exchange, pass B), max over "
+                        "ranks: alltoall = only the z-bit words each slab reads (W*H*D/(8 world) bytes received per rank), "
+                        "peer = pass B reads the other ranks' rows in NVLink peer-mapped symmetric memory (no exchange "
+                        "buffer), allgather = the whole bit array (W*H*D/8 bytes) on every rank"},
             "n_gpus": world, "scaling": "strong", "occupied": int(occ.item()), "slab_of_rank0": list(span),
             "note": "whole Python call per rank (mask upload, table lookup, slab kernel), x-slab per rank, max over ranks; "
                     "no collective on the data path"}

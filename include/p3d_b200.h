@@ -361,6 +361,15 @@ int p3d_part_carve_slab_pass_a(const uint8_t* grid_slab, int W, int H, int D, in
                                uint8_t* out_slab, void* workspace, size_t workspace_bytes, p3d_stream_t stream);
 int p3d_part_carve_slab_pass_b(int W, int H, int D, int x_begin, int x_count, int c, int c2, uint8_t* out_slab,
                                void* workspace, size_t workspace_bytes, p3d_stream_t stream);
+/* pass B fused with the exchange: instead of gathering the other ranks' occupancy rows first, the kernel reads every
+ * source row straight from the workspace of the rank that owns it.  peer_workspaces: DEVICE array of n_ranks pointers,
+ * entry r = rank r's workspace (the same layout on every rank) mapped into this process -- NVLink peer mappings, e.g.
+ * torch symmetric memory; W must divide by n_ranks (rank r owns rows [r W/n, (r+1) W/n)).  The caller orders the call
+ * after pass A of EVERY rank (any stream-ordered collective on `stream` does) and keeps the workspaces untouched until
+ * every rank's pass B is done. */
+int p3d_part_carve_slab_pass_b_peers(int W, int H, int D, int x_begin, int x_count, int c, int c2, uint8_t* out_slab,
+                                     void* workspace, size_t workspace_bytes, const void* const* peer_workspaces,
+                                     int n_ranks, p3d_stream_t stream);
 
 /* Building blocks of the general-angle part_carve and of left_right_guided_carve :163-210. */
 int p3d_crop_occupancy(const uint8_t* grid, int W, int H, int D, int x0, int y0, int z0, int w, int h, int d,

@@ -683,7 +683,10 @@ constexpr int kClearRowW = kClearZW + 1;   // staged words per source row (the c
 // alive voxels whose source is empty are rewritten.
 __global__ void __launch_bounds__(kClearX)
 part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict__ occz,
-                  const uint32_t* __restrict__ alive, uint8_t* __restrict__ out, int x_begin, int x_count) {
+                  const uint32_t* __restrict__ alive, uint8_t* __restrict__ out, int x_begin, int x_count,
+                  const uint32_t* const* __restrict__ peer_occ, int rows_per_rank) {
+  // peer_occ != nullptr (multi-GPU, sharded input): source row sx lives in the occupancy array of rank sx / rows_per_rank,
+  // peer_occ[rank] = that rank's array (same full-grid layout, mapped over NVLink); the row is read straight from there
   // output x in [x_begin, x_begin + x_count); `out` starts at the slab's first voxel; bit arrays are indexed by the
   // full grid
   __shared__ uint32_t s_occ[kClearX * kClearRowW];          // row stride 9 words: conflict-free both ways
@@ -721,18 +724,20 @@ part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict
       const int sx = c - zw0 * 32 - (int)threadIdx.x;        // source row of z = z0 + threadIdx.x
       const int wb = (x_begin + xb * kClearX + c2) >> 5;      // arithmetic shift; bits outside [0, D) read 0
       const bool row_ok = sx >= 0 && sx < W;
-      const uint32_t* row = occz + ((size_t)(row_ok ? sx : 0) * H + y) * words;
+      const uint32_t* base = occz;
+      if (peer_occ != nullptr && row_ok) base = peer_occ[sx / rows_per_rank];
+      const uint32_t* row = base + ((size_t)(row_ok ? sx : 0) * H + y) * words;
       uint32_t* so = s_occ + threadIdx.x * kClearRowW;
       if (vec && ((x_begin + xb * kClearX + c2) & (kClearX - 1)) == 0 && wb >= 0 && wb + kClearZW <= words) {
         uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;      // aligned tile (c2 = 0, the usual fold): one sector per row
-        if (row_ok) { v0 = __ldg(reinterpret_cast<const uint4*>(row + wb)); v1 = __ldg(reinterpret_cast<const uint4*>(row + wb) + 1); }
+        if (row_ok) { v0 = __ldcg(reinterpret_cast<const uint4*>(row + wb)); v1 = __ldcg(reinterpret_cast<const uint4*>(row + wb) + 1); }
         so[0] = v0.x; so[1] = v0.y; so[2] = v0.z; so[3] = v0.w; so[4] = v1.x; so[5] = v1.y; so[6] = v1.z; so[7] = v1.w;
         so[8] = 0u;
       } else {
 #pragma unroll
         for (int k = 0; k < kClearRowW; ++k) {
           const int w = wb + k;
-          so[k] = (row_ok && w >= 0 && w < words) ? __ldg(row + w) : 0u;
+          so[k] = (row_ok && w >= 0 && w < words) ? __ldcg(row + w) : 0u;
         }
       }
     }
@@ -1519,7 +1524,7 @@ P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, c
   part_copy_bits_kernel<<<grid_for(n16, 256, pcb_waves), 256, 0, st>>>(grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp,
                                                               occz, alive, out, magic_gpr, magic_h, 0u, (uint32_t)n16, 0u);
   const int64_t tasks = (int64_t)H * ((D / 32 + kClearZW - 1) / kClearZW) * ((W + kClearX - 1) / kClearX);
-  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out, 0, W);
+  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out, 0, W, nullptr, 1);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -1567,7 +1572,7 @@ P3D_API int p3d_part_carve_fold_bits_slab(const uint8_t* grid, int W, int H, int
   part_copy_bits_kernel<<<grid_for((int64_t)x_count * gps, 256, 256), 256, 0, st>>>(
       grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp, nullptr, alive, out_slab, magic_gpr, magic_h, g_begin, g_end, 0u);
   const int64_t tasks = (int64_t)H * ((words + kClearZW - 1) / kClearZW) * ((x_count + kClearX - 1) / kClearX);
-  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out_slab, x_begin, x_count);
+  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out_slab, x_begin, x_count, nullptr, 1);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -1628,7 +1633,32 @@ P3D_API int p3d_part_carve_slab_pass_b(int W, int H, int D, int x_begin, int x_c
   const uint32_t* alive = reinterpret_cast<const uint32_t*>(ws + zbits);
   const int64_t tasks = (int64_t)H * ((words + kClearZW - 1) / kClearZW) * ((x_count + kClearX - 1) / kClearX);
   part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, p3d::as_stream(stream)>>>(W, H, D, c, c2, occz, alive, out_slab,
-                                                                                  x_begin, x_count);
+                                                                                  x_begin, x_count, nullptr, 1);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+P3D_API int p3d_part_carve_slab_pass_b_peers(int W, int H, int D, int x_begin, int x_count, int c, int c2,
+                                             uint8_t* out_slab, void* workspace, size_t workspace_bytes,
+                                             const void* const* peer_workspaces, int n_ranks, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0, "part_carve_slab_pass_b_peers: bad shape");
+  P3D_REQUIRE(x_begin >= 0 && x_count >= 0 && x_begin + x_count <= W, "part_carve_slab_pass_b_peers: bad x slab");
+  P3D_REQUIRE(n_ranks >= 1 && W % n_ranks == 0, "part_carve_slab_pass_b_peers: %d rows do not divide over %d ranks", W, n_ranks);
+  if (x_count == 0) return P3D_OK;
+  P3D_REQUIRE(out_slab && workspace && peer_workspaces, "part_carve_slab_pass_b_peers: null pointer");
+  const int words = D / 32;
+  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)words * 4, 256);
+  if (workspace_bytes < 2 * zbits) {
+    p3d::set_error("part_carve_slab_pass_b_peers: workspace too small");
+    return P3D_E_WORKSPACE;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const uint32_t* occz = reinterpret_cast<const uint32_t*>(ws);
+  const uint32_t* alive = reinterpret_cast<const uint32_t*>(ws + zbits);
+  const int64_t tasks = (int64_t)H * ((words + kClearZW - 1) / kClearZW) * ((x_count + kClearX - 1) / kClearX);
+  part_clear_kernel<<<grid_for(tasks, 1, 16), kClearX, 0, p3d::as_stream(stream)>>>(
+      W, H, D, c, c2, occz, alive, out_slab, x_begin, x_count, reinterpret_cast<const uint32_t* const*>(peer_workspaces),
+      W / n_ranks);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

@@ -157,12 +157,38 @@ def carve_sharded(carve_slab, W: int, group=None, gather: bool = False):
     return full, (0, W)
 
 
-def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None, slab_cls=None):
+_SYMM = {}                # (group name, bytes, device) -> (symmetric buffer, rendezvous handle, pointer table)
+
+
+def symmetric_workspace(nbytes: int, device, group=None):
+    """A uint8 workspace of >= nbytes in NVLink peer-mapped (torch symmetric) memory, identical on every rank, plus the
+    device table of every rank's base pointer.  Collective on first use per (group, size); cached afterwards."""
+    import torch.distributed._symmetric_memory as symm
+    group = group if group is not None else dist.group.WORLD
+    key = (group.group_name, int(nbytes), str(device))
+    hit = _SYMM.get(key)
+    if hit is None:
+        buf = symm.empty(int(nbytes), dtype=torch.uint8, device=device)
+        hdl = symm.rendezvous(buf, group.group_name)
+        ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        hit = _SYMM[key] = (buf, hdl, ptrs)
+    return hit
+
+
+def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None, slab_cls=None, exchange="alltoall"):
     """part_carve of a grid whose x rows are sharded over the ranks (rank r holds rows shard_range(W, world, r); W must
-    divide evenly): pass A per slab, ONE all-gather of the slabs' occupancy bits (W*H*D/8 bytes in total, 1/24 of the RGB
-    grid; NCCL on GPUs), pass B per slab.  Returns (output slab, (x0, x1)).  The exchange is real: the fold of
-    voxel_carving_utils.py:139-160 reads occ[W - z, y, x], the x<->z transposed source.  `slab_cls` replaces
-    voxel_carving_utils.PartCarveSlab (same begin / occ / finish interface) in the CPU tests of this plumbing."""
+    divide evenly): pass A per slab, ONE exchange of occupancy bits, pass B per slab.  Returns (output slab, (x0, x1)).
+    The exchange is real: the fold of voxel_carving_utils.py:139-160 reads occ[W - z, y, x], the x<->z transposed source.
+
+    exchange = "alltoall" (default): pass B of the slab [x0, x1) reads only the z-bit range [x0 + c2, x1 + c2) of every
+               source row, so each rank sends every other rank just that word range of its own rows -- W*H*D/(8 world)
+               bytes received per rank instead of the whole bit array;
+             = "peer": no exchange buffer at all -- the workspaces live in NVLink peer-mapped symmetric memory and pass B
+               reads the other ranks' rows in place (p3d_part_carve_slab_pass_b_peers), ordered by two tiny collectives
+               (after every rank's pass A, after every rank's pass B).  NCCL only;
+             = "allgather": the whole bit array on every rank (W*H*D/8 bytes; the round-1 form).
+    `slab_cls` replaces voxel_carving_utils.PartCarveSlab (same begin / occ / needed_words / finish interface) in the
+    CPU tests of this plumbing."""
     if slab_cls is None:
         from . import voxel_carving_utils as vc
         slab_cls = vc.PartCarveSlab
@@ -171,9 +197,39 @@ def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None,
     rank = dist.get_rank(group) if inited else 0
     if W % world:
         raise ValueError(f"part_carve_sharded: width {W} does not divide over {world} ranks")
+    if exchange not in ("alltoall", "peer", "allgather"):
+        raise ValueError(f"exchange={exchange!r}")
     x0, x1 = shard_range(W, world, rank)
+    if world > 1 and exchange == "peer":
+        H, D = int(grid_slab.shape[1]), int(grid_slab.shape[2])
+        nbytes = slab_cls.workspace_bytes(W, H, D, min(len(list(group_jobs)), 32))
+        buf, hdl, ptrs = symmetric_workspace(nbytes, grid_slab.device, group)
+        token = torch.zeros(1, dtype=torch.int32, device=grid_slab.device)
+        job = slab_cls(grid_slab, semantic_mask, group_jobs, W, (x0, x1), workspace=buf).begin()
+        dist.all_reduce(token, group=group)                  # every rank's pass A is done (stream-ordered)
+        out = job.finish(peers=ptrs, n_ranks=world)
+        dist.all_reduce(token, group=group)                  # every rank's pass B is done: the workspaces may be reused
+        return out, (x0, x1)
     job = slab_cls(grid_slab, semantic_mask, group_jobs, W, (x0, x1)).begin()
-    if world > 1:
+    if world > 1 and exchange == "allgather":
         mine = job.occ[x0:x1].clone()
         dist.all_gather_into_tensor(job.occ.view(-1), mine.view(-1), group=group)
+    elif world > 1:
+        spans = [shard_range(W, world, r) for r in range(world)]
+        send = [job.occ[x0:x1, :, slice(*job.needed_words(a, b))].contiguous() for a, b in spans]
+        lo, hi = job.needed_words(x0, x1)
+        recv = [job.occ.new_empty((b - a, job.occ.shape[1], hi - lo)) for a, b in spans]
+        # pairwise exchange as ONE batch of sends/receives (NCCL groups them into a single launch; gloo, used by the CPU
+        # tests, has no list all-to-all)
+        ops = []
+        for r in range(world):
+            if r != rank:
+                peer = r if group is None else dist.get_global_rank(group, r)
+                ops.append(dist.P2POp(dist.isend, send[r], peer, group))
+                ops.append(dist.P2POp(dist.irecv, recv[r], peer, group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for r, (a, b) in enumerate(spans):
+            if r != rank:
+                job.occ[a:b, :, lo:hi] = recv[r]
     return job.finish(), (x0, x1)

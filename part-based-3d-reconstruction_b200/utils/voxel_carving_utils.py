@@ -486,7 +486,7 @@ class PartCarveSlab:
     (x1-x0, H, D, 3) output slab.  Only the all-90-degree bit path can be sharded this way (ValueError otherwise: carve
     a replicated grid with part_carve(..., x_range=...) instead)."""
 
-    def __init__(self, grid_slab, semantic_mask, group_jobs, W, x_range):
+    def __init__(self, grid_slab, semantic_mask, group_jobs, W, x_range, workspace=None):
         self.as_tensor = _is_tensor(grid_slab)
         dev = nv.require_cuda(grid_slab.device if self.as_tensor and grid_slab.is_cuda else None)
         self.grid = _to_dev_u8(grid_slab, dev, "grid_slab")
@@ -517,7 +517,12 @@ class PartCarveSlab:
         self.gm_hw = torch.from_numpy(_group_image(jobs, H, W).view(np.int32)).to(dev)
         self.bits, self.n_groups = bits, len(jobs)
         self.ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
-        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        if workspace is not None:                             # caller-owned scratch, e.g. symmetric (peer-mapped) memory
+            if workspace.numel() < self.ws_bytes or workspace.dtype != torch.uint8 or workspace.device != dev:
+                raise ValueError(f"workspace must be a uint8 tensor of >= {self.ws_bytes} bytes on {dev}")
+            self.ws = workspace[:self.ws_bytes]
+        else:
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         words = D // 32
         self.occ = self.ws[:W * H * words * 4].view(torch.int32).view(W, H, words)
         self.out = torch.empty_like(self.grid)
@@ -531,11 +536,30 @@ class PartCarveSlab:
             _launched(2)
         return self
 
-    def finish(self):
+    @staticmethod
+    def workspace_bytes(W, H, D, n_groups):
+        return int(lib.p3d_part_carve_bits_workspace_bytes(int(W), int(H), int(D), int(n_groups)))
+
+    def needed_words(self, x0, x1):
+        """Word range [lo, hi) of every occupancy row that pass B of the output slab [x0, x1) reads: the fold takes
+        occ[c - z, y, x + c2], i.e. the z-bit range [x0 + c2, x1 + c2) of EVERY source row -- 1/world of the bits."""
+        c2, words = self.bits[2], self.D // 32
+        lo = max(0, (x0 + c2) // 32 - 1)
+        hi = min(words, (x1 + c2 + 31) // 32 + 1)
+        return lo, max(hi, lo)
+
+    def finish(self, peers=None, n_ranks=1):
+        """peers: int64 device tensor of `n_ranks` workspace pointers (one per rank, peer-mapped): pass B then reads the
+        other ranks' occupancy rows in place instead of from this rank's copy."""
         if self.x1 > self.x0:
-            check(lib.p3d_part_carve_slab_pass_b(self.W, self.H, self.D, self.x0, self.x1 - self.x0, self.bits[1],
-                                                 self.bits[2], ptr(self.out), ptr(self.ws), self.ws_bytes, stream_ptr()),
-                  "p3d_part_carve_slab_pass_b")
+            if peers is not None:
+                check(lib.p3d_part_carve_slab_pass_b_peers(self.W, self.H, self.D, self.x0, self.x1 - self.x0, self.bits[1],
+                                                           self.bits[2], ptr(self.out), ptr(self.ws), self.ws_bytes, ptr(peers),
+                                                           int(n_ranks), stream_ptr()), "p3d_part_carve_slab_pass_b_peers")
+            else:
+                check(lib.p3d_part_carve_slab_pass_b(self.W, self.H, self.D, self.x0, self.x1 - self.x0, self.bits[1],
+                                                     self.bits[2], ptr(self.out), ptr(self.ws), self.ws_bytes, stream_ptr()),
+                      "p3d_part_carve_slab_pass_b")
             _launched()
         return _ret(self.out, self.as_tensor)
 

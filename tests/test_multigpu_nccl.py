@@ -43,6 +43,35 @@ def _worker(rank, world, port, out_dir):
     # ... and with the INPUT sharded as well: each rank passes only its rows, one all-gather of occupancy bits
     a, b = sw.shard_range(binm.shape[1], world, rank)
     ps, _ = sw.part_carve_sharded(full[a:b].contiguous(), ext, GROUP_JOBS, binm.shape[1])
+    # every exchange form of the sharded-input part_carve on a 256-wide grid that is NOT 4-way symmetric (8 bit words per
+    # row: the all-to-all moves a strict subset; "peer" reads the other rank's rows over NVLink), against part_carve of
+    # the whole grid on this GPU
+    rng2 = np.random.default_rng(5)
+    W2, H2 = 256, 6
+    sem2 = np.zeros((H2, W2, 3), np.uint8)
+    sem2[:, :] = cfg.PART_COLORS["background"]
+    sem2[:, 40:200] = cfg.PART_COLORS["full_building"]
+    sem2[:, 90:120] = cfg.PART_COLORS["dome"]
+    sem2[:2, 130:170] = cfg.PART_COLORS["plinth"]
+    g2 = np.zeros((W2, H2, W2, 3), np.uint8)
+    occ2 = rng2.random((W2, H2, W2)) < 0.5
+    g2[occ2] = sem2.transpose(1, 0, 2)[:, :, None, :].repeat(W2, axis=2)[occ2]
+    g2[np.all(g2 == np.asarray(cfg.PART_COLORS["background"], np.uint8), axis=-1)] = 0
+    g2d = torch.from_numpy(g2).cuda()
+    want2 = vc.part_carve(g2d, sem2, GROUP_JOBS)
+    a2, b2 = sw.shard_range(W2, world, rank)
+    modes_ok = {}
+    for mode in ("alltoall", "allgather", "peer"):
+        for rep in range(2):                                 # twice: the symmetric workspace is reused
+            try:
+                got2, _ = sw.part_carve_sharded(g2d[a2:b2].contiguous(), sem2, GROUP_JOBS, W2, exchange=mode)
+                modes_ok[mode] = bool(torch.equal(got2, want2[a2:b2]))
+            except Exception as exc:                         # reported, asserted by the parent
+                modes_ok[mode] = repr(exc)
+                break
+    import json
+    with open(os.path.join(out_dir, f"modes{rank}.json"), "w") as fh:
+        json.dump(modes_ok, fh)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), best_s=best_s, best_i=best_i, scores=scores, d_iou=d_iou, d_i=d_i,
              d_local=d_local, d_lo=d_span[0], carve=full.cpu().numpy(), partcarve=pc.cpu().numpy(),
              partcarve_slab=ps.cpu().numpy(), slab=np.array([a, b]))
@@ -82,3 +111,7 @@ def test_sharded_paths_over_nccl(tmp_path, carve_golden):
         a, b = (int(v) for v in z["slab"])
         assert np.array_equal(z["partcarve_slab"], carve_golden["syn_rect40x64_partcarve"][a:b])
     assert np.array_equal(got_ious, want_ious)
+    import json
+    for r in range(world):
+        modes = json.load(open(tmp_path / f"modes{r}.json"))
+        assert modes == {"alltoall": True, "allgather": True, "peer": True}, modes

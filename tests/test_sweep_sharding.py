@@ -177,7 +177,7 @@ class OraclePartCarveSlab:
     finish() rebuilds a full grid from the gathered bits (other ranks' rows only need their occupancy: the reference
     selects a group's voxels with the 2-D mask, voxel_carving_utils.py:143-152) and slices the oracle's part_carve."""
 
-    def __init__(self, grid_slab, semantic_mask, group_jobs, W, x_range):
+    def __init__(self, grid_slab, semantic_mask, group_jobs, W, x_range, workspace=None):
         import torch
         self.rows, self.sem, self.jobs, self.W = np.asarray(grid_slab), semantic_mask, group_jobs, W
         self.x0, self.x1 = x_range
@@ -189,6 +189,12 @@ class OraclePartCarveSlab:
         bits = np.packbits(self.rows.any(-1), axis=-1, bitorder="little")                  # (rows, H, D/8) uint8
         self.occ[self.x0:self.x1] = torch.from_numpy(bits.view(np.int32).reshape(self.x1 - self.x0, self.H, self.D // 32).copy())
         return self
+
+    def needed_words(self, x0, x1):
+        """z-bit words [lo, hi) of every source row that the output slab [x0, x1) depends on (fold source = occ[c - z, y,
+        x + c2] with |c2| <= 1: the slab's own x range as z bits, one word of slack)."""
+        words = self.D // 32
+        return max(0, (x0 - 1) // 32), min(words, (x1 + 1 + 31) // 32)
 
     def finish(self):
         from oracle import oracle as orc
@@ -209,6 +215,24 @@ def _part_carve_worker(rank, world, port, out_dir):
     a, b = sw.shard_range(grid.shape[0], world, rank)
     slab, span = sw.part_carve_sharded(np.ascontiguousarray(grid[a:b]), ext, GROUP_JOBS, grid.shape[0], slab_cls=OraclePartCarveSlab)
     assert span == (a, b)
+    slab2, _ = sw.part_carve_sharded(np.ascontiguousarray(grid[a:b]), ext, GROUP_JOBS, grid.shape[0], slab_cls=OraclePartCarveSlab,
+                                     exchange="allgather")
+    assert np.array_equal(slab, slab2)
+    # a wider grid (8 bit words per row): every rank receives only the word range its slab reads, the rest stays zero
+    rng = np.random.default_rng(5)
+    W2, H2 = 256, 3
+    sem2 = np.zeros((H2, W2, 3), np.uint8)
+    sem2[:, :, :] = ext[0, 0]
+    from oracle import oracle as orc
+    sem2[:, 40:200] = orc.PART_COLORS["full_building"]
+    sem2[:, 90:120] = orc.PART_COLORS["dome"]
+    g2 = np.zeros((W2, H2, W2, 3), np.uint8)
+    occ2 = rng.random((W2, H2, W2)) < 0.5
+    g2[occ2] = sem2.transpose(1, 0, 2)[:, :, None, :].repeat(W2, axis=2)[occ2]
+    g2[np.all(g2 == np.asarray(ext[0, 0]), axis=-1)] = 0
+    a2, b2 = sw.shard_range(W2, world, rank)
+    wide, _ = sw.part_carve_sharded(np.ascontiguousarray(g2[a2:b2]), sem2, GROUP_JOBS, W2, slab_cls=OraclePartCarveSlab)
+    assert np.array_equal(wide, orc.part_carve(g2, sem2, GROUP_JOBS)[a2:b2])
     np.savez(os.path.join(out_dir, f"p{rank}.npz"), slab=slab, a=a, b=b)
     if world == 2:
         with pytest.raises(ValueError):
@@ -218,8 +242,9 @@ def _part_carve_worker(rank, world, port, out_dir):
 
 @pytest.mark.parametrize("world", [2, 4])
 def test_part_carve_sharded_gloo(tmp_path, world, carve_golden):
-    """Host logic of the sharded-input part_carve (slab ranges, ONE all-gather of occupancy bits into the full bit array,
-    the divisibility rule) over gloo with an oracle-backed slab; the CUDA slab passes are covered by the GPU tests."""
+    """Host logic of the sharded-input part_carve (slab ranges, the all-to-all of just the z-bit words each slab reads --
+    checked on a 256-wide asymmetric grid where that is a strict subset -- the all-gather form, the divisibility rule)
+    over gloo with an oracle-backed slab; the CUDA slab passes are covered by the GPU tests."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
