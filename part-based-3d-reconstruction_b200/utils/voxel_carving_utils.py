@@ -496,12 +496,9 @@ class PartCarveSlab:
         if not (0 <= self.x0 <= self.x1 <= self.W) or n != self.x1 - self.x0:
             raise ValueError(f"slab of {n} rows does not match x_range {x_range} of width {W}")
         semantic_mask = semantic_mask if isinstance(semantic_mask, _PackedMask) else _PackedMask(semantic_mask)
-        jobs = []
-        for names, angle in group_jobs:
-            m2d = _mask2d_bool(semantic_mask, [PART_COLORS[nm] for nm in names])
-            if m2d.any():
-                jobs.append((m2d, angle))
-        ok = bool(jobs) and all(a == 90 for _, a in jobs) and len(jobs) <= 32 and D == W and D % 32 == 0
+        jobs = list(group_jobs)
+        ok = (bool(jobs) and all(a == 90 for _, a in jobs) and len(jobs) <= 32 and D == W and D % 32 == 0
+              and semantic_mask.is_rgb_u8 and tuple(semantic_mask.shape[:2]) == (H, W))
         bits = None
         if ok:
             M, off = _pass_transform((W, H, D), 90)
@@ -512,9 +509,9 @@ class PartCarveSlab:
                 bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev)))
                 ok = bits is not None and bits[2] is not None
         if not ok:
-            raise ValueError("sharded-input part_carve needs the all-90-degree bit path (cubic grid, D % 32 == 0, at "
-                             "least one non-empty group); carve a replicated grid with part_carve(..., x_range=...)")
-        self.gm_hw = torch.from_numpy(_group_image(jobs, H, W).view(np.int32)).to(dev)
+            raise ValueError("sharded-input part_carve needs the all-90-degree bit path (cubic grid, D % 32 == 0, an RGB "
+                             "uint8 mask of the grid's (H,W)); carve a replicated grid with part_carve(..., x_range=...)")
+        self.gm_hw = _group_image_device(semantic_mask, [[PART_COLORS[nm] for nm in names] for names, _ in jobs], dev)
         self.bits, self.n_groups = bits, len(jobs)
         self.ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
         if workspace is not None:                             # caller-owned scratch, e.g. symmetric (peer-mapped) memory
