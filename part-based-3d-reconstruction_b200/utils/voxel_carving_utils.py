@@ -745,17 +745,24 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
     of multi-GPU sharding (utils.sweep.carve_sharded); supported on the 90-degree fast path."""
     as_tensor = return_tensor or _is_tensor(binary_mask)
     dev = nv.require_cuda(device if device is not None else (binary_mask.device if _is_tensor(binary_mask) and binary_mask.is_cuda else None))
-    bm = binary_mask.cpu().numpy() if _is_tensor(binary_mask) else np.asarray(binary_mask)
-    if bm.ndim != 2:
+    bm_dev = binary_mask if (_is_tensor(binary_mask) and binary_mask.is_cuda) else None     # device mask: never copied to the host
+    bm = None if bm_dev is not None else (binary_mask.numpy() if _is_tensor(binary_mask) else np.asarray(binary_mask))
+    if (bm_dev if bm_dev is not None else bm).ndim != 2:
         raise ValueError("binary_mask must be 2-D (H,W)")
-    h, w = bm.shape
+    h, w = (int(v) for v in (bm_dev if bm_dev is not None else bm).shape)
     W, H, D = w, h, w
     col = _to_dev_u8(semantic_mask_exterior, dev, "semantic_mask_exterior")
     if tuple(col.shape) != (H, W, 3):
         raise ValueError(f"semantic_mask_exterior {tuple(col.shape)} does not match (H,W,3)=({H},{W},3)")
     # (W,H) mask of the reference (:279-283).  W, H come from binary_mask itself, so _mask_to_wh always takes its
     # (H,W) -> .T branch here and the (H,W) form the fold kernels want is simply `bm != 0`.
-    m_hw_np = bm != 0
+    m_hw_np = None if bm is None else bm != 0
+
+    def mask_hw_device():
+        if bm_dev is not None:
+            return bm_dev.contiguous() if bm_dev.dtype == torch.uint8 else (bm_dev != 0).to(torch.uint8)
+        return torch.from_numpy(m_hw_np.view(np.uint8) if m_hw_np.flags.c_contiguous else
+                                np.ascontiguousarray(m_hw_np).view(np.uint8)).to(dev)
     x0, x1 = (0, W) if x_range is None else (int(x_range[0]), int(x_range[1]))
     if not (0 <= x0 <= x1 <= W):
         raise ValueError(f"x_range {x_range} outside [0, {W}]")
@@ -766,8 +773,7 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
         if np.array_equal(M0, np.eye(3)) and not off0.any():
             table, foldable = _fold_table(W, D, M, off, dev)
             if foldable:
-                m_hw = torch.from_numpy(m_hw_np.view(np.uint8) if m_hw_np.flags.c_contiguous else
-                                        np.ascontiguousarray(m_hw_np).view(np.uint8)).to(dev)
+                m_hw = mask_hw_device()                   # any non-zero byte counts as foreground
                 bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
                 if bits is not None:                      # z-separable table: bit-packed mask, 10x fewer loads
                     out = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
@@ -785,8 +791,8 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
                     _launched()
     if out is None:
         vol = torch.ones((W, H, D), dtype=torch.uint8, device=dev)
-        m_wh = np.ascontiguousarray(_mask_to_wh(m_hw_np, W, H))                       # (W,H) bool
-        carved = _process_device(vol, torch.from_numpy(m_wh.astype(np.uint8)).to(dev), angle_interval)
+        m_wh_d = (_mask_to_wh(mask_hw_device(), W, H) != 0).to(torch.uint8).contiguous()   # (W,H)
+        carved = _process_device(vol, m_wh_d, angle_interval)
         out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
         check(lib.p3d_colourise(ptr(carved), W, H, D, ptr(col), ptr(out), stream_ptr()), "p3d_colourise")
         _launched()

@@ -122,6 +122,21 @@ def test_remaining_monuments_match_reference(vc, case, capsys):
         assert np.array_equal(out, g[key + "_partwise"]) and np.array_equal(grid, g[key + "_global"])
 
 
+def test_device_resident_masks_give_the_same_bytes(vc, carve_golden):
+    """Masks handed over as CUDA tensors (no host round trip inside the call) against the NumPy-mask path, on the bit
+    fast path (64 wide), a ragged width and the general-angle path."""
+    g = carve_golden
+    for key, angle in (("syn_sq64", 90), ("syn_rect40x64", 90), ("syn_rect50x31", 90), ("syn_rect40x64", 45)):
+        ext, binm = g[key + "_ext"], g[key + "_bin"]
+        want = vc.global_carve(binm, ext, angle)
+        got = vc.global_carve(torch.from_numpy(binm).cuda(), torch.from_numpy(ext).cuda(), angle)
+        assert got.is_cuda and np.array_equal(got.cpu().numpy(), want), (key, angle)
+        got255 = vc.global_carve((torch.from_numpy(binm) * 255).to(torch.uint8).cuda(), torch.from_numpy(ext).cuda(), angle)
+        assert np.array_equal(got255.cpu().numpy(), want), (key, angle)      # any non-zero value is foreground (:279-283)
+        jobs = GROUP_JOBS
+        assert np.array_equal(vc.part_carve(got, torch.from_numpy(ext).cuda(), jobs).cpu().numpy(), vc.part_carve(want, ext, jobs))
+
+
 def test_synthetic_quirk_cases_match_reference(vc, carve_golden):
     """Square image (_mask_to_wh transposes), foreground in the last column, widths with the odd FP offsets."""
     g = carve_golden
