@@ -414,6 +414,10 @@ int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int
  * camera_estimation.py:263 (extract_minaret_masks_by_label).  Workspace: p3d_label6_workspace_bytes(H*W). */
 int p3d_label8_2d(const uint8_t* mask, int H, int W, int32_t* labels, int32_t* n_components, void* workspace,
                   size_t workspace_bytes, p3d_stream_t stream);
+/* scipy.ndimage.label with structure = ones((3,3,3)) (26-connectivity; extract_top_k_components, voxel_utils.py:22-31);
+ * same workspace and id order as p3d_label6. */
+int p3d_label26(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components, void* workspace,
+                size_t workspace_bytes, p3d_stream_t stream);
 /* Per component: bbox (n,6) int32 = min0,min1,min2,max0,max1,max2 (inclusive) and sums (n,4) int64 =
  * voxel count and coordinate sums per axis (:184-185, :258-259). */
 int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, int n_components, int32_t* bbox,

@@ -752,3 +752,36 @@ def point_segments(pts, labels, L):
     rec[:, 1] = (p[chunk, 2] & 0xffff) | ((cnt - 1) << 16) | ((T[chunk] - 1) << 20) | (labels[first][chunk].astype(np.int64) << 26)
     rec[:, 2] = first[chunk] + r
     return rec, int((~ok).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# utils/voxel_utils.py:22-31 and :36-49 (viewer-side helpers next to the path)
+# ------------------------------------------------------------------------------------------------
+def extract_top_k_components(voxel_grid, color, k=4):
+    """voxel_utils.py:22-31: 26-connected components of `color`; the k with the largest np.ptp along axis 1 stay (stable
+    sort: ties keep the lower id), the others are blanked."""
+    import scipy.ndimage
+    voxel_grid = np.asarray(voxel_grid)
+    mask = np.all(voxel_grid == np.asarray(color), axis=-1)
+    labeled, n = scipy.ndimage.label(mask, structure=np.ones((3, 3, 3)))
+    heights = []
+    for i in range(1, n + 1):
+        ys = np.argwhere(labeled == i)[:, 1]
+        heights.append((i, int(ys.max() - ys.min())))
+    top = [i for i, _ in sorted(heights, key=lambda t: -t[1])[:k]]
+    out = voxel_grid.copy()
+    out[mask & ~np.isin(labeled, top)] = 0
+    return out
+
+
+def scalar_grid_points(grid, axis="z", stride=2):
+    """voxel_utils.py:36-47 for a scalar grid, up to the colormap call: (pts float32 (N,3), vals float64 (N), (H, W, D))
+    with the reference's own pairing of index arrays and extents (np.where order named zs, ys, xs; 'x' divides the
+    axis-2 indices by shape[0] - 1, ...)."""
+    grid = np.asarray(grid)
+    W, H, D = grid.shape[:3]
+    mask_ds = (grid != 0)[::stride, ::stride, ::stride]
+    zs, ys, xs = np.where(mask_ds)
+    pts = np.stack([xs, ys, zs], axis=1).astype(np.float32) * stride
+    vals = {"x": xs, "y": ys, "z": zs}[axis] / {"x": W - 1, "y": H - 1, "z": D - 1}[axis]
+    return pts, vals, (H, W, D)

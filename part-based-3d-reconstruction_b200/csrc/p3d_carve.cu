@@ -941,6 +941,30 @@ ccl_merge_kernel(const uint8_t* __restrict__ mask, int n0, int n1, int n2, int32
   }
 }
 
+// 26-connected 3-D variant (scipy.ndimage.label with structure = ones((3,3,3)), voxel_utils.py:24): the 13 neighbours
+// that precede a voxel in raster order.
+__global__ void __launch_bounds__(256)
+ccl_merge26_kernel(const uint8_t* __restrict__ mask, int n0, int n1, int n2, int32_t* __restrict__ parent) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  const int64_t plane = (int64_t)n1 * n2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!mask[i]) continue;
+    const int c = (int)(i % n2);
+    const int64_t r = i / n2;
+    const int b = (int)(r % n1);
+    const int a = (int)(r / n1);
+    for (int da = -1; da <= 0; ++da)
+      for (int db = -1; db <= 1; ++db)
+        for (int dc = -1; dc <= 1; ++dc) {
+          if (da == 0 && (db > 0 || (db == 0 && dc >= 0))) continue;       // only raster-order predecessors
+          const int aa = a + da, bb = b + db, cc = c + dc;
+          if (aa < 0 || bb < 0 || bb >= n1 || cc < 0 || cc >= n2) continue;
+          const int64_t j = i + da * plane + (int64_t)db * n2 + dc;
+          if (mask[j]) uf_union(parent, (int32_t)i, (int32_t)j);
+        }
+  }
+}
+
 // 8-connected 2-D variant (skimage.measure.label's default for images, camera_estimation.py:263): W, N, NW, NE.
 __global__ void __launch_bounds__(256)
 ccl_merge8_kernel(const uint8_t* __restrict__ mask, int H, int W, int32_t* __restrict__ parent) {
@@ -1758,7 +1782,7 @@ P3D_API size_t p3d_label6_workspace_bytes(int64_t n) {
   return p3d_align_up((size_t)n * 4, 256) + p3d_align_up((size_t)n, 256) + p3d_align_up((size_t)(tiles + 1) * 4, 256);
 }
 
-static int label_components(const uint8_t* mask, int n0, int n1, int n2, bool eight2d, int32_t* labels,
+static int label_components(const uint8_t* mask, int n0, int n1, int n2, int conn /* 6, 26 (3-D) or 8 (2-D) */, int32_t* labels,
                             int32_t* n_components, void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
   P3D_REQUIRE(n0 >= 0 && n1 >= 0 && n2 >= 0 && n_components, "label6: bad arguments");
   const int64_t n = (int64_t)n0 * n1 * n2;
@@ -1778,7 +1802,8 @@ static int label_components(const uint8_t* mask, int n0, int n1, int n2, bool ei
   const int blocks = grid_for(n, 256, 16);
   int32_t* parent = labels;                              // labels doubles as the union-find forest
   ccl_init_kernel<<<blocks, 256, 0, st>>>(mask, n, parent);
-  if (eight2d) ccl_merge8_kernel<<<blocks, 256, 0, st>>>(mask, n1, n2, parent);
+  if (conn == 8) ccl_merge8_kernel<<<blocks, 256, 0, st>>>(mask, n1, n2, parent);
+  else if (conn == 26) ccl_merge26_kernel<<<blocks, 256, 0, st>>>(mask, n0, n1, n2, parent);
   else ccl_merge_kernel<<<blocks, 256, 0, st>>>(mask, n0, n1, n2, parent);
   ccl_flatten_kernel<<<blocks, 256, 0, st>>>(n, parent, is_root);
   root_count_kernel<<<tiles, kRankThreads, 0, st>>>(is_root, n, tiles_buf);
@@ -1792,12 +1817,17 @@ static int label_components(const uint8_t* mask, int n0, int n1, int n2, bool ei
 
 P3D_API int p3d_label6(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components,
                        void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
-  return label_components(mask, n0, n1, n2, false, labels, n_components, workspace, workspace_bytes, stream);
+  return label_components(mask, n0, n1, n2, 6, labels, n_components, workspace, workspace_bytes, stream);
+}
+
+P3D_API int p3d_label26(const uint8_t* mask, int n0, int n1, int n2, int32_t* labels, int32_t* n_components,
+                        void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  return label_components(mask, n0, n1, n2, 26, labels, n_components, workspace, workspace_bytes, stream);
 }
 
 P3D_API int p3d_label8_2d(const uint8_t* mask, int H, int W, int32_t* labels, int32_t* n_components, void* workspace,
                           size_t workspace_bytes, p3d_stream_t stream) {
-  return label_components(mask, 1, H, W, true, labels, n_components, workspace, workspace_bytes, stream);
+  return label_components(mask, 1, H, W, 8, labels, n_components, workspace, workspace_bytes, stream);
 }
 
 P3D_API int p3d_component_stats(const int32_t* labels, int n0, int n1, int n2, int n_components, int32_t* bbox,

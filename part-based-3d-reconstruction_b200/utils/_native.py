@@ -113,6 +113,7 @@ _SIGNATURES = {
     "p3d_label6_workspace_bytes": ([_i64], _sz),
     "p3d_label6": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp], _i32),
     "p3d_label8_2d": ([_vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp], _i32),
+    "p3d_label26": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp], _i32),
     "p3d_component_stats": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "p3d_label_equals": ([_vp, _i64, _i32, _vp, _vp], _i32),
     "p3d_coords_extremes": ([_vp, _i64, _i32, _vp, _vp, _vp], _i32),

@@ -564,7 +564,7 @@ class PartCarveSlab:
 _STATS_CAP = 1024         # components whose statistics are gathered before the one host read-back
 
 
-def _label_components(mask_u8, extra=None):
+def _label_components(mask_u8, extra=None, conn=6):
     """scipy.ndimage.label (6-connectivity) on device: (labels int32, n, bbox (n,6) ndarray, sums (n,4) ndarray).
     Labelling and the per-component statistics of up to _STATS_CAP components are enqueued back to back and read with
     ONE synchronisation (more components: a second statistics pass).  `extra`: a small device tensor whose host copy is
@@ -576,7 +576,8 @@ def _label_components(mask_u8, extra=None):
     ncomp = torch.zeros(1, dtype=torch.int32, device=dev)
     ws_bytes = int(lib.p3d_label6_workspace_bytes(nvox))
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
-    check(lib.p3d_label6(ptr(mask_u8), n0, n1, n2, ptr(labels), ptr(ncomp), ptr(ws), ws_bytes, stream_ptr()), "p3d_label6")
+    fn = lib.p3d_label26 if conn == 26 else lib.p3d_label6
+    check(fn(ptr(mask_u8), n0, n1, n2, ptr(labels), ptr(ncomp), ptr(ws), ws_bytes, stream_ptr()), "p3d_label")
     _launched(7)
 
     def stats(cap):

@@ -56,16 +56,39 @@ def get_voxel_points_by_parts(grid, part_colors, part_names, device=None):
 
 
 @nv.on_device
+def extract_top_k_components(voxel_grid, color, k=4, device=None):
+    """voxel_utils.py:22-31: among the 26-connected components of `color`, keep the k with the largest extent along axis
+    1 (ties: the lower scipy id, Python's stable sort) and blank the others.  Returns a fresh grid (NumPy in -> NumPy
+    out, CUDA tensor in -> CUDA tensor out)."""
+    from . import voxel_carving_utils as vc
+    as_tensor = isinstance(voxel_grid, torch.Tensor)
+    dev = nv.require_cuda(device if device is not None else (voxel_grid.device if as_tensor and voxel_grid.is_cuda else None))
+    grid = vc._to_dev_u8(voxel_grid, dev, "voxel_grid")
+    out = grid.clone()
+    labels, n, bbox, _ = vc._label_components(vc._colour_mask(grid, color), conn=26)
+    if n:
+        heights = [(i, int(bbox[i - 1, 4]) - int(bbox[i - 1, 1])) for i in range(1, n + 1)]      # np.ptp of axis 1
+        keep = {i for i, _ in sorted(heights, key=lambda t: -t[1])[:k]}
+        flags = np.array([0 if i in keep else 1 for i in range(1, n + 1)], np.uint8)
+        if flags.any():
+            fl = torch.from_numpy(flags).to(dev)
+            nv.check(nv.lib.p3d_recolour_components(nv.ptr(labels), nv.ptr(fl), labels.numel(), 0, 0, 0, nv.ptr(out),
+                                                    nv.stream_ptr()), "p3d_recolour_components")
+            eng._launched(1)
+    return vc._ret(out, as_tensor)
+
+
+@nv.on_device
 def voxel_grid_to_points(grid, axis="z", colormap="viridis", stride=2, device=None):
     """voxel_utils.py:35-51 for RGB grids: every `stride`-th voxel along each axis that is not black, as
     (pts float32 (N,3) = [a2, a1, a0] * stride, colors uint8 (N,3), (H, W, D)) with the reference's shape tuple
-    (it unpacks `W, H, D = grid.shape[:3]` and returns `(H, W, D)`).  Scalar grids are coloured through a matplotlib
-    colormap in the reference (a viewer concern) and are not handled here."""
+    (it unpacks `W, H, D = grid.shape[:3]` and returns `(H, W, D)`).  Scalar (W,H,D) grids take the colormap branch
+    (:47-49, `_scalar_grid_to_points`)."""
     dev = nv.require_cuda(device)
     g = grid if isinstance(grid, torch.Tensor) else np.asarray(grid)
-    if g.ndim != 4 or g.shape[3] != 3:
-        raise NotImplementedError("voxel_grid_to_points: only (A0,A1,A2,3) RGB grids (the scalar branch needs matplotlib)")
     stride = int(stride)
+    if not (g.ndim == 4 and g.shape[3] == 3):
+        return _scalar_grid_to_points(g, axis, colormap, stride, dev)
     with torch.cuda.device(dev):
         t = grid_to_device(g, dev)
         A0, A1, A2 = (int(v) for v in t.shape[:3])
@@ -80,6 +103,32 @@ def voxel_grid_to_points(grid, axis="z", colormap="viridis", stride=2, device=No
                                                 nv.stream_ptr()), "p3d_gather_scale_points")
         eng._launched(1 if pts.shape[0] else 0)
         return pts.cpu().numpy(), cols.cpu().numpy(), (A1, A0, A2)
+
+
+def _scalar_grid_to_points(g, axis, colormap, stride, dev):
+    """voxel_utils.py:36-49, the scalar branch: occupancy `grid != 0` on the sub-sampled lattice, points in np.where
+    order, colours from a matplotlib colormap of the normalised index along `axis` -- with the reference's own pairing
+    (its `xs` are the axis-2 indices but are divided by shape[0] - 1, and so on).  The occupancy and the ordered
+    compaction run on the device; the colormap lookup is the same matplotlib call the reference makes, on the host (it
+    is a viewer colouring of N points, and matplotlib's table is the definition of the result)."""
+    if g.ndim != 3:
+        raise ValueError(f"expected a (W,H,D) scalar grid or a (W,H,D,3) colour grid, got {tuple(g.shape)}")
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError as exc:
+        raise ImportError("voxel_grid_to_points on a scalar grid colours the points with a matplotlib colormap, exactly as "
+                          "the reference does (voxel_utils.py:47-49); matplotlib is not installed") from exc
+    with torch.cuda.device(dev):
+        t = g if isinstance(g, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(g))
+        t = t.to(dev)
+        W, H, D = (int(v) for v in t.shape)
+        mask = (t[::stride, ::stride, ::stride] != 0).to(torch.uint8).contiguous()
+        pts, _ = eng.compact_points(mask)                                   # [x = a2, y = a1, z = a0], np.where order
+        p = pts.cpu().numpy()
+    xs, ys, zs = p[:, 0].astype(np.int64), p[:, 1].astype(np.int64), p[:, 2].astype(np.int64)
+    vals = {"x": xs, "y": ys, "z": zs}[axis] / {"x": W - 1, "y": H - 1, "z": D - 1}[axis]
+    colors = (plt.get_cmap(colormap)(vals)[:, :3] * 255).astype(np.uint8)
+    return (p * np.float32(stride)).astype(np.float32), colors, (H, W, D)
 
 
 def meshify_colored_voxel_grid(colored_voxel_grid, stride=1):

@@ -625,6 +625,27 @@ def real5_golden():
     np.savez_compressed(os.path.join(HERE, "real5_golden.npz"), **out)
 
 
+def topk_golden():
+    """extract_top_k_components of the live reference (voxel_utils.py:22-31: 26-connectivity, np.ptp along axis 1, stable
+    sort) on small random grids, incl. corner-touching blobs and height ties."""
+    import utils.voxel_utils as rvu
+    rng = np.random.default_rng(SEED + 31)
+    out = {}
+    colour = np.array(C.PART_COLORS["front_minarets"])
+    cases = []
+    for i, (shape, p) in enumerate([((14, 20, 12), 0.2), ((9, 30, 9), 0.3), ((12, 12, 12), 0.07), ((6, 25, 6), 0.45)]):
+        grid = np.zeros(shape + (3,), np.uint8)
+        grid[rng.random(shape) < p] = colour
+        grid[rng.random(shape) < 0.1] = C.PART_COLORS["dome"]
+        out[f"g{i}"] = grid
+        for k in (1, 2, 4):
+            out[f"g{i}_k{k}"] = rvu.extract_top_k_components(grid, colour, k)
+        cases.append(i)
+    out["n"] = np.array(len(cases))
+    out["colour"] = colour
+    np.savez_compressed(os.path.join(HERE, "topk_golden.npz"), **out)
+
+
 def partcarve_asym_golden():
     """part_carve (voxel_carving_utils.py:139-160) of grids that are NOT 4-way symmetric: the inputs on which the rotated
     source occupancy decides (global_carve's output never is).  Random sparse grids coloured column-wise from a blocky
@@ -676,6 +697,8 @@ if __name__ == "__main__":
         partcarve_asym_golden()
     if "real5" in which:
         real5_golden()
-    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz", "handoff_golden.npz", "tables_golden.npz", "partcarve_asym_golden.npz", "real5_golden.npz"):
+    if "topk" in which:
+        topk_golden()
+    for f in ("camera_golden.npz", "carve_golden.npz", "aligner_golden.npz", "depth_golden.npz", "deform_golden.npz", "init_golden.npz", "handoff_golden.npz", "tables_golden.npz", "partcarve_asym_golden.npz", "real5_golden.npz", "topk_golden.npz"):
         if os.path.exists(os.path.join(HERE, f)):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
