@@ -1174,6 +1174,10 @@ coords_extreme_sums_kernel(const int32_t* __restrict__ coords, int64_t n, int ax
   }
 }
 
+__global__ void fold_info_init_kernel(int* info) {           // (max, min, max2, min2) seeds of fold_analyse_kernel
+  if (threadIdx.x < 4) info[threadIdx.x] = (threadIdx.x & 1) ? 0x7fffffff : -0x7fffffff;
+}
+
 __global__ void coords_mm_init_kernel(int32_t* mm) {
   if (threadIdx.x == 0) { mm[0] = 0x7fffffff; mm[1] = (int)0x80000000; }
 }
@@ -1441,8 +1445,7 @@ P3D_API int p3d_fold_analyse(const int32_t* table, int W, int D, uint32_t* insid
   P3D_REQUIRE(W > 0 && D > 0 && D % 32 == 0, "fold_analyse: D must be a multiple of 32");
   P3D_REQUIRE(table && inside_bits && info, "fold_analyse: null pointer");
   cudaStream_t st = p3d::as_stream(stream);
-  const int init[4] = {-0x7fffffff, 0x7fffffff, -0x7fffffff, 0x7fffffff};
-  P3D_CUDA(cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  fold_info_init_kernel<<<1, 32, 0, st>>>(info);             // device-side seed: no pageable copy, legal under stream capture
   const int n = W * (D / 32);
   fold_analyse_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, W, D, inside_bits, info);
   P3D_LAUNCH_CHECK();

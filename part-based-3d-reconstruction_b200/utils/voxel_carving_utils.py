@@ -53,7 +53,14 @@ def _to_dev_u8(a, dev, what="array"):
     if t.dtype == torch.bool:
         t = t.to(torch.uint8)
     if t.dtype != torch.uint8:
-        raise TypeError(f"{what} must be uint8 (got {t.dtype})")
+        # the reference takes any dtype; other integer types are accepted when every value fits a byte (the grids and
+        # masks of this pipeline are 0..255 by construction), anything else is refused rather than silently wrapped
+        if t.dtype in (torch.int8, torch.int16, torch.int32, torch.int64) and t.numel() and int(t.min()) >= 0 and int(t.max()) <= 255:
+            t = t.to(torch.uint8)
+        elif t.dtype in (torch.int8, torch.int16, torch.int32, torch.int64) and not t.numel():
+            t = t.to(torch.uint8)
+        else:
+            raise TypeError(f"{what} must hold values 0..255 in an integer or bool dtype (got {t.dtype})")
     return t.to(dev).contiguous()
 
 
@@ -80,6 +87,14 @@ def _upload_u8(arr, dev):
     out.view(-1).copy_(stage, non_blocking=True)
     torch.cuda.current_stream().synchronize()              # the staging buffer is reused by the next call
     return out
+
+
+def _first3(a):
+    """Channels 0..2 of an image with more than three (the reference reads `mask[..., c] for c in range(3)`, :134-135,
+    so an RGBA mask works there)."""
+    if getattr(a, "ndim", 0) == 3 and a.shape[2] > 3:
+        return a[..., :3]
+    return a
 
 
 def _ret(t, as_tensor):
@@ -348,7 +363,7 @@ def apply_colored_mask_to_voxel_grid(carved_voxel_grid, colored_mask):
     dev = nv.require_cuda(carved_voxel_grid.device if as_tensor and carved_voxel_grid.is_cuda else None)
     W, H, D = carved_voxel_grid.shape
     carved = _to_dev_u8(carved_voxel_grid, dev, "carved_voxel_grid")
-    col = _to_dev_u8(colored_mask, dev, "colored_mask")
+    col = _to_dev_u8(_first3(colored_mask), dev, "colored_mask")
     if tuple(col.shape) != (H, W, 3):
         raise ValueError(f"colored_mask {tuple(col.shape)} does not match (H,W,3)=({H},{W},3)")
     out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
@@ -752,7 +767,7 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
         raise ValueError("binary_mask must be 2-D (H,W)")
     h, w = (int(v) for v in (bm_dev if bm_dev is not None else bm).shape)
     W, H, D = w, h, w
-    col = _to_dev_u8(semantic_mask_exterior, dev, "semantic_mask_exterior")
+    col = _to_dev_u8(_first3(semantic_mask_exterior), dev, "semantic_mask_exterior")
     if tuple(col.shape) != (H, W, 3):
         raise ValueError(f"semantic_mask_exterior {tuple(col.shape)} does not match (H,W,3)=({H},{W},3)")
     # (W,H) mask of the reference (:279-283).  W, H come from binary_mask itself, so _mask_to_wh always takes its

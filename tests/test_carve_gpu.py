@@ -137,6 +137,24 @@ def test_device_resident_masks_give_the_same_bytes(vc, carve_golden):
         assert np.array_equal(vc.part_carve(got, torch.from_numpy(ext).cuda(), jobs).cpu().numpy(), vc.part_carve(want, ext, jobs))
 
 
+def test_lenient_inputs_like_the_reference(vc, carve_golden):
+    """What the reference accepts beyond uint8 RGB: integer grids / masks of another dtype (values 0..255), an RGBA
+    colour mask (it reads channels 0..2 only, :134-135).  Values that do not fit a byte are refused, not wrapped."""
+    g = carve_golden
+    ext, binm = g["syn_rect40x64_ext"], g["syn_rect40x64_bin"]
+    want = vc.global_carve(binm, ext, 90)
+    rgba = np.concatenate([ext, np.full(ext.shape[:2] + (1,), 255, np.uint8)], axis=-1)
+    assert np.array_equal(vc.global_carve(binm.astype(np.int64), rgba, 90), want)
+    carved = (want.any(-1)).astype(np.int32)
+    assert np.array_equal(vc.apply_colored_mask_to_voxel_grid(carved, rgba), vc.apply_colored_mask_to_voxel_grid(carved.astype(np.uint8), ext))
+    occ = want.any(-1).astype(np.int16)
+    assert np.array_equal(vc.process_voxel_grid(occ, binm, 90), vc.process_voxel_grid(occ.astype(np.uint8), binm, 90))
+    with pytest.raises(TypeError):
+        vc.process_voxel_grid(occ * 300, binm, 90)
+    with pytest.raises(TypeError):
+        vc.process_voxel_grid(occ.astype(np.float32), binm, 90)
+
+
 def test_synthetic_quirk_cases_match_reference(vc, carve_golden):
     """Square image (_mask_to_wh transposes), foreground in the last column, widths with the odd FP offsets."""
     g = carve_golden
