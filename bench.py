@@ -571,16 +571,46 @@ def carve_sharded_bench(N, dev, world, rank, dist):
             except Exception as exc:
                 print(f"sharded-input part_carve ({mode}) failed:", repr(exc), file=sys.stderr)
                 sharded_ms[mode] = 0.0
+        # the same peer form with the PartCarveSlab object (its tables, output and symmetric workspace) reused: what is
+        # left is pass A, a tiny all-reduce, pass B reading the peers over NVLink, a tiny all-reduce
+        try:
+            nbytes = vc.PartCarveSlab.workspace_bytes(N, N, N, len(jobs90))
+            buf, _, ptrs = sw.symmetric_workspace(nbytes, dev)
+            job = vc.PartCarveSlab(slab_in, ext, jobs90, N, span, workspace=buf)
+            token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+            def steady():
+                job.begin()
+                dist.all_reduce(token)
+                out = job.finish(peers=ptrs, n_ranks=world)
+                dist.all_reduce(token)
+                return out
+            assert torch.equal(steady(), want)
+            for _ in range(2):
+                steady()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(10):
+                steady()
+            eb.record()
+            torch.cuda.synchronize()
+            sharded_ms["peer_steady"] = ea.elapsed_time(eb) / 10
+            del job
+        except Exception as exc:
+            print("sharded-input part_carve (peer, steady) failed:", repr(exc), file=sys.stderr)
         del want, slab_in
     except Exception as exc:
         print("sharded-input part_carve timing failed:", repr(exc), file=sys.stderr)
     sms, xms = sharded_ms.get("alltoall", 0.0), sharded_ms.get("peer", 0.0)
     gms_ag = sharded_ms.get("allgather", 0.0)
-    t = torch.tensor([e0.elapsed_time(e1) / reps, kms, pms, sms, xms, gms_ag], dtype=torch.float64, device=dev)
+    pst = sharded_ms.get("peer_steady", 0.0)
+    t = torch.tensor([e0.elapsed_time(e1) / reps, kms, pms, sms, xms, gms_ag, pst], dtype=torch.float64, device=dev)
     occ = torch.count_nonzero(slab.view(-1, 3).any(dim=1)).to(torch.float64).reshape(1)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(occ, op=dist.ReduceOp.SUM)
-    ms, kms, pms, sms, xms, gms_ag = (float(v) for v in t.tolist())
+    ms, kms, pms, sms, xms, gms_ag, pst = (float(v) for v in t.tolist())
     return {"global_carve_sharded_gvoxel_s": round(N ** 3 / (ms * 1e-3) / 1e9, 2), "grid": N, "ms_per_call": round(ms, 4),
             "kernel_ms_max_over_ranks": round(kms, 4),
             "kernel_gvoxel_s": round(N ** 3 / (kms * 1e-3) / 1e9, 2) if kms > 0 else None,
@@ -588,6 +618,8 @@ def carve_sharded_bench(N, dev, world, rank, dist):
             "part_carve_gvoxel_s": round(N ** 3 / (pms * 1e-3) / 1e9, 2) if pms > 0 else None,
             "part_carve_sharded_input": {
                 "alltoall_ms": round(sms, 4), "peer_ms": round(xms, 4), "allgather_ms": round(gms_ag, 4),
+                "peer_steady_ms": round(pst, 4),
+                "peer_steady_gvoxel_s": round(N ** 3 / (pst * 1e-3) / 1e9, 2) if pst > 0 else None,
                 "best_gvoxel_s": round(N ** 3 / (min(v for v in (sms, xms, gms_ag) if v > 0) * 1e-3) / 1e9, 2) if max(sms, xms, gms_ag) > 0 else None,
                 "note": "whole part_carve_sharded call per rank (PartCarveSlab set-up, pass A, exchange, pass B), max over "
                         "ranks: alltoall = only the z-bit words each slab reads (W*H*D/(8 world) bytes received per rank), "

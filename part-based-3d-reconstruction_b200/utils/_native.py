@@ -167,21 +167,31 @@ def on_device(fn):
     import inspect
     sig = inspect.signature(fn)
 
+    names = list(sig.parameters)
+    dev_pos = names.index("device") if "device" in names else -1
+
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
+        if not args and not kwargs:
+            return fn()
+        # fast resolution (this wrapper sits on calls that take ~100 us): the `device` argument by keyword or position,
+        # else the first CUDA tensor among the positional and keyword arguments
+        d = kwargs.get("device")
+        if d is None and 0 <= dev_pos < len(args):
+            d = args[dev_pos]
         dev = None
-        try:
-            bound = sig.bind_partial(*args, **kwargs).arguments
-        except TypeError:
-            bound = {}
-        d = bound.get("device")
         if d is not None:
-            dev = torch.device(d)
+            dev = d if isinstance(d, torch.device) else torch.device(d)
         else:
-            for v in bound.values():
+            for v in args:
                 if isinstance(v, torch.Tensor) and v.is_cuda:
                     dev = v.device
                     break
+            else:
+                for v in kwargs.values():
+                    if isinstance(v, torch.Tensor) and v.is_cuda:
+                        dev = v.device
+                        break
         if dev is None or dev.type != "cuda" or dev.index is None or not torch.cuda.is_available() \
                 or dev.index == torch.cuda.current_device():
             return fn(*args, **kwargs)

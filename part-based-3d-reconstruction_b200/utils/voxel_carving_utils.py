@@ -199,6 +199,30 @@ def _fold_bits(table, W, D, cache_key):
     return res if res[0] is not None else None
 
 
+_FOLD_PLAN = {}           # (W, H, D, device) -> (table, bits) of the 0/90-degree fold, or None when it does not apply
+
+
+def _fold_plan(W, H, D, dev):
+    """Everything global_carve / part_carve need to know about the 90-degree index fold of a (W,H,D) grid, behind ONE
+    dictionary lookup: (table, bits) when pass 0 is the identity and pass 90 is an exact index fold (bits = its
+    z-separable bit form, or None), else None.  The tables depend only on the shape."""
+    key = (W, H, D, dev.index)
+    if key in _FOLD_PLAN:
+        return _FOLD_PLAN[key]
+    plan = None
+    M0, off0 = _pass_transform((W, H, D), 0)
+    M, off = _pass_transform((W, H, D), 90)
+    if np.array_equal(M0, np.eye(3)) and not off0.any():
+        table, foldable = _fold_table(W, D, M, off, dev)
+        if foldable:
+            bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
+            plan = (table, bits)
+    if len(_FOLD_PLAN) >= 32:
+        _FOLD_PLAN.pop(next(iter(_FOLD_PLAN)))
+    _FOLD_PLAN[key] = plan
+    return plan
+
+
 def _process_device(vol, mask_wh, angle_interval):
     """process_voxel_grid on device tensors: vol (n0,n1,n2) u8, mask_wh (n0,n1) u8 -> carved (n0,n1,n2) u8.
     Index folds (multiples of 90 degrees, when the table says so) run one by one; every run of consecutive resample
@@ -439,14 +463,11 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_ra
     # device (an empty group simply contributes no bits; the reference skips it, :148-149).
     if (group_jobs and all(a == 90 for _, a in group_jobs) and len(group_jobs) <= 32 and D == W
             and semantic_mask.is_rgb_u8 and tuple(semantic_mask.shape[:2]) == (H, W)):
-        M, off = _pass_transform((W, H, D), 90)
-        table, foldable = _fold_table(W, D, M, off, dev)
-        M0, off0 = _pass_transform((W, H, D), 0)
-        identity0 = np.array_equal(M0, np.eye(3)) and not off0.any()
-        if foldable and identity0:
+        plan = _fold_plan(W, H, D, dev)
+        if plan is not None:
+            table, bits = plan
             n_groups = len(group_jobs)
             gm_hw = _group_image_device(semantic_mask, [[PART_COLORS[n] for n in names] for names, _ in group_jobs], dev)
-            bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
             if x_range is not None and bits is not None and bits[2] is not None and x1 > x0:
                 ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -516,13 +537,9 @@ class PartCarveSlab:
               and semantic_mask.is_rgb_u8 and tuple(semantic_mask.shape[:2]) == (H, W))
         bits = None
         if ok:
-            M, off = _pass_transform((W, H, D), 90)
-            table, foldable = _fold_table(W, D, M, off, dev)
-            M0, off0 = _pass_transform((W, H, D), 0)
-            ok = foldable and np.array_equal(M0, np.eye(3)) and not off0.any()
-            if ok:
-                bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev)))
-                ok = bits is not None and bits[2] is not None
+            plan = _fold_plan(W, H, D, dev)
+            bits = plan[1] if plan is not None else None
+            ok = bits is not None and bits[2] is not None
         if not ok:
             raise ValueError("sharded-input part_carve needs the all-90-degree bit path (cubic grid, D % 32 == 0, an RGB "
                              "uint8 mask of the grid's (H,W)); carve a replicated grid with part_carve(..., x_range=...)")
@@ -783,28 +800,25 @@ def global_carve(binary_mask, semantic_mask_exterior, angle_interval=90, stride=
     if not (0 <= x0 <= x1 <= W):
         raise ValueError(f"x_range {x_range} outside [0, {W}]")
     out = None
-    if angle_interval == 90:
-        M0, off0 = _pass_transform((W, H, D), 0)
-        M, off = _pass_transform((W, H, D), 90)
-        if np.array_equal(M0, np.eye(3)) and not off0.any():
-            table, foldable = _fold_table(W, D, M, off, dev)
-            if foldable:
-                m_hw = mask_hw_device()                   # any non-zero byte counts as foreground
-                bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
-                if bits is not None:                      # z-separable table: bit-packed mask, 10x fewer loads
-                    out = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
-                    wpr = (W + 31) // 32 + 2
-                    mbits = torch.empty((H, wpr), dtype=torch.int32, device=dev)
-                    check(lib.p3d_pack_mask_bits(ptr(m_hw), H, W, ptr(mbits), wpr, stream_ptr()), "p3d_pack_mask_bits")
-                    check(lib.p3d_global_carve_fold_bits(W, H, D, x0, x1 - x0, ptr(bits[0]), bits[1], ptr(mbits), wpr,
-                                                         ptr(col), 1, ptr(out), stream_ptr()), "p3d_global_carve_fold_bits")
-                    _launched(2)
-                    x0, x1 = 0, out.shape[0]              # the slab has been applied
-                else:
-                    out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
-                    check(lib.p3d_global_carve_fold(W, H, D, ptr(table), ptr(m_hw), ptr(col), 1, ptr(out),
-                                                    stream_ptr()), "p3d_global_carve_fold")
-                    _launched()
+    plan = _fold_plan(W, H, D, dev) if angle_interval == 90 else None
+    if plan is not None:
+        table, bits = plan
+        m_hw = mask_hw_device()                           # any non-zero byte counts as foreground
+        if bits is not None:                              # z-separable table: bit-packed mask, 10x fewer loads
+            out = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
+            wpr = (W + 31) // 32 + 2
+            mbits = torch.empty((H, wpr), dtype=torch.int32, device=dev)
+            st = stream_ptr()
+            check(lib.p3d_pack_mask_bits(ptr(m_hw), H, W, ptr(mbits), wpr, st), "p3d_pack_mask_bits")
+            check(lib.p3d_global_carve_fold_bits(W, H, D, x0, x1 - x0, ptr(bits[0]), bits[1], ptr(mbits), wpr,
+                                                 ptr(col), 1, ptr(out), st), "p3d_global_carve_fold_bits")
+            _launched(2)
+            x0, x1 = 0, out.shape[0]                      # the slab has been applied
+        else:
+            out = torch.empty((W, H, D, 3), dtype=torch.uint8, device=dev)
+            check(lib.p3d_global_carve_fold(W, H, D, ptr(table), ptr(m_hw), ptr(col), 1, ptr(out),
+                                            stream_ptr()), "p3d_global_carve_fold")
+            _launched()
     if out is None:
         vol = torch.ones((W, H, D), dtype=torch.uint8, device=dev)
         m_wh_d = (_mask_to_wh(mask_hw_device(), W, H) != 0).to(torch.uint8).contiguous()   # (W,H)
