@@ -373,11 +373,24 @@ __device__ __forceinline__ bool seg_is_start(const float* __restrict__ pts, cons
          bx != __ldg(a) + 1.f || ((int)bx % chunk) == 0;
 }
 
-// points in the chunk that starts at i
+// Points in the chunk that starts at point i = tile_base + t.  s_start holds the tile's start flags as a bitmask (bit t
+// = point tile_base + t starts a chunk), so the length is the distance to the next set bit; only a chunk that runs past
+// the tile's end looks at the following points one by one.
 __device__ __forceinline__ int seg_chunk_points(const float* __restrict__ pts, const uint8_t* __restrict__ lab, int64_t i,
-                                                int64_t n, int chunk) {
-  int len = 1;
-  while (len < chunk && i + len < n && !seg_is_start(pts, lab, i + len, chunk)) ++len;
+                                                int64_t n, int chunk, const uint32_t* s_start, int t) {
+  int len = 1, pos = t + 1;
+  while (pos < kSegTile && len < chunk) {
+    const uint32_t w = s_start[pos >> 5] >> (pos & 31);      // flags of pos .. end of its word
+    if (w) {
+      len += __ffs(w) - 1;
+      return len < chunk ? len : chunk;
+    }
+    const int step = 32 - (pos & 31);
+    len += step;
+    pos += step;
+  }
+  if (len >= chunk) return chunk;
+  while (len < chunk && i + len < n && !seg_is_start(pts, lab, i + len, chunk)) ++len;   // beyond the tile
   return len;
 }
 
@@ -406,13 +419,18 @@ __global__ void __launch_bounds__(kSegTile) segments_count_kernel(const float* _
                                                                   int64_t* __restrict__ tile_counts,
                                                                   unsigned long long* __restrict__ bad) {
   __shared__ int warp_sums[kSegTile / 32];
+  __shared__ uint32_t s_start[kSegTile / 32];
   __shared__ int s_bad;
   if (threadIdx.x == 0) s_bad = 0;
   const int64_t i = (int64_t)blockIdx.x * kSegTile + threadIdx.x;
+  const bool start = i < n && seg_is_start(pts, lab, i, 32 * L);
+  const uint32_t ms = __ballot_sync(0xffffffffu, start || i >= n);          // the end of the list ends a chunk, too
+  if ((threadIdx.x & 31) == 0) s_start[threadIdx.x >> 5] = ms;
+  __syncthreads();
   int mine = 0;
   bool isbad = false;
   if (i < n) {
-    if (seg_is_start(pts, lab, i, 32 * L)) mine = (seg_chunk_points(pts, lab, i, n, 32 * L) + L - 1) / L;
+    if (start) mine = (seg_chunk_points(pts, lab, i, n, 32 * L, s_start, threadIdx.x) + L - 1) / L;
     isbad = !seg_point_ok(pts + 3 * i, lab[i]);
   }
   int total;
@@ -431,10 +449,15 @@ __global__ void __launch_bounds__(kSegTile) segments_fill_kernel(const float* __
                                                                  const int64_t* __restrict__ tile_offsets,
                                                                  uint4* __restrict__ segs, int64_t capacity) {
   __shared__ int warp_sums[kSegTile / 32];
+  __shared__ uint32_t s_start[kSegTile / 32];
   const int64_t i = (int64_t)blockIdx.x * kSegTile + threadIdx.x;
+  const bool start = i < n && seg_is_start(pts, lab, i, 32 * L);
+  const uint32_t ms = __ballot_sync(0xffffffffu, start || i >= n);
+  if ((threadIdx.x & 31) == 0) s_start[threadIdx.x >> 5] = ms;
+  __syncthreads();
   int len = 0, T = 0;
-  if (i < n && seg_is_start(pts, lab, i, 32 * L)) {
-    len = seg_chunk_points(pts, lab, i, n, 32 * L);
+  if (start) {
+    len = seg_chunk_points(pts, lab, i, n, 32 * L, s_start, threadIdx.x);
     T = (len + L - 1) / L;
   }
   int total;
