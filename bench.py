@@ -350,12 +350,15 @@ def run_ours(args):
         if not args.no_cpu_baseline:
             try:
                 out["carve"]["cpu_baseline"] = carve_cpu_baseline()
+                if out["carve"]["cpu_baseline"]["parity"]["ok"] is False:
+                    out.setdefault("parity", {})["carve_ok"] = False
             except Exception as exc:
                 out["carve"]["cpu_baseline"] = {"error": repr(exc)}
     _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
-    failed = (parity is not None and parity.get("ok") is False) or (out.get("parity", {}).get("config5_ok") is False)
+    failed = ((parity is not None and parity.get("ok") is False) or out.get("parity", {}).get("config5_ok") is False
+              or out.get("parity", {}).get("carve_ok") is False)
     if failed:
         print("PARITY GATE FAILED: " + json.dumps(out.get("parity")), file=sys.stderr)
         sys.exit(1)
@@ -1066,22 +1069,49 @@ def extra_configs(dev, with_cpu):
 
 
 def carve_cpu_baseline():
-    """The same Bibi@256 pipeline through the oracle (scipy restatement in C + NumPy), single process."""
-    from oracle import oracle as orc
+    """The Bibi@256 pipeline (BASELINE.json configs[0]) through the reference's OWN global_carve + partwise_carve
+    (baseline/_ref, single process: the carving path has no cheap CPU-parallel form), with the
+    bytes of its result compared with the GPU pipeline's; the C/NumPy restatement under oracle/ only if baseline/_ref is
+    absent."""
+    import contextlib
+    import io
+    import harness
     cfg = importlib.import_module(PKG + ".utils.config")
     mu = importlib.import_module(PKG + ".utils.mask_utils")
+    vc = importlib.import_module(PKG + ".utils.voxel_carving_utils")
     data = os.path.join(ROOT, "tests", "golden", "data")
     sem, sem_ext, binary = mu.load_and_prepare_masks(data, "Bibi", "front", 256, cfg.PART_COLORS_NP, cfg.INTERIOR_PARTS)
     jobs = [(["full_building"], 90), (["chhatris"], 90), (["plinth"], 90), (["front_minarets"], 90),
             (["small_minarets"], 90), (["dome"], 90)]
     sym = {"dome": 5, "chhatris": 45, "front_minarets": 5, "small_minarets": 5}
     ext_d = {"main_door": 20, "windows": 10}
-    t0 = time.perf_counter()
-    g = orc.global_carve(binary, sem_ext, 90)
-    orc.partwise_carve(g, sem_ext, sem, orc.PART_COLORS_NP, jobs, sym, ext_d)
-    dt = time.perf_counter() - t0
-    return {"wall_ms": round(dt * 1e3, 1), "cores": 1, "kind": "port",
-            "sample": "Bibi@256 global_carve + partwise_carve through oracle/ (C restatement of scipy affine/label + NumPy)"}
+    buf_ours = io.StringIO()
+    with contextlib.redirect_stdout(buf_ours):
+        ours = vc.partwise_carve(vc.global_carve(binary, sem_ext, 90), sem_ext, sem, cfg.PART_COLORS_NP, jobs, sym, ext_d)
+    buf = io.StringIO()
+    if harness.available():
+        ref = harness.Reference()
+        kind, rvc, colors = "reference", ref.voxel_carving_utils, ref.config.PART_COLORS_NP
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(buf):
+            g = rvc.global_carve(binary, sem_ext, 90)
+            out = rvc.partwise_carve(g, sem_ext, sem, colors, jobs, sym, ext_d)
+        dt = time.perf_counter() - t0
+        sample = "Bibi@256 global_carve + partwise_carve through the reference's own functions (baseline/_ref), 1 process"
+    else:
+        from oracle import oracle as orc
+        kind = "port"
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(buf):
+            g = orc.global_carve(binary, sem_ext, 90)
+            out = orc.partwise_carve(g, sem_ext, sem, orc.PART_COLORS_NP, jobs, sym, ext_d)
+        dt = time.perf_counter() - t0
+        sample = "Bibi@256 global_carve + partwise_carve through oracle/ (C restatement of scipy affine/label + NumPy)"
+    same = bool(np.array_equal(np.asarray(out), ours))
+    res = {"wall_ms": round(dt * 1e3, 1), "cores": 1, "kind": kind, "sample": sample,
+           "parity": {"ok": same, "what": "bytes of the carved (D,H,W,3) grid against the GPU pipeline's",
+                      "log_identical": (buf.getvalue() == buf_ours.getvalue()) if kind == "reference" else None}}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
