@@ -64,15 +64,17 @@ def _to_dev_u8(a, dev, what="array"):
     return t.to(dev).contiguous()
 
 
-_PINNED = {}              # staging buffers for the NumPy boundary (one per direction), grown on demand
-_PIN_MIN_BYTES = 1 << 20  # below this a pageable copy is as fast as staging
+import threading
+
+_PINNED = threading.local()   # staging buffers for the NumPy boundary (one per direction and thread), grown on demand
+_PIN_MIN_BYTES = 1 << 20      # below this a pageable copy is as fast as staging
 
 
 def _pinned(kind, nbytes):
-    buf = _PINNED.get(kind)
+    buf = getattr(_PINNED, kind, None)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        _PINNED[kind] = buf
+        setattr(_PINNED, kind, buf)
     return buf[:nbytes]
 
 
