@@ -269,6 +269,16 @@ def run_ours(args):
         parity, cpu = parity_gate(args, scorer, gt, parts, cand_all, step_block(s_last), gate_counts, gate_scores, gate_best,
                                   offsets[s_last], B, H, W, dev, world, rank, dist, sweep_mod)
 
+    # ---- N > 1: BASELINE.json configs[4] across the box: the 1024^3 / 2048^2 sweep, candidates sharded -------------
+    config5 = None
+    if world > 1 and not args.no_extra:
+        try:
+            del scorer
+            torch.cuda.empty_cache()
+            config5 = config5_sweep(dev, world, rank, dist, not args.no_cpu_baseline)
+        except Exception as exc:
+            config5 = {"error": repr(exc)}
+
     # ---- N > 1: carving of a 1024^3 grid sharded by x-slab, max over ranks --------------------------
     carve_multi = None
     if world > 1 and not args.no_carve:
@@ -298,7 +308,7 @@ def run_ours(args):
             traffic = int(tj["traffic_bytes_per_launch"])
     except Exception:
         pass
-    seg_on = scorer.segs is not None and os.environ.get("P3D_SPLAT_POINTS") != "1"
+    seg_on = n_points >= int(os.environ.get("P3D_SEG_MIN_POINTS", "6000000")) and os.environ.get("P3D_SPLAT_POINTS") != "1"
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel": ("splat_seg_kernel<double, joint-packed> (x-run segments, FP32 filter + exact FP64 queue)" if seg_on
@@ -343,6 +353,10 @@ def run_ours(args):
             out.setdefault("parity", {})["config5_ok"] = False
     if carve_multi is not None:
         out["carve"] = carve_multi
+    if config5 is not None:
+        out["config5_sweep"] = config5
+        if isinstance(config5.get("parity"), dict) and config5["parity"].get("ok") is False:
+            out.setdefault("parity", {})["config5_ok"] = False
     if world == 1 and not args.no_carve:
         del scorer
         torch.cuda.empty_cache()
@@ -362,6 +376,73 @@ def run_ours(args):
     if failed:
         print("PARITY GATE FAILED: " + json.dumps(out.get("parity")), file=sys.stderr)
         sys.exit(1)
+
+
+def config5_sweep(dev, world, rank, dist, with_cpu):
+    """BASELINE.json configs[4] across the GPUs of the box: the 1024^3 synthetic monument (174.8 M points) against a
+    2048x2048 mask, 128 candidates per GPU per pass (weak scaling, contiguous shards of 128 * world candidates), with the
+    16-byte all-gather of the best candidate.  CUDA events, max over ranks; per-GPU fraction of the streaming roofline
+    (G*1 B + 9 B*H*W per candidate); rank 0 checks one candidate of its shard against the reference's functions."""
+    import torch
+    syn = importlib.import_module(PKG + ".synthetic")
+    ce = importlib.import_module(PKG + ".utils.camera_estimation")
+    cfg = importlib.import_module(PKG + ".utils.config")
+    sweep_mod = importlib.import_module(PKG + ".utils.sweep")
+    N, H, W, B = 1024, 2048, 2048, 128
+    rgb = torch.from_numpy(syn.label_lut()).to(dev)[syn.monument_labels(N, dev).long()]
+    base = syn.base_camera(N, H, W, "front")
+    full = ce.CandidateScorer(rgb, torch.zeros((H, W, 3), dtype=torch.uint8, device=dev), cfg.PART_COLORS, syn.PART_NAMES)
+    gt = full.render(ce.row_to_params(base + HIDDEN_DELTA))
+    del full
+    sc = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, syn.PART_NAMES)
+    del rgb
+    cand = syn.candidates(base, B * world)
+    mine = torch.from_numpy(np.ascontiguousarray(cand[rank * B:(rank + 1) * B])).to(dev)
+    reducer = sweep_mod.BestReducer(dev, world)
+
+    def step():
+        counts, scores, best = sc.score_device(mine)
+        return reducer.reduce(scores, best, rank * B), counts, scores
+    step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        res, counts, scores = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / reps
+    peak, _ = peaks()
+    model = peak * 1e9 / (N ** 3 + 9 * H * W)
+    value = B * world / (ms * 1e-3)
+    out = {"value": round(value, 1), "unit": UNIT, "n_gpus": world, "per_gpu": round(value / world, 1),
+           "grid": N, "mask": [H, W], "points": sc.n_points, "candidates_per_gpu": B, "ms_per_pass": round(ms, 3),
+           "scaling": "weak", "best": {"index": int(res[1]), "score": float(res[0])},
+           "roofline": {"bound": "hbm", "model_candidates_per_s_per_gpu": round(model, 1), "peak": peak, "unit": "GB/s",
+                        "achieved": round(value / world * (N ** 3 + 9 * H * W) / 1e9, 1), "frac": round(value / world / model, 4),
+                        "note": "whole sweep call per GPU (splat + score + clear + best reduction) over the streaming model "
+                                "G*1 B + 9 B*H*W per candidate, max over ranks"}}
+    if with_cpu and rank == 0:
+        try:
+            import cpu_arm
+            pts = sc.pts.cpu().numpy()
+            lut = np.zeros((256, 3), np.uint8)
+            lut[1:1 + len(sc.colours)] = np.array(sc.colours, np.uint8)
+            cols = lut[sc.pt_label.cpu().numpy()]
+            cpu = cpu_arm.CpuScorer(pts, cols, gt, syn.PART_NAMES, part_colors=cfg.PART_COLORS)
+            pick = [B - 1]
+            gc = counts.cpu().numpy()[pick][:, sc._cols, :]
+            dt, n, bad, identical = compare_with_cpu(cpu, cand[pick], gc, scores.cpu().numpy()[pick], 1)
+            out["parity"] = {"checked": n, "ok": not bad, "kind": cpu.kind, "scores_bit_identical": identical, "mismatches": bad[:2]}
+        except MemoryError as exc:
+            out["parity"] = {"checked": 0, "ok": None, "error": repr(exc)}
+    del sc
+    torch.cuda.empty_cache()
+    return out
 
 
 def whole_sweep(ce, cfg, sweep_mod, nv, rgb, gt, parts, cand_all, B, dev, world, rank, dist):
