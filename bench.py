@@ -1098,8 +1098,17 @@ def extra_configs(dev, with_cpu):
         full = ce.CandidateScorer(rgb, torch.zeros((H, W, 3), dtype=torch.uint8, device=dev), cfg.PART_COLORS, syn.PART_NAMES)
         gt = full.render(ce.row_to_params(base + HIDDEN_DELTA))
         sc = ce.CandidateScorer(rgb, gt, cfg.PART_COLORS, syn.PART_NAMES)
+        v256 = rate(sc, syn.candidates(base, 4096), reps=2)
+        peak256, _ = peaks()
+        model256 = peak256 * 1e9 / (N ** 3 + 9 * H * W)
         out["synthetic_256_4096cand"] = {"points": sc.n_points, "mask": [H, W], "candidates": 4096,
-                                         "value": round(rate(sc, syn.candidates(base, 4096), reps=2), 1), "unit": UNIT}
+                                         "value": round(v256, 1), "unit": UNIT,
+                                         "roofline": {"bound": "hbm", "model_candidates_per_s": round(model256, 1), "peak": peak256,
+                                                      "unit": "GB/s", "achieved": round(v256 * (N ** 3 + 9 * H * W) / 1e9, 1),
+                                                      "frac": round(v256 / model256, 4),
+                                                      "note": "BASELINE.json configs[2]; whole sweep call over the streaming model "
+                                                              "G*1 B + 9 B*H*W per candidate; 2.7 M points take the per-point splat "
+                                                              "(voxel pitch 3.4 px: every lane of an early-out load in its own sector)"}}
     except Exception as exc:
         out["synthetic_256_4096cand"] = {"error": repr(exc)}
     try:        # BASELINE.json configs[4] on one GPU: 1024^3 grid, 2048x2048 masks (front + aerial views)
