@@ -71,3 +71,12 @@ with contextlib.redirect_stdout(io.StringIO()):
         oriented = torch.empty((D, H, W, 3), dtype=torch.uint8, device=cur.device)
         stage("reorient", lambda: vc.check(vc.lib.p3d_reorient(vc.ptr(cur), W, H, D, vc.ptr(oriented), vc.stream_ptr())))
         stage("recolour", lambda: vc.recolor_backward_components(oriented, cfg.PART_COLORS_NP["front_minarets"], new_color=cfg.PART_COLORS_NP["back_minarets"], k=2, sort_axis=0))
+
+# portrait mask (Charminar@256: grid 177 x 256 x 177 -- no multiple of 32, table-driven kernels): whole calls
+g5 = np.load(os.path.join(ROOT, "tests", "golden", "real5_golden.npz"))
+for key in ("real_Charminar_256", "real_Itimad_256"):
+    ext5, bin5 = torch.from_numpy(g5[key + "_ext"]).cuda(), torch.from_numpy(g5[key + "_bin"]).cuda()
+    gg = vc.global_carve(bin5, ext5, 90)
+    t_g5, _ = best(lambda: vc.global_carve(bin5, ext5, 90))
+    t_p5, _ = best(lambda: vc.part_carve(gg, ext5, jobs))
+    print(f"{key}: grid {tuple(gg.shape[:3])} ({gg.numel() / 1e6:.1f} MB): global_carve call {t_g5:.3f} ms, part_carve call {t_p5:.3f} ms")
