@@ -1073,7 +1073,6 @@ inline bool splat_points_only() {
 struct p3d_sweep_ctx {
   cudaStream_t helper = nullptr;
   cudaEvent_t splatted[2] = {nullptr, nullptr}, scored[2] = {nullptr, nullptr};
-  bool scored_pending[2] = {false, false};
   int device = -1;
   int last_launches = 0;
   bool timing = false;
@@ -1156,7 +1155,7 @@ int fast_cameras(const T* cams, int K, const float* bbox, int H, int W, float* f
 // trick (H W <= 2^22) and the launch's z-buffer set stays below 4 GiB (32-bit byte offsets)
 inline bool use_segments(const void* segs, int64_t n_seg, bool filtered, int K, int H, int W) {
   return segs != nullptr && n_seg > 0 && filtered && !splat_points_only() && (int64_t)H * W <= (1ll << 22) &&
-         (int64_t)K * H * W * 4 < (1ll << 32);
+         (int64_t)K * H * W * 4 < (1ll << 32);   // (keys: the caller checks n < 2^32 - 2^10, so key0 + 7 step cannot wrap)
 }
 
 template <typename T>
@@ -1173,7 +1172,7 @@ int splat(const float* pts, const uint8_t* pt_label, int64_t n, const T* cams, i
   P3D_REQUIRE(mode == P3D_MODE_JOINT || pt_label, "splat: this mode needs pt_label");
   const bool filtered = fast != nullptr && bbox != nullptr && !splat_exact_only();
   cudaStream_t st = p3d::as_stream(stream);
-  if (use_segments(segs, n_seg, filtered, K, H, W)) {
+  if (use_segments(segs, n_seg, filtered, K, H, W) && n < 0xfffffc00ll) {
     P3D_REQUIRE(pt_label, "splat: the segment path needs pt_label");
     const int64_t tiles = (n_seg + kSegThreads - 1) / kSegThreads;
     P3D_REQUIRE(tiles < (1ll << 31), "splat: too many tiles");
