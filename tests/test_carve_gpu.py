@@ -218,6 +218,43 @@ def test_building_blocks_vs_oracle(vc, oracle, carve_golden):
         vc.carve_voxel_grid_with_masks(occ, np.ones((5, 7), np.uint8))
 
 
+def test_guided_carve_with_overlapping_component_boxes(vc, oracle, capsys):
+    """left_right_guided_carve when the bounding boxes of two components of the colour interlock (two L-shaped blobs),
+    when one box contains another, and with many small components: the reference's loop order decides which paste
+    survives (:199-201), so the batched path falls back to one paste per component in id order; arrays and printed log
+    against the oracle, at every notebook angle."""
+    cfg = pkg("utils.config")
+    colour, other = cfg.PART_COLORS_NP["front_minarets"], cfg.PART_COLORS_NP["dome"]
+    rng = np.random.default_rng(9)
+    W, H, D = 40, 30, 40
+    grid = np.zeros((W, H, D, 3), np.uint8)
+    grid[2:20, 2:6, 2:6] = colour                 # L number one
+    grid[2:6, 2:22, 2:6] = colour
+    grid[8:24, 18:22, 2:6] = colour               # L number two, interlocking boxes, not touching (gap at x = 6, 7 / y = 6..17)
+    grid[20:24, 8:22, 2:6] = colour
+    grid[26:38, 4:28, 10:36] = other              # a big blob of another colour ...
+    grid[30:33, 10:14, 20:24] = colour            # ... with a small component of the colour inside its box
+    grid[28:36, 6:26, 12:14] = colour             # and a plate whose box contains the small one's x/y range
+    for _ in range(25):                           # speckle: many tiny components
+        x, y, z = (int(rng.integers(1, n - 1)) for n in (W, H, D))
+        if not grid[x - 1:x + 2, y - 1:y + 2, z - 1:z + 2].any():
+            grid[x, y, z] = colour
+    sem = np.zeros((H, W, 3), np.uint8)
+    sem[:, :] = cfg.PART_COLORS_NP["background"]
+    sem[2:24, 1:26] = colour
+    sem[5:27, 27:37] = colour
+    sem[rng.random((H, W)) < 0.1] = cfg.PART_COLORS_NP["background"]
+    assert vc._boxes_overlap([(2, 2, 2, 18, 20, 4), (8, 8, 2, 16, 14, 4)])
+    for angle in (5, 45, 60, 90):
+        capsys.readouterr()
+        got = vc.left_right_guided_carve(grid, sem, colour, angle)
+        log = capsys.readouterr().out
+        want_log = []
+        want = oracle.left_right_guided_carve(grid, sem, colour, angle, log=want_log)
+        assert np.array_equal(got, want), angle
+        assert log.strip("\n") == "\n".join(want_log), angle
+
+
 def test_device_tensor_chain(vc, carve_golden):
     """CUDA tensors in -> CUDA tensors out, same bytes as the NumPy path."""
     g = carve_golden
