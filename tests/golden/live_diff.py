@@ -191,6 +191,14 @@ for t in range(max(4, T // 4)):
     pa, ca = orc.voxel_grid_to_points(g, stride=stride)[:2]
     pb, cb = ref.vu.voxel_grid_to_points(g, stride=stride)[:2]
     tally("voxel_grid_to_points", np.array_equal(pa, pb) and np.array_equal(ca, cb))
+    # extract_top_k_components (voxel_utils.py:22-31): speckled grid, 26-connectivity, ptp along axis 1, stable sort
+    shp = tuple(int(v) for v in rng.integers(6, 22, 3))
+    tg = np.zeros(shp + (3,), np.uint8)
+    col = np.array(C.PART_COLORS[str(rng.choice(names))])
+    tg[rng.random(shp) < rng.choice([0.08, 0.2, 0.35])] = col
+    tg[rng.random(shp) < 0.1] = C.PART_COLORS["dome"]
+    k = int(rng.choice([1, 2, 4]))
+    tally("extract_top_k_components", np.array_equal(orc.extract_top_k_components(tg, col, k), ref.vu.extract_top_k_components(tg, col, k)))
 
 print("\nfunction                                   trials  mismatches")
 bad = 0
