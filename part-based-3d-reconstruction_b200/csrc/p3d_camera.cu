@@ -1114,9 +1114,9 @@ int setup_cameras(const T* cand, int K, T* cams, p3d_stream_t stream) {
 
 // cameras handled by one CTA: enough CTAs for ~8 waves when the point list is short
 #ifndef P3D_SEG_MAXCAMS
-#define P3D_SEG_MAXCAMS 64
+#define P3D_SEG_MAXCAMS 32
 #endif
-constexpr int kSegMaxCams = P3D_SEG_MAXCAMS;   // cameras per CTA of the segment splat (192 B of shared memory each; 128 measured slower)
+constexpr int kSegMaxCams = P3D_SEG_MAXCAMS;   // cameras per CTA of the segment splat (8: 33.9, 16: 37.3, 24: 37.9, 32: 38.7, 64: 38.3, 96: 36.8, 128: 34.5 k cand/s)
 inline int pick_cams_per_block(int64_t tiles, int K, int max_cams = 64) {
   const int64_t want = (int64_t)p3d::sm_count() * 24;
   int groups = (int)((want + tiles - 1) / (tiles > 0 ? tiles : 1));
