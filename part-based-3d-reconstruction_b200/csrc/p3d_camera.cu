@@ -397,7 +397,10 @@ splat_filtered_kernel(const float* __restrict__ pts, const uint8_t* __restrict__
 #endif
 constexpr int kSegLen = P3D_SEG_LEN;          // points per segment (p3d_segment_length())
 constexpr int kSegGroup = P3D_SEG_GROUP;      // points whose early-out loads are in flight together
-constexpr int kSegThreads = 128;
+#ifndef P3D_SEG_THREADS
+#define P3D_SEG_THREADS 128
+#endif
+constexpr int kSegThreads = P3D_SEG_THREADS;
 constexpr int kSegFlushEvery = 64 / kSegLen;  // cameras between queue flushes: kSegLen bits per camera in a 64-bit mask
 constexpr uint32_t kCamInView = 1u;           // cam_flags bit: every decided point of this camera is inside the image
 static_assert(kSegLen % kSegGroup == 0 && kSegGroup % 2 == 0 && 64 % kSegLen == 0, "segment shape");
@@ -1114,9 +1117,9 @@ int setup_cameras(const T* cand, int K, T* cams, p3d_stream_t stream) {
 
 // cameras handled by one CTA: enough CTAs for ~8 waves when the point list is short
 #ifndef P3D_SEG_MAXCAMS
-#define P3D_SEG_MAXCAMS 32
+#define P3D_SEG_MAXCAMS 48
 #endif
-constexpr int kSegMaxCams = P3D_SEG_MAXCAMS;   // cameras per CTA of the segment splat (8: 33.9, 16: 37.3, 24: 37.9, 32: 38.7, 64: 38.3, 96: 36.8, 128: 34.5 k cand/s)
+constexpr int kSegMaxCams = P3D_SEG_MAXCAMS;   // cameras per CTA of the segment splat (8: 33.9, 16: 37.3, 24: 37.9, 32: 38.7, 48: 38.9, 64: 38.3, 96: 36.8, 128: 34.5 k cand/s; 64 / 256 threads per CTA: 38.1 / 38.4)
 inline int pick_cams_per_block(int64_t tiles, int K, int max_cams = 64) {
   const int64_t want = (int64_t)p3d::sm_count() * 24;
   int groups = (int)((want + tiles - 1) / (tiles > 0 ? tiles : 1));
