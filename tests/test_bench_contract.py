@@ -31,3 +31,38 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_parity_gate_helper_detects_mismatches():
+    """bench.compare_with_cpu: identical counts/scores pass; a single differing count, or a score off by more than 1e-5
+    relative, is reported (bench.py then exits 1)."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeCpu:
+        def __init__(self, counts, scores):
+            self.counts, self.scores = counts, scores
+
+        def run(self, rows, processes=1):
+            return 0.5, self.counts, self.scores
+
+    counts = np.arange(24, dtype=np.int64).reshape(3, 4, 2)
+    scores = np.array([0.25, 0.5, 0.75])
+    rows = np.zeros((3, 9))
+    dt, n, bad, ident = bench.compare_with_cpu(FakeCpu(counts, scores), rows, counts.copy(), scores.copy(), 1)
+    assert n == 3 and bad == [] and ident
+    c2 = counts.copy()
+    c2[1, 2, 0] += 1
+    _, _, bad, _ = bench.compare_with_cpu(FakeCpu(counts, scores), rows, c2, scores.copy(), 1)
+    assert len(bad) == 1 and bad[0].startswith("counts[1]")
+    s2 = scores.copy()
+    s2[2] *= 1 + 3e-5
+    _, _, bad, ident = bench.compare_with_cpu(FakeCpu(counts, scores), rows, counts.copy(), s2, 1)
+    assert len(bad) == 1 and bad[0].startswith("score[2]") and not ident
+    s3 = scores.copy()
+    s3[0] *= 1 + 1e-7                                        # inside the tolerance: no mismatch, but not bit-identical
+    _, _, bad, ident = bench.compare_with_cpu(FakeCpu(counts, scores), rows, counts.copy(), s3, 1)
+    assert bad == [] and not ident
