@@ -583,12 +583,12 @@ def carve_sharded_bench(N, dev, world, rank, dist):
     binm = (front > 0).astype(np.uint8)
     binm_d = torch.from_numpy(binm).to(dev)                  # masks resident on the device, as for a caller chaining stages
     carve = lambda a, b: vc.global_carve(binm_d, ext, 90, return_tensor=True, x_range=(a, b))
-    for _ in range(3):
+    for _ in range(5):
         slab, span = sw.carve_sharded(carve, N)
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    reps = 5
+    reps = 40        # (round 2 timed 5 calls: the empty-queue start-up of the window was a third of the figure at N = 8)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -641,17 +641,18 @@ def carve_sharded_bench(N, dev, world, rank, dist):
             try:
                 got, _ = sw.part_carve_sharded(slab_in, ext, jobs90, N, exchange=mode)
                 assert torch.equal(got, want), mode
-                for _ in range(2):
+                for _ in range(3):
                     sw.part_carve_sharded(slab_in, ext, jobs90, N, exchange=mode)
                 torch.cuda.synchronize()
                 dist.barrier()
+                torch.cuda.synchronize()
                 ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ea.record()
-                for _ in range(5):
+                for _ in range(20):
                     sw.part_carve_sharded(slab_in, ext, jobs90, N, exchange=mode)
                 eb.record()
                 torch.cuda.synchronize()
-                sharded_ms[mode] = ea.elapsed_time(eb) / 5
+                sharded_ms[mode] = ea.elapsed_time(eb) / 20
             except Exception as exc:
                 print(f"sharded-input part_carve ({mode}) failed:", repr(exc), file=sys.stderr)
                 sharded_ms[mode] = 0.0
@@ -659,28 +660,28 @@ def carve_sharded_bench(N, dev, world, rank, dist):
         # left is pass A, a tiny all-reduce, pass B reading the peers over NVLink, a tiny all-reduce
         try:
             nbytes = vc.PartCarveSlab.workspace_bytes(N, N, N, len(jobs90))
-            buf, _, ptrs = sw.symmetric_workspace(nbytes, dev)
+            buf, hdl, ptrs = sw.symmetric_workspace(nbytes, dev)
             job = vc.PartCarveSlab(slab_in, ext, jobs90, N, span, workspace=buf)
-            token = torch.zeros(1, dtype=torch.int32, device=dev)
 
             def steady():
                 job.begin()
-                dist.all_reduce(token)
+                sw.peer_barrier(hdl)
                 out = job.finish(peers=ptrs, n_ranks=world)
-                dist.all_reduce(token)
+                sw.peer_barrier(hdl)
                 return out
             assert torch.equal(steady(), want)
-            for _ in range(2):
+            for _ in range(3):
                 steady()
             torch.cuda.synchronize()
             dist.barrier()
+            torch.cuda.synchronize()
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ea.record()
-            for _ in range(10):
+            for _ in range(20):
                 steady()
             eb.record()
             torch.cuda.synchronize()
-            sharded_ms["peer_steady"] = ea.elapsed_time(eb) / 10
+            sharded_ms["peer_steady"] = ea.elapsed_time(eb) / 20
             del job
         except Exception as exc:
             print("sharded-input part_carve (peer, steady) failed:", repr(exc), file=sys.stderr)

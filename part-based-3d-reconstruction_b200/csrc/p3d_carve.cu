@@ -352,7 +352,7 @@ global_fold_kernel(int W, int H, int D, const int32_t* __restrict__ table, const
 // entry satisfies src0(x,z) = c - z for one constant c (checked by fold_analyse_kernel on the actual table, true
 // for the 90-degree pass) -- the 16 mask lookups of a thread are 16 consecutive bits of the bit-packed mask row,
 // read in reverse, and the 16 table lookups collapse to 16 bits of an "inside" bit matrix.
-//   inside_bits : (W, D/32) uint32, bit z%32 of word [x][z/32] = table[x][z] >= 0
+//   inside_bits : (W, ceil(D/32)) uint32, bit z%32 of word [x][z/32] = table[x][z] >= 0
 //   mask_bits   : (H, wpr) uint32 with one zero word of padding on each side: pixel x is bit (x+32)%32 of word
 //                 [y][(x+32)/32]
 // ------------------------------------------------------------------------------------------
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256)
 fold_analyse_kernel(const int32_t* __restrict__ table, int W, int D, uint32_t* __restrict__ inside_bits,
                     int* __restrict__ info /* over in-range entries: [0] = max(src0+z), [1] = min(src0+z),
                                               [2] = max(src2-x), [3] = min(src2-x) */) {
-  const int words = D >> 5;
+  const int words = (D + 31) >> 5;                              // a ragged last word keeps zero bits beyond D
   const int i = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per (x, word)
   if (i >= W * words) return;
   const int x = i / words, w = i - x * words;
@@ -368,6 +368,7 @@ fold_analyse_kernel(const int32_t* __restrict__ table, int W, int D, uint32_t* _
   int mx = -0x7fffffff, mn = 0x7fffffff, mx2 = -0x7fffffff, mn2 = 0x7fffffff;
   for (int j = 0; j < 32; ++j) {
     const int z = w * 32 + j;
+    if (z >= D) break;
     const int32_t e = table[(size_t)x * D + z];
     if (e >= 0) {
       bits |= 1u << j;
@@ -522,6 +523,106 @@ global_fold_bits_kernel(int W, int H, int D, int x_begin, int x_count, const uin
 }
 
 // ------------------------------------------------------------------------------------------
+// The same bit-level kernels for RAGGED rows (D % 32 != 0, e.g. the 88 / 177 / 246 wide grids of a portrait mask): a
+// z-row is then neither a whole number of 16-voxel groups nor 16-byte aligned, so the groups are cut from the FLAT
+// voxel order instead -- group g = voxels [16 g, 16 g + 16), 48 aligned bytes wherever the rows fall -- and a group
+// spans at most two z-rows (D >= 16).  Each piece (row, z, n voxels) gets its bits exactly like an aligned group: the
+// inside bits by a funnel shift of two words, the mask pixels c - z .. c - z - 15 as 16 reversed bits of the padded
+// mask row; the two pieces are merged by position.  Loads, stores and the per-warp staging stay as in the aligned
+// kernels; only a grid whose byte count is no multiple of 16 ends in a byte-wise tail.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t inside16_ragged(const uint32_t* __restrict__ inside_bits, int x, int words, int z, int n) {
+  const uint32_t* ir = inside_bits + (size_t)x * words;
+  const int wi = z >> 5;
+  const uint32_t w0 = __ldg(ir + wi), w1 = wi + 1 < words ? __ldg(ir + wi + 1) : 0u;
+  return __funnelshift_r(w0, w1, z & 31) & ((1u << n) - 1u);  // n in 1..16
+}
+
+// OR the RGB bytes of `col` into the 48-byte image `o` of a group at every voxel position whose bit is set
+__device__ __forceinline__ void paint16(uint32_t bits, uint32_t col, uint32_t* o) {
+  const uint32_t r8 = col & 0xff, g8 = (col >> 8) & 0xff, b8 = (col >> 16) & 0xff;
+  const uint32_t w0 = r8 | (g8 << 8) | (b8 << 16) | (r8 << 24);
+  const uint32_t w1 = g8 | (b8 << 8) | (r8 << 16) | (g8 << 24);
+  const uint32_t w2 = b8 | (r8 << 8) | (g8 << 16) | (b8 << 24);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t t[3];
+    expand4((bits >> (4 * q)) & 0xfu, w0, w1, w2, t);
+    o[3 * q] |= t[0]; o[3 * q + 1] |= t[1]; o[3 * q + 2] |= t[2];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+global_fold_bits_ragged_kernel(int W, int H, int D, int x_begin, int x_count, const uint32_t* __restrict__ inside_bits,
+                               int c, const uint32_t* __restrict__ mask_bits, int wpr, const uint8_t* __restrict__ colour_hw,
+                               uint8_t* __restrict__ out, unsigned long long magic_d, unsigned long long magic_h) {
+  __shared__ uint4 stage[8][96];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rows = (uint32_t)x_count * (uint32_t)H;
+  const uint32_t nvox = rows * (uint32_t)D;                    // < 2^31 (the host splits larger slabs)
+  const uint32_t groups = (nvox + 15u) >> 4;
+  const uint32_t warp_groups = (groups + 31u) >> 5;
+  const uint32_t full16 = (uint32_t)(((uint64_t)nvox * 3u) >> 4), tail = (uint32_t)(((uint64_t)nvox * 3u) & 15u);
+  const int words = (D + 31) >> 5;
+  for (uint32_t wg = blockIdx.x * 8u + warp; wg < warp_groups; wg += gridDim.x * 8u) {
+    const uint32_t g = wg * 32u + lane;
+    uint32_t o[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) o[k] = 0u;
+    if (g < groups) {
+      const uint32_t v0 = g << 4;
+      uint32_t row = div_magic(v0, (uint32_t)D, magic_d);
+      int z = (int)(v0 - row * (uint32_t)D), done = 0;
+#pragma unroll
+      for (int piece = 0; piece < 2; ++piece) {
+        if (done < 16 && row < rows) {
+          const int n = min(16 - done, D - z);
+          const uint32_t xi = div_magic(row, (uint32_t)H, magic_h);
+          const uint32_t y = row - xi * (uint32_t)H;
+          const int x = x_begin + (int)xi, xb = x + 32;
+          const uint32_t* mrow = mask_bits + (size_t)y * wpr;
+          if ((__ldg(mrow + (xb >> 5)) >> (xb & 31)) & 1u) {
+            const uint32_t in16 = inside16_ragged(inside_bits, x, words, z, n);
+            const int lo = c - z - 15 + 32;                  // >= 17 and inside the padded row whenever in16 != 0
+            uint32_t m16 = 0;
+            if (in16 && lo >= 0 && (lo >> 5) + 1 < wpr) {
+              const uint32_t w0 = __ldg(mrow + (lo >> 5)), w1 = __ldg(mrow + (lo >> 5) + 1);
+              m16 = __funnelshift_r(w0, w1, lo & 31) & 0xffffu;
+            }
+            const uint32_t bits = in16 & (__brev(m16) >> 16);
+            if (bits) {
+              const uint8_t* cc = colour_hw + ((size_t)y * W + x) * 3;
+              paint16(bits << done, (uint32_t)cc[0] | ((uint32_t)cc[1] << 8) | ((uint32_t)cc[2] << 16), o);
+            }
+          }
+          done += n;
+          ++row;
+          z = 0;
+        }
+      }
+    }
+    uint4* mine = &stage[warp][lane * 3];
+    mine[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    mine[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    mine[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)wg * 96;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const uint32_t q = wg * 96u + (uint32_t)(p * 32 + lane);  // uint4 index within the slab
+      if (q < full16) {
+        __stcs(dst + p * 32 + lane, stage[warp][p * 32 + lane]);
+      } else if (q == full16 && tail) {                        // the slab's last bytes: fewer than 16
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(&stage[warp][p * 32 + lane]);
+        uint8_t* db = reinterpret_cast<uint8_t*>(dst + p * 32 + lane);
+        for (uint32_t b = 0; b < tail; ++b) db[b] = sb[b];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Bit-level fast path of the fused part_carve kernel (all groups at 90 degrees, z-separable table with
 // src0 = c - z and src2 = x + c2):
 //   keep(x,y,z) = grid[x,y,z] != 0 && inside(x,z) && occ[c-z, y, x+c2] && OR_g (g in gm[y][x] && g in gm[y][c-z])
@@ -659,6 +760,91 @@ part_copy_bits_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, con
   }
 }
 
+// pass A for ragged rows (see global_fold_bits_ragged_kernel): thread = 16 voxels in FLAT order, at most two z-row
+// pieces.  The z-packed occupancy / alive words of a row no longer belong to one lane pair, so every piece ORs its bits
+// into the (zeroed) arrays with at most two atomics each -- only occupied / surviving pieces issue any.
+__global__ void __launch_bounds__(256)
+part_copy_bits_ragged_kernel(const uint8_t* __restrict__ grid, int W, int H, int D, const uint32_t* __restrict__ inside_bits,
+                             int c, const uint32_t* __restrict__ gm_hw, const uint32_t* __restrict__ gbits, int xwp,
+                             uint32_t* __restrict__ occz, uint32_t* __restrict__ alive, uint8_t* __restrict__ out,
+                             unsigned long long magic_d, unsigned long long magic_h, uint32_t nvox) {
+  const uint32_t groups = (nvox + 15u) >> 4;
+  const uint32_t rows = (uint32_t)W * (uint32_t)H;
+  const int words = (D + 31) >> 5;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const uint32_t v0 = g << 4;
+    const bool whole = v0 + 16u <= nvox;                      // false only for the last group of a grid with nvox % 16 != 0
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, cc = a;
+    if (whole) {
+      const uint4* src = reinterpret_cast<const uint4*>(grid + (size_t)v0 * 3);
+      a = __ldg(src); b = __ldg(src + 1); cc = __ldg(src + 2);
+    } else {
+      uint32_t w[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) w[k] = 0u;
+      const uint32_t nb = (nvox - v0) * 3u;
+      for (uint32_t k = 0; k < nb; ++k) w[k >> 2] |= (uint32_t)grid[(size_t)v0 * 3 + k] << (8 * (k & 3u));
+      a = make_uint4(w[0], w[1], w[2], w[3]); b = make_uint4(w[4], w[5], w[6], w[7]); cc = make_uint4(w[8], w[9], w[10], w[11]);
+    }
+    const uint32_t occ = rgb16_occupancy(a, b, cc);
+    uint32_t keep = 0;
+    if (occ) {
+      uint32_t row = div_magic(v0, (uint32_t)D, magic_d);
+      int z = (int)(v0 - row * (uint32_t)D), done = 0;
+#pragma unroll
+      for (int piece = 0; piece < 2; ++piece) {
+        if (done < 16 && row < rows) {
+          const int n = min(16 - done, D - z);
+          const uint32_t o = (occ >> done) & ((1u << n) - 1u);
+          if (o) {
+            const size_t wbase = (size_t)row * words + (z >> 5);
+            const int sh = z & 31;
+            atomicOr(occz + wbase, o << sh);
+            if (sh + n > 32) atomicOr(occz + wbase + 1, o >> (32 - sh));
+            const uint32_t xq = div_magic(row, (uint32_t)H, magic_h);
+            const int y = (int)(row - xq * (uint32_t)H), x = (int)xq;
+            const uint32_t self = __ldg(gm_hw + (size_t)y * W + x);
+            uint32_t k = self ? o & inside16_ragged(inside_bits, x, words, z, n) : 0u;
+            if (k) {
+              const int lo = c - z - 15 + 32;
+              uint32_t grp = 0, rem = self;
+              while (rem) {
+                const int gi = __ffs(rem) - 1;
+                rem &= rem - 1;
+                grp |= rev16_bits(gbits + ((size_t)gi * H + y) * xwp, lo, xwp);
+              }
+              k &= grp;
+            }
+            if (k) {
+              atomicOr(alive + wbase, k << sh);
+              if (sh + n > 32) atomicOr(alive + wbase + 1, k >> (32 - sh));
+              keep |= k << done;
+            }
+          }
+          done += n;
+          ++row;
+          z = 0;
+        }
+      }
+    }
+    uint32_t m[12];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) expand4((keep >> (4 * q)) & 0xfu, 0xffffffffu, 0xffffffffu, 0xffffffffu, m + 3 * q);
+    const uint4 r0 = make_uint4(a.x & m[0], a.y & m[1], a.z & m[2], a.w & m[3]);
+    const uint4 r1 = make_uint4(b.x & m[4], b.y & m[5], b.z & m[6], b.w & m[7]);
+    const uint4 r2 = make_uint4(cc.x & m[8], cc.y & m[9], cc.z & m[10], cc.w & m[11]);
+    if (whole) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)v0 * 3);
+      dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    } else {
+      const uint32_t w[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+      const uint32_t nb = (nvox - v0) * 3u;
+      for (uint32_t k = 0; k < nb; ++k) out[(size_t)v0 * 3 + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3u)));
+    }
+  }
+}
+
 // 32x32 bit-matrix transpose across a warp: lane l enters with row l, lane b leaves with column b (bit j = row j's
 // bit b).  Five butterfly stages (swap the off-diagonal s x s blocks), one shuffle each.
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t v, int lane) {
@@ -691,7 +877,8 @@ part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict
   // full grid
   __shared__ uint32_t s_occ[kClearX * kClearRowW];          // row stride 9 words: conflict-free both ways
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int words = D >> 5;
+  const int words = (D + 31) >> 5;                            // ragged rows: the last word's bits beyond D are never alive
+  const bool rows16 = (D & 15) == 0;                          // 32-voxel runs start on 16-byte boundaries
   const int xb_n = (x_count + kClearX - 1) / kClearX, zb_n = (words + kClearZW - 1) / kClearZW;
   const int x_end = x_begin + x_count;
   out -= (size_t)x_begin * H * D * 3;
@@ -750,13 +937,22 @@ part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict
       // bit j = occ[c - (z0 + 32k + j), y, x + c2]
       const uint32_t* rp = s_occ + (k * 32 + lane) * kClearRowW + warp;
       const uint32_t src = warp_transpose32(__funnelshift_r(rp[0], rp[1], sh), lane);
-      const uint32_t clear = a[k] & ~src;
+      uint32_t clear = a[k] & ~src;
       if (clear == 0u) continue;
-      uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)x * H + y) * D + (size_t)(zw0 + k) * 32) * 3);
-      uint4 v[6] = {dst[0], dst[1], dst[2], dst[3], dst[4], dst[5]};
-      mask96(v, a[k] & src);
+      uint8_t* run = out + (((size_t)x * H + y) * D + (size_t)(zw0 + k) * 32) * 3;
+      if (rows16 && (zw0 + k) * 32 + 32 <= D) {
+        uint4* dst = reinterpret_cast<uint4*>(run);
+        uint4 v[6] = {dst[0], dst[1], dst[2], dst[3], dst[4], dst[5]};
+        mask96(v, a[k] & src);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) dst[q] = v[q];
+        for (int q = 0; q < 6; ++q) dst[q] = v[q];
+      } else {                                                 // ragged row or its last partial word: voxel by voxel
+        while (clear) {
+          const int j = __ffs(clear) - 1;
+          clear &= clear - 1u;
+          run[3 * j] = 0; run[3 * j + 1] = 0; run[3 * j + 2] = 0;
+        }
+      }
     }
   }
 }
@@ -1476,11 +1672,11 @@ P3D_API int p3d_mask_carve(const uint8_t* grid, int W, int H, int D, int channel
 }
 
 P3D_API int p3d_fold_analyse(const int32_t* table, int W, int D, uint32_t* inside_bits, int* info, p3d_stream_t stream) {
-  P3D_REQUIRE(W > 0 && D > 0 && D % 32 == 0, "fold_analyse: D must be a multiple of 32");
+  P3D_REQUIRE(W > 0 && D > 0, "fold_analyse: bad shape");
   P3D_REQUIRE(table && inside_bits && info, "fold_analyse: null pointer");
   cudaStream_t st = p3d::as_stream(stream);
   fold_info_init_kernel<<<1, 32, 0, st>>>(info);             // device-side seed: no pageable copy, legal under stream capture
-  const int n = W * (D / 32);
+  const int n = W * ((D + 31) / 32);
   fold_analyse_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, W, D, inside_bits, info);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
@@ -1499,12 +1695,31 @@ P3D_API int p3d_pack_mask_bits(const uint8_t* mask_hw, int H, int W, uint32_t* b
 P3D_API int p3d_global_carve_fold_bits(int W, int H, int D, int x_begin, int x_count, const uint32_t* inside_bits, int c,
                                        const uint32_t* mask_bits, int words_per_row, const uint8_t* colour_hw, int rgb,
                                        uint8_t* out, p3d_stream_t stream) {
-  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0, "global_carve_fold_bits: D must be a multiple of 32");
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && (D % 32 == 0 || (D >= 16 && rgb)),
+              "global_carve_fold_bits: D must be a multiple of 32, or at least 16 with an RGB colour image");
   P3D_REQUIRE(x_begin >= 0 && x_count >= 0 && x_begin + x_count <= W, "global_carve_fold_bits: bad x slab");
   if (x_count == 0) return P3D_OK;
   P3D_REQUIRE(words_per_row >= (W + 31) / 32 + 2, "global_carve_fold_bits: words_per_row too small");
   P3D_REQUIRE(inside_bits && mask_bits && colour_hw && out, "global_carve_fold_bits: null pointer");
   P3D_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "global_carve_fold_bits: out must be 16-byte aligned");
+  if (D % 32 != 0) {                                           // ragged rows: flat 16-voxel groups
+    const uint64_t plane = (uint64_t)H * (uint64_t)D;
+    int planes_max = (int)((((1ull << 31) - 1) / plane) & ~15ull);   // multiples of 16 planes keep every launch 16-byte aligned
+    P3D_REQUIRE(planes_max >= 16 || (uint64_t)x_count * plane < (1ull << 31), "global_carve_fold_bits: x plane too large");
+    if (planes_max < 16 || planes_max > x_count) planes_max = x_count;
+    const unsigned long long magic_d = magic_for((uint64_t)planes_max * plane, (uint64_t)D);
+    const unsigned long long magic_h = magic_for((uint64_t)planes_max * H, (uint64_t)H);
+    cudaStream_t st = p3d::as_stream(stream);
+    for (int xs = 0; xs < x_count; xs += planes_max) {
+      const int xc = x_count - xs < planes_max ? x_count - xs : planes_max;
+      const int64_t warp_groups = (((int64_t)xc * (int64_t)plane + 15) / 16 + 31) / 32;
+      global_fold_bits_ragged_kernel<<<grid_for(warp_groups, 8, 64), 256, 0, st>>>(
+          W, H, D, x_begin + xs, xc, inside_bits, c, mask_bits, words_per_row, colour_hw, out + (size_t)xs * plane * 3, magic_d,
+          magic_h);
+    }
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+  }
   const uint64_t gpr = (uint64_t)D / 16, plane_groups = (uint64_t)H * gpr;
   P3D_REQUIRE(plane_groups < (1ull << 31), "global_carve_fold_bits: x plane too large");
   int slab_max = (int)(((1ull << 31) - 1) / plane_groups);      // x planes per launch: 32-bit group indices in the kernel
@@ -1558,7 +1773,8 @@ P3D_API size_t p3d_part_carve_bits_workspace_bytes(int W, int H, int D, int n_gr
 P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, const uint32_t* inside_bits, int c, int c2,
                                      const uint32_t* group_mask_hw, int n_groups, uint8_t* out, void* workspace,
                                      size_t workspace_bytes, p3d_stream_t stream) {
-  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0 && n_groups >= 1 && n_groups <= 32, "part_carve_fold_bits: bad shape");
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && (D % 32 == 0 || D >= 16) && n_groups >= 1 && n_groups <= 32,
+              "part_carve_fold_bits: bad shape (D must be a multiple of 32 or at least 16)");
   P3D_REQUIRE(grid && inside_bits && group_mask_hw && out && workspace && grid != out, "part_carve_fold_bits: null/aliased");
   P3D_REQUIRE(((reinterpret_cast<uintptr_t>(grid) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
               "part_carve_fold_bits: grids must be 16-byte aligned");
@@ -1566,14 +1782,27 @@ P3D_API int p3d_part_carve_fold_bits(const uint8_t* grid, int W, int H, int D, c
     p3d::set_error("part_carve_fold_bits: workspace too small");
     return P3D_E_WORKSPACE;
   }
-  const int xwp = (W + 31) / 32 + 2;
-  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)(D / 32) * 4, 256);
+  const int xwp = (W + 31) / 32 + 2, words = (D + 31) / 32;
+  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)words * 4, 256);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   uint32_t* occz = reinterpret_cast<uint32_t*>(ws);
   uint32_t* alive = reinterpret_cast<uint32_t*>(ws + zbits);
   uint32_t* gbits = reinterpret_cast<uint32_t*>(ws + 2 * zbits);
   cudaStream_t st = p3d::as_stream(stream);
   pack_group_bits_kernel<<<grid_for((int64_t)H * xwp, 8, 32), 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
+  if (D % 32 != 0) {                                           // ragged rows: flat groups, bit words by atomicOr
+    const int64_t nvox = (int64_t)W * H * D;
+    P3D_REQUIRE(nvox < (1ll << 31), "part_carve_fold_bits: grid too large for 32-bit voxel indices");
+    P3D_CUDA(cudaMemsetAsync(ws, 0, 2 * zbits, st));
+    const unsigned long long magic_d = magic_for((uint64_t)nvox, (uint64_t)D);
+    const unsigned long long magic_hh = magic_for((uint64_t)W * H, (uint64_t)H);
+    part_copy_bits_ragged_kernel<<<grid_for((nvox + 15) / 16, 256, 256), 256, 0, st>>>(
+        grid, W, H, D, inside_bits, c, group_mask_hw, gbits, xwp, occz, alive, out, magic_d, magic_hh, (uint32_t)nvox);
+    const int64_t rtasks = (int64_t)H * ((words + kClearZW - 1) / kClearZW) * ((W + kClearX - 1) / kClearX);
+    part_clear_kernel<<<grid_for(rtasks, 1, 16), kClearX, 0, st>>>(W, H, D, c, c2, occz, alive, out, 0, W, nullptr, 1);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+  }
   const int64_t n16 = (int64_t)W * H * D / 16;
   P3D_REQUIRE(n16 < (1ll << 31), "part_carve_fold_bits: grid too large for 32-bit group indices");
   const unsigned long long magic_gpr = magic_for((uint64_t)n16, (uint64_t)D / 16);

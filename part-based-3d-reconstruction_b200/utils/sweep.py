@@ -175,6 +175,17 @@ def symmetric_workspace(nbytes: int, device, group=None):
     return hit
 
 
+def peer_barrier(hdl, group=None):
+    """Stream-ordered barrier over the ranks of a symmetric-memory rendezvous: one tiny kernel that raises a flag in every
+    peer's signal pad over NVLink and waits for theirs (no NCCL launch, no payload).  Falls back to a one-element
+    all-reduce when this torch build's handle has no barrier."""
+    if hasattr(hdl, "barrier"):
+        hdl.barrier(channel=0)
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=dev), group=group)
+
+
 def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None, slab_cls=None, exchange="alltoall"):
     """part_carve of a grid whose x rows are sharded over the ranks (rank r holds rows shard_range(W, world, r); W must
     divide evenly): pass A per slab, ONE exchange of occupancy bits, pass B per slab.  Returns (output slab, (x0, x1)).
@@ -184,8 +195,9 @@ def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None,
                source row, so each rank sends every other rank just that word range of its own rows -- W*H*D/(8 world)
                bytes received per rank instead of the whole bit array;
              = "peer": no exchange buffer at all -- the workspaces live in NVLink peer-mapped symmetric memory and pass B
-               reads the other ranks' rows in place (p3d_part_carve_slab_pass_b_peers), ordered by two tiny collectives
-               (after every rank's pass A, after every rank's pass B).  NCCL only;
+               reads the other ranks' rows in place (p3d_part_carve_slab_pass_b_peers), ordered by two signal-pad barriers
+               (after every rank's pass A, after every rank's pass B: one flag per peer over NVLink, no NCCL launch).
+               CUDA only;
              = "allgather": the whole bit array on every rank (W*H*D/8 bytes; the round-1 form).
     `slab_cls` replaces voxel_carving_utils.PartCarveSlab (same begin / occ / needed_words / finish interface) in the
     CPU tests of this plumbing."""
@@ -204,11 +216,10 @@ def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None,
         H, D = int(grid_slab.shape[1]), int(grid_slab.shape[2])
         nbytes = slab_cls.workspace_bytes(W, H, D, min(len(list(group_jobs)), 32))
         buf, hdl, ptrs = symmetric_workspace(nbytes, grid_slab.device, group)
-        token = torch.zeros(1, dtype=torch.int32, device=grid_slab.device)
         job = slab_cls(grid_slab, semantic_mask, group_jobs, W, (x0, x1), workspace=buf).begin()
-        dist.all_reduce(token, group=group)                  # every rank's pass A is done (stream-ordered)
+        peer_barrier(hdl, group)                             # every rank's pass A is done (stream-ordered)
         out = job.finish(peers=ptrs, n_ranks=world)
-        dist.all_reduce(token, group=group)                  # every rank's pass B is done: the workspaces may be reused
+        peer_barrier(hdl, group)                             # every rank's pass B is done: the workspaces may be reused
         return out, (x0, x1)
     job = slab_cls(grid_slab, semantic_mask, group_jobs, W, (x0, x1)).begin()
     if world > 1 and exchange == "allgather":

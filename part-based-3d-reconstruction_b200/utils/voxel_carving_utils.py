@@ -184,12 +184,12 @@ _FOLD_BITS_CACHE = {}
 
 
 def _fold_bits(table, W, D, cache_key):
-    """(inside_bits (W, D/32) int32 tensor, c, c2 | None) when the table is z-separable (src0 = c - z; c2 is set when
+    """(inside_bits (W, ceil(D/32)) int32 tensor, c, c2 | None) when the table is z-separable (src0 = c - z; c2 is set when
     additionally src2 = x + c2), else None.  Cached."""
     hit = _FOLD_BITS_CACHE.get(cache_key)
     if hit is not None:
         return hit if hit[0] is not None else None
-    inside = torch.empty((W, D // 32), dtype=torch.int32, device=table.device)
+    inside = torch.empty((W, (D + 31) // 32), dtype=torch.int32, device=table.device)
     info = torch.empty(4, dtype=torch.int32, device=table.device)
     check(lib.p3d_fold_analyse(ptr(table), W, D, ptr(inside), ptr(info), stream_ptr()), "p3d_fold_analyse")
     _launched()
@@ -217,7 +217,8 @@ def _fold_plan(W, H, D, dev):
     if np.array_equal(M0, np.eye(3)) and not off0.any():
         table, foldable = _fold_table(W, D, M, off, dev)
         if foldable:
-            bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D % 32 == 0 else None
+            # bit form: aligned kernels for D % 32 == 0, the flat-group ("ragged") kernels for any other D >= 16
+            bits = _fold_bits(table, W, D, (W, D, M.tobytes(), off.tobytes(), str(dev))) if D >= 16 else None
             plan = (table, bits)
     if len(_FOLD_PLAN) >= 32:
         _FOLD_PLAN.pop(next(iter(_FOLD_PLAN)))
@@ -411,13 +412,32 @@ def _group_image(jobs, H, W):
 
 
 _GROUP_KEYS = {}          # (device, colours per group) -> (keys u32, group_of i32) device tensors
+_NAME_COLOURS = {}        # part names per group -> their PART_COLORS as nested int tuples (PART_COLORS is a constant table)
+
+
+def _job_colours(group_jobs):
+    """PART_COLORS of every group's part names as nested tuples of ints (cached per name structure)."""
+    key = tuple(tuple(names) for names, _ in group_jobs)
+    hit = _NAME_COLOURS.get(key)
+    if hit is None:
+        if len(_NAME_COLOURS) >= 64:
+            _NAME_COLOURS.clear()
+        hit = _NAME_COLOURS[key] = _flat_colours([[PART_COLORS[n] for n in names] for names in key])
+    return hit
+
+
+def _flat_colours(group_colours):
+    if isinstance(group_colours, tuple) and all(isinstance(g, tuple) and all(isinstance(c, tuple) for c in g)
+                                                for g in group_colours):
+        return group_colours                                  # already the nested-tuple form of _job_colours
+    return tuple(tuple(tuple(int(v) for v in np.asarray(c).reshape(3)) for c in cols) for cols in group_colours)
 
 
 def _group_image_device(semantic_mask, group_colours, dev):
     """(H,W) int32 device image of group bits (p3d_group_image): bit g where the pixel's colour belongs to group g, for a
     square image also at the transposed pixel (the reference's _mask_to_wh quirk).  Colours outside 0..255 match
     nothing, as in the reference's comparison with a uint8 image."""
-    flat = tuple(tuple(tuple(int(v) for v in np.asarray(c).reshape(3)) for c in cols) for cols in group_colours)
+    flat = _flat_colours(group_colours)
     hit = _GROUP_KEYS.get((str(dev), flat))
     if hit is None:
         keys, grp = [], []
@@ -469,8 +489,8 @@ def part_carve(colored_grid, semantic_mask, group_jobs, visualize=False, *, x_ra
         if plan is not None:
             table, bits = plan
             n_groups = len(group_jobs)
-            gm_hw = _group_image_device(semantic_mask, [[PART_COLORS[n] for n in names] for names, _ in group_jobs], dev)
-            if x_range is not None and bits is not None and bits[2] is not None and x1 > x0:
+            gm_hw = _group_image_device(semantic_mask, _job_colours(group_jobs), dev)
+            if x_range is not None and bits is not None and bits[2] is not None and x1 > x0 and D % 32 == 0:
                 ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 slab = torch.empty((x1 - x0, H, D, 3), dtype=torch.uint8, device=dev)
@@ -545,7 +565,7 @@ class PartCarveSlab:
         if not ok:
             raise ValueError("sharded-input part_carve needs the all-90-degree bit path (cubic grid, D % 32 == 0, an RGB "
                              "uint8 mask of the grid's (H,W)); carve a replicated grid with part_carve(..., x_range=...)")
-        self.gm_hw = _group_image_device(semantic_mask, [[PART_COLORS[nm] for nm in names] for names, _ in jobs], dev)
+        self.gm_hw = _group_image_device(semantic_mask, _job_colours(jobs), dev)
         self.bits, self.n_groups = bits, len(jobs)
         self.ws_bytes = int(lib.p3d_part_carve_bits_workspace_bytes(W, H, D, len(jobs)))
         if workspace is not None:                             # caller-owned scratch, e.g. symmetric (peer-mapped) memory

@@ -54,6 +54,13 @@ def test_fold_fast_path_is_taken_for_cubic_90(vc):
         assert foldable, W
     M, off = vc._pass_transform((43, 3, 44), 90)
     assert not vc._fold_table(43, 44, M, off, dev)[1]          # half-integer offsets: genuine blend
+    # the bit-packed form of the fold is available for ragged widths too (portrait masks: Charminar is 88 / 177 / 246
+    # wide), not only for multiples of 32; below 16 voxels the table-driven kernels remain
+    for W in (16, 17, 31, 48, 63, 88, 100, 177, 246, 255, 256):
+        plan = vc._fold_plan(W, 5, W, dev)
+        assert plan is not None and plan[1] is not None and plan[1][2] is not None, W
+        assert tuple(plan[1][0].shape) == (W, (W + 31) // 32)
+    assert vc._fold_plan(15, 5, 15, dev)[1] is None
     M, off = vc._pass_transform((32, 3, 32), 5)
     assert not vc._fold_table(32, 32, M, off, dev)[1]
 
@@ -405,3 +412,47 @@ def test_part_carve_asymmetric_golden_full_and_slabs(vc):
             a.occ[cut:] = b.occ[cut:]
             b.occ[:cut] = a.occ[:cut]
             assert np.array_equal(np.concatenate([a.finish(), b.finish()], axis=0), want), tag
+
+
+def _random_part_scene(rng, oracle, W, H, names, uniform, density=0.55):
+    sem = np.empty((H, W, 3), np.uint8)
+    sem[:] = oracle.PART_COLORS["background"]
+    lab = rng.integers(0, len(names) + 1, (H, W))
+    if uniform:
+        lab[:] = 2
+        lab[:, :3] = 0
+        lab[H // 2:, W // 2:] = 3
+    for k, n in enumerate(names):
+        sem[lab == k + 1] = oracle.PART_COLORS[n]
+    grid = np.zeros((W, H, W, 3), np.uint8)
+    occ = rng.random((W, H, W)) < density
+    grid[occ] = sem.transpose(1, 0, 2)[:, :, None, :].repeat(W, axis=2)[occ]
+    return sem, grid
+
+
+def test_ragged_widths_take_the_bit_path_and_match_the_oracle(vc, oracle):
+    """Widths that are no multiple of 32 (and heights that make the voxel count no multiple of 16: byte-wise tails) on
+    the flat-group bit kernels: global_carve with x-slabs and part_carve on asymmetric grids (the clear pass works
+    voxel by voxel there), against the oracle."""
+    rng = np.random.default_rng(1234)
+    names = ["full_building", "plinth", "dome", "front_minarets"]
+    jobs = [([n], 90) for n in names]
+    dev = torch.device("cuda")
+    for (W, H), uniform in (((16, 3), False), ((17, 5), True), ((31, 7), False), ((48, 9), True), ((63, 4), False),
+                            ((88, 11), True), ((100, 3), False), ((177, 6), True), ((246, 2), True), ((255, 3), False)):
+        assert vc._fold_plan(W, H, W, dev)[1] is not None
+        sem, grid = _random_part_scene(rng, oracle, W, H, names, uniform)
+        got = vc.part_carve(grid, sem, jobs)
+        want = oracle.part_carve(grid, sem, jobs)
+        assert np.array_equal(got, want), (W, H)
+        assert 0 < np.count_nonzero(want.any(-1)) < np.count_nonzero(grid.any(-1))
+        cut = W // 2 + 1
+        slabs = [vc.part_carve(grid, sem, jobs, x_range=r) for r in ((0, cut), (cut, W))]
+        assert np.array_equal(np.concatenate(slabs, axis=0), want), (W, H)
+        # global_carve: blobby binary mask + the random semantic image as colours
+        binm = (rng.random((H, W)) < 0.7).astype(np.uint8)
+        binm[:, W // 3:W // 3 + 2] = 1
+        full = vc.global_carve(binm, sem, 90)
+        assert np.array_equal(full, oracle.global_carve(binm, sem, 90)), (W, H)
+        for a, b in ((0, 1), (1, cut), (cut, W)):
+            assert np.array_equal(vc.global_carve(binm, sem, 90, x_range=(a, b)), full[a:b]), (W, H, a, b)
