@@ -309,11 +309,12 @@ int p3d_fold_gather(const uint8_t* vol_in, int n0, int n1, int n2, const int32_t
 int p3d_global_carve_fold(int W, int H, int D, const int32_t* table, const uint8_t* mask_hw,
                           const uint8_t* colour_hw, int rgb, uint8_t* out, p3d_stream_t stream);
 /* Bit-level form of p3d_global_carve_fold for z-separable tables (src0(x,z) = c - z on every in-range entry; true
- * for the 90-degree pass).  p3d_fold_analyse packs table >= 0 into inside_bits (W, D/32) and writes
+ * for the 90-degree pass).  p3d_fold_analyse packs table >= 0 into inside_bits (W, ceil(D/32)) and writes
  * info (4 ints) = [max, min] of src0 + z and [max, min] of src2 - x over the in-range entries (z-separable iff
  * info[0] == info[1] =: c).  p3d_pack_mask_bits packs
  * mask_hw (H,W) into rows of words_per_row >= ceil(W/32) + 2 words with one zero word of padding on each side.
- * D must be a multiple of 32 and out 16-byte aligned.  Same output bytes as p3d_global_carve_fold.
+ * out must be 16-byte aligned; D a multiple of 32, or any D >= 16 with rgb != 0 (ragged rows: 16-voxel groups cut from
+ * the flat voxel order, each spanning at most two z-rows).  Same output bytes as p3d_global_carve_fold.
  * [x_begin, x_begin + x_count) selects an x-slab: out is then the (x_count,H,D[,3]) slab -- the unit of multi-GPU
  * sharding (each output voxel depends only on the 2-D masks, so slabs need no exchange). */
 int p3d_fold_analyse(const int32_t* table, int W, int D, uint32_t* inside_bits, int* info, p3d_stream_t stream);
@@ -336,7 +337,7 @@ int p3d_part_carve_fold(const uint8_t* grid, int W, int H, int D, const int32_t*
                         const uint32_t* group_mask_hw, uint8_t* out, p3d_stream_t stream);
 
 /* Bit-level form of p3d_part_carve_fold for z-separable tables with src0 = c - z and src2 = x + c2 (p3d_fold_analyse:
- * info[0] == info[1] =: c, info[2] == info[3] =: c2).  Needs D % 32 == 0, 16-byte aligned grids and
+ * info[0] == info[1] =: c, info[2] == info[3] =: c2).  Needs D % 32 == 0 or D >= 16 (ragged rows), 16-byte aligned grids and
  * p3d_part_carve_bits_workspace_bytes() of scratch (z-packed occupancy and "alive" bits + per-group mask bits).
  * Two passes: the output is first written from the voxel-local terms, then the runs whose rotated source voxel is
  * empty are cleared (none for an already 4-way-symmetric grid). */

@@ -100,3 +100,29 @@ def test_sweep_workspace_follows_the_batch_rule():
     assert ws(33, 1024, 1024) >= 2 * 33 * per        # just above the floor: two sets, capacity limited by K
     huge = ws(4096, 2048, 2048)                      # 2048^2: 16 cameras per set (268 MB, the floor rule), two sets
     assert 2 * 16 * 4 * per <= huge < 2 * 32 * 4 * per + 8 * mb
+
+
+def test_job_colours_are_cached_per_name_structure():
+    """Host logic of part_carve: the per-group colour lists come from PART_COLORS by part name (cached per name
+    structure) and are recognised as already flat by the group-image helper; anything else is normalised."""
+    import numpy as np
+    vc = pkg("utils.voxel_carving_utils")
+    cfg = pkg("utils.config")
+    jobs = [(["dome", "plinth"], 90), (["front_minarets"], 90), ([], 90)]
+    flat = vc._job_colours(jobs)
+    assert flat == tuple(tuple(tuple(int(v) for v in cfg.PART_COLORS[n]) for n in names) for names, _ in jobs)
+    assert vc._job_colours([(list(n), 45) for n, _ in jobs]) is flat          # the angle is not part of the key
+    assert vc._flat_colours(flat) is flat
+    loose = [[np.asarray(cfg.PART_COLORS[n]) for n in names] for names, _ in jobs]
+    assert vc._flat_colours(loose) == flat
+
+
+def test_bit_workspace_covers_ragged_rows():
+    """p3d_part_carve_bits_workspace_bytes (host arithmetic): two z-packed bit arrays of ceil(D/32) words per row plus
+    the per-group mask rows, for widths that are no multiple of 32 as well."""
+    nv = pkg("utils._native")
+    for W, H, G in ((177, 256, 6), (88, 128, 6), (256, 160, 4), (16, 3, 1)):
+        words, xwp = (W + 31) // 32, (W + 31) // 32 + 2
+        need = 2 * W * H * words * 4 + G * H * xwp * 4
+        got = int(nv.lib.p3d_part_carve_bits_workspace_bytes(W, H, W, G))
+        assert need <= got <= need + 3 * 256, (W, H, G)
