@@ -660,15 +660,18 @@ def carve_sharded_bench(N, dev, world, rank, dist):
         # left is pass A, a tiny all-reduce, pass B reading the peers over NVLink, a tiny all-reduce
         try:
             nbytes = vc.PartCarveSlab.workspace_bytes(N, N, N, len(jobs90))
-            buf, hdl, ptrs = sw.symmetric_workspace(nbytes, dev)
-            job = vc.PartCarveSlab(slab_in, ext, jobs90, N, span, workspace=buf)
+            slots = []                      # two slab objects on two symmetric workspaces used in turn: one barrier per call
+            for slot in (0, 1):
+                buf, hdl, ptrs = sw.symmetric_workspace(nbytes, dev, slot=slot)
+                slots.append((vc.PartCarveSlab(slab_in, ext, jobs90, N, span, workspace=buf), hdl, ptrs))
+            turn = [0]
 
             def steady():
+                job, hdl, ptrs = slots[turn[0] & 1]
+                turn[0] += 1
                 job.begin()
                 sw.peer_barrier(hdl)
-                out = job.finish(peers=ptrs, n_ranks=world)
-                sw.peer_barrier(hdl)
-                return out
+                return job.finish(peers=ptrs, n_ranks=world)
             assert torch.equal(steady(), want)
             for _ in range(3):
                 steady()
@@ -682,7 +685,7 @@ def carve_sharded_bench(N, dev, world, rank, dist):
             eb.record()
             torch.cuda.synchronize()
             sharded_ms["peer_steady"] = ea.elapsed_time(eb) / 20
-            del job
+            del slots
         except Exception as exc:
             print("sharded-input part_carve (peer, steady) failed:", repr(exc), file=sys.stderr)
         del want, slab_in

@@ -915,16 +915,28 @@ part_clear_kernel(int W, int H, int D, int c, int c2, const uint32_t* __restrict
       if (peer_occ != nullptr && row_ok) base = peer_occ[sx / rows_per_rank];
       const uint32_t* row = base + ((size_t)(row_ok ? sx : 0) * H + y) * words;
       uint32_t* so = s_occ + threadIdx.x * kClearRowW;
-      if (vec && ((x_begin + xb * kClearX + c2) & (kClearX - 1)) == 0 && wb >= 0 && wb + kClearZW <= words) {
-        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;      // aligned tile (c2 = 0, the usual fold): one sector per row
-        if (row_ok) { v0 = __ldcg(reinterpret_cast<const uint4*>(row + wb)); v1 = __ldcg(reinterpret_cast<const uint4*>(row + wb) + 1); }
-        so[0] = v0.x; so[1] = v0.y; so[2] = v0.z; so[3] = v0.w; so[4] = v1.x; so[5] = v1.y; so[6] = v1.z; so[7] = v1.w;
-        so[8] = 0u;
-      } else {
 #pragma unroll
-        for (int k = 0; k < kClearRowW; ++k) {
-          const int w = wb + k;
-          so[k] = (row_ok && w >= 0 && w < words) ? __ldcg(row + w) : 0u;
+      for (int k = 0; k < kClearRowW; ++k) so[k] = 0u;
+      if (row_ok) {
+        // only the words this tile's x range consumes: bits [xs, xs + nb) of the row.  A 128-wide slab of an 8-GPU run
+        // needs ONE 16-byte load per source row (these are the loads that cross NVLink in the peer form); the first
+        // version always fetched 32 bytes, and nine scalar words per row whenever the slab did not start on a multiple
+        // of 256 (every odd rank).
+        const int xs = x_begin + xb * kClearX + c2;
+        const int nb = min(kClearX, x_end - (x_begin + xb * kClearX));
+        const int wlo = max(wb, 0), whi = min(wb + (((xs & 31) + nb + 31) >> 5), words);
+        if ((words & 3) == 0) {                              // every bit row starts on a 16-byte boundary
+          for (int q = wlo & ~3; q < whi; q += 4) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(row + q));
+            const uint32_t t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = q + e - wb;
+              if (k >= 0 && k < kClearRowW) so[k] = t[e];
+            }
+          }
+        } else {
+          for (int w = wlo; w < whi; ++w) so[w - wb] = __ldcg(row + w);
         }
       }
     }

@@ -157,15 +157,16 @@ def carve_sharded(carve_slab, W: int, group=None, gather: bool = False):
     return full, (0, W)
 
 
-_SYMM = {}                # (group name, bytes, device) -> (symmetric buffer, rendezvous handle, pointer table)
+_SYMM = {}                # (group name, bytes, device, slot) -> (symmetric buffer, rendezvous handle, pointer table)
+_PEER_TURN = {}           # (group name, bytes, device) -> number of peer-form calls so far (all ranks call in lockstep)
 
 
-def symmetric_workspace(nbytes: int, device, group=None):
+def symmetric_workspace(nbytes: int, device, group=None, slot: int = 0):
     """A uint8 workspace of >= nbytes in NVLink peer-mapped (torch symmetric) memory, identical on every rank, plus the
-    device table of every rank's base pointer.  Collective on first use per (group, size); cached afterwards."""
+    device table of every rank's base pointer.  Collective on first use per (group, size, slot); cached afterwards."""
     import torch.distributed._symmetric_memory as symm
     group = group if group is not None else dist.group.WORLD
-    key = (group.group_name, int(nbytes), str(device))
+    key = (group.group_name, int(nbytes), str(device), int(slot))
     hit = _SYMM.get(key)
     if hit is None:
         buf = symm.empty(int(nbytes), dtype=torch.uint8, device=device)
@@ -195,9 +196,9 @@ def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None,
                source row, so each rank sends every other rank just that word range of its own rows -- W*H*D/(8 world)
                bytes received per rank instead of the whole bit array;
              = "peer": no exchange buffer at all -- the workspaces live in NVLink peer-mapped symmetric memory and pass B
-               reads the other ranks' rows in place (p3d_part_carve_slab_pass_b_peers), ordered by two signal-pad barriers
-               (after every rank's pass A, after every rank's pass B: one flag per peer over NVLink, no NCCL launch).
-               CUDA only;
+               reads the other ranks' rows in place (p3d_part_carve_slab_pass_b_peers), ordered by ONE signal-pad barrier
+               per call (after every rank's pass A: one flag per peer over NVLink, no NCCL launch; two workspaces used
+               in turn make a second barrier after pass B unnecessary).  CUDA only;
              = "allgather": the whole bit array on every rank (W*H*D/8 bytes; the round-1 form).
     `slab_cls` replaces voxel_carving_utils.PartCarveSlab (same begin / occ / needed_words / finish interface) in the
     CPU tests of this plumbing."""
@@ -215,12 +216,18 @@ def part_carve_sharded(grid_slab, semantic_mask, group_jobs, W: int, group=None,
     if world > 1 and exchange == "peer":
         H, D = int(grid_slab.shape[1]), int(grid_slab.shape[2])
         nbytes = slab_cls.workspace_bytes(W, H, D, min(len(list(group_jobs)), 32))
-        buf, hdl, ptrs = symmetric_workspace(nbytes, grid_slab.device, group)
+        # Two workspaces used in turn, ONE barrier per call: call k writes its occupancy rows into workspace k % 2 and
+        # the barrier orders every rank's pass A(k) before any pass B(k).  A peer may read workspace k % 2 until its
+        # pass B(k) ends, and that lies before the barrier of call k + 1 in its stream -- which this rank passes before
+        # pass A(k + 2) touches the same workspace again.  (One workspace needs a second barrier after pass B.)
+        gname = (group if group is not None else dist.group.WORLD).group_name
+        ckey = (gname, int(nbytes), str(grid_slab.device))
+        turn = _PEER_TURN.get(ckey, 0)
+        _PEER_TURN[ckey] = turn + 1
+        buf, hdl, ptrs = symmetric_workspace(nbytes, grid_slab.device, group, slot=turn & 1)
         job = slab_cls(grid_slab, semantic_mask, group_jobs, W, (x0, x1), workspace=buf).begin()
         peer_barrier(hdl, group)                             # every rank's pass A is done (stream-ordered)
-        out = job.finish(peers=ptrs, n_ranks=world)
-        peer_barrier(hdl, group)                             # every rank's pass B is done: the workspaces may be reused
-        return out, (x0, x1)
+        return job.finish(peers=ptrs, n_ranks=world), (x0, x1)
     job = slab_cls(grid_slab, semantic_mask, group_jobs, W, (x0, x1)).begin()
     if world > 1 and exchange == "allgather":
         mine = job.occ[x0:x1].clone()

@@ -60,12 +60,18 @@ def _worker(rank, world, port, out_dir):
     g2d = torch.from_numpy(g2).cuda()
     want2 = vc.part_carve(g2d, sem2, GROUP_JOBS)
     a2, b2 = sw.shard_range(W2, world, rank)
+    # a second grid (other occupancy), carved in alternation with the first: the peer form uses two symmetric
+    # workspaces in turn with one barrier per call, so a stale or prematurely overwritten workspace shows up as a
+    # wrong slab on one of the five back-to-back calls
+    g3d = torch.flip(g2d, dims=[2]).contiguous()
+    want3 = vc.part_carve(g3d, sem2, GROUP_JOBS)
     modes_ok = {}
     for mode in ("alltoall", "allgather", "peer"):
-        for rep in range(2):                                 # twice: the symmetric workspace is reused
+        for rep in range(5):
             try:
-                got2, _ = sw.part_carve_sharded(g2d[a2:b2].contiguous(), sem2, GROUP_JOBS, W2, exchange=mode)
-                modes_ok[mode] = bool(torch.equal(got2, want2[a2:b2]))
+                src, want = (g2d, want2) if rep % 2 == 0 else (g3d, want3)
+                got2, _ = sw.part_carve_sharded(src[a2:b2].contiguous(), sem2, GROUP_JOBS, W2, exchange=mode)
+                modes_ok[mode] = modes_ok.get(mode, True) and bool(torch.equal(got2, want[a2:b2]))
             except Exception as exc:                         # reported, asserted by the parent
                 modes_ok[mode] = repr(exc)
                 break
