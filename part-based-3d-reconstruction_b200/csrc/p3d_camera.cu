@@ -489,24 +489,6 @@ __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 
 #pragma unroll
     for (int jj = 0; jj < kSegGroup; ++jj)
       if (hit[jj]) cur[jj] = __ldcg(addr[jj]);
-#ifdef P3D_SEG_MERGEBR
-    // experiment: one branch around the group's reductions (most groups need none) instead of one per point
-    bool need[kSegGroup], any = false;
-#pragma unroll
-    for (int jj = 0; jj < kSegGroup; ++jj) {
-      need[jj] = hit[jj] && (MODE != P3D_MODE_PER_PART ? cur[jj] < kmax : (cur[jj] & key0) != key0);
-      any = any || need[jj];
-    }
-    if (any) {
-#pragma unroll
-      for (int jj = 0; jj < kSegGroup; ++jj) {
-        if (need[jj]) {
-          if (MODE != P3D_MODE_PER_PART) atomicMax(addr[jj], key0 + (uint32_t)(g * kSegGroup + jj) * kstep);
-          else atomicOr(addr[jj], key0);
-        }
-      }
-    }
-#else
 #pragma unroll
     for (int jj = 0; jj < kSegGroup; ++jj) {
       if (MODE != P3D_MODE_PER_PART) {
@@ -515,7 +497,6 @@ __device__ __forceinline__ uint32_t seg_camera_pass(const f32x2 (&QX)[kSegLen / 
         if (hit[jj] && (cur[jj] & key0) != key0) atomicOr(addr[jj], key0);
       }
     }
-#endif
   }
   return und;
 }
