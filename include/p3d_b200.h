@@ -362,6 +362,14 @@ int p3d_part_carve_slab_pass_a(const uint8_t* grid_slab, int W, int H, int D, in
                                uint8_t* out_slab, void* workspace, size_t workspace_bytes, p3d_stream_t stream);
 int p3d_part_carve_slab_pass_b(int W, int H, int D, int x_begin, int x_count, int c, int c2, uint8_t* out_slab,
                                void* workspace, size_t workspace_bytes, p3d_stream_t stream);
+/* pass A split for callers that carve many grids with ONE mask and job list (the groups of voxel_carving_utils.py:143-146
+ * do not depend on the grid): p3d_part_carve_pack_groups writes the per-group mask bits into the workspace once,
+ * p3d_part_carve_slab_pass_a_packed is pass A without that step. */
+int p3d_part_carve_pack_groups(const uint32_t* group_mask_hw, int W, int H, int D, int n_groups, void* workspace,
+                               size_t workspace_bytes, p3d_stream_t stream);
+int p3d_part_carve_slab_pass_a_packed(const uint8_t* grid_slab, int W, int H, int D, int x_begin, int x_count,
+                                      const uint32_t* inside_bits, int c, const uint32_t* group_mask_hw, int n_groups,
+                                      uint8_t* out_slab, void* workspace, size_t workspace_bytes, p3d_stream_t stream);
 /* pass B fused with the exchange: instead of gathering the other ranks' occupancy rows first, the kernel reads every
  * source row straight from the workspace of the rank that owns it.  peer_workspaces: DEVICE array of n_ranks pointers,
  * entry r = rank r's workspace (the same layout on every rank) mapped into this process -- NVLink peer mappings, e.g.

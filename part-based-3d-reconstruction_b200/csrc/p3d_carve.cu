@@ -1883,9 +1883,47 @@ P3D_API int p3d_part_carve_fold_bits_slab(const uint8_t* grid, int W, int H, int
 // output and its rows of the z-packed occupancy / alive bits; the ranks then exchange the occupancy rows (the first
 // W*H*(D/32) uint32 of the workspace, [x][y][word], slab rows contiguous: one all-gather, 1/24 of the grid bytes) and pass
 // B clears the runs whose rotated source is empty.
+static int slab_pass_a(const uint8_t* grid_slab, int W, int H, int D, int x_begin, int x_count, const uint32_t* inside_bits,
+                       int c, const uint32_t* group_mask_hw, int n_groups, uint8_t* out_slab, void* workspace,
+                       size_t workspace_bytes, p3d_stream_t stream, bool pack_groups);
+
 P3D_API int p3d_part_carve_slab_pass_a(const uint8_t* grid_slab, int W, int H, int D, int x_begin, int x_count,
                                        const uint32_t* inside_bits, int c, const uint32_t* group_mask_hw, int n_groups,
                                        uint8_t* out_slab, void* workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  return slab_pass_a(grid_slab, W, H, D, x_begin, x_count, inside_bits, c, group_mask_hw, n_groups, out_slab, workspace,
+                     workspace_bytes, stream, true);
+}
+
+// The same pass with the per-group mask bits already in the workspace (p3d_part_carve_pack_groups): a caller that carves
+// many grids with one mask and one job list packs them once.
+P3D_API int p3d_part_carve_slab_pass_a_packed(const uint8_t* grid_slab, int W, int H, int D, int x_begin, int x_count,
+                                              const uint32_t* inside_bits, int c, const uint32_t* group_mask_hw,
+                                              int n_groups, uint8_t* out_slab, void* workspace, size_t workspace_bytes,
+                                              p3d_stream_t stream) {
+  return slab_pass_a(grid_slab, W, H, D, x_begin, x_count, inside_bits, c, group_mask_hw, n_groups, out_slab, workspace,
+                     workspace_bytes, stream, false);
+}
+
+P3D_API int p3d_part_carve_pack_groups(const uint32_t* group_mask_hw, int W, int H, int D, int n_groups, void* workspace,
+                                       size_t workspace_bytes, p3d_stream_t stream) {
+  P3D_REQUIRE(W > 0 && H > 0 && D > 0 && n_groups >= 1 && n_groups <= 32, "part_carve_pack_groups: bad shape");
+  P3D_REQUIRE(group_mask_hw && workspace, "part_carve_pack_groups: null pointer");
+  if (workspace_bytes < p3d_part_carve_bits_workspace_bytes(W, H, D, n_groups)) {
+    p3d::set_error("part_carve_pack_groups: workspace too small");
+    return P3D_E_WORKSPACE;
+  }
+  const int xwp = (W + 31) / 32 + 2;
+  const size_t zbits = p3d_align_up((size_t)W * H * (size_t)((D + 31) / 32) * 4, 256);
+  uint32_t* gbits = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(workspace) + 2 * zbits);
+  pack_group_bits_kernel<<<grid_for((int64_t)H * xwp, 8, 32), 256, 0, p3d::as_stream(stream)>>>(group_mask_hw, H, W, n_groups,
+                                                                                              xwp, gbits);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+static int slab_pass_a(const uint8_t* grid_slab, int W, int H, int D, int x_begin, int x_count, const uint32_t* inside_bits,
+                       int c, const uint32_t* group_mask_hw, int n_groups, uint8_t* out_slab, void* workspace,
+                       size_t workspace_bytes, p3d_stream_t stream, bool pack_groups) {
   P3D_REQUIRE(W > 0 && H > 0 && D > 0 && D % 32 == 0 && n_groups >= 1 && n_groups <= 32, "part_carve_slab_pass_a: bad shape");
   P3D_REQUIRE(x_begin >= 0 && x_count >= 0 && x_begin + x_count <= W, "part_carve_slab_pass_a: bad x slab");
   if (x_count == 0) return P3D_OK;
@@ -1904,7 +1942,8 @@ P3D_API int p3d_part_carve_slab_pass_a(const uint8_t* grid_slab, int W, int H, i
   uint32_t* alive = reinterpret_cast<uint32_t*>(ws + zbits);
   uint32_t* gbits = reinterpret_cast<uint32_t*>(ws + 2 * zbits);
   cudaStream_t st = p3d::as_stream(stream);
-  pack_group_bits_kernel<<<grid_for((int64_t)H * xwp, 8, 32), 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
+  if (pack_groups)
+    pack_group_bits_kernel<<<grid_for((int64_t)H * xwp, 8, 32), 256, 0, st>>>(group_mask_hw, H, W, n_groups, xwp, gbits);
   const int64_t n16 = (int64_t)W * H * D / 16;
   P3D_REQUIRE(n16 < (1ll << 31), "part_carve_slab_pass_a: grid too large for 32-bit group indices");
   const unsigned long long magic_gpr = magic_for((uint64_t)n16, (uint64_t)D / 16);

@@ -101,6 +101,8 @@ _SIGNATURES = {
     "p3d_part_carve_fold_bits": ([_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp], _i32),
     "p3d_part_carve_fold_bits_slab": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp], _i32),
     "p3d_part_carve_slab_pass_a": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _sz, _vp], _i32),
+    "p3d_part_carve_slab_pass_a_packed": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _sz, _vp], _i32),
+    "p3d_part_carve_pack_groups": ([_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp], _i32),
     "p3d_part_carve_slab_pass_b": ([_i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp], _i32),
     "p3d_part_carve_slab_pass_b_peers": ([_i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp, _i32, _vp], _i32),
     "p3d_crop_occupancy": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], _i32),

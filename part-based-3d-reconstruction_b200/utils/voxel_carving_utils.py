@@ -577,14 +577,19 @@ class PartCarveSlab:
         words = D // 32
         self.occ = self.ws[:W * H * words * 4].view(torch.int32).view(W, H, words)
         self.out = torch.empty_like(self.grid)
+        # the per-group mask bits depend on the mask and the job list only: packed once per object, so that begin() /
+        # finish() can be repeated (e.g. on new contents of the same input tensor) with two launches
+        check(lib.p3d_part_carve_pack_groups(ptr(self.gm_hw), self.W, self.H, self.D, self.n_groups, ptr(self.ws),
+                                             self.ws_bytes, stream_ptr()), "p3d_part_carve_pack_groups")
+        _launched()
 
     def begin(self):
         if self.x1 > self.x0:
-            check(lib.p3d_part_carve_slab_pass_a(ptr(self.grid), self.W, self.H, self.D, self.x0, self.x1 - self.x0,
-                                                 ptr(self.bits[0]), self.bits[1], ptr(self.gm_hw), self.n_groups,
-                                                 ptr(self.out), ptr(self.ws), self.ws_bytes, stream_ptr()),
-                  "p3d_part_carve_slab_pass_a")
-            _launched(2)
+            check(lib.p3d_part_carve_slab_pass_a_packed(ptr(self.grid), self.W, self.H, self.D, self.x0, self.x1 - self.x0,
+                                                        ptr(self.bits[0]), self.bits[1], ptr(self.gm_hw), self.n_groups,
+                                                        ptr(self.out), ptr(self.ws), self.ws_bytes, stream_ptr()),
+                  "p3d_part_carve_slab_pass_a_packed")
+            _launched()
         return self
 
     @staticmethod
