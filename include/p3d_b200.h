@@ -265,6 +265,20 @@ int p3d_strided_occupancy(const uint8_t* grid_rgb, int A0, int A1, int A2, int s
 int p3d_gather_scale_points(const uint8_t* grid_rgb, int A0, int A1, int A2, int stride, float* pts, int64_t n,
                             uint8_t* rgb, p3d_stream_t stream);
 
+/* meshify_colored_voxel_grid             utils/voxel_utils.py:53-95 (the marching-cubes call at :69-72)
+ *   Marching cubes of a 0/1 volume `mask` (B0,B1,B2) at level 0.5 in this project's canonical order (scikit-image's
+ *   Lewiner order is not reproduced: DESIGN.md 4.7): vertices = midpoints of the grid edges whose voxels differ, by (flat
+ *   index of the lower voxel, axis); faces per cell in flat order from a 256-case table (ambiguous faces separate the
+ *   occupied corners; counter-clockwise seen from the empty side); normals = normalised negated central-difference
+ *   gradient.  p3d_mesh_count fills the workspace and writes totals (DEVICE, 2 x int64: vertices, faces); the caller
+ *   reads them, allocates verts / normals (n_vertices,3) f32 in (a0,a1,a2) and faces (n_faces,3) i32, and calls
+ *   p3d_mesh_emit with the same workspace. */
+size_t p3d_mesh_workspace_bytes(int B0, int B1, int B2);
+int p3d_mesh_count(const uint8_t* mask, int B0, int B1, int B2, void* workspace, size_t workspace_bytes, int64_t* totals,
+                   p3d_stream_t stream);
+int p3d_mesh_emit(const uint8_t* mask, int B0, int B1, int B2, void* workspace, size_t workspace_bytes, int64_t n_vertices,
+                  int64_t n_faces, float* verts, float* normals, int32_t* faces, p3d_stream_t stream);
+
 /* compute_binary_gt                      utils/eval_helpers_intra.py:274-285
  *   p3d_colour_presence: present (p3d_colour_presence_bytes() = 2 MiB, one bit per 24-bit colour r | g<<8 | b<<16)
  *                        = the non-black colours occurring in grid_rgb (n voxels).

@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libp3d_b200.so")
-SOURCES = ["p3d_core.cu", "p3d_camera.cu", "p3d_carve.cu", "p3d_deform.cu"]
-HEADERS = ["p3d_common.cuh", "p3d_project.cuh", os.path.join("..", "..", "include", "p3d_b200.h")]
+SOURCES = ["p3d_core.cu", "p3d_camera.cu", "p3d_carve.cu", "p3d_deform.cu", "p3d_mesh.cu"]
+HEADERS = ["p3d_common.cuh", "p3d_project.cuh", "p3d_mc_table.inc", os.path.join("..", "..", "include", "p3d_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -45,6 +45,9 @@ _SIGNATURES = {
     "p3d_points_fill": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp], _i32),
     "p3d_strided_occupancy": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
     "p3d_gather_scale_points": ([_vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp], _i32),
+    "p3d_mesh_workspace_bytes": ([_i32, _i32, _i32], _sz),
+    "p3d_mesh_count": ([_vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp], _i32),
+    "p3d_mesh_emit": ([_vp, _i32, _i32, _i32, _vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp], _i32),
     "p3d_colour_presence_bytes": ([], _sz),
     "p3d_colour_presence": ([_vp, _i64, _vp, _vp], _i32),
     "p3d_colour_lookup": ([_vp, _i64, _vp, _vp, _vp], _i32),
