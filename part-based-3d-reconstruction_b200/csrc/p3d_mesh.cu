@@ -100,7 +100,10 @@ mesh_count_kernel(const uint8_t* __restrict__ m, int B0, int B1, int B2, uint8_t
   if (threadIdx.x == 0) block_sums[blockIdx.x] = (int32_t)total;
 }
 
-// one CTA: exclusive scans of the per-CTA vertex and triangle counts, totals[0] = vertices, totals[1] = triangles
+// one CTA: exclusive scans of the per-CTA vertex and triangle counts, totals[0] = vertices, totals[1] = triangles.
+// Every thread owns kScanItems consecutive sums per round (the first form, one sum per thread and round, took 1.5 ms for
+// the 524 288 CTAs of a 512^3 volume).
+constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(1024)
 mesh_scan_kernel(const int32_t* __restrict__ block_sums, int64_t nb, int32_t* __restrict__ block_v, int32_t* __restrict__ block_t,
                  int64_t* __restrict__ totals) {
@@ -109,11 +112,17 @@ mesh_scan_kernel(const int32_t* __restrict__ block_sums, int64_t nb, int32_t* __
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { carry_v = 0; carry_t = 0; }
   __syncthreads();
-  for (int64_t base = 0; base < nb; base += 1024) {
-    const int64_t b = base + threadIdx.x;
-    const uint32_t s = b < nb ? (uint32_t)block_sums[b] : 0u;
-    long long iv = s & 0xffffu, it = s >> 16;
-    const long long ov = iv, ot = it;
+  for (int64_t base = 0; base < nb; base += 1024 * kScanItems) {
+    const int64_t b0 = base + (int64_t)threadIdx.x * kScanItems;
+    uint32_t s[kScanItems];
+    long long iv = 0, it = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+      s[q] = b0 + q < nb ? (uint32_t)block_sums[b0 + q] : 0u;
+      iv += s[q] & 0xffffu;
+      it += s[q] >> 16;
+    }
+    const long long ov = iv, ot = it;                        // this thread's totals
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const long long tv = __shfl_up_sync(0xffffffffu, iv, d), tt = __shfl_up_sync(0xffffffffu, it, d);
@@ -126,9 +135,15 @@ mesh_scan_kernel(const int32_t* __restrict__ block_sums, int64_t nb, int32_t* __
       if (w < warp) { bv += warp_v[w]; bt += warp_t[w]; }
       av += warp_v[w]; at += warp_t[w];
     }
-    if (b < nb) {
-      block_v[b] = (int32_t)(bv + iv - ov);     // the host refuses meshes with 2^31 or more vertices / triangles
-      block_t[b] = (int32_t)(bt + it - ot);
+    long long ev = bv + iv - ov, et = bt + it - ot;           // exclusive prefix of this thread's first sum
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+      if (b0 + q < nb) {
+        block_v[b0 + q] = (int32_t)ev;                       // the host refuses meshes with 2^31 or more vertices / triangles
+        block_t[b0 + q] = (int32_t)et;
+      }
+      ev += s[q] & 0xffffu;
+      et += s[q] >> 16;
     }
     __syncthreads();
     if (threadIdx.x == 0) { carry_v += av; carry_t += at; }
