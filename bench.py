@@ -351,6 +351,10 @@ def run_ours(args):
         p5 = out["other_configs"].get("synthetic_1024_2048mask", {}).get("parity")
         if p5 is not None and p5.get("ok") is False:
             out.setdefault("parity", {})["config5_ok"] = False
+        for key in ("taj_front_minarets", "taj_drone_minarets"):          # the real-data checks fail the run as well
+            pt = out["other_configs"].get(key, {}).get("parity")
+            if pt is not None and pt.get("ok") is False:
+                out.setdefault("parity", {})["taj_ok"] = False
     if carve_multi is not None:
         out["carve"] = carve_multi
     if config5 is not None:
@@ -372,7 +376,7 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     failed = ((parity is not None and parity.get("ok") is False) or out.get("parity", {}).get("config5_ok") is False
-              or out.get("parity", {}).get("carve_ok") is False)
+              or out.get("parity", {}).get("carve_ok") is False or out.get("parity", {}).get("taj_ok") is False)
     if failed:
         print("PARITY GATE FAILED: " + json.dumps(out.get("parity")), file=sys.stderr)
         sys.exit(1)
@@ -1024,6 +1028,28 @@ def extra_configs(dev, with_cpu):
                                          "sample": "first 64 candidates, 1 process, 1 BLAS thread"}
                 entry["parity"] = {"checked": n, "ok": not bad, "scores_bit_identical": identical, "mismatches": bad[:2]}
             out["taj_front_" + tag] = entry
+        # BASELINE.json configs[1] names front + aerial masks: the same sweep against the drone view's mask and stored camera
+        try:
+            drone = mu.load_mask(data, "Taj", "drone", int(max(grid.shape)))
+            cd = cams["drone"]
+            base_d = np.array([*cd["cam_pos"], *cd["target"], cd["f"], cd["cx"], cd["cy"]])
+            cand_d = syn.candidates(base_d, 4096)
+            for tag, parts in (("minarets", ["front_minarets", "back_minarets"]), ("all_parts", syn.PART_NAMES)):
+                sc = ce.CandidateScorer(gdev, drone, cfg.PART_COLORS, parts)
+                entry = {"points": sc.n_points, "mask": list(drone.shape[:2]), "candidates": len(cand_d),
+                         "value": round(rate(sc, cand_d), 1), "unit": UNIT}
+                if with_cpu and tag == "minarets":
+                    import cpu_arm
+                    lut = np.zeros((256, 3), np.uint8)
+                    lut[1:1 + len(sc.colours)] = np.array(sc.colours, np.uint8)
+                    cpu = cpu_arm.CpuScorer(sc.pts.cpu().numpy(), lut[sc.pt_label.cpu().numpy()], drone, parts,
+                                            part_colors=cfg.PART_COLORS)
+                    g_scores, g_counts, _ = sc.score(cand_d[:32])
+                    dt, n, bad, identical = compare_with_cpu(cpu, cand_d[:32], g_counts, g_scores, 1)
+                    entry["parity"] = {"checked": n, "ok": not bad, "scores_bit_identical": identical, "mismatches": bad[:2]}
+                out["taj_drone_" + tag] = entry
+        except Exception as exc:
+            out["taj_drone_error"] = repr(exc)
         # notebook 3's part-wise deformation sweep on the same grid: dome, fixed final camera
         try:
             de = importlib.import_module(PKG + ".utils.deformation_estimation")
