@@ -442,8 +442,31 @@ def config5_sweep(dev, world, rank, dist, with_cpu):
             gc = counts.cpu().numpy()[pick][:, sc._cols, :]
             dt, n, bad, identical = compare_with_cpu(cpu, cand[pick], gc, scores.cpu().numpy()[pick], 1)
             out["parity"] = {"checked": n, "ok": not bad, "kind": cpu.kind, "scores_bit_identical": identical, "mismatches": bad[:2]}
+            del pts, cols, cpu
         except MemoryError as exc:
             out["parity"] = {"checked": 0, "ok": None, "error": repr(exc)}
+    # the second view of the "multi-view" sweep: the same point list against the aerial mask (CandidateScorer.set_image)
+    try:
+        base_a = syn.base_camera(N, H, W, "aerial")
+        sc.set_image(sc.render(ce.row_to_params(base_a + HIDDEN_DELTA)))
+        cand_a = syn.candidates(base_a, B * world)
+        mine = torch.from_numpy(np.ascontiguousarray(cand_a[rank * B:(rank + 1) * B])).to(dev)
+        step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            res_a, _, _ = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ta = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        va = B * world / (float(ta.item()) / reps * 1e-3)
+        out["aerial"] = {"value": round(va, 1), "per_gpu": round(va / world, 1), "frac": round(va / world / model, 4),
+                         "best": {"index": int(res_a[1]), "score": float(res_a[0])}}
+    except Exception as exc:
+        out["aerial"] = {"error": repr(exc)}
     del sc
     torch.cuda.empty_cache()
     return out

@@ -111,13 +111,9 @@ class CandidateScorer:
                 raise ValueError("a part colour of (0,0,0) is indistinguishable from empty pixels")
             if len(self.colours) > nv.MAX_PARTS:
                 raise ValueError(f"at most {nv.MAX_PARTS} distinct part colours")
-            img = nv.to_device(image, torch.uint8, self.device)
-            self.H, self.W = int(img.shape[0]), int(img.shape[1])
-            self.gt_label = image_labels(img, self.colours, self.device)
-            self.gt_any = None
-            if self.mode == nv.MODE_PER_PART:
-                bg = part_colors.get("background", (0, 0, 0)) if background is None else background
-                self.gt_any = (image_labels(img, [tuple(int(v) for v in bg)], self.device) == 0).to(torch.uint8)
+            bg = part_colors.get("background", (0, 0, 0)) if background is None else background
+            self._background = tuple(int(v) for v in bg)
+            self.set_image(image)
             self.pal = nv.palette_tensor(self.colours, self.device)
             self.workspace = eng.SweepWorkspace(self.device)
             # x-run segments of the point list (ascending flat index => rows are consecutive in x): the sweep's
@@ -132,6 +128,18 @@ class CandidateScorer:
         self.P = len(self.colours)
         self._cols = [self.label_of[p] - 1 for p in self.parts]
         self._dedup = len(self.colours) != len(self.parts)
+
+    def set_image(self, image):
+        """Score against another 2-D mask (another view of the same monument: the front and the drone mask of notebook 2)
+        without rebuilding the point list and its segments: only the ground-truth label image changes."""
+        with torch.cuda.device(self.device):
+            img = nv.to_device(image, torch.uint8, self.device)
+            self.H, self.W = int(img.shape[0]), int(img.shape[1])
+            self.gt_label = image_labels(img, self.colours, self.device)
+            self.gt_any = None
+            if self.mode == nv.MODE_PER_PART:
+                self.gt_any = (image_labels(img, [self._background], self.device) == 0).to(torch.uint8)
+        return self
 
     @property
     def n_points(self) -> int:

@@ -142,6 +142,25 @@ def test_per_part_mode(mods, camera_golden, taj):
     assert np.array_equal(counts[1], counts[0])
 
 
+def test_set_image_switches_the_view_without_a_rebuild(mods, taj):
+    """CandidateScorer.set_image: the drone mask scored by a scorer built on the front mask equals a scorer built on the
+    drone mask (joint and per-part mode, images of different sizes), and switching back restores the front scores."""
+    cams = taj["cams"]
+    rows = {v: np.array([*cams[v]["cam_pos"], *cams[v]["target"], cams[v]["f"], cams[v]["cx"], cams[v]["cy"]]) for v in ("front", "drone")}
+    cand = {v: mods.ce.random_candidates(rows[v], 9, np.random.default_rng(2)) for v in rows}
+    for mode in ("joint", "per_part"):
+        a = mods.ce.CandidateScorer(taj["grid"], taj["front"], mods.cfg.PART_COLORS, MINARETS, mode=mode)
+        f0 = a.score(cand["front"])
+        a.set_image(taj["drone"])
+        assert (a.H, a.W) == taj["drone"].shape[:2]
+        d0 = a.score(cand["drone"])
+        b = mods.ce.CandidateScorer(taj["grid"], taj["drone"], mods.cfg.PART_COLORS, MINARETS, mode=mode)
+        d1 = b.score(cand["drone"])
+        assert np.array_equal(d0[0], d1[0]) and np.array_equal(d0[1], d1[1]) and d0[2] == d1[2]
+        f1 = a.set_image(taj["front"]).score(cand["front"])
+        assert np.array_equal(f0[0], f1[0]) and np.array_equal(f0[1], f1[1])
+
+
 def test_batching_determinism_and_ties(mods, taj):
     """K larger than one z-buffer batch; repeated runs byte-identical; duplicate best -> first index."""
     p = taj["cams"]["front"]
