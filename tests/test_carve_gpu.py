@@ -456,3 +456,5 @@ def test_ragged_widths_take_the_bit_path_and_match_the_oracle(vc, oracle):
         assert np.array_equal(full, oracle.global_carve(binm, sem, 90)), (W, H)
         for a, b in ((0, 1), (1, cut), (cut, W)):
             assert np.array_equal(vc.global_carve(binm, sem, 90, x_range=(a, b)), full[a:b]), (W, H, a, b)
+    with pytest.raises(ValueError):                          # the sharded-input form still needs whole 32-voxel words
+        vc.PartCarveSlab(np.ascontiguousarray(grid[:cut]), sem, jobs, W, (0, cut))
