@@ -167,8 +167,11 @@ __device__ __forceinline__ void gradient(const uint8_t* __restrict__ m, int i, i
 
 __global__ void __launch_bounds__(kMeshThreads)
 mesh_vertices_kernel(const uint8_t* __restrict__ m, int B0, int B1, int B2, const uint8_t* __restrict__ code,
-                     const int32_t* __restrict__ block_v, int32_t* __restrict__ voff, float* __restrict__ verts,
-                     float* __restrict__ normals) {
+                     const int32_t* __restrict__ block_sums, const int32_t* __restrict__ block_v, int32_t* __restrict__ voff,
+                     float* __restrict__ verts, float* __restrict__ normals) {
+  // a CTA without vertices has nothing to write: its voxels' offsets are never read either (a face only refers to voxels
+  // that own a vertex) -- most of a monument grid is empty space or solid interior
+  if (((uint32_t)block_sums[blockIdx.x] & 0xffffu) == 0u) return;
   const int64_t n = (int64_t)B0 * B1 * B2;
   const int64_t v = (int64_t)blockIdx.x * kMeshThreads + threadIdx.x;
   const uint32_t c = v < n ? code[v] : 0u;
@@ -212,7 +215,9 @@ mesh_vertices_kernel(const uint8_t* __restrict__ m, int B0, int B1, int B2, cons
 
 __global__ void __launch_bounds__(kMeshThreads)
 mesh_faces_kernel(const uint8_t* __restrict__ m, int B0, int B1, int B2, const uint8_t* __restrict__ code,
-                  const int32_t* __restrict__ block_t, const int32_t* __restrict__ voff, int32_t* __restrict__ faces) {
+                  const int32_t* __restrict__ block_sums, const int32_t* __restrict__ block_t, const int32_t* __restrict__ voff,
+                  int32_t* __restrict__ faces) {
+  if (((uint32_t)block_sums[blockIdx.x] >> 16) == 0u) return;
   const int64_t n = (int64_t)B0 * B1 * B2;
   const int64_t v = (int64_t)blockIdx.x * kMeshThreads + threadIdx.x;
   const uint32_t c = v < n ? code[v] : 0u;
@@ -276,9 +281,9 @@ P3D_API int p3d_mesh_emit(const uint8_t* mask, int B0, int B1, int B2, void* wor
   }
   const MeshWs w = mesh_layout(workspace, B0, B1, B2);
   cudaStream_t st = p3d::as_stream(stream);
-  mesh_vertices_kernel<<<(unsigned)w.nb, kMeshThreads, 0, st>>>(mask, B0, B1, B2, w.code, w.block_v, w.voff, verts, normals);
+  mesh_vertices_kernel<<<(unsigned)w.nb, kMeshThreads, 0, st>>>(mask, B0, B1, B2, w.code, w.block_sums, w.block_v, w.voff, verts, normals);
   if (n_faces > 0)
-    mesh_faces_kernel<<<(unsigned)w.nb, kMeshThreads, 0, st>>>(mask, B0, B1, B2, w.code, w.block_t, w.voff, faces);
+    mesh_faces_kernel<<<(unsigned)w.nb, kMeshThreads, 0, st>>>(mask, B0, B1, B2, w.code, w.block_sums, w.block_t, w.voff, faces);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
