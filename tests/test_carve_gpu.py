@@ -458,3 +458,21 @@ def test_ragged_widths_take_the_bit_path_and_match_the_oracle(vc, oracle):
             assert np.array_equal(vc.global_carve(binm, sem, 90, x_range=(a, b)), full[a:b]), (W, H, a, b)
     with pytest.raises(ValueError):                          # the sharded-input form still needs whole 32-voxel words
         vc.PartCarveSlab(np.ascontiguousarray(grid[:cut]), sem, jobs, W, (0, cut))
+
+
+def test_ragged_random_shapes_vs_oracle(vc, oracle):
+    """Thirty random (W, H) with W in 16..90 (every residue mod 16 and mod 32, H from 1) -- rows whose byte length is no
+    multiple of 4, groups straddling rows at every offset, voxel counts with every remainder mod 16 -- global_carve and
+    part_carve against the oracle."""
+    rng = np.random.default_rng(2024)
+    names = ["full_building", "plinth", "dome", "front_minarets"]
+    jobs = [([n], 90) for n in names]
+    seen = set()
+    for t in range(30):
+        W, H = int(rng.integers(16, 91)), int(rng.integers(1, 8))
+        seen.add((W * H * W) % 16)
+        sem, grid = _random_part_scene(rng, oracle, W, H, names, uniform=bool(t % 2), density=float(rng.uniform(0.3, 0.8)))
+        assert np.array_equal(vc.part_carve(grid, sem, jobs), oracle.part_carve(grid, sem, jobs)), (W, H)
+        binm = (rng.random((H, W)) < rng.uniform(0.4, 0.95)).astype(np.uint8)
+        assert np.array_equal(vc.global_carve(binm, sem, 90), oracle.global_carve(binm, sem, 90)), (W, H)
+    assert len(seen) >= 6
